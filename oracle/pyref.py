@@ -1,0 +1,338 @@
+"""ctypes binding of the CPU oracle (oracle/libref_dsp.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product (libusc.so and its Python mirror) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libref_dsp.so")
+
+f32p = C.POINTER(C.c_float)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+
+REF_MAX_RADICES = 8
+
+
+class FftPlan(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("nrad", C.c_uint32), ("rad", C.c_uint32 * REF_MAX_RADICES),
+                ("tw", f32p), ("tw_n", C.c_uint32)]
+
+
+class RfftInstance(C.Structure):
+    _fields_ = [("fftLenRFFT", C.c_uint16), ("cplx", FftPlan)]
+
+
+class CfftInstance(C.Structure):
+    _fields_ = [("fftLen", C.c_uint16), ("plan", FftPlan)]
+
+
+class FirInstance(C.Structure):
+    _fields_ = [("numTaps", C.c_uint16), ("pState", f32p), ("pCoeffs", f32p)]
+
+
+class ChirpParams(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("fs", C.c_float), ("f0", C.c_float), ("f1", C.c_float),
+                ("sweep_T", C.c_float), ("phase", C.c_float)]
+
+
+class History(C.Structure):
+    _fields_ = [("mag_max", C.c_float), ("mag_max_left", C.c_float), ("mag_max_right", C.c_float),
+                ("max_freq", C.c_int32), ("max_freq_left", C.c_int32), ("max_freq_right", C.c_int32),
+                ("max_idx", C.c_uint32), ("max_idx_left", C.c_uint32), ("max_idx_right", C.c_uint32),
+                ("mag_mean", C.c_float), ("snr", C.c_float), ("rank", C.c_char)]
+
+
+class Receiver(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("fs", C.c_float), ("bandwidth", C.c_uint32),
+                ("bandwidth2", C.c_uint32), ("idx_left_zero", C.c_uint32), ("hann", f32p),
+                ("up_chirp", f32p), ("down_chirp", f32p), ("S", RfftInstance)]
+
+
+class Compressor(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("fs", C.c_float), ("window", f32p), ("H_up", f32p),
+                ("H_down", f32p), ("S", RfftInstance)]
+
+
+def build(force=False):
+    """Compile the oracle (gcc, seconds).  Building the checker is not using it."""
+    if force or not os.path.exists(_LIB_PATH) or \
+            os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f))
+                                              for f in ("ref_dsp.c", "ref_dsp.h")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env=dict(os.environ, CC="gcc"))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.ref_arm_cos_f32.restype = C.c_float
+        L.ref_arm_cos_f32.argtypes = [C.c_float]
+        L.ref_idx2freq.restype = C.c_int32
+        L.ref_fft_radices.restype = C.c_uint32
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(f32p)
+
+
+def _up(a):
+    return a.ctypes.data_as(u32p)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---- primitives -------------------------------------------------------------------------------
+def arm_cos_f32(x):
+    L = lib()
+    x = np.atleast_1d(np.asarray(x, dtype=np.float32))
+    return np.array([L.ref_arm_cos_f32(C.c_float(float(v))) for v in x], dtype=np.float32)
+
+
+def arm_sin_cos_f32(theta_deg):
+    s, c = C.c_float(), C.c_float()
+    lib().ref_arm_sin_cos_f32(C.c_float(float(theta_deg)), C.byref(s), C.byref(c))
+    return np.float32(s.value), np.float32(c.value)
+
+
+def hann_window(n, symmetric=False):
+    w = np.empty(n, np.float32)
+    lib().ref_hann_window(_fp(w), C.c_uint32(n), C.c_int(1 if symmetric else 0))
+    return w
+
+
+def generate_ref_chirp(variant, n, fs, f0, f1, sweep_T, phase, up):
+    v = {"R": 0, "S": 1, "T": 2, "F": 3}[variant]
+    out = np.empty(2 * n if variant == "S" else n, np.float32)
+    p = ChirpParams(n, fs, f0, f1, sweep_T, phase)
+    lib().ref_generate_ref_chirp(C.c_int(v), C.byref(p), C.c_int(1 if up else 0), _fp(out))
+    return out
+
+
+def arm_mult_f32(a, b):
+    a, b = f32(a), f32(b)
+    d = np.empty_like(a)
+    lib().ref_arm_mult_f32(_fp(a), _fp(b), _fp(d), C.c_uint32(a.size))
+    return d
+
+
+def arm_scale_f32(a, s):
+    a = f32(a)
+    d = np.empty_like(a)
+    lib().ref_arm_scale_f32(_fp(a), C.c_float(s), _fp(d), C.c_uint32(a.size))
+    return d
+
+
+def arm_mean_f32(a):
+    a = f32(a)
+    r = C.c_float()
+    lib().ref_arm_mean_f32(_fp(a), C.c_uint32(a.size), C.byref(r))
+    return np.float32(r.value)
+
+
+def arm_max_f32(a):
+    a = f32(a)
+    r, i = C.c_float(), C.c_uint32()
+    lib().ref_arm_max_f32(_fp(a), C.c_uint32(a.size), C.byref(r), C.byref(i))
+    return np.float32(r.value), int(i.value)
+
+
+def arm_cmplx_mult_cmplx_f32(a, b):
+    a, b = f32(a), f32(b)
+    d = np.empty_like(a)
+    lib().ref_arm_cmplx_mult_cmplx_f32(_fp(a), _fp(b), _fp(d), C.c_uint32(a.size // 2))
+    return d
+
+
+def arm_cmplx_mult_real_f32(a, r):
+    a, r = f32(a), f32(r)
+    d = np.empty_like(a)
+    lib().ref_arm_cmplx_mult_real_f32(_fp(a), _fp(r), _fp(d), C.c_uint32(r.size))
+    return d
+
+
+def arm_cmplx_mag_f32(a):
+    a = f32(a)
+    d = np.empty(a.size // 2, np.float32)
+    lib().ref_arm_cmplx_mag_f32(_fp(a), _fp(d), C.c_uint32(a.size // 2))
+    return d
+
+
+class Rfft:
+    """arm_rfft_fast_instance_f32 + arm_rfft_fast_f32 (packed spectrum)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.S = RfftInstance()
+        st = lib().ref_arm_rfft_fast_init_f32(C.byref(self.S), C.c_uint32(n))
+        if st != 0:
+            raise ValueError("ARM_MATH_ARGUMENT_ERROR")
+
+    def __call__(self, x, inverse=False):
+        x = f32(x).copy()
+        out = np.empty(self.n, np.float32)
+        lib().ref_arm_rfft_fast_f32(C.byref(self.S), _fp(x), _fp(out), C.c_uint8(1 if inverse else 0))
+        return out
+
+    def __del__(self):
+        try:
+            lib().ref_arm_rfft_fast_free(C.byref(self.S))
+        except Exception:
+            pass
+
+
+class Cfft:
+    """arm_cfft_instance_f32 + arm_cfft_f32 (in place, interleaved, natural order)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.S = CfftInstance()
+        st = lib().ref_arm_cfft_init_f32(C.byref(self.S), C.c_uint32(n))
+        if st != 0:
+            raise ValueError("ARM_MATH_ARGUMENT_ERROR")
+
+    def __call__(self, x, inverse=False):
+        x = f32(x).copy()
+        lib().ref_arm_cfft_f32(C.byref(self.S), _fp(x), C.c_uint8(1 if inverse else 0), C.c_uint8(1))
+        return x
+
+    def __del__(self):
+        try:
+            lib().ref_arm_cfft_free(C.byref(self.S))
+        except Exception:
+            pass
+
+
+class Fir:
+    def __init__(self, coeffs_reversed, block):
+        self.c = f32(coeffs_reversed)
+        self.block = block
+        self.state = np.zeros(self.c.size + block - 1, np.float32)
+        self.S = FirInstance()
+        lib().ref_arm_fir_init_f32(C.byref(self.S), C.c_uint16(self.c.size), _fp(self.c),
+                                   _fp(self.state), C.c_uint32(block))
+
+    def __call__(self, x):
+        x = f32(x)
+        d = np.empty_like(x)
+        lib().ref_arm_fir_f32(C.byref(self.S), _fp(x), _fp(d), C.c_uint32(x.size))
+        return d
+
+
+def twiddle(j, n):
+    re, im = C.c_float(), C.c_float()
+    lib().ref_twiddle(C.c_uint32(j), C.c_uint32(n), C.byref(re), C.byref(im))
+    return np.float32(re.value), np.float32(im.value)
+
+
+def fft_radices(n):
+    rad = (C.c_uint32 * REF_MAX_RADICES)()
+    c = lib().ref_fft_radices(C.c_uint32(n), rad)
+    return [int(rad[i]) for i in range(c)]
+
+
+# ---- receiver chain ---------------------------------------------------------------------------
+class RefReceiver:
+    """receiver/Src/main.c DSP chain (variant R tables)."""
+
+    def __init__(self, n=2048, fs=78125.0, f0=16000.0, f1=19000.0, sweep_T=0.0205):
+        self.rx = Receiver()
+        if lib().ref_receiver_init(C.byref(self.rx), C.c_uint32(n), C.c_float(fs), C.c_float(f0),
+                                   C.c_float(f1), C.c_float(sweep_T)) != 0:
+            raise RuntimeError("ref_receiver_init failed")
+        self.n = n
+
+    @property
+    def bandwidth2(self):
+        return int(self.rx.bandwidth2)
+
+    @property
+    def idx_left_zero(self):
+        return int(self.rx.idx_left_zero)
+
+    def table(self, name):
+        return np.ctypeslib.as_array(getattr(self.rx, name), shape=(self.n,)).copy()
+
+    def idx2freq(self, idx):
+        return int(lib().ref_idx2freq(C.byref(self.rx), C.c_uint32(idx)))
+
+    def pipeline(self, signal, up):
+        s = f32(signal).copy()
+        lib().ref_pipeline(C.byref(self.rx), _fp(s), C.c_int(1 if up else 0))
+        return s
+
+    def dsp(self, fifo, sync_position, mag_mean, up):
+        fifo = f32(fifo)
+        h = History()
+        lib().ref_dsp(C.byref(self.rx), _fp(fifo), C.c_uint32(sync_position), C.byref(h),
+                      C.c_float(mag_mean), C.c_int(1 if up else 0))
+        return h
+
+    def demod_frames(self, pcm, nthreads=1):
+        """pcm: (nframes, n) int32 or float32 -> (mag_up, idx_up, mag_down, idx_down)."""
+        pcm = np.ascontiguousarray(pcm)
+        nf = pcm.size // self.n
+        mu, md = np.empty(nf, np.float32), np.empty(nf, np.float32)
+        iu, idn = np.empty(nf, np.uint32), np.empty(nf, np.uint32)
+        if pcm.dtype == np.int32:
+            lib().ref_demod_frames_i32(C.byref(self.rx), pcm.ctypes.data_as(i32p), C.c_size_t(nf),
+                                       _fp(mu), _up(iu), _fp(md), _up(idn), C.c_int(nthreads))
+        elif pcm.dtype == np.float32:
+            lib().ref_demod_frames_f32(C.byref(self.rx), _fp(pcm), C.c_size_t(nf),
+                                       _fp(mu), _up(iu), _fp(md), _up(idn), C.c_int(nthreads))
+        else:
+            raise TypeError(pcm.dtype)
+        return mu, iu, md, idn
+
+    def __del__(self):
+        try:
+            lib().ref_receiver_free(C.byref(self.rx))
+        except Exception:
+            pass
+
+
+class RefCompressor:
+    """experiments/chirp_compression_time_domain chain."""
+
+    def __init__(self, n=2048, fs=100000.0, f1=17000.0, f2=18000.0):
+        self.c = Compressor()
+        if lib().ref_compressor_init(C.byref(self.c), C.c_uint32(n), C.c_float(fs), C.c_float(f1),
+                                     C.c_float(f2)) != 0:
+            raise RuntimeError("ref_compressor_init failed")
+        self.n = n
+
+    def table(self, name):
+        return np.ctypeslib.as_array(getattr(self.c, name), shape=(self.n,)).copy()
+
+    def compress(self, frame, use_up=False):
+        s = f32(frame).copy()
+        lib().ref_compress_chirp(C.byref(self.c), _fp(s), C.c_int(1 if use_up else 0))
+        return s
+
+    def compress_frames(self, pcm, use_up=False, nthreads=1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        nf = pcm.size // self.n
+        mv, mi = np.empty(nf, np.float32), np.empty(nf, np.uint32)
+        lib().ref_compress_frames_i32(C.byref(self.c), pcm.ctypes.data_as(i32p), C.c_size_t(nf),
+                                      C.c_int(1 if use_up else 0), _fp(mv), _up(mi), C.c_int(nthreads))
+        return mv, mi
+
+    def __del__(self):
+        try:
+            lib().ref_compressor_free(C.byref(self.c))
+        except Exception:
+            pass

@@ -1,0 +1,553 @@
+/*
+ * ref_dsp.c — CPU ORACLE (test infrastructure, NOT product code).  See ref_dsp.h.
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -fPIC -shared  (oracle/Makefile).
+ * -ffp-contract=off is REQUIRED: the canonical arithmetic places every FMA explicitly.
+ */
+#include "ref_dsp.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define FMA(a, b, c) __builtin_fmaf((a), (b), (c))
+
+/* ------------------------------------------------------------------------------------------ */
+/* arm_cos_f32 — arm_math.h:5685.  CMSIS-DSP V1.4.5 published algorithm: 512-entry sine table  */
+/* (literals with 8 decimals in arm_common_tables.c) + linear interpolation.  Call sites:      */
+/* receiver/Src/main.c:392 (Hann), experiments/chirp_compression_time_domain/Src/chirp.c:42,64 */
+/* PINNED: reproduces all 24 device .flt captures (PCM x Hann) with 0 mismatches.              */
+/* ------------------------------------------------------------------------------------------ */
+#define FAST_MATH_TABLE_SIZE 512
+static float g_sin_table[FAST_MATH_TABLE_SIZE + 1];
+static int g_sin_table_ready = 0;
+
+static void sin_table_init(void) {
+    if (g_sin_table_ready) return;
+    char buf[32];
+    for (int i = 0; i <= FAST_MATH_TABLE_SIZE; ++i) {
+        snprintf(buf, sizeof buf, "%.8f", sin(2.0 * M_PI * (double) i / (double) FAST_MATH_TABLE_SIZE));
+        g_sin_table[i] = strtof(buf, NULL);
+    }
+    g_sin_table_ready = 1;
+}
+
+float32_t ref_arm_cos_f32(float32_t x) {
+    sin_table_init();
+    float in = x * 0.159154943092f + 0.25f;      /* x/(2*pi) + quarter turn */
+    int32_t n = (int32_t) in;
+    if (in < 0.0f) n--;
+    in = in - (float) n;
+    float findex = (float) FAST_MATH_TABLE_SIZE * in;
+    uint16_t index = ((uint16_t) findex) & 0x1ff;
+    float fract = findex - (float) index;
+    float a = g_sin_table[index];
+    float b = g_sin_table[index + 1];
+    return (1.0f - fract) * a + fract * b;
+}
+
+/* arm_sin_cos_f32 — arm_math.h:4634-4637 (degrees in).  Call sites: receiver/Src/chirp.c:36,
+ * experiments/synchronization/Src/chirp.c:37, experiments/iq_modulation/Src/iq_modem.c:43.
+ * UNPINNED (no capture holds a chirp table).  Defined as the correctly rounded value of
+ * sin/cos(theta_deg * pi/180) evaluated in double: the device's table interpolation differs by
+ * <= ~1e-6, far below the 1e-4 budget and below the 1e-4 rad phase error already carried by the
+ * float32 theta itself (ulp(186000 deg) = 0.0156 deg). */
+void ref_arm_sin_cos_f32(float32_t theta_deg, float32_t *pSinVal, float32_t *pCosVal) {
+    double rad = (double) theta_deg * (M_PI / 180.0);
+    *pSinVal = (float) sin(rad);
+    *pCosVal = (float) cos(rad);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* element-wise primitives                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* arm_mult_f32 — arm_math.h:1938-1942 */
+void ref_arm_mult_f32(const float32_t *a, const float32_t *b, float32_t *dst, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) dst[i] = a[i] * b[i];
+}
+/* arm_scale_f32 — arm_math.h:2508 */
+void ref_arm_scale_f32(const float32_t *src, float32_t scale, float32_t *dst, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) dst[i] = src[i] * scale;
+}
+/* arm_copy_f32 — arm_math.h:2819 */
+void ref_arm_copy_f32(const float32_t *src, float32_t *dst, uint32_t n) {
+    memmove(dst, src, (size_t) n * sizeof(float));
+}
+/* arm_mean_f32 — arm_math.h:6192.  Sequential left-to-right sum, then one division. */
+void ref_arm_mean_f32(const float32_t *src, uint32_t n, float32_t *result) {
+    float sum = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) sum = sum + src[i];
+    *result = sum / (float) n;
+}
+/* arm_max_f32 — arm_math.h:6537-6541.  First occurrence of the maximum (strict '<' update). */
+void ref_arm_max_f32(const float32_t *src, uint32_t n, float32_t *result, uint32_t *index) {
+    float out = src[0];
+    uint32_t oi = 0;
+    for (uint32_t i = 1; i < n; ++i)
+        if (out < src[i]) { out = src[i]; oi = i; }
+    *result = out;
+    *index = oi;
+}
+/* arm_cmplx_mult_cmplx_f32 — arm_math.h:6579-6583.  (a+jb)(c+jd), no conjugate.
+ * canonical: re = fma(a,c,-(b*d)); im = fma(a,d,b*c). */
+static inline void cmul(float ar, float ai, float br, float bi, float *re, float *im) {
+    float t0 = ai * bi;
+    float t1 = ai * br;
+    *re = FMA(ar, br, -t0);
+    *im = FMA(ar, bi, t1);
+}
+void ref_arm_cmplx_mult_cmplx_f32(const float32_t *a, const float32_t *b, float32_t *dst, uint32_t ncplx) {
+    for (uint32_t i = 0; i < ncplx; ++i) {
+        float re, im;
+        cmul(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], &re, &im);
+        dst[2 * i] = re;
+        dst[2 * i + 1] = im;
+    }
+}
+/* arm_cmplx_mult_real_f32 — arm_math.h:6425-6429 */
+void ref_arm_cmplx_mult_real_f32(const float32_t *cplx, const float32_t *real, float32_t *dst, uint32_t ncplx) {
+    for (uint32_t i = 0; i < ncplx; ++i) {
+        float r = real[i];
+        float re = cplx[2 * i] * r, im = cplx[2 * i + 1] * r;
+        dst[2 * i] = re;
+        dst[2 * i + 1] = im;
+    }
+}
+/* arm_cmplx_mag_f32 — arm_math.h:6312-6315.  canonical: sqrt(fma(re,re,im*im)), IEEE sqrt. */
+static inline float cmag(float re, float im) { return sqrtf(FMA(re, re, im * im)); }
+void ref_arm_cmplx_mag_f32(const float32_t *src, float32_t *dst, uint32_t ncplx) {
+    for (uint32_t i = 0; i < ncplx; ++i) dst[i] = cmag(src[2 * i], src[2 * i + 1]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* canonical FFT                                                              */
+/* ------------------------------------------------------------------------------------------ */
+void ref_twiddle(uint32_t j, uint32_t n, float *re, float *im) {
+    double a = 2.0 * M_PI * (double) j / (double) n;
+    *re = (float) cos(a);
+    *im = (float) -sin(a);
+}
+
+/* Radix rule: peel 32s from the right while the remainder exceeds 32; the remainder goes first.
+ * 1024 -> [32,32]; 2048 -> [2,32,32]; 512 -> [16,32]; 32768 -> [32,32,32]. */
+uint32_t ref_fft_radices(uint32_t n, uint32_t *rad) {
+    if (n < 2 || (n & (n - 1))) return 0;
+    uint32_t tmp[REF_MAX_RADICES], cnt = 0;
+    while (n > 32) { tmp[cnt++] = 32; n /= 32; if (cnt >= REF_MAX_RADICES - 1) return 0; }
+    tmp[cnt++] = n;
+    for (uint32_t i = 0; i < cnt; ++i) rad[i] = tmp[cnt - 1 - i];
+    return cnt;
+}
+
+static int plan_init(ref_fft_plan *p, uint32_t n, uint32_t tw_n) {
+    p->n = n;
+    p->nrad = ref_fft_radices(n, p->rad);
+    if (!p->nrad) return -1;
+    p->tw_n = tw_n;
+    p->tw = (float *) malloc(sizeof(float) * 2 * tw_n);
+    if (!p->tw) return -1;
+    for (uint32_t j = 0; j < tw_n; ++j) ref_twiddle(j, tw_n, &p->tw[2 * j], &p->tw[2 * j + 1]);
+    return 0;
+}
+
+typedef struct { float r, i; } cf;
+
+/* Base kernel: radix-2 decimation-in-time recursion on r <= 32 points, forward transform.
+ *   j == 0   : s = E + O,           d = E - O
+ *   j == r/4 : t = -j*O,            s = E + t, d = E - t
+ *   otherwise: s = E + w*O via two chained FMAs per component, d = 2E - s (one FMA). */
+static void base_fft(const ref_fft_plan *p, uint32_t r, const cf *in, uint32_t stride, cf *out) {
+    if (r == 1) { out[0] = in[0]; return; }
+    cf e[16], o[16];
+    uint32_t h = r / 2;
+    base_fft(p, h, in, stride * 2, e);
+    base_fft(p, h, in + stride, stride * 2, o);
+    uint32_t step = p->tw_n / r;
+    for (uint32_t j = 0; j < h; ++j) {
+        cf E = e[j], O = o[j], s, d;
+        if (j == 0) {
+            s.r = E.r + O.r; s.i = E.i + O.i;
+            d.r = E.r - O.r; d.i = E.i - O.i;
+        } else if (4 * j == r) {
+            s.r = E.r + O.i; s.i = E.i - O.r;
+            d.r = E.r - O.i; d.i = E.i + O.r;
+        } else {
+            float wr = p->tw[2 * j * step], wi = p->tw[2 * j * step + 1];
+            s.r = FMA(O.r, wr, FMA(-O.i, wi, E.r));
+            s.i = FMA(O.r, wi, FMA(O.i, wr, E.i));
+            d.r = FMA(2.0f, E.r, -s.r);
+            d.i = FMA(2.0f, E.i, -s.i);
+        }
+        out[j] = s;
+        out[j + h] = d;
+    }
+}
+
+/* Mixed-radix step.  n = A*B with B = rad[0]:  m = a + A*b,  k = B*c + d.
+ *   1. V_a[d]  = base_fft_B over b of in[a + A*b]
+ *   2. V_a[d] *= W_n^(a*d)           (skipped when a*d == 0: exact identity)
+ *   3. out[B*c + d] = fft_A over a of V_.[d]      (recursive with rad[1..]) */
+static void fft_rec(const ref_fft_plan *p, uint32_t n, const uint32_t *rad, uint32_t nrad,
+                    const cf *in, uint32_t stride, cf *out, cf *scratch) {
+    if (nrad == 1) { base_fft(p, n, in, stride, out); return; }
+    uint32_t B = rad[0], A = n / B;
+    cf *tmp = scratch;                 /* B rows of A */
+    cf *next = scratch + n;
+    uint32_t step = p->tw_n / n;
+    cf v[32];
+    for (uint32_t a = 0; a < A; ++a) {
+        base_fft(p, B, in + (size_t) a * stride, stride * A, v);
+        for (uint32_t d = 0; d < B; ++d) {
+            cf x = v[d];
+            if (a != 0 && d != 0) {
+                size_t j = (size_t) a * d * step;
+                float re, im;
+                cmul(x.r, x.i, p->tw[2 * j], p->tw[2 * j + 1], &re, &im);
+                x.r = re; x.i = im;
+            }
+            tmp[(size_t) d * A + a] = x;
+        }
+    }
+    cf *y = next;                      /* A outputs */
+    for (uint32_t d = 0; d < B; ++d) {
+        fft_rec(p, A, rad + 1, nrad - 1, tmp + (size_t) d * A, 1, y, next + A);
+        for (uint32_t c = 0; c < A; ++c) out[(size_t) B * c + d] = y[c];
+    }
+}
+
+/* forward, unscaled, natural order, out of place (in may not alias out) */
+static void fft_forward(const ref_fft_plan *p, const cf *in, cf *out) {
+    cf *scratch = (cf *) malloc(sizeof(cf) * (size_t) p->n * 4 + 64);
+    fft_rec(p, p->n, p->rad, p->nrad, in, 1, out, scratch);
+    free(scratch);
+}
+
+static inline void swap_ri(cf *x, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) { float t = x[i].r; x[i].r = x[i].i; x[i].i = t; }
+}
+
+/* arm_cfft_f32 — arm_math.h:2149-2153; consts arm_const_structs.h:49-57.  In place, interleaved.
+ * Forward unscaled; inverse = swap(re,im) -> forward -> swap, scaled by 1/N (exact power of two).
+ * bitReverseFlag must be 1 (natural-order output), the only mode the reference uses
+ * (experiments/synchronization/Src/main.c:153, experiments/iq_modulation/Src/main.c:129). */
+ref_status ref_arm_cfft_init_f32(ref_cfft_instance_f32 *S, uint32_t fftLen) {
+    if (fftLen < 16 || fftLen > 65536 || (fftLen & (fftLen - 1))) return REF_MATH_ARGUMENT_ERROR;
+    S->fftLen = (uint16_t) fftLen;
+    return plan_init(&S->plan, fftLen, fftLen) ? REF_MATH_ARGUMENT_ERROR : REF_MATH_SUCCESS;
+}
+void ref_arm_cfft_free(ref_cfft_instance_f32 *S) { free(S->plan.tw); S->plan.tw = NULL; }
+
+void ref_arm_cfft_f32(const ref_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag) {
+    (void) bitReverseFlag;
+    uint32_t n = S->plan.n;
+    cf *in = (cf *) malloc(sizeof(cf) * n), *out = (cf *) malloc(sizeof(cf) * n);
+    memcpy(in, p1, sizeof(cf) * n);
+    if (ifftFlag) swap_ri(in, n);
+    fft_forward(&S->plan, in, out);
+    if (ifftFlag) {
+        swap_ri(out, n);
+        float sc = 1.0f / (float) n;
+        for (uint32_t i = 0; i < n; ++i) { out[i].r *= sc; out[i].i *= sc; }
+    }
+    memcpy(p1, out, sizeof(cf) * n);
+    free(in); free(out);
+}
+
+/* arm_rfft_fast_init_f32 / arm_rfft_fast_f32 — arm_math.h:2242-2249.
+ * Forward output is packed [X0.re, X(N/2).re, X1.re, X1.im, ...] (N floats); inverse takes the
+ * same packing and is normalised so irfft(rfft(x)) == x.  The reference's in-place aliasing
+ * (hazard H2, experiments/chirp_compression_time_domain/Src/chirp.c:72-73,80,82) is DEFINED as the
+ * mathematically correct result: we read everything before writing. */
+ref_status ref_arm_rfft_fast_init_f32(ref_rfft_fast_instance_f32 *S, uint32_t fftLen) {
+    if (fftLen < 32 || fftLen > 131072 || (fftLen & (fftLen - 1))) return REF_MATH_ARGUMENT_ERROR;
+    S->fftLenRFFT = (uint16_t) fftLen;
+    return plan_init(&S->cplx, fftLen / 2, fftLen) ? REF_MATH_ARGUMENT_ERROR : REF_MATH_SUCCESS;
+}
+void ref_arm_rfft_fast_free(ref_rfft_fast_instance_f32 *S) { free(S->cplx.tw); S->cplx.tw = NULL; }
+
+static void rfft_forward(const ref_fft_plan *p, const float *a, float *out) {
+    uint32_t h = p->n;                         /* N/2 */
+    cf *Z = (cf *) malloc(sizeof(cf) * h);
+    fft_forward(p, (const cf *) a, Z);         /* z[m] = a[2m] + j a[2m+1] */
+    float x0 = Z[0].r + Z[0].i, xn = Z[0].r - Z[0].i;
+    for (uint32_t k = 1; k < h; ++k) {
+        cf Zk = Z[k], Zc = Z[h - k];
+        float pr = Zk.r + Zc.r, pi = Zk.i - Zc.i;
+        float qr = Zk.i + Zc.i, qi = Zc.r - Zk.r;
+        float cr = p->tw[2 * k], si = -p->tw[2 * k + 1];       /* W_N^k = cr - j si */
+        float xr = FMA(qr, cr, FMA(qi, si, pr));
+        float xi = FMA(qi, cr, FMA(-qr, si, pi));
+        out[2 * k] = 0.5f * xr;
+        out[2 * k + 1] = 0.5f * xi;
+    }
+    out[0] = x0;
+    out[1] = xn;
+    free(Z);
+}
+
+static void rfft_inverse(const ref_fft_plan *p, const float *X, float *out) {
+    uint32_t h = p->n;
+    cf *Z = (cf *) malloc(sizeof(cf) * h), *z = (cf *) malloc(sizeof(cf) * h);
+    /* 2Z[k] = (Xk + conj Xc) + j W_N^{-k} (Xk - conj Xc),  Xc = X[N/2-k] */
+    Z[0].r = X[0] + X[1];
+    Z[0].i = X[0] - X[1];
+    for (uint32_t k = 1; k < h; ++k) {
+        float xkr = X[2 * k], xki = X[2 * k + 1], xcr = X[2 * (h - k)], xci = X[2 * (h - k) + 1];
+        float pr = xkr + xcr, pi = xki - xci;
+        float qr = xkr - xcr, qi = xki + xci;
+        float cr = p->tw[2 * k], si = -p->tw[2 * k + 1];
+        Z[k].r = FMA(-qi, cr, FMA(-qr, si, pr));
+        Z[k].i = FMA(qr, cr, FMA(-qi, si, pi));
+    }
+    swap_ri(Z, h);
+    fft_forward(p, Z, z);
+    float sc = 1.0f / (float) (2 * h);           /* 0.5 (from 2Z) * 1/(N/2) = 1/N, exact */
+    for (uint32_t m = 0; m < h; ++m) {            /* swap back: re <- z.i, im <- z.r */
+        out[2 * m] = z[m].i * sc;
+        out[2 * m + 1] = z[m].r * sc;
+    }
+    free(Z); free(z);
+}
+
+void ref_arm_rfft_fast_f32(const ref_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag) {
+    uint32_t n = S->fftLenRFFT ? S->fftLenRFFT : 2 * S->cplx.n;
+    n = 2 * S->cplx.n;
+    float *tmp = (float *) malloc(sizeof(float) * n);
+    if (ifftFlag) rfft_inverse(&S->cplx, p, tmp);
+    else rfft_forward(&S->cplx, p, tmp);
+    memcpy(pOut, tmp, sizeof(float) * n);
+    free(tmp);
+}
+
+/* arm_fir_init_f32 / arm_fir_f32 — arm_math.h:1194-1214.  pState holds numTaps+blockSize-1 floats
+ * (zeroed by init); pCoeffs are in time-reversed order {b[numTaps-1] .. b[0]}.
+ * y[n] = sum_i state[n+i]*coeffs[i], accumulated left to right with one FMA per tap from acc=0.
+ * UNPINNED.  Call sites: experiments/iq_modulation/Src/iq_modem.c:48-49, 63-64. */
+void ref_arm_fir_init_f32(ref_fir_instance_f32 *S, uint16_t numTaps, const float32_t *pCoeffs,
+                          float32_t *pState, uint32_t blockSize) {
+    S->numTaps = numTaps;
+    S->pCoeffs = pCoeffs;
+    memset(pState, 0, sizeof(float) * (numTaps + blockSize - 1));
+    S->pState = pState;
+}
+void ref_arm_fir_f32(const ref_fir_instance_f32 *S, const float32_t *pSrc, float32_t *pDst, uint32_t blockSize) {
+    uint32_t T = S->numTaps;
+    float *st = S->pState;
+    memcpy(st + (T - 1), pSrc, sizeof(float) * blockSize);   /* pSrc may alias pDst: copy first */
+    for (uint32_t n = 0; n < blockSize; ++n) {
+        float acc = 0.0f;
+        for (uint32_t i = 0; i < T; ++i) acc = FMA(st[n + i], S->pCoeffs[i], acc);
+        pDst[n] = acc;
+    }
+    memmove(st, st + blockSize, sizeof(float) * (T - 1));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* tables                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+/* Periodic: receiver/Src/main.c:99,390-393  (WINDOW_SCALE = 2.0f * M_PI / (float) NN, double expr)
+ * Symmetric: experiments/chirp_compression_time_domain/Src/chirp.c:13,63-65
+ *            (WINDOW_SCALE = 2.0f * PI / (float)(PCM_SAMPLES - 1), PI = 3.14159265358979f: float expr) */
+void ref_hann_window(float32_t *w, uint32_t n, ref_hann_kind kind) {
+    float scale;
+    if (kind == REF_HANN_PERIODIC) scale = (float) (2.0f * M_PI / (float) n);
+    else scale = 2.0f * 3.14159265358979f / (float) (n - 1);
+    for (uint32_t i = 0; i < n; ++i) w[i] = 0.5f - 0.5f * ref_arm_cos_f32((float) i * scale);
+}
+
+void ref_generate_ref_chirp(ref_chirp_variant v, const ref_chirp_params *p, int up, float32_t *out) {
+    float t = 0.0f;
+    if (v == REF_CHIRP_R || v == REF_CHIRP_S) {
+        /* receiver/Src/chirp.c:16-40, experiments/synchronization/Src/chirp.c:16-44.
+         * F0,F1 are ints in the reference; freq/theta expressions are evaluated in double
+         * (the literals 2.0 and 360.0 are double) and stored to float. */
+        float delta_f = (float) (p->f1 - p->f0) / p->sweep_T;
+        float delta_t = p->sweep_T / (p->sweep_T * p->fs);
+        for (uint32_t n = 0; n < p->n; ++n) {
+            float freq;
+            if (up) freq = (float) ((double) p->f0 + (double) (delta_f * t) / 2.0);
+            else freq = (float) ((double) p->f1 - (double) (delta_f * t) / 2.0);
+            float theta = (float) (360.0 * (double) freq * (double) t + (double) p->phase);
+            t = t + delta_t;
+            float s, c;
+            ref_arm_sin_cos_f32(theta, &s, &c);
+            if (v == REF_CHIRP_R) out[n] = s * 1.0f;          /* chirp.c:37-38: sin overwrites cos */
+            else { out[2 * n] = c * 1.0f; out[2 * n + 1] = s * 1.0f; }
+        }
+    } else {
+        /* experiments/chirp_compression_time_domain/Src/chirp.c:25-45 (T, F1/F2 float literals) and
+         * experiments/chirp_compression_freq_domain/Src/chirp.c:15-35 (F, int F1/F2, phase ignored). */
+        float time_frame = (float) p->n / p->fs;
+        float delta_f = (p->f1 - p->f0) / time_frame;
+        float delta_t = time_frame / (time_frame * p->fs);
+        for (uint32_t i = 0; i < p->n; ++i) {
+            float freq = up ? p->f0 + delta_f * t : p->f1 - delta_f * t;
+            float arg;
+            if (v == REF_CHIRP_T) arg = (float) (2.0 * (double) 3.14159265358979f * (double) freq * (double) t + (double) p->phase);
+            else arg = (float) (2.0 * (double) 3.14159265358979f * (double) freq * (double) t);
+            t = t + delta_t;
+            out[i] = ref_arm_cos_f32(arg) * 1.0f;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* receiver chain                                                                              */
+/* ------------------------------------------------------------------------------------------ */
+int ref_receiver_init(ref_receiver *rx, uint32_t n, float fs, float f0, float f1, float sweep_T) {
+    memset(rx, 0, sizeof *rx);
+    rx->n = n;
+    rx->fs = fs;
+    /* main.c:372-374: bandwidth = (F1 - F0) * NN / fs  (int * unsigned long -> float division -> uint32) */
+    rx->bandwidth = (uint32_t) ((float) ((unsigned long) (int) (f1 - f0) * (unsigned long) n) / fs);
+    rx->bandwidth2 = rx->bandwidth * 2;
+    rx->idx_left_zero = n - rx->bandwidth2;
+    rx->hann = (float *) malloc(sizeof(float) * n);
+    rx->up_chirp = (float *) malloc(sizeof(float) * n);
+    rx->down_chirp = (float *) malloc(sizeof(float) * n);
+    if (!rx->hann || !rx->up_chirp || !rx->down_chirp) return -1;
+    if (ref_arm_rfft_fast_init_f32(&rx->S, n) != REF_MATH_SUCCESS) return -1;      /* main.c:377 */
+    ref_chirp_params cp = { n, fs, f0, f1, sweep_T, -90.0f };
+    ref_generate_ref_chirp(REF_CHIRP_R, &cp, 1, rx->up_chirp);                     /* chirp.c:43 */
+    ref_generate_ref_chirp(REF_CHIRP_R, &cp, 0, rx->down_chirp);                   /* chirp.c:44 */
+    ref_hann_window(rx->hann, n, REF_HANN_PERIODIC);                               /* main.c:390-393 */
+    return 0;
+}
+void ref_receiver_free(ref_receiver *rx) {
+    free(rx->hann); free(rx->up_chirp); free(rx->down_chirp);
+    ref_arm_rfft_fast_free(&rx->S);
+    memset(rx, 0, sizeof *rx);
+}
+
+/* main.c:154-160: integer arithmetic with fs truncated to int32 */
+int32_t ref_idx2freq(const ref_receiver *rx, uint32_t idx) {
+    uint32_t nn = rx->n;
+    if (idx < nn / 2) return (int32_t) ((uint32_t) (int32_t) rx->fs * idx / nn);
+    return (int32_t) ((uint32_t) (int32_t) rx->fs * (nn - idx) / nn) * -1;
+}
+
+/* main.c:163-180 */
+void ref_pipeline(const ref_receiver *rx, float32_t *signal, int up) {
+    uint32_t n = rx->n;
+    float *buf = (float *) malloc(sizeof(float) * n);
+    ref_arm_mult_f32(signal, up ? rx->up_chirp : rx->down_chirp, signal, n);       /* chirp.c:47-53 */
+    ref_arm_mult_f32(signal, rx->hann, signal, n);                                 /* main.c:171 */
+    ref_arm_rfft_fast_f32(&rx->S, signal, buf, 0);                                 /* main.c:174 */
+    ref_arm_copy_f32(buf, signal, n);                                              /* main.c:175 */
+    /* main.c:178 asks for NN complex magnitudes = 2*NN floats, reading NN floats of uninitialised
+     * stack beyond the spectrum (hazard H1).  DEFINED: those read as zero -> mags[n/2..n) = 0. */
+    ref_arm_cmplx_mag_f32(signal, buf, n / 2);
+    memcpy(signal, buf, sizeof(float) * (n / 2));
+    memset(signal + n / 2, 0, sizeof(float) * (n / 2));
+    free(buf);
+}
+
+/* main.c:183-231 */
+void ref_dsp(const ref_receiver *rx, const float32_t *fifo, uint32_t sync_position,
+             ref_history *h, float mag_mean, int up) {
+    uint32_t n = rx->n;
+    float *tf = (float *) malloc(sizeof(float) * n);
+    for (uint32_t i = 0; i < n; ++i) tf[i] = fifo[sync_position + i];               /* main.c:196-198 */
+    ref_pipeline(rx, tf, up);
+    float ml, mr, mm;
+    uint32_t il, ir, im;
+    ref_arm_max_f32(&tf[rx->idx_left_zero], rx->bandwidth2, &ml, &il);             /* main.c:206 */
+    ref_arm_max_f32(&tf[0], rx->bandwidth2, &mr, &ir);                             /* main.c:208 */
+    if (ml > mr) { mm = ml; im = rx->idx_left_zero + il; }                         /* main.c:209-215 */
+    else { mm = mr; im = ir; }
+    h->mag_max = mm; h->mag_max_left = ml; h->mag_max_right = mr;
+    h->max_idx = im; h->max_idx_left = rx->idx_left_zero + il; h->max_idx_right = ir;
+    h->max_freq = ref_idx2freq(rx, im);
+    h->max_freq_left = ref_idx2freq(rx, rx->idx_left_zero + il);
+    h->max_freq_right = ref_idx2freq(rx, ir);
+    h->mag_mean = mag_mean;
+    h->snr = (mm - mag_mean) / mag_mean;                                           /* main.c:229 */
+    free(tf);
+}
+
+static void demod_one(const ref_receiver *rx, const float *frame, float *fifo,
+                      float *mu, uint32_t *iu, float *md, uint32_t *id) {
+    /* aligned frame = dsp() at sync_position 0 of a fifo that starts with the frame */
+    (void) fifo;
+    ref_history h;
+    ref_dsp(rx, frame, 0, &h, 1.0f, 1);
+    *mu = h.mag_max; *iu = h.max_idx;
+    ref_dsp(rx, frame, 0, &h, 1.0f, 0);
+    *md = h.mag_max; *id = h.max_idx;
+}
+
+void ref_demod_frames_f32(const ref_receiver *rx, const float *pcm, size_t nframes,
+                          float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
+                          int nthreads) {
+    uint32_t n = rx->n;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (long f = 0; f < (long) nframes; ++f)
+        demod_one(rx, pcm + (size_t) f * n, NULL, &mag_up[f], &idx_up[f], &mag_down[f], &idx_down[f]);
+}
+
+void ref_demod_frames_i32(const ref_receiver *rx, const int32_t *pcm, size_t nframes,
+                          float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
+                          int nthreads) {
+    uint32_t n = rx->n;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (long f = 0; f < (long) nframes; ++f) {
+        float *fr = (float *) malloc(sizeof(float) * n);
+        /* main.c:663-665: fifo_queue[...] = (float) buf[i] — the whole PCM scaling */
+        for (uint32_t i = 0; i < n; ++i) fr[i] = (float) pcm[(size_t) f * n + i];
+        demod_one(rx, fr, NULL, &mag_up[f], &idx_up[f], &mag_down[f], &idx_down[f]);
+        free(fr);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* frequency-domain compression chain                                                          */
+/* ------------------------------------------------------------------------------------------ */
+/* experiments/chirp_compression_time_domain/Src/chirp.c:52-75 */
+int ref_compressor_init(ref_compressor *c, uint32_t n, float fs, float f1, float f2) {
+    memset(c, 0, sizeof *c);
+    c->n = n; c->fs = fs;
+    c->window = (float *) malloc(sizeof(float) * n);
+    c->H_up = (float *) malloc(sizeof(float) * n);
+    c->H_down = (float *) malloc(sizeof(float) * n);
+    if (!c->window || !c->H_up || !c->H_down) return -1;
+    if (ref_arm_rfft_fast_init_f32(&c->S, n) != REF_MATH_SUCCESS) return -1;       /* chirp.c:55 */
+    ref_chirp_params cp = { n, fs, f1, f2, 0.0f, (float) (-3.14159265358979f / 2.0) };
+    ref_generate_ref_chirp(REF_CHIRP_T, &cp, 1, c->H_up);                          /* chirp.c:58 */
+    ref_generate_ref_chirp(REF_CHIRP_T, &cp, 0, c->H_down);                        /* chirp.c:59 */
+    ref_hann_window(c->window, n, REF_HANN_SYMMETRIC);                             /* chirp.c:63-65 */
+    ref_arm_mult_f32(c->H_up, c->window, c->H_up, n);                              /* chirp.c:68 */
+    ref_arm_mult_f32(c->H_down, c->window, c->H_down, n);                          /* chirp.c:69 */
+    ref_arm_rfft_fast_f32(&c->S, c->H_up, c->H_up, 0);                             /* chirp.c:72 */
+    ref_arm_rfft_fast_f32(&c->S, c->H_down, c->H_down, 0);                         /* chirp.c:73 */
+    return 0;
+}
+void ref_compressor_free(ref_compressor *c) {
+    free(c->window); free(c->H_up); free(c->H_down);
+    ref_arm_rfft_fast_free(&c->S);
+    memset(c, 0, sizeof *c);
+}
+/* chirp.c:78-83 */
+void ref_compress_chirp(const ref_compressor *c, float32_t *inout, int use_up) {
+    uint32_t n = c->n;
+    ref_arm_mult_f32(inout, c->window, inout, n);                                  /* windowing() */
+    ref_arm_rfft_fast_f32(&c->S, inout, inout, 0);
+    ref_arm_cmplx_mult_cmplx_f32(inout, use_up ? c->H_up : c->H_down, inout, n / 2);
+    ref_arm_rfft_fast_f32(&c->S, inout, inout, 1);
+}
+/* experiments/chirp_compression_time_domain/Src/main.c:171-189 */
+void ref_compress_frames_i32(const ref_compressor *c, const int32_t *pcm, size_t nframes, int use_up,
+                             float *max_val, uint32_t *max_idx, int nthreads) {
+    uint32_t n = c->n;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (long f = 0; f < (long) nframes; ++f) {
+        float *fr = (float *) malloc(sizeof(float) * n);
+        for (uint32_t i = 0; i < n; ++i) fr[i] = (float) pcm[(size_t) f * n + i];
+        ref_compress_chirp(c, fr, use_up);
+        ref_arm_max_f32(fr, n, &max_val[f], &max_idx[f]);                          /* main.c:189 */
+        free(fr);
+    }
+}

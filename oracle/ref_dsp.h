@@ -1,0 +1,179 @@
+/*
+ * ref_dsp.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the arithmetic on the reference's demodulation hot path:
+ * the CMSIS-DSP V1.4.5b operator surface the receiver calls (contracts from
+ * receiver/Drivers/CMSIS/Include/arm_math.h) plus the receiver / experiment DSP chains built on
+ * it (receiver/Src/main.c, receiver/Src/chirp.c, experiments/<x>/Src/<y>.c).  Every function cites
+ * the reference file:line it follows.  All paths are relative to /root/reference.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * link or call this file.  The product library (libusc.so) never does.
+ *
+ * PARITY PINNING:
+ *   pinned by device captures (agent/chirp_experiment, agent/vaccum_cleaner .raw/.flt/.fft):
+ *     int32->float cast, ref_arm_cos_f32 (bit-exact: 0 mismatches in 24x2048 .flt samples),
+ *     periodic Hann table, ref_arm_mult_f32, forward ref_arm_rfft_fast_f32 + ref_arm_cmplx_mag_f32
+ *     + ref_arm_scale_f32 (to the 6-decimal print precision / fp32 rounding), arg-max bin.
+ *   pinned by notebook known-answers: the de-chirp peak-location law (ChirpSynchronization.ipynb).
+ *   UNPINNED by any reference artefact (no input/output pairs exist): arm_cmplx_mult_cmplx_f32,
+ *     inverse rfft, arm_cfft_f32, arm_fir_f32, arm_mean_f32, arm_sin_cos_f32, the state machine.
+ *     Those follow the arm_math.h contracts and are cross-checked against numpy float64.
+ *
+ * CANONICAL ARITHMETIC.  CMSIS-DSP is vendored only as an ARM-Thumb archive, so bit-equality with
+ * the device FFT is impossible.  Instead this file fixes one fp32 operation order ("canonical
+ * arithmetic") that the CUDA kernels reproduce operation for operation, so that
+ * integer outputs (arg-max bins, sync offsets, symbols) are bit-identical by construction and
+ * float outputs are bit-identical too.  Build with -ffp-contract=off: every fused multiply-add in
+ * the spec is an explicit fmaf().
+ */
+#ifndef REF_DSP_H_
+#define REF_DSP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef float float32_t;                       /* arm_math.h:407 */
+
+typedef enum {                                 /* arm_math.h:373-382 */
+    REF_MATH_SUCCESS = 0,
+    REF_MATH_ARGUMENT_ERROR = -1
+} ref_status;
+
+#define REF_MAX_RADICES 8
+
+/* Canonical FFT plan: master twiddle table W_N^j and the radix list. */
+typedef struct {
+    uint32_t n;                 /* complex length */
+    uint32_t nrad;
+    uint32_t rad[REF_MAX_RADICES];
+    float *tw;                  /* 2*tw_n floats: (cos, -sin)(2*pi*j/tw_n), j < tw_n */
+    uint32_t tw_n;              /* master table length (n for cfft, 2n for the rfft that owns it) */
+} ref_fft_plan;
+
+typedef struct {                /* mirrors arm_rfft_fast_instance_f32, arm_math.h:2235-2240 */
+    uint16_t fftLenRFFT;
+    ref_fft_plan cplx;          /* N/2 complex plan sharing the N-entry master table */
+} ref_rfft_fast_instance_f32;
+
+typedef struct {                /* mirrors arm_cfft_instance_f32, arm_math.h:2141-2147 */
+    uint16_t fftLen;
+    ref_fft_plan plan;
+} ref_cfft_instance_f32;
+
+typedef struct {                /* mirrors arm_fir_instance_f32, arm_math.h:1059-1064 */
+    uint16_t numTaps;
+    float32_t *pState;
+    const float32_t *pCoeffs;
+} ref_fir_instance_f32;
+
+/* ---- CMSIS-shaped primitives (arm_math.h line numbers in ref_dsp.c) ---- */
+float32_t ref_arm_cos_f32(float32_t x);
+void ref_arm_sin_cos_f32(float32_t theta_deg, float32_t *pSinVal, float32_t *pCosVal);
+void ref_arm_mult_f32(const float32_t *a, const float32_t *b, float32_t *dst, uint32_t n);
+void ref_arm_scale_f32(const float32_t *src, float32_t scale, float32_t *dst, uint32_t n);
+void ref_arm_copy_f32(const float32_t *src, float32_t *dst, uint32_t n);
+void ref_arm_mean_f32(const float32_t *src, uint32_t n, float32_t *result);
+void ref_arm_max_f32(const float32_t *src, uint32_t n, float32_t *result, uint32_t *index);
+void ref_arm_cmplx_mult_cmplx_f32(const float32_t *a, const float32_t *b, float32_t *dst, uint32_t ncplx);
+void ref_arm_cmplx_mult_real_f32(const float32_t *cplx, const float32_t *real, float32_t *dst, uint32_t ncplx);
+void ref_arm_cmplx_mag_f32(const float32_t *src, float32_t *dst, uint32_t ncplx);
+ref_status ref_arm_rfft_fast_init_f32(ref_rfft_fast_instance_f32 *S, uint32_t fftLen);
+void ref_arm_rfft_fast_free(ref_rfft_fast_instance_f32 *S);
+void ref_arm_rfft_fast_f32(const ref_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag);
+ref_status ref_arm_cfft_init_f32(ref_cfft_instance_f32 *S, uint32_t fftLen);
+void ref_arm_cfft_free(ref_cfft_instance_f32 *S);
+void ref_arm_cfft_f32(const ref_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
+void ref_arm_fir_init_f32(ref_fir_instance_f32 *S, uint16_t numTaps, const float32_t *pCoeffs,
+                          float32_t *pState, uint32_t blockSize);
+void ref_arm_fir_f32(const ref_fir_instance_f32 *S, const float32_t *pSrc, float32_t *pDst, uint32_t blockSize);
+
+/* Exposed for tests: canonical twiddle (cos, -sin)(2*pi*j/n) rounded once from double. */
+void ref_twiddle(uint32_t j, uint32_t n, float *re, float *im);
+/* Canonical radix list for a complex length. Returns count, 0 if unsupported. */
+uint32_t ref_fft_radices(uint32_t n, uint32_t *rad);
+
+/* ---- tables ---- */
+typedef enum { REF_HANN_PERIODIC = 0, REF_HANN_SYMMETRIC = 1 } ref_hann_kind;
+void ref_hann_window(float32_t *w, uint32_t n, ref_hann_kind kind);
+
+typedef enum {
+    REF_CHIRP_R = 0,   /* receiver/Src/chirp.c:16-40: real, sin(theta-90deg), degrees, /2 law */
+    REF_CHIRP_S = 1,   /* experiments/synchronization/Src/chirp.c:16-44: complex (cos,sin) interleaved */
+    REF_CHIRP_T = 2,   /* experiments/chirp_compression_time_domain/Src/chirp.c:25-45: real cos, rad, no /2 */
+    REF_CHIRP_F = 3    /* experiments/chirp_compression_freq_domain/Src/chirp.c:15-35: as T, phase ignored */
+} ref_chirp_variant;
+
+typedef struct {
+    uint32_t n;            /* samples per frame (NN / PCM_SAMPLES) */
+    float fs;              /* sampling rate as the firmware holds it (float) */
+    float f0, f1;          /* sweep range (F0,F1 or F1,F2 in the reference headers) */
+    float sweep_T;         /* TIME_FRAME for R/S (0.0205f); ignored by T/F (they use n/fs) */
+    float phase;           /* -90.0f (deg) for R/S; -PI/2 (rad) for T; ignored by F */
+} ref_chirp_params;
+
+/* out: n floats (R,T,F) or 2n floats (S). up != 0 -> up-chirp. */
+void ref_generate_ref_chirp(ref_chirp_variant v, const ref_chirp_params *p, int up, float32_t *out);
+
+/* ---- receiver chain (receiver/Src/main.c) ---- */
+typedef struct {                         /* receiver/Src/main.c:124-136 (timing fields dropped) */
+    float mag_max, mag_max_left, mag_max_right;
+    int32_t max_freq, max_freq_left, max_freq_right;
+    uint32_t max_idx, max_idx_left, max_idx_right;   /* raw bins (not in the reference struct) */
+    float mag_mean, snr;
+    char rank;
+} ref_history;
+
+typedef struct {
+    uint32_t n;                 /* NN */
+    float fs;
+    uint32_t bandwidth, bandwidth2, idx_left_zero;   /* main.c:372-374 */
+    float *hann;                /* periodic Hann, main.c:390-393 */
+    float *up_chirp, *down_chirp;   /* variant R tables */
+    ref_rfft_fast_instance_f32 S;
+} ref_receiver;
+
+int ref_receiver_init(ref_receiver *rx, uint32_t n, float fs, float f0, float f1, float sweep_T);
+void ref_receiver_free(ref_receiver *rx);
+int32_t ref_idx2freq(const ref_receiver *rx, uint32_t idx);                  /* main.c:154-160 */
+/* main.c:163-180.  signal: n floats in, n floats out: mags of the n/2 packed bins in [0,n/2),
+ * zeros in [n/2,n) (hazard H1 defined: the uninitialised upper half reads as zero). */
+void ref_pipeline(const ref_receiver *rx, float32_t *signal, int up);
+/* main.c:183-231.  fifo: 3n floats. */
+void ref_dsp(const ref_receiver *rx, const float32_t *fifo, uint32_t sync_position,
+             ref_history *h, float mag_mean, int up);
+
+/* Batched aligned-frame demodulation = dsp() for UP and DOWN on every frame (config 2).
+ * pcm: nframes*n int32 samples.  out arrays have nframes entries. */
+void ref_demod_frames_i32(const ref_receiver *rx, const int32_t *pcm, size_t nframes,
+                          float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
+                          int nthreads);
+void ref_demod_frames_f32(const ref_receiver *rx, const float *pcm, size_t nframes,
+                          float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
+                          int nthreads);
+
+/* ---- frequency-domain compression chain (experiments/chirp_compression_time_domain) ---- */
+typedef struct {
+    uint32_t n;
+    float fs;
+    float *window;              /* symmetric Hann, chirp.c:13,63-65 */
+    float *H_up, *H_down;       /* packed spectra of the windowed reference chirps, chirp.c:58-73 */
+    ref_rfft_fast_instance_f32 S;
+} ref_compressor;
+
+int ref_compressor_init(ref_compressor *c, uint32_t n, float fs, float f1, float f2);
+void ref_compressor_free(ref_compressor *c);
+/* chirp.c:78-83: window -> rfft -> x H (packed, n/2 complex, DC/Nyquist quirk) -> irfft. in place */
+void ref_compress_chirp(const ref_compressor *c, float32_t *inout, int use_up);
+/* main.c:171-189 batched: compress + signed arm_max over all n lags. */
+void ref_compress_frames_i32(const ref_compressor *c, const int32_t *pcm, size_t nframes, int use_up,
+                             float *max_val, uint32_t *max_idx, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REF_DSP_H_ */
