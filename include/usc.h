@@ -1,0 +1,174 @@
+/*
+ * usc.h — C-ABI of libusc.so: the B200 (sm_100a) demodulation chain of the ultrasonic chirp receiver.
+ *
+ * This is the drop-in boundary for the reference's hot path: the CMSIS-DSP V1.4.5b
+ * operator surface the receiver calls (receiver/Drivers/CMSIS/Include/arm_math.h) in batched,
+ * device-pointer form, plus fused stage-level entry points that mirror the reference's own
+ * functions (pipeline/dsp/compress_chirp/...).  Paths below are relative to the reference tree.
+ *
+ * Conventions
+ *   - plain C, no CUDA or torch types; device buffers are raw device addresses (float*, int32_t*)
+ *     obtained from usc_malloc() or from any CUDA allocator in the same process (e.g. torch).
+ *   - every call is asynchronous on the handle's stream (usc_set_stream, default stream 0) unless
+ *     stated; usc_sync() waits.  No hidden allocation on the hot calls.
+ *   - return 0 on success; USC_ERR_ARGUMENT (-1, == ARM_MATH_ARGUMENT_ERROR, arm_math.h:373-382) for
+ *     bad arguments; USC_ERR_CUDA_BASE - cudaError for CUDA failures.  Nothing throws.
+ *   - there is NO CPU fallback: without a usable CUDA device usc_create() fails.
+ *   - complex data is interleaved (re, im) (arm_math.h:181-184); real-FFT spectra use the CMSIS
+ *     packed layout [X0.re, X(N/2).re, X1.re, X1.im, ...] (arm_math.h:2246-2249).
+ *   - arithmetic is fp32 in the fixed operation order of DESIGN.md §3 ("canonical arithmetic"),
+ *     bit-identical to the CPU oracle; integer results (bins, offsets, symbols) are exact.
+ */
+#ifndef USC_H_
+#define USC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USC_OK 0
+#define USC_ERR_ARGUMENT (-1)
+#define USC_ERR_NOMEM (-2)
+#define USC_ERR_CUDA_BASE (-1000)
+
+/* reference chirp table variants */
+#define USC_CHIRP_R 0u /* receiver/Src/chirp.c:16-40: real sin(theta-90deg), degrees, /2 law, sweep_T */
+#define USC_CHIRP_S 1u /* experiments/synchronization/Src/chirp.c:16-44: complex (cos,sin) */
+#define USC_CHIRP_T 2u /* experiments/chirp_compression_time_domain/Src/chirp.c:25-45: real cos, no /2 */
+#define USC_CHIRP_F 3u /* experiments/chirp_compression_freq_domain/Src/chirp.c:15-35 */
+
+#define USC_HANN_PERIODIC 0u  /* receiver/Src/main.c:99,390-393 */
+#define USC_HANN_SYMMETRIC 1u /* experiments/chirp_compression_time_domain/Src/chirp.c:13,63-65 */
+
+#define USC_PCM_F32 0u /* frames already cast to float (the reference's fifo_queue) */
+#define USC_PCM_I32 1u /* raw DFSDM words; the cast of receiver/Src/main.c:663-665 is fused in */
+
+#define USC_UP 1   /* receiver/Inc/chirp.h:12-14 */
+#define USC_DOWN 0
+
+/* Compile-time constants of the reference gathered in one POD (receiver/Inc/main.h:97-98,
+ * receiver/Inc/chirp.h:16-19, receiver/Src/dfsdm.c:59-61,69). */
+typedef struct usc_config {
+    uint32_t n;             /* NN / PCM_SAMPLES: samples per frame, power of two, 32..4096        */
+    float fs;               /* sampling rate as the firmware computes it (78125.0f)               */
+    float f0, f1;           /* sweep range F0,F1 (receiver) or F1,F2 (experiments)                */
+    float sweep_T;          /* TIME_FRAME (0.0205f) for variants R,S; T,F use n/fs                */
+    uint32_t chirp_variant; /* USC_CHIRP_*                                                        */
+    uint32_t window;        /* USC_HANN_*                                                         */
+    float snr_threshold;    /* SNR_THRESHOLD (2.0f)                                               */
+    uint32_t reserved[4];
+} usc_config;
+
+typedef struct usc_handle usc_handle;
+
+/* One dsp() result — struct history of receiver/Src/main.c:124-136 without the tick stamps,
+ * plus the raw bins the frequencies were derived from. 48 bytes. */
+typedef struct usc_history {
+    float mag_max, mag_max_left, mag_max_right;
+    int32_t max_freq, max_freq_left, max_freq_right;
+    uint32_t max_idx, max_idx_left, max_idx_right;
+    float mag_mean, snr;
+    uint32_t rank; /* the reference's char rank, widened */
+} usc_history;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+/* Fills cfg with the final receiver's constants (n=2048, fs=78125, 16-19 kHz, variant R, periodic). */
+void usc_default_config(usc_config *cfg);
+/* Builds every table the config implies on the host in C (Hann via the arm_cos_f32 table algorithm,
+ * reference chirps, twiddles), uploads them to `device`.  Replaces arm_rfft_fast_init_f32
+ * (receiver/Src/main.c:377), init_ref_chirp (receiver/Src/chirp.c:42-45) and the Hann loop
+ * (receiver/Src/main.c:390-393). */
+int usc_create(const usc_config *cfg, int device, usc_handle **out);
+void usc_destroy(usc_handle *h);
+int usc_set_stream(usc_handle *h, void *cuda_stream);
+int usc_sync(usc_handle *h);
+const char *usc_error_string(int code);
+/* geometry derived as in receiver/Src/main.c:372-374 */
+int usc_get_geometry(const usc_handle *h, uint32_t *bandwidth, uint32_t *bandwidth2, uint32_t *idx_left_zero);
+/* Copies a host-built table back to the caller (what == "hann", "up", "down", "twiddle", "H_up",
+ * "H_down"); cap = capacity of dst in floats; returns the table length in floats or <0. */
+int usc_get_table(const usc_handle *h, const char *what, float *dst, size_t cap);
+/* number of kernel launches issued through this handle since creation (bench evidence) */
+uint64_t usc_launch_count(const usc_handle *h);
+
+/* device memory helpers so a plain-C host needs no CUDA headers */
+int usc_malloc(void **dptr, size_t bytes);
+int usc_free(void *dptr);
+int usc_malloc_host(void **hptr, size_t bytes); /* pinned */
+int usc_free_host(void *hptr);
+int usc_memcpy_h2d(usc_handle *h, void *dst, const void *src, size_t bytes); /* async on the stream */
+int usc_memcpy_d2h(usc_handle *h, void *dst, const void *src, size_t bytes); /* async on the stream */
+int usc_memset(usc_handle *h, void *dst, int value, size_t bytes);
+
+/* ---- batched CMSIS-shaped operators (device pointers) ------------------------------------------
+ * `batch` independent vectors laid out back to back with the given strides (in floats).  A
+ * broadcast operand has stride 0.  Each mirrors the arm_math.h function named in its comment.   */
+/* (float) buf[i] — the ingest cast, receiver/Src/main.c:663-665 */
+int usc_i32_to_f32(usc_handle *h, const int32_t *src, float *dst, size_t count);
+/* arm_mult_f32, arm_math.h:1938-1942 */
+int usc_arm_mult_f32_batch(usc_handle *h, const float *a, size_t stride_a, const float *b, size_t stride_b,
+                           float *dst, size_t stride_dst, uint32_t block_size, uint32_t batch);
+/* arm_scale_f32, arm_math.h:2508 */
+int usc_arm_scale_f32_batch(usc_handle *h, const float *src, float scale, float *dst, uint32_t block_size,
+                            uint32_t batch);
+/* arm_cmplx_mult_cmplx_f32, arm_math.h:6579-6583 (num_samples complex; no conjugate) */
+int usc_arm_cmplx_mult_cmplx_f32_batch(usc_handle *h, const float *a, size_t stride_a, const float *b,
+                                       size_t stride_b, float *dst, size_t stride_dst, uint32_t num_samples,
+                                       uint32_t batch);
+/* arm_cmplx_mult_real_f32, arm_math.h:6425-6429 */
+int usc_arm_cmplx_mult_real_f32_batch(usc_handle *h, const float *cplx, size_t stride_c, const float *real,
+                                      size_t stride_r, float *dst, size_t stride_dst, uint32_t num_samples,
+                                      uint32_t batch);
+/* arm_cmplx_mag_f32, arm_math.h:6312-6315 */
+int usc_arm_cmplx_mag_f32_batch(usc_handle *h, const float *src, size_t stride_src, float *dst,
+                                size_t stride_dst, uint32_t num_samples, uint32_t batch);
+/* arm_max_f32, arm_math.h:6537-6541: first occurrence of the maximum */
+int usc_arm_max_f32_batch(usc_handle *h, const float *src, size_t stride_src, uint32_t block_size,
+                          float *result, uint32_t *index, uint32_t batch);
+/* arm_mean_f32, arm_math.h:6192: sequential sum / block_size */
+int usc_arm_mean_f32_batch(usc_handle *h, const float *src, size_t stride_src, uint32_t block_size,
+                           float *result, uint32_t batch);
+/* arm_rfft_fast_f32, arm_math.h:2246-2249.  fft_len real points per vector (32..8192, power of two);
+ * in == out allowed (hazard H2 is defined away: the result is always the mathematically right one). */
+int usc_arm_rfft_fast_f32_batch(usc_handle *h, uint32_t fft_len, const float *in, float *out, uint8_t ifft_flag,
+                                uint32_t batch);
+/* arm_cfft_f32, arm_math.h:2149-2153 with bitReverseFlag = 1: in place, fft_len complex points
+ * (16..4096); forward unscaled, inverse scaled by 1/fft_len. */
+int usc_arm_cfft_f32_batch(usc_handle *h, uint32_t fft_len, float *data, uint8_t ifft_flag, uint32_t batch);
+/* arm_fir_f32, arm_math.h:1194-1214.  coeffs (host pointer) in CMSIS time-reversed order; state:
+ * batch x (num_taps-1) floats on the device carrying the filter history between calls (zero it to
+ * start, like arm_fir_init_f32). */
+int usc_arm_fir_f32_batch(usc_handle *h, const float *coeffs_host, uint32_t num_taps, float *state,
+                          const float *src, float *dst, uint32_t block_size, uint32_t batch);
+
+/* ---- fused stage-level operators ---------------------------------------------------------------- */
+/* K1.  dsp() for UP and DOWN on `nframes` aligned frames (receiver/Src/main.c:163-215 twice per
+ * frame): de-chirp x Hann x RFFT x |.| x arg-max over bins [0, bandwidth2) in ONE pass over the
+ * PCM.  pcm: nframes*n samples of pcm_format.  Outputs (device, nframes each; any may be NULL):
+ * peak magnitude and bin per hypothesis, and the symbol decision bit = !(mag_down > mag_up)
+ * (receiver/Src/main.c:523: down wins only if strictly greater). */
+int usc_demod_frames(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, float *mag_up,
+                     uint32_t *idx_up, float *mag_down, uint32_t *idx_down, uint8_t *bit);
+/* pipeline() of receiver/Src/main.c:163-180 on `batch` frames, one hypothesis: frames (n floats
+ * each, stride n) -> n floats each: magnitudes of the n/2 packed bins, zeros above (hazard H1). */
+int usc_pipeline(usc_handle *h, const float *frames, float *mags, int updown, uint32_t batch);
+/* dsp() of receiver/Src/main.c:183-231 for `batch` streams: stream s reads n samples at
+ * fifo + s*fifo_stride + sync_position[s] (fifo_stride >= 3n in the reference), runs the pipeline
+ * for hypothesis `updown`, the two windowed arg-max, side choice, idx2freq and SNR against
+ * mag_mean[s].  hist: batch usc_history records on the device. */
+int usc_dsp(usc_handle *h, const float *fifo, size_t fifo_stride, const uint32_t *sync_position,
+            const float *mag_mean, int updown, usc_history *hist, uint32_t batch);
+/* K2.  compress_chirp() of experiments/chirp_compression_time_domain/Src/chirp.c:78-83 followed
+ * by the signed arm_max_f32 over all n lags (.../Src/main.c:189) on `nframes` frames; the handle
+ * must be created with chirp_variant T and the symmetric window.  out_frames (nframes*n floats)
+ * may be NULL when only the peaks are wanted. */
+int usc_compress_chirp(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, int use_up,
+                       float *out_frames, float *max_val, uint32_t *max_idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USC_H_ */

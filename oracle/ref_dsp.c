@@ -186,7 +186,7 @@ static void base_fft(const ref_fft_plan *p, uint32_t r, const cf *in, uint32_t s
 
 /* Mixed-radix step.  n = A*B with B = rad[0]:  m = a + A*b,  k = B*c + d.
  *   1. V_a[d]  = base_fft_B over b of in[a + A*b]
- *   2. V_a[d] *= W_n^(a*d)           (skipped when a*d == 0: exact identity)
+ *   2. V_a[d] *= W_n^(a*d)  for d != 0  (d == 0 is skipped; a == 0 multiplies by W^0 = (1,-0))
  *   3. out[B*c + d] = fft_A over a of V_.[d]      (recursive with rad[1..]) */
 static void fft_rec(const ref_fft_plan *p, uint32_t n, const uint32_t *rad, uint32_t nrad,
                     const cf *in, uint32_t stride, cf *out, cf *scratch) {
@@ -200,7 +200,7 @@ static void fft_rec(const ref_fft_plan *p, uint32_t n, const uint32_t *rad, uint
         base_fft(p, B, in + (size_t) a * stride, stride * A, v);
         for (uint32_t d = 0; d < B; ++d) {
             cf x = v[d];
-            if (a != 0 && d != 0) {
+            if (d != 0) {
                 size_t j = (size_t) a * d * step;
                 float re, im;
                 cmul(x.r, x.i, p->tw[2 * j], p->tw[2 * j + 1], &re, &im);

@@ -1,0 +1,188 @@
+// k_elementwise.cu — batched CMSIS-shaped element-wise and reduction operators.
+// Each is a single streaming pass (bound: HBM); they exist so a caller can run the reference's
+// chain operator by operator.  The hot path uses the fused kernels instead.
+#include "usc_kernels.cuh"
+#include "usc_launch.h"
+
+namespace usc {
+
+static inline int blocks_for(size_t work, int threads) {
+    size_t b = (work + threads - 1) / threads;
+    if (b > 148u * 32u) b = 148u * 32u;         // grid-stride beyond 32 CTAs per SM
+    return b ? (int) b : 1;
+}
+
+// (float) buf[i]  — receiver/Src/main.c:663-665
+__global__ void k_i32_to_f32(const int32_t* __restrict__ src, float* __restrict__ dst, size_t count) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x, step = (size_t) gridDim.x * blockDim.x;
+    const size_t n4 = count / 4;
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    if (aligned) {
+        for (size_t j = i; j < n4; j += step) {
+            int4 v = s4[j];
+            d4[j] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+        }
+        for (size_t j = n4 * 4 + i; j < count; j += step) dst[j] = __int2float_rn(src[j]);
+    } else {
+        for (size_t j = i; j < count; j += step) dst[j] = __int2float_rn(src[j]);
+    }
+}
+
+// arm_mult_f32 — arm_math.h:1938-1942
+__global__ void k_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                       uint32_t len, uint32_t batch) {
+    const size_t total = (size_t) len * batch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        size_t v = i / len, e = i - v * len;
+        dst[v * sd + e] = __fmul_rn(a[v * sa + e], b[v * sb + e]);
+    }
+}
+
+// arm_scale_f32 — arm_math.h:2508
+__global__ void k_scale(const float* src, float scale, float* dst, size_t total) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = __fmul_rn(src[i], scale);
+}
+
+// arm_cmplx_mult_cmplx_f32 — arm_math.h:6579-6583
+__global__ void k_cmul(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                       uint32_t ncplx, uint32_t batch) {
+    const size_t total = (size_t) ncplx * batch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        size_t v = i / ncplx, e = i - v * ncplx;
+        const float* pa = a + v * sa + 2 * e;
+        const float* pb = b + v * sb + 2 * e;
+        float ar = pa[0], ai = pa[1], br = pb[0], bi = pb[1], re, im;
+        cmul(ar, ai, br, bi, re, im);
+        float* pd = dst + v * sd + 2 * e;
+        pd[0] = re;
+        pd[1] = im;
+    }
+}
+
+// arm_cmplx_mult_real_f32 — arm_math.h:6425-6429
+__global__ void k_cmul_real(const float* c, size_t sc, const float* r, size_t sr, float* dst, size_t sd,
+                            uint32_t ncplx, uint32_t batch) {
+    const size_t total = (size_t) ncplx * batch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        size_t v = i / ncplx, e = i - v * ncplx;
+        float w = r[v * sr + e];
+        float re = c[v * sc + 2 * e], im = c[v * sc + 2 * e + 1];
+        dst[v * sd + 2 * e] = __fmul_rn(re, w);
+        dst[v * sd + 2 * e + 1] = __fmul_rn(im, w);
+    }
+}
+
+// arm_cmplx_mag_f32 — arm_math.h:6312-6315
+__global__ void k_cmag(const float* src, size_t ss, float* dst, size_t sd, uint32_t ncplx, uint32_t batch) {
+    const size_t total = (size_t) ncplx * batch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        size_t v = i / ncplx, e = i - v * ncplx;
+        float re = src[v * ss + 2 * e], im = src[v * ss + 2 * e + 1];
+        dst[v * sd + e] = cmag(re, im);
+    }
+}
+
+// arm_max_f32 — arm_math.h:6537-6541.  One warp per vector; first occurrence of the maximum.
+__global__ void k_max(const float* src, size_t ss, uint32_t len, float* result, uint32_t* index, uint32_t batch) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    for (size_t v = warp; v < batch; v += nwarps) {
+        const float* p = src + v * ss;
+        float best = -INFINITY;
+        uint32_t bi = 0xffffffffu;
+        for (uint32_t e = lane; e < len; e += 32) {
+            float x = p[e];
+            if (bi == 0xffffffffu || best < x) { best = x; bi = e; }
+        }
+        warp_argmax(best, bi);
+        if (lane == 0) {
+            result[v] = best;
+            if (index) index[v] = bi;
+        }
+    }
+}
+
+// arm_mean_f32 — arm_math.h:6192.  The sum is sequential left to right (canonical order), so one
+// thread per vector; vectors here are short (the reference's call is 8 elements, main.c:431).
+__global__ void k_mean(const float* src, size_t ss, uint32_t len, float* result, uint32_t batch) {
+    for (size_t v = (size_t) blockIdx.x * blockDim.x + threadIdx.x; v < batch; v += (size_t) gridDim.x * blockDim.x) {
+        const float* p = src + v * ss;
+        float sum = 0.0f;
+        for (uint32_t e = 0; e < len; ++e) sum = __fadd_rn(sum, p[e]);
+        result[v] = __fdiv_rn(sum, (float) len);
+    }
+}
+
+// arm_fir_f32 — arm_math.h:1194-1214.  One CTA per stream; y[n] = sum_i hist[n+i]*coeffs[i] with one
+// FMA per tap from acc = 0, hist = [state (taps-1) | src block].  State is updated for the next call.
+__global__ void k_fir(const float* __restrict__ coeffs, uint32_t taps, float* state, const float* src,
+                      float* dst, uint32_t len, uint32_t batch) {
+    extern __shared__ float s_fir[];           // taps coeffs + (taps-1+len) history
+    float* s_c = s_fir;
+    float* s_h = s_fir + taps;
+    for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < taps; i += blockDim.x) s_c[i] = coeffs[i];
+        for (uint32_t i = threadIdx.x; i < taps - 1; i += blockDim.x) s_h[i] = state[(size_t) v * (taps - 1) + i];
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) s_h[taps - 1 + i] = src[(size_t) v * len + i];
+        __syncthreads();
+        for (uint32_t n = threadIdx.x; n < len; n += blockDim.x) {
+            float acc = 0.0f;
+            for (uint32_t i = 0; i < taps; ++i) acc = __fmaf_rn(s_h[n + i], s_c[i], acc);
+            dst[(size_t) v * len + n] = acc;
+        }
+        for (uint32_t i = threadIdx.x; i < taps - 1; i += blockDim.x) state[(size_t) v * (taps - 1) + i] = s_h[len + i];
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st) {
+    k_i32_to_f32<<<blocks_for(count / 4 + 1, 256), 256, 0, st>>>(src, dst, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                        uint32_t len, uint32_t batch, cudaStream_t st) {
+    k_mult<<<blocks_for((size_t) len * batch, 256), 256, 0, st>>>(a, sa, b, sb, dst, sd, len, batch);
+    return cudaGetLastError();
+}
+cudaError_t launch_scale(const float* src, float scale, float* dst, size_t total, cudaStream_t st) {
+    k_scale<<<blocks_for(total, 256), 256, 0, st>>>(src, scale, dst, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_cmul(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                        uint32_t ncplx, uint32_t batch, cudaStream_t st) {
+    k_cmul<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(a, sa, b, sb, dst, sd, ncplx, batch);
+    return cudaGetLastError();
+}
+cudaError_t launch_cmul_real(const float* c, size_t sc, const float* r, size_t sr, float* dst, size_t sd,
+                             uint32_t ncplx, uint32_t batch, cudaStream_t st) {
+    k_cmul_real<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(c, sc, r, sr, dst, sd, ncplx, batch);
+    return cudaGetLastError();
+}
+cudaError_t launch_cmag(const float* src, size_t ss, float* dst, size_t sd, uint32_t ncplx, uint32_t batch,
+                        cudaStream_t st) {
+    k_cmag<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(src, ss, dst, sd, ncplx, batch);
+    return cudaGetLastError();
+}
+cudaError_t launch_max(const float* src, size_t ss, uint32_t len, float* result, uint32_t* index,
+                       uint32_t batch, cudaStream_t st) {
+    k_max<<<blocks_for((size_t) batch * 32, 256), 256, 0, st>>>(src, ss, len, result, index, batch);
+    return cudaGetLastError();
+}
+cudaError_t launch_mean(const float* src, size_t ss, uint32_t len, float* result, uint32_t batch,
+                        cudaStream_t st) {
+    k_mean<<<blocks_for(batch, 128), 128, 0, st>>>(src, ss, len, result, batch);
+    return cudaGetLastError();
+}
+cudaError_t launch_fir(const float* coeffs_dev, uint32_t taps, float* state, const float* src, float* dst,
+                       uint32_t len, uint32_t batch, cudaStream_t st) {
+    size_t smem = sizeof(float) * ((size_t) taps + taps - 1 + len);
+    int grid = batch < 148u * 8u ? (int) batch : 148 * 8;
+    k_fir<<<grid, 256, smem, st>>>(coeffs_dev, taps, state, src, dst, len, batch);
+    return cudaGetLastError();
+}
+
+}  // namespace usc

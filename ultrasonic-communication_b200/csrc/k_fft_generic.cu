@@ -1,0 +1,165 @@
+// k_fft_generic.cu — the canonical mixed-radix FFT for any supported length, one CTA per transform
+// with the whole transform resident in shared memory.  Serves the CMSIS-shaped
+// operators usc_arm_rfft_fast_f32_batch / usc_arm_cfft_f32_batch; the fused 2048-point chains use
+// the warp-per-frame kernels instead.  Same arithmetic as the oracle's fft_rec():
+//   level l works on contiguous sub-blocks of n_l points; B = rad[l], A = n_l / B
+//     for each a < A: gather x[a + A b] (b < B) -> base FFT -> element d *= W_{n_l}^(a d) (d != 0)
+//                     -> scatter to the SAME addresses (position a + A d)
+//   after the last level element (d0, d1, ...) of output index k = d0 + B0 (d1 + B1 (...)) sits at
+//   position d0 A0 + d1 A1 + ...; a digit-reversal copy restores natural order.
+#include "usc_kernels.cuh"
+#include "usc_launch.h"
+
+namespace usc {
+
+constexpr int kFftThreads = 256;
+
+template <int B>
+__device__ __forceinline__ void level_items(float2* s, uint32_t n_total, uint32_t n_l, const float2* tw,
+                                            uint32_t tw_n, bool last) {
+    const uint32_t A = n_l / B;
+    const uint32_t items = n_total / B;
+    const uint32_t tw_step = tw_n / n_l;
+    for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+        const uint32_t blk = it / A, a = it - blk * A;
+        float2* base = s + (size_t) blk * n_l + a;
+        float re[B], im[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            float2 v = base[(size_t) A * b];
+            re[b] = v.x;
+            im[b] = v.y;
+        }
+        fft_base<B>(re, im);
+#pragma unroll
+        for (int d = 0; d < B; ++d) {
+            float xr = re[d], xi = im[d];
+            if (!last && d != 0) {
+                float2 w = tw[(size_t) a * d * tw_step];
+                cmul(re[d], im[d], w.x, w.y, xr, xi);
+            }
+            base[(size_t) A * d] = make_float2(xr, xi);
+        }
+    }
+}
+
+__device__ __forceinline__ void run_levels(float2* s, const fft_plan_dev& plan) {
+    uint32_t n_l = plan.n;
+    for (uint32_t l = 0; l < plan.nrad; ++l) {
+        const bool last = l + 1 == plan.nrad;
+        switch (plan.rad[l]) {
+            case 2: level_items<2>(s, plan.n, n_l, plan.tw, plan.tw_n, last); break;
+            case 4: level_items<4>(s, plan.n, n_l, plan.tw, plan.tw_n, last); break;
+            case 8: level_items<8>(s, plan.n, n_l, plan.tw, plan.tw_n, last); break;
+            case 16: level_items<16>(s, plan.n, n_l, plan.tw, plan.tw_n, last); break;
+            default: level_items<32>(s, plan.n, n_l, plan.tw, plan.tw_n, last); break;
+        }
+        n_l /= plan.rad[l];
+        __syncthreads();
+    }
+}
+
+// position in the level buffer of output index k
+__device__ __forceinline__ uint32_t out_position(const fft_plan_dev& plan, uint32_t k) {
+    uint32_t pos = 0, n_l = plan.n;
+    for (uint32_t l = 0; l < plan.nrad; ++l) {
+        const uint32_t B = plan.rad[l], A = n_l / B;
+        const uint32_t d = k % B;
+        k /= B;
+        pos += d * A;
+        n_l = A;
+    }
+    return pos;
+}
+
+// Shared memory: two buffers of n float2 (work, natural-order copy).
+template <int MODE>
+__global__ void __launch_bounds__(kFftThreads) k_fft_generic(fft_plan_dev plan, const float* in, float* out,
+                                                             uint32_t batch) {
+    extern __shared__ float2 s_fft[];
+    float2* work = s_fft;
+    float2* nat = s_fft + plan.n;
+    const uint32_t n = plan.n;
+    for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
+        const float2* src = reinterpret_cast<const float2*>(in) + (size_t) v * n;
+        float2* dst = reinterpret_cast<float2*>(out) + (size_t) v * n;
+        if (MODE == FFT_C2R) {
+            // merge: packed X -> 2Z (natural) -> swap(re,im) for the inverse-by-forward trick
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+                float zr, zi;
+                if (k == 0) {
+                    float2 x0 = src[0];
+                    zr = __fadd_rn(x0.x, x0.y);
+                    zi = __fsub_rn(x0.x, x0.y);
+                } else {
+                    float2 xk = src[k], xc = src[n - k];
+                    float2 w = plan.tw[k];                   // master table has 2n entries: W_N^k
+                    rfft_merge(xk.x, xk.y, xc.x, xc.y, w.x, -w.y, zr, zi);
+                }
+                work[k] = make_float2(zi, zr);
+            }
+        } else {
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+                float2 x = src[k];
+                work[k] = MODE == FFT_C2C_INV ? make_float2(x.y, x.x) : x;
+            }
+        }
+        __syncthreads();
+        run_levels(work, plan);
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) nat[k] = work[out_position(plan, k)];
+        __syncthreads();
+        if (MODE == FFT_C2C_FWD) {
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) dst[k] = nat[k];
+        } else if (MODE == FFT_C2C_INV) {
+            const float sc = 1.0f / (float) n;
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x)
+                dst[k] = make_float2(__fmul_rn(nat[k].y, sc), __fmul_rn(nat[k].x, sc));
+        } else if (MODE == FFT_C2R) {
+            const float sc = 1.0f / (float) (2 * n);
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x)
+                dst[k] = make_float2(__fmul_rn(nat[k].y, sc), __fmul_rn(nat[k].x, sc));
+        } else {   // FFT_R2C: split into the packed spectrum
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+                float xr, xi;
+                if (k == 0) {
+                    xr = __fadd_rn(nat[0].x, nat[0].y);
+                    xi = __fsub_rn(nat[0].x, nat[0].y);
+                } else {
+                    float2 zk = nat[k], zc = nat[n - k];
+                    float2 w = plan.tw[k];
+                    rfft_split(zk.x, zk.y, zc.x, zc.y, w.x, -w.y, xr, xi);
+                }
+                dst[k] = make_float2(xr, xi);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t fft_generic_prepare() {
+    const int max_smem = 200 * 1024;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2C_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2C_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_R2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2R>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_fft_generic(int mode, const fft_plan_dev& plan, const float* in, float* out, uint32_t batch,
+                               cudaStream_t st) {
+    const size_t smem = sizeof(float2) * 2 * (size_t) plan.n;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    int grid = batch < 148u * 16u ? (int) batch : 148 * 16;
+    if (grid < 1) grid = 1;
+    switch (mode) {
+        case FFT_C2C_FWD: k_fft_generic<FFT_C2C_FWD><<<grid, kFftThreads, smem, st>>>(plan, in, out, batch); break;
+        case FFT_C2C_INV: k_fft_generic<FFT_C2C_INV><<<grid, kFftThreads, smem, st>>>(plan, in, out, batch); break;
+        case FFT_R2C: k_fft_generic<FFT_R2C><<<grid, kFftThreads, smem, st>>>(plan, in, out, batch); break;
+        case FFT_C2R: k_fft_generic<FFT_C2R><<<grid, kFftThreads, smem, st>>>(plan, in, out, batch); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace usc

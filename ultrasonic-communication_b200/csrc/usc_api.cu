@@ -1,0 +1,437 @@
+// usc_api.cu — the C-ABI of libusc.so (include/usc.h).  Thin: argument checks, table ownership,
+// launches.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "../../include/usc.h"
+#include "usc_kernels.cuh"
+#include "usc_launch.h"
+#include "usc_tables.h"
+
+using namespace usc;
+
+static_assert(sizeof(usc_history) == sizeof(history_rec), "usc_history layout");
+
+struct usc_handle {
+    usc_config cfg;
+    int device;
+    int num_sms;
+    cudaStream_t stream;
+    uint32_t bandwidth, bandwidth2, idx_left_zero;
+    std::vector<float> hann, up, down, H_up, H_down;
+    float *d_hann, *d_up, *d_down, *d_H_up, *d_H_down;
+    float2 *d_tw_pass, *d_tw_split;
+    float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
+    std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
+    std::map<uint32_t, std::vector<float>> tw_host;
+    uint64_t launches;
+};
+
+static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? USC_OK : USC_ERR_CUDA_BASE - (int) e; }
+#define CK(expr)                                   \
+    do {                                           \
+        cudaError_t e__ = (expr);                  \
+        if (e__ != cudaSuccess) return cuda_rc(e__); \
+    } while (0)
+
+static bool pow2(uint32_t n) { return n && !(n & (n - 1)); }
+
+static int upload(const void* host, size_t bytes, void** dev) {
+    CK(cudaMalloc(dev, bytes));
+    CK(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    return USC_OK;
+}
+
+// master twiddle table of `len` entries on the device (cached per handle)
+static int get_twiddles(usc_handle* h, uint32_t len, float2** out) {
+    auto it = h->tw_cache.find(len);
+    if (it != h->tw_cache.end()) { *out = it->second; return USC_OK; }
+    std::vector<float> tw(2 * (size_t) len);
+    usc_host_twiddles(tw.data(), len);
+    void* d = nullptr;
+    int rc = upload(tw.data(), tw.size() * sizeof(float), &d);
+    if (rc) return rc;
+    h->tw_cache[len] = (float2*) d;
+    h->tw_host[len] = std::move(tw);
+    *out = (float2*) d;
+    return USC_OK;
+}
+
+static int make_plan(usc_handle* h, uint32_t n_complex, uint32_t tw_len, fft_plan_dev* plan) {
+    plan->n = n_complex;
+    plan->nrad = usc_host_radices(n_complex, plan->rad);
+    if (!plan->nrad) return USC_ERR_ARGUMENT;
+    plan->tw_n = tw_len;
+    float2* tw = nullptr;
+    int rc = get_twiddles(h, tw_len, &tw);
+    if (rc) return rc;
+    plan->tw = tw;
+    return USC_OK;
+}
+
+extern "C" {
+
+void usc_default_config(usc_config* cfg) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->n = 2048;                    /* receiver/Inc/main.h:97 */
+    cfg->fs = 78125.0f;               /* 80 MHz / 32 / 32 / 1, receiver/Src/dfsdm.c:59-61,69 */
+    cfg->f0 = 16000.0f;               /* receiver/Inc/chirp.h:18 */
+    cfg->f1 = 19000.0f;               /* receiver/Inc/chirp.h:19 */
+    cfg->sweep_T = 0.0205f;           /* receiver/Inc/chirp.h:16 */
+    cfg->chirp_variant = USC_CHIRP_R;
+    cfg->window = USC_HANN_PERIODIC;
+    cfg->snr_threshold = 2.0f;        /* receiver/Inc/main.h:98 */
+}
+
+const char* usc_error_string(int code) {
+    if (code == USC_OK) return "ok";
+    if (code == USC_ERR_ARGUMENT) return "argument error (ARM_MATH_ARGUMENT_ERROR)";
+    if (code == USC_ERR_NOMEM) return "out of host memory";
+    if (code <= USC_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t) (USC_ERR_CUDA_BASE - code));
+    return "unknown error";
+}
+
+int usc_create(const usc_config* cfg, int device, usc_handle** out) {
+    if (!cfg || !out) return USC_ERR_ARGUMENT;
+    *out = nullptr;
+    if (!pow2(cfg->n) || cfg->n < 32 || cfg->n > 4096) return USC_ERR_ARGUMENT;
+    if (!(cfg->fs > 0.0f) || cfg->chirp_variant > USC_CHIRP_F || cfg->window > USC_HANN_SYMMETRIC) return USC_ERR_ARGUMENT;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));                    // no device -> error: there is no CPU fallback
+    if (device < 0 || device >= ndev) return USC_ERR_ARGUMENT;
+    CK(cudaSetDevice(device));
+    usc_handle* h = new (std::nothrow) usc_handle();
+    if (!h) return USC_ERR_NOMEM;
+    h->cfg = *cfg;
+    h->device = device;
+    h->stream = 0;
+    h->launches = 0;
+    h->d_hann = h->d_up = h->d_down = h->d_H_up = h->d_H_down = nullptr;
+    h->d_tw_pass = h->d_tw_split = nullptr;
+    h->d_fir_coeffs = nullptr;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    const uint32_t n = cfg->n;
+    h->bandwidth = usc_host_bandwidth(n, cfg->fs, cfg->f0, cfg->f1);        /* main.c:372 */
+    h->bandwidth2 = h->bandwidth * 2;                                       /* main.c:373 */
+    h->idx_left_zero = n - h->bandwidth2;                                   /* main.c:374 */
+
+    const bool cplx = cfg->chirp_variant == USC_CHIRP_S;
+    h->hann.resize(n);
+    h->up.resize(cplx ? 2 * n : n);
+    h->down.resize(cplx ? 2 * n : n);
+    usc_host_hann(h->hann.data(), n, cfg->window);
+    float phase = (cfg->chirp_variant <= USC_CHIRP_S) ? -90.0f : (float) (-3.14159265358979f / 2.0);
+    usc_host_ref_chirp(cfg->chirp_variant, n, cfg->fs, cfg->f0, cfg->f1, cfg->sweep_T, phase, 1, h->up.data());
+    usc_host_ref_chirp(cfg->chirp_variant, n, cfg->fs, cfg->f0, cfg->f1, cfg->sweep_T, phase, 0, h->down.data());
+
+    int rc;
+    if ((rc = upload(h->hann.data(), h->hann.size() * 4, (void**) &h->d_hann))) { usc_destroy(h); return rc; }
+    if ((rc = upload(h->up.data(), h->up.size() * 4, (void**) &h->d_up))) { usc_destroy(h); return rc; }
+    if ((rc = upload(h->down.data(), h->down.size() * 4, (void**) &h->d_down))) { usc_destroy(h); return rc; }
+    if (cudaMalloc((void**) &h->d_fir_coeffs, 256 * sizeof(float)) != cudaSuccess) { usc_destroy(h); return USC_ERR_CUDA_BASE - (int) cudaErrorMemoryAllocation; }
+    cudaError_t e = fft_generic_prepare();
+    if (e != cudaSuccess) { usc_destroy(h); return cuda_rc(e); }
+
+    // master table W_n (n entries) serves the n-point real FFT (n/2 complex) and its split stage
+    float2* d_master = nullptr;
+    if ((rc = get_twiddles(h, n, &d_master))) { usc_destroy(h); return rc; }
+    if (n == 2048) {
+        // fused-kernel tables: pass twiddles W_1024^(a d) laid out [d][a]; split table (cos, sin)(2 pi k / 2048)
+        const std::vector<float>& tw = h->tw_host[n];
+        std::vector<float> pass(2 * 1024), split(2 * 1024);
+        for (uint32_t d = 0; d < 32; ++d)
+            for (uint32_t a = 0; a < 32; ++a) {
+                const uint32_t j = a * d * 2;                    // W_1024^(ad) = W_2048^(2ad)
+                pass[2 * (d * 32 + a)] = tw[2 * j];
+                pass[2 * (d * 32 + a) + 1] = tw[2 * j + 1];
+            }
+        for (uint32_t k = 0; k < 1024; ++k) {
+            split[2 * k] = tw[2 * k];
+            split[2 * k + 1] = -tw[2 * k + 1];
+        }
+        if ((rc = upload(pass.data(), pass.size() * 4, (void**) &h->d_tw_pass))) { usc_destroy(h); return rc; }
+        if ((rc = upload(split.data(), split.size() * 4, (void**) &h->d_tw_split))) { usc_destroy(h); return rc; }
+    }
+    if (cfg->chirp_variant == USC_CHIRP_T) {
+        // init_ref_chirp of experiments/chirp_compression_time_domain/Src/chirp.c:52-75:
+        // H = rfft(window * chirp), computed once on the device with the same canonical FFT.
+        std::vector<float> wu(n), wd(n);
+        for (uint32_t i = 0; i < n; ++i) { wu[i] = h->up[i] * h->hann[i]; wd[i] = h->down[i] * h->hann[i]; }
+        if ((rc = upload(wu.data(), n * 4, (void**) &h->d_H_up))) { usc_destroy(h); return rc; }
+        if ((rc = upload(wd.data(), n * 4, (void**) &h->d_H_down))) { usc_destroy(h); return rc; }
+        fft_plan_dev plan;
+        if ((rc = make_plan(h, n / 2, n, &plan))) { usc_destroy(h); return rc; }
+        if ((e = launch_fft_generic(FFT_R2C, plan, h->d_H_up, h->d_H_up, 1, 0)) != cudaSuccess ||
+            (e = launch_fft_generic(FFT_R2C, plan, h->d_H_down, h->d_H_down, 1, 0)) != cudaSuccess ||
+            (e = cudaDeviceSynchronize()) != cudaSuccess) { usc_destroy(h); return cuda_rc(e); }
+        h->H_up.resize(n);
+        h->H_down.resize(n);
+        cudaMemcpy(h->H_up.data(), h->d_H_up, n * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h->H_down.data(), h->d_H_down, n * 4, cudaMemcpyDeviceToHost);
+    }
+    *out = h;
+    return USC_OK;
+}
+
+void usc_destroy(usc_handle* h) {
+    if (!h) return;
+    cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
+    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs);
+    for (auto& kv : h->tw_cache) cudaFree(kv.second);
+    delete h;
+}
+
+int usc_set_stream(usc_handle* h, void* cuda_stream) {
+    if (!h) return USC_ERR_ARGUMENT;
+    h->stream = (cudaStream_t) cuda_stream;
+    return USC_OK;
+}
+
+int usc_sync(usc_handle* h) {
+    if (!h) return USC_ERR_ARGUMENT;
+    CK(cudaStreamSynchronize(h->stream));
+    return USC_OK;
+}
+
+int usc_get_geometry(const usc_handle* h, uint32_t* bandwidth, uint32_t* bandwidth2, uint32_t* idx_left_zero) {
+    if (!h) return USC_ERR_ARGUMENT;
+    if (bandwidth) *bandwidth = h->bandwidth;
+    if (bandwidth2) *bandwidth2 = h->bandwidth2;
+    if (idx_left_zero) *idx_left_zero = h->idx_left_zero;
+    return USC_OK;
+}
+
+int usc_get_table(const usc_handle* h, const char* what, float* dst, size_t cap) {
+    if (!h || !what) return USC_ERR_ARGUMENT;
+    const std::vector<float>* t = nullptr;
+    if (!strcmp(what, "hann")) t = &h->hann;
+    else if (!strcmp(what, "up")) t = &h->up;
+    else if (!strcmp(what, "down")) t = &h->down;
+    else if (!strcmp(what, "H_up")) t = &h->H_up;
+    else if (!strcmp(what, "H_down")) t = &h->H_down;
+    else if (!strcmp(what, "twiddle")) {
+        auto it = h->tw_host.find(h->cfg.n);
+        if (it != h->tw_host.end()) t = &it->second;
+    }
+    if (!t || t->empty()) return USC_ERR_ARGUMENT;
+    if (dst) {
+        if (cap < t->size()) return USC_ERR_ARGUMENT;
+        memcpy(dst, t->data(), t->size() * sizeof(float));
+    }
+    return (int) t->size();
+}
+
+uint64_t usc_launch_count(const usc_handle* h) { return h ? h->launches : 0; }
+
+int usc_malloc(void** dptr, size_t bytes) {
+    if (!dptr) return USC_ERR_ARGUMENT;
+    CK(cudaMalloc(dptr, bytes));
+    return USC_OK;
+}
+int usc_free(void* dptr) {
+    CK(cudaFree(dptr));
+    return USC_OK;
+}
+int usc_malloc_host(void** hptr, size_t bytes) {
+    if (!hptr) return USC_ERR_ARGUMENT;
+    CK(cudaMallocHost(hptr, bytes));
+    return USC_OK;
+}
+int usc_free_host(void* hptr) {
+    CK(cudaFreeHost(hptr));
+    return USC_OK;
+}
+int usc_memcpy_h2d(usc_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h) return USC_ERR_ARGUMENT;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return USC_OK;
+}
+int usc_memcpy_d2h(usc_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h) return USC_ERR_ARGUMENT;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return USC_OK;
+}
+int usc_memset(usc_handle* h, void* dst, int value, size_t bytes) {
+    if (!h) return USC_ERR_ARGUMENT;
+    CK(cudaMemsetAsync(dst, value, bytes, h->stream));
+    return USC_OK;
+}
+
+/* ---- batched CMSIS-shaped operators ---- */
+#define LAUNCHED(h, expr)        \
+    do {                         \
+        CK(expr);                \
+        (h)->launches++;         \
+    } while (0)
+
+int usc_i32_to_f32(usc_handle* h, const int32_t* src, float* dst, size_t count) {
+    if (!h || !src || !dst) return USC_ERR_ARGUMENT;
+    if (!count) return USC_OK;
+    LAUNCHED(h, launch_i32_to_f32(src, dst, count, h->stream));
+    return USC_OK;
+}
+int usc_arm_mult_f32_batch(usc_handle* h, const float* a, size_t sa, const float* b, size_t sb, float* dst,
+                           size_t sd, uint32_t block_size, uint32_t batch) {
+    if (!h || !a || !b || !dst) return USC_ERR_ARGUMENT;
+    if (!block_size || !batch) return USC_OK;
+    LAUNCHED(h, launch_mult(a, sa, b, sb, dst, sd, block_size, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_scale_f32_batch(usc_handle* h, const float* src, float scale, float* dst, uint32_t block_size,
+                            uint32_t batch) {
+    if (!h || !src || !dst) return USC_ERR_ARGUMENT;
+    if (!block_size || !batch) return USC_OK;
+    LAUNCHED(h, launch_scale(src, scale, dst, (size_t) block_size * batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_cmplx_mult_cmplx_f32_batch(usc_handle* h, const float* a, size_t sa, const float* b, size_t sb,
+                                       float* dst, size_t sd, uint32_t num_samples, uint32_t batch) {
+    if (!h || !a || !b || !dst) return USC_ERR_ARGUMENT;
+    if (!num_samples || !batch) return USC_OK;
+    LAUNCHED(h, launch_cmul(a, sa, b, sb, dst, sd, num_samples, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_cmplx_mult_real_f32_batch(usc_handle* h, const float* cplx, size_t sc, const float* real, size_t sr,
+                                      float* dst, size_t sd, uint32_t num_samples, uint32_t batch) {
+    if (!h || !cplx || !real || !dst) return USC_ERR_ARGUMENT;
+    if (!num_samples || !batch) return USC_OK;
+    LAUNCHED(h, launch_cmul_real(cplx, sc, real, sr, dst, sd, num_samples, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_cmplx_mag_f32_batch(usc_handle* h, const float* src, size_t ss, float* dst, size_t sd,
+                                uint32_t num_samples, uint32_t batch) {
+    if (!h || !src || !dst) return USC_ERR_ARGUMENT;
+    if (!num_samples || !batch) return USC_OK;
+    LAUNCHED(h, launch_cmag(src, ss, dst, sd, num_samples, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_max_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t block_size, float* result,
+                          uint32_t* index, uint32_t batch) {
+    if (!h || !src || !result || !block_size) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    LAUNCHED(h, launch_max(src, ss, block_size, result, index, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_mean_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t block_size, float* result,
+                           uint32_t batch) {
+    if (!h || !src || !result || !block_size) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    LAUNCHED(h, launch_mean(src, ss, block_size, result, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in, float* out, uint8_t ifft_flag,
+                                uint32_t batch) {
+    /* supported lengths: CMSIS's 32..4096 (arm_math.h:2242-2244 returns ARM_MATH_ARGUMENT_ERROR
+     * otherwise) extended to 8192 while one transform fits shared memory */
+    if (!h || !in || !out || !pow2(fft_len) || fft_len < 32 || fft_len > 8192) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    fft_plan_dev plan;
+    int rc = make_plan(h, fft_len / 2, fft_len, &plan);
+    if (rc) return rc;
+    LAUNCHED(h, launch_fft_generic(ifft_flag ? FFT_C2R : FFT_R2C, plan, in, out, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t ifft_flag, uint32_t batch) {
+    if (!h || !data || !pow2(fft_len) || fft_len < 16 || fft_len > 4096) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    fft_plan_dev plan;
+    int rc = make_plan(h, fft_len, fft_len, &plan);
+    if (rc) return rc;
+    LAUNCHED(h, launch_fft_generic(ifft_flag ? FFT_C2C_INV : FFT_C2C_FWD, plan, data, data, batch, h->stream));
+    return USC_OK;
+}
+int usc_arm_fir_f32_batch(usc_handle* h, const float* coeffs_host, uint32_t num_taps, float* state,
+                          const float* src, float* dst, uint32_t block_size, uint32_t batch) {
+    if (!h || !coeffs_host || !state || !src || !dst || num_taps < 1 || num_taps > 256 || !block_size ||
+        block_size > 8192)
+        return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    CK(cudaMemcpyAsync(h->d_fir_coeffs, coeffs_host, num_taps * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    LAUNCHED(h, launch_fir(h->d_fir_coeffs, num_taps, state, src, dst, block_size, batch, h->stream));
+    return USC_OK;
+}
+
+/* ---- fused stage-level operators ---- */
+static void fill_common(const usc_handle* h, demod_params* p) {
+    memset(p, 0, sizeof *p);
+    p->chirp_up = (const float2*) h->d_up;
+    p->chirp_down = (const float2*) h->d_down;
+    p->hann = (const float2*) h->d_hann;
+    p->tw_pass = h->d_tw_pass;
+    p->tw_split = h->d_tw_split;
+    p->bandwidth2 = h->bandwidth2;
+    p->idx_left_zero = h->idx_left_zero;
+    p->fs_int = (int32_t) h->cfg.fs;
+}
+
+int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, float* mag_up,
+                     uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
+    if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;      /* frames are read as 8-byte pairs */
+    if (!nframes) return USC_OK;
+    demod_params p;
+    fill_common(h, &p);
+    p.pcm = pcm;
+    p.nframes = nframes;
+    p.mag_up = mag_up; p.idx_up = idx_up; p.mag_down = mag_down; p.idx_down = idx_down; p.bit = bit;
+    LAUNCHED(h, launch_demod2048(p, pcm_format, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_dsp(usc_handle* h, const float* fifo, size_t fifo_stride, const uint32_t* sync_position,
+            const float* mag_mean, int updown, usc_history* hist, uint32_t batch) {
+    if (!h || !fifo || !sync_position || !mag_mean || !hist) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    demod_params p;
+    fill_common(h, &p);
+    p.pcm = fifo;
+    p.nframes = batch;
+    p.fifo_stride = fifo_stride;
+    p.sync_position = sync_position;
+    p.mag_mean = mag_mean;
+    p.hist = (history_rec*) hist;
+    p.updown = updown ? 1 : 0;
+    LAUNCHED(h, launch_dsp2048(p, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_pipeline(usc_handle* h, const float* frames, float* mags, int updown, uint32_t batch) {
+    /* operator-by-operator form of receiver/Src/main.c:163-180 (full spectrum wanted, so nothing
+     * to prune): mult, mult, rfft, mag into the lower half, zeros above (hazard H1 defined). */
+    if (!h || !frames || !mags) return USC_ERR_ARGUMENT;
+    if (h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    const uint32_t n = h->cfg.n;
+    int rc;
+    if ((rc = usc_arm_mult_f32_batch(h, frames, n, updown ? h->d_up : h->d_down, 0, mags, n, n, batch))) return rc;
+    if ((rc = usc_arm_mult_f32_batch(h, mags, n, h->d_hann, 0, mags, n, n, batch))) return rc;
+    if ((rc = usc_arm_rfft_fast_f32_batch(h, n, mags, mags, 0, batch))) return rc;
+    LAUNCHED(h, launch_pipeline_tail(mags, n, batch, h->stream));
+    return USC_OK;
+}
+
+int usc_compress_chirp(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, int use_up,
+                       float* out_frames, float* max_val, uint32_t* max_idx) {
+    if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant != USC_CHIRP_T || !h->d_H_up) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 7u) != 0 || ((uintptr_t) out_frames & 7u) != 0) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    LAUNCHED(h, launch_compress2048(pcm, pcm_format, nframes, (const float2*) h->d_hann,
+                                    (const float2*) (use_up ? h->d_H_up : h->d_H_down), h->d_tw_pass,
+                                    h->d_tw_split, out_frames, max_val, max_idx, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// usc_kernels.cuh — device kernels of libusc (sm_100a).  See DESIGN.md §4 for the data layout and
+// the roofline of each kernel.  All arithmetic goes through usc_arith.cuh (canonical fp32 order).
+#pragma once
+#include "usc_arith.cuh"
+
+namespace usc {
+
+struct history_rec {   // == usc_history (include/usc.h)
+    float mag_max, mag_max_left, mag_max_right;
+    int32_t max_freq, max_freq_left, max_freq_right;
+    uint32_t max_idx, max_idx_left, max_idx_right;
+    float mag_mean, snr;
+    uint32_t rank;
+};
+
+// ------------------------------------------------------------------------------------------------
+// element-wise / reduction operators (one HBM pass each; bound: HBM)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_i32_to_f32(const int32_t* __restrict__ src, float* __restrict__ dst, size_t count);
+__global__ void k_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                       uint32_t len, uint32_t batch);
+__global__ void k_scale(const float* src, float scale, float* dst, size_t total);
+__global__ void k_cmul(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                       uint32_t ncplx, uint32_t batch);
+__global__ void k_cmul_real(const float* c, size_t sc, const float* r, size_t sr, float* dst, size_t sd,
+                            uint32_t ncplx, uint32_t batch);
+__global__ void k_cmag(const float* src, size_t ss, float* dst, size_t sd, uint32_t ncplx, uint32_t batch);
+__global__ void k_max(const float* src, size_t ss, uint32_t len, float* result, uint32_t* index, uint32_t batch);
+__global__ void k_mean(const float* src, size_t ss, uint32_t len, float* result, uint32_t batch);
+__global__ void k_fir(const float* __restrict__ coeffs, uint32_t taps, float* state, const float* src,
+                      float* dst, uint32_t len, uint32_t batch);
+
+// ------------------------------------------------------------------------------------------------
+// generic canonical FFT: one CTA per transform, data resident in shared memory
+// ------------------------------------------------------------------------------------------------
+struct fft_plan_dev {
+    uint32_t n;          // complex length
+    uint32_t nrad;
+    uint32_t rad[8];
+    uint32_t tw_n;       // master table length
+    const float2* tw;    // device master table (cos, -sin)
+};
+enum fft_mode : int { FFT_C2C_FWD = 0, FFT_C2C_INV = 1, FFT_R2C = 2, FFT_C2R = 3 };
+template <int MODE>
+__global__ void k_fft_generic(fft_plan_dev plan, const float* in, float* out, uint32_t batch);
+
+// ------------------------------------------------------------------------------------------------
+// K1: fused receiver demodulator, N = 2048 (one warp per frame)
+// ------------------------------------------------------------------------------------------------
+struct demod_params {
+    const void* pcm;            // nframes x 2048 samples (or fifo base when gather != 0)
+    size_t nframes;
+    const float2* chirp_up;     // 1024 float2 = 2048 floats
+    const float2* chirp_down;
+    const float2* hann;
+    const float2* tw_pass;      // [d][a] layout: W_1024^(a*d), 32x32 float2
+    const float2* tw_split;     // (cos, sin)(2*pi*k/2048), k < 1024
+    uint32_t bandwidth2;        // arg-max window [0, bandwidth2)
+    float* mag_up; uint32_t* idx_up; float* mag_down; uint32_t* idx_down; uint8_t* bit;
+    // dsp() mode
+    size_t fifo_stride; const uint32_t* sync_position; const float* mag_mean; history_rec* hist;
+    uint32_t idx_left_zero; int32_t fs_int; int updown;
+};
+template <typename PCM, int NB>
+__global__ void k_demod2048(demod_params p);
+template <int NB>
+__global__ void k_dsp2048(demod_params p);
+
+}  // namespace usc

@@ -1,0 +1,33 @@
+// usc_launch.h — host-side launchers (one per kernel family), called by the C-ABI layer usc_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "usc_kernels.cuh"
+
+namespace usc {
+cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st);
+cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                        uint32_t len, uint32_t batch, cudaStream_t st);
+cudaError_t launch_scale(const float* src, float scale, float* dst, size_t total, cudaStream_t st);
+cudaError_t launch_cmul(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
+                        uint32_t ncplx, uint32_t batch, cudaStream_t st);
+cudaError_t launch_cmul_real(const float* c, size_t sc, const float* r, size_t sr, float* dst, size_t sd,
+                             uint32_t ncplx, uint32_t batch, cudaStream_t st);
+cudaError_t launch_cmag(const float* src, size_t ss, float* dst, size_t sd, uint32_t ncplx, uint32_t batch,
+                        cudaStream_t st);
+cudaError_t launch_max(const float* src, size_t ss, uint32_t len, float* result, uint32_t* index,
+                       uint32_t batch, cudaStream_t st);
+cudaError_t launch_mean(const float* src, size_t ss, uint32_t len, float* result, uint32_t batch,
+                        cudaStream_t st);
+cudaError_t launch_fir(const float* coeffs_dev, uint32_t taps, float* state, const float* src, float* dst,
+                       uint32_t len, uint32_t batch, cudaStream_t st);
+// mode: fft_mode.  in/out: batch vectors of 2n floats (C2C) or 2n floats real (R2C/C2R, n = N/2).
+cudaError_t launch_fft_generic(int mode, const fft_plan_dev& plan, const float* in, float* out, uint32_t batch,
+                               cudaStream_t st);
+cudaError_t fft_generic_prepare();   // opt in to large dynamic shared memory (once)
+cudaError_t launch_demod2048(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
+cudaError_t launch_dsp2048(const demod_params& p, int num_sms, cudaStream_t st);
+cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* window,
+                                const float2* H, const float2* tw_pass, const float2* tw_split, float* out_frames,
+                                float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st);
+cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaStream_t st);
+}  // namespace usc

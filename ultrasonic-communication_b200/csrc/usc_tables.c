@@ -1,0 +1,110 @@
+/* usc_tables.c — see usc_tables.h.  Plain C, compiled with -ffp-contract=off: the float/double
+ * expression types below follow the reference's C source literally, because the exact table
+ * values decide bit-parity of everything downstream. */
+#include "usc_tables.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define SINE_TABLE_SIZE 512
+static float s_sine[SINE_TABLE_SIZE + 1];
+static int s_sine_ready;
+
+/* The CMSIS table (arm_common_tables.c, sinTable_f32) holds sin(2*pi*i/512) as decimal literals
+ * with 8 fractional digits; reproducing the literals — not the exact sines — is what makes the
+ * Hann window agree with the device captures to the last printed digit. */
+static void sine_table_init(void) {
+    if (s_sine_ready) return;
+    char lit[32];
+    for (int i = 0; i <= SINE_TABLE_SIZE; ++i) {
+        snprintf(lit, sizeof lit, "%.8f", sin(2.0 * M_PI * (double) i / (double) SINE_TABLE_SIZE));
+        s_sine[i] = strtof(lit, NULL);
+    }
+    s_sine_ready = 1;
+}
+
+float usc_host_arm_cos_f32(float x) {
+    sine_table_init();
+    float turns = x * 0.159154943092f + 0.25f;
+    int32_t whole = (int32_t) turns;
+    if (turns < 0.0f) whole--;
+    turns = turns - (float) whole;
+    float pos = (float) SINE_TABLE_SIZE * turns;
+    uint16_t idx = ((uint16_t) pos) & 0x1ff;
+    float frac = pos - (float) idx;
+    return (1.0f - frac) * s_sine[idx] + frac * s_sine[idx + 1];
+}
+
+void usc_host_arm_sin_cos_f32(float theta_deg, float *s, float *c) {
+    double rad = (double) theta_deg * (M_PI / 180.0);
+    *s = (float) sin(rad);
+    *c = (float) cos(rad);
+}
+
+void usc_host_hann(float *w, uint32_t n, uint32_t kind) {
+    /* periodic: `2.0f * M_PI / (float) NN` is a double expression; symmetric: `2.0f * PI /
+     * (float)(PCM_SAMPLES - 1)` with CMSIS's float PI is a float expression. */
+    float scale = kind == 0 ? (float) (2.0f * M_PI / (float) n)
+                            : 2.0f * 3.14159265358979f / (float) (n - 1);
+    for (uint32_t i = 0; i < n; ++i) w[i] = 0.5f - 0.5f * usc_host_arm_cos_f32((float) i * scale);
+}
+
+void usc_host_ref_chirp(uint32_t variant, uint32_t n, float fs, float f0, float f1, float sweep_T,
+                        float phase, int up, float *out) {
+    float t = 0.0f;
+    if (variant <= 1u) {
+        /* degrees; `/ 2.0` and `360.0 *` promote to double before the store to float */
+        float slope = (float) (f1 - f0) / sweep_T;
+        float dt = sweep_T / (sweep_T * fs);
+        for (uint32_t i = 0; i < n; ++i) {
+            double half = (double) (slope * t) / 2.0;
+            float freq = up ? (float) ((double) f0 + half) : (float) ((double) f1 - half);
+            float theta = (float) (360.0 * (double) freq * (double) t + (double) phase);
+            t = t + dt;
+            float sv, cv;
+            usc_host_arm_sin_cos_f32(theta, &sv, &cv);
+            if (variant == 0u) out[i] = sv * 1.0f;
+            else { out[2 * i] = cv * 1.0f; out[2 * i + 1] = sv * 1.0f; }
+        }
+    } else {
+        /* radians, float slope law without the /2, T = n/fs */
+        const double two_pi = 2.0 * (double) 3.14159265358979f;
+        float T = (float) n / fs;
+        float slope = (f1 - f0) / T;
+        float dt = T / (T * fs);
+        for (uint32_t i = 0; i < n; ++i) {
+            float freq = up ? f0 + slope * t : f1 - slope * t;
+            double a = two_pi * (double) freq * (double) t;
+            float arg = variant == 2u ? (float) (a + (double) phase) : (float) a;
+            t = t + dt;
+            out[i] = usc_host_arm_cos_f32(arg) * 1.0f;
+        }
+    }
+}
+
+void usc_host_twiddles(float *tw, uint32_t n) {
+    for (uint32_t j = 0; j < n; ++j) {
+        double a = 2.0 * M_PI * (double) j / (double) n;
+        tw[2 * j] = (float) cos(a);
+        tw[2 * j + 1] = (float) -sin(a);
+    }
+}
+
+uint32_t usc_host_radices(uint32_t n, uint32_t *rad) {
+    if (n < 2 || (n & (n - 1))) return 0;
+    uint32_t rev[USC_MAX_RADICES], cnt = 0;
+    while (n > 32) {
+        if (cnt >= USC_MAX_RADICES - 1) return 0;
+        rev[cnt++] = 32;
+        n /= 32;
+    }
+    rev[cnt++] = n;
+    for (uint32_t i = 0; i < cnt; ++i) rad[i] = rev[cnt - 1 - i];
+    return cnt;
+}
+
+uint32_t usc_host_bandwidth(uint32_t n, float fs, float f0, float f1) {
+    unsigned long span = (unsigned long) (int) (f1 - f0) * (unsigned long) n;
+    return (uint32_t) ((float) span / fs);
+}

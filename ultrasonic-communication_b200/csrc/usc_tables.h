@@ -1,0 +1,33 @@
+/* usc_tables.h — host-side (plain C) builders of the constant tables the kernels consume.
+ * Product code: replaces the init-time table generation of the reference firmware
+ * (receiver/Src/main.c:372-374,390-393; receiver/Src/chirp.c:16-45 and the experiment variants). */
+#ifndef USC_TABLES_H_
+#define USC_TABLES_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USC_MAX_RADICES 8
+
+/* arm_cos_f32 (arm_math.h:5685): CMSIS-DSP V1.4.5 512-entry table + linear interpolation. */
+float usc_host_arm_cos_f32(float x);
+/* arm_sin_cos_f32 (arm_math.h:4634-4637), degrees. */
+void usc_host_arm_sin_cos_f32(float theta_deg, float *s, float *c);
+/* Hann window: kind 0 periodic (receiver/Src/main.c:99,390-393), 1 symmetric
+ * (experiments/chirp_compression_time_domain/Src/chirp.c:13,63-65). */
+void usc_host_hann(float *w, uint32_t n, uint32_t kind);
+/* Reference chirp tables, variants R/S/T/F (see usc.h). out: n floats (2n for S). */
+void usc_host_ref_chirp(uint32_t variant, uint32_t n, float fs, float f0, float f1, float sweep_T,
+                        float phase, int up, float *out);
+/* Master twiddle table: (cos, -sin)(2*pi*j/n), j < n, each rounded once from double. 2n floats. */
+void usc_host_twiddles(float *tw, uint32_t n);
+/* Radix list of the canonical mixed-radix plan. Returns the count, 0 if bad. */
+uint32_t usc_host_radices(uint32_t n, uint32_t *rad);
+/* (F1 - F0) * NN / fs truncated to uint32 (receiver/Src/main.c:372). */
+uint32_t usc_host_bandwidth(uint32_t n, float fs, float f0, float f1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

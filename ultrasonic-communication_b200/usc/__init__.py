@@ -1,0 +1,269 @@
+"""usc — Python mirror of the libusc.so C-ABI (include/usc.h), used by the tests and bench.py.
+
+Product code: it binds ONLY libusc.so (hand-written sm_100a kernels behind a C ABI).  There is no
+CPU fallback: if the library is missing or no CUDA device is usable, construction raises.
+Device buffers are plain integers (device addresses) or anything exposing `.data_ptr()` (torch
+tensors) / `__cuda_array_interface__`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libusc.so")
+
+USC_OK = 0
+USC_ERR_ARGUMENT = -1
+CHIRP_R, CHIRP_S, CHIRP_T, CHIRP_F = 0, 1, 2, 3
+HANN_PERIODIC, HANN_SYMMETRIC = 0, 1
+PCM_F32, PCM_I32 = 0, 1
+UP, DOWN = 1, 0
+
+
+class Config(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("fs", C.c_float), ("f0", C.c_float), ("f1", C.c_float),
+                ("sweep_T", C.c_float), ("chirp_variant", C.c_uint32), ("window", C.c_uint32),
+                ("snr_threshold", C.c_float), ("reserved", C.c_uint32 * 4)]
+
+
+history_dtype = np.dtype([("mag_max", "f4"), ("mag_max_left", "f4"), ("mag_max_right", "f4"),
+                          ("max_freq", "i4"), ("max_freq_left", "i4"), ("max_freq_right", "i4"),
+                          ("max_idx", "u4"), ("max_idx_left", "u4"), ("max_idx_right", "u4"),
+                          ("mag_mean", "f4"), ("snr", "f4"), ("rank", "u4")])
+
+# every symbol include/usc.h declares (tests/test_abi.py checks the .so exports each one)
+SYMBOLS = [
+    "usc_default_config", "usc_create", "usc_destroy", "usc_set_stream", "usc_sync", "usc_error_string",
+    "usc_get_geometry", "usc_get_table", "usc_launch_count", "usc_malloc", "usc_free", "usc_malloc_host",
+    "usc_free_host", "usc_memcpy_h2d", "usc_memcpy_d2h", "usc_memset", "usc_i32_to_f32",
+    "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
+    "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
+    "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+]
+
+_lib = None
+
+
+def load():
+    """dlopen libusc.so; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libusc.so not built: run `python ultrasonic-communication_b200/build.py` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.usc_error_string.restype = C.c_char_p
+        L.usc_launch_count.restype = C.c_uint64
+        L.usc_launch_count.argtypes = [C.c_void_p]
+        for name in SYMBOLS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+class UscError(RuntimeError):
+    def __init__(self, code):
+        self.code = code
+        super().__init__("usc error %d: %s" % (code, load().usc_error_string(code).decode()))
+
+
+def _ck(rc):
+    if rc != 0:
+        raise UscError(rc)
+
+
+def _ptr(x):
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    if hasattr(x, "__cuda_array_interface__"):
+        return C.c_void_p(x.__cuda_array_interface__["data"][0])
+    if hasattr(x, "ptr"):
+        return C.c_void_p(x.ptr)
+    raise TypeError("not a device buffer: %r" % (type(x),))
+
+
+class DeviceBuffer:
+    """usc_malloc'd device memory with numpy round trips (for tests and the plain-C style host)."""
+
+    def __init__(self, handle, nbytes):
+        self.h = handle
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        _ck(load().usc_malloc(C.byref(p), C.c_size_t(max(self.nbytes, 1))))
+        self.ptr = p.value
+
+    @classmethod
+    def from_numpy(cls, handle, arr):
+        arr = np.ascontiguousarray(arr)
+        b = cls(handle, arr.nbytes)
+        if arr.nbytes:
+            _ck(load().usc_memcpy_h2d(handle._h, C.c_void_p(b.ptr), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes)))
+            handle.sync()
+        return b
+
+    def to_numpy(self, dtype, count=None):
+        dtype = np.dtype(dtype)
+        n = self.nbytes // dtype.itemsize if count is None else count
+        out = np.empty(n, dtype)
+        if out.nbytes:
+            _ck(load().usc_memcpy_d2h(self.h._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), C.c_size_t(out.nbytes)))
+            self.h.sync()
+        return out
+
+    def free(self):
+        if self.ptr:
+            load().usc_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def default_config(**over):
+    cfg = Config()
+    load().usc_default_config(C.byref(cfg))
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Handle:
+    """usc_handle: tables + stream for one receiver configuration on one GPU."""
+
+    def __init__(self, cfg=None, device=0, **over):
+        L = load()
+        self.cfg = cfg if cfg is not None else default_config(**over)
+        self._h = C.c_void_p()
+        _ck(L.usc_create(C.byref(self.cfg), C.c_int(device), C.byref(self._h)))
+        self.n = int(self.cfg.n)
+
+    def close(self):
+        if self._h:
+            load().usc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- lifecycle -------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        _ck(load().usc_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def sync(self):
+        _ck(load().usc_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(load().usc_launch_count(self._h))
+
+    def geometry(self):
+        b, b2, z = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _ck(load().usc_get_geometry(self._h, C.byref(b), C.byref(b2), C.byref(z)))
+        return b.value, b2.value, z.value
+
+    def table(self, what):
+        n = load().usc_get_table(self._h, what.encode(), None, C.c_size_t(0))
+        if n < 0:
+            raise UscError(n)
+        out = np.empty(n, np.float32)
+        r = load().usc_get_table(self._h, what.encode(), out.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(n))
+        if r < 0:
+            raise UscError(r)
+        return out
+
+    def buffer(self, arr):
+        return DeviceBuffer.from_numpy(self, arr)
+
+    def empty(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    # -- batched CMSIS-shaped operators (device pointers) ------------------------------------------
+    def i32_to_f32(self, src, dst, count):
+        _ck(load().usc_i32_to_f32(self._h, _ptr(src), _ptr(dst), C.c_size_t(count)))
+
+    def arm_mult_f32(self, a, stride_a, b, stride_b, dst, stride_dst, block_size, batch):
+        _ck(load().usc_arm_mult_f32_batch(self._h, _ptr(a), C.c_size_t(stride_a), _ptr(b), C.c_size_t(stride_b),
+                                          _ptr(dst), C.c_size_t(stride_dst), C.c_uint32(block_size), C.c_uint32(batch)))
+
+    def arm_scale_f32(self, src, scale, dst, block_size, batch):
+        _ck(load().usc_arm_scale_f32_batch(self._h, _ptr(src), C.c_float(scale), _ptr(dst), C.c_uint32(block_size),
+                                           C.c_uint32(batch)))
+
+    def arm_cmplx_mult_cmplx_f32(self, a, stride_a, b, stride_b, dst, stride_dst, num_samples, batch):
+        _ck(load().usc_arm_cmplx_mult_cmplx_f32_batch(self._h, _ptr(a), C.c_size_t(stride_a), _ptr(b),
+                                                      C.c_size_t(stride_b), _ptr(dst), C.c_size_t(stride_dst),
+                                                      C.c_uint32(num_samples), C.c_uint32(batch)))
+
+    def arm_cmplx_mult_real_f32(self, cplx, stride_c, real, stride_r, dst, stride_dst, num_samples, batch):
+        _ck(load().usc_arm_cmplx_mult_real_f32_batch(self._h, _ptr(cplx), C.c_size_t(stride_c), _ptr(real),
+                                                     C.c_size_t(stride_r), _ptr(dst), C.c_size_t(stride_dst),
+                                                     C.c_uint32(num_samples), C.c_uint32(batch)))
+
+    def arm_cmplx_mag_f32(self, src, stride_src, dst, stride_dst, num_samples, batch):
+        _ck(load().usc_arm_cmplx_mag_f32_batch(self._h, _ptr(src), C.c_size_t(stride_src), _ptr(dst),
+                                               C.c_size_t(stride_dst), C.c_uint32(num_samples), C.c_uint32(batch)))
+
+    def arm_max_f32(self, src, stride_src, block_size, result, index, batch):
+        _ck(load().usc_arm_max_f32_batch(self._h, _ptr(src), C.c_size_t(stride_src), C.c_uint32(block_size),
+                                         _ptr(result), _ptr(index), C.c_uint32(batch)))
+
+    def arm_mean_f32(self, src, stride_src, block_size, result, batch):
+        _ck(load().usc_arm_mean_f32_batch(self._h, _ptr(src), C.c_size_t(stride_src), C.c_uint32(block_size),
+                                          _ptr(result), C.c_uint32(batch)))
+
+    def arm_rfft_fast_f32(self, fft_len, src, dst, ifft_flag, batch):
+        _ck(load().usc_arm_rfft_fast_f32_batch(self._h, C.c_uint32(fft_len), _ptr(src), _ptr(dst),
+                                               C.c_uint8(1 if ifft_flag else 0), C.c_uint32(batch)))
+
+    def arm_cfft_f32(self, fft_len, data, ifft_flag, batch):
+        _ck(load().usc_arm_cfft_f32_batch(self._h, C.c_uint32(fft_len), _ptr(data), C.c_uint8(1 if ifft_flag else 0),
+                                          C.c_uint32(batch)))
+
+    def arm_fir_f32(self, coeffs_host, state, src, dst, block_size, batch):
+        c = np.ascontiguousarray(coeffs_host, np.float32)
+        _ck(load().usc_arm_fir_f32_batch(self._h, c.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(c.size),
+                                         _ptr(state), _ptr(src), _ptr(dst), C.c_uint32(block_size), C.c_uint32(batch)))
+
+    # -- fused stage-level operators -----------------------------------------------------------------
+    def demod_frames(self, pcm, pcm_format, nframes, mag_up=None, idx_up=None, mag_down=None, idx_down=None,
+                     bit=None):
+        _ck(load().usc_demod_frames(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes), _ptr(mag_up),
+                                    _ptr(idx_up), _ptr(mag_down), _ptr(idx_down), _ptr(bit)))
+
+    def pipeline(self, frames, mags, updown, batch):
+        _ck(load().usc_pipeline(self._h, _ptr(frames), _ptr(mags), C.c_int(updown), C.c_uint32(batch)))
+
+    def dsp(self, fifo, fifo_stride, sync_position, mag_mean, updown, hist, batch):
+        _ck(load().usc_dsp(self._h, _ptr(fifo), C.c_size_t(fifo_stride), _ptr(sync_position), _ptr(mag_mean),
+                           C.c_int(updown), _ptr(hist), C.c_uint32(batch)))
+
+    def compress_chirp(self, pcm, pcm_format, nframes, use_up, out_frames=None, max_val=None, max_idx=None):
+        _ck(load().usc_compress_chirp(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes),
+                                      C.c_int(1 if use_up else 0), _ptr(out_frames), _ptr(max_val), _ptr(max_idx)))
+
+    # -- numpy convenience (host arrays in, host arrays out; used by tests) --------------------------
+    def demod_frames_host(self, pcm):
+        pcm = np.ascontiguousarray(pcm)
+        fmt = PCM_I32 if pcm.dtype == np.int32 else PCM_F32
+        if fmt == PCM_F32:
+            pcm = pcm.astype(np.float32, copy=False)
+        nf = pcm.size // self.n
+        d_in = self.buffer(pcm)
+        outs = [self.empty(4 * nf) for _ in range(4)]
+        d_bit = self.empty(nf)
+        self.demod_frames(d_in, fmt, nf, outs[0], outs[1], outs[2], outs[3], d_bit)
+        self.sync()
+        return (outs[0].to_numpy(np.float32), outs[1].to_numpy(np.uint32), outs[2].to_numpy(np.float32),
+                outs[3].to_numpy(np.uint32), d_bit.to_numpy(np.uint8))
