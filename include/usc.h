@@ -152,6 +152,14 @@ int usc_arm_fir_f32_batch(usc_handle *h, const float *coeffs_host, uint32_t num_
  * (receiver/Src/main.c:523: down wins only if strictly greater). */
 int usc_demod_frames(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, float *mag_up,
                      uint32_t *idx_up, float *mag_down, uint32_t *idx_down, uint8_t *bit);
+/* The same chain on HOST buffers (the call a firmware-style host makes once per capture): frames are
+ * cut into chunks that flow through three stream lanes (H2D copy, K1, D2H of the results) so the
+ * copies overlap the kernel.  Blocking: results are in the host arrays on return.  pcm_host should
+ * be pinned (usc_malloc_host) for the copies to overlap.  usc_host_workspace() sizes the device
+ * staging explicitly (frames per chunk); it is called with 4096 on first use otherwise. */
+int usc_host_workspace(usc_handle *h, size_t chunk_frames);
+int usc_demod_frames_host(usc_handle *h, const void *pcm_host, uint32_t pcm_format, size_t nframes,
+                          float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down, uint8_t *bit);
 /* pipeline() of receiver/Src/main.c:163-180 on `batch` frames, one hypothesis: frames (n floats
  * each, stride n) -> n floats each: magnitudes of the n/2 packed bins, zeros above (hazard H1). */
 int usc_pipeline(usc_handle *h, const float *frames, float *mags, int updown, uint32_t batch);

@@ -1,0 +1,29 @@
+"""Short driver for ncu: a few launches of the fused kernels on the config-2 batch."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "ultrasonic-communication_b200"))
+import torch  # noqa: E402
+import usc  # noqa: E402
+import bench  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "demod"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda", 0)
+pcm, bits = bench.make_device_frames(torch, bench.NFRAMES, dev, seed=1000)
+F = bench.NFRAMES
+o = [torch.empty(F, dtype=torch.float32, device=dev) for _ in range(4)]
+b = torch.empty(F, dtype=torch.uint8, device=dev)
+if which == "demod":
+    h = usc.Handle()
+    for _ in range(reps):
+        h.demod_frames(pcm, usc.PCM_I32, F, o[0], o[1], o[2], o[3], b)
+elif which == "compress":
+    h = usc.Handle(usc.default_config(fs=100000.0, f0=17000.0, f1=18000.0, chirp_variant=usc.CHIRP_T,
+                                      window=usc.HANN_SYMMETRIC))
+    for _ in range(reps):
+        h.compress_chirp(pcm, usc.PCM_I32, F, False, None, o[0], o[1])
+torch.cuda.synchronize()
+print("done", which, reps)

@@ -31,6 +31,14 @@ struct usc_handle {
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
     std::map<uint32_t, std::vector<float>> tw_host;
     uint64_t launches;
+    // host-buffer path (usc_demod_frames_host): kLanes chunk pipelines, each with its own stream
+    static const int kLanes = 3;
+    size_t lane_frames;                                // frames per chunk
+    cudaStream_t lane_stream[3];
+    void* lane_in[3];
+    float *lane_mu[3], *lane_md[3];
+    uint32_t *lane_iu[3], *lane_id[3];
+    uint8_t* lane_bit[3];
 };
 
 static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? USC_OK : USC_ERR_CUDA_BASE - (int) e; }
@@ -115,6 +123,8 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->d_hann = h->d_up = h->d_down = h->d_H_up = h->d_H_down = nullptr;
     h->d_tw_pass = h->d_tw_split = nullptr;
     h->d_fir_coeffs = nullptr;
+    h->lane_frames = 0;
+    for (int i = 0; i < 3; ++i) { h->lane_stream[i] = nullptr; h->lane_in[i] = nullptr; h->lane_mu[i] = h->lane_md[i] = nullptr; h->lane_iu[i] = h->lane_id[i] = nullptr; h->lane_bit[i] = nullptr; }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
@@ -186,6 +196,11 @@ void usc_destroy(usc_handle* h) {
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
     cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
+    for (int i = 0; i < 3; ++i) {
+        cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
+        cudaFree(h->lane_id[i]); cudaFree(h->lane_bit[i]);
+        if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
+    }
     delete h;
 }
 
@@ -385,6 +400,63 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     p.nframes = nframes;
     p.mag_up = mag_up; p.idx_up = idx_up; p.mag_down = mag_down; p.idx_down = idx_down; p.bit = bit;
     LAUNCHED(h, launch_demod2048(p, pcm_format, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_host_workspace(usc_handle* h, size_t chunk_frames) {
+    if (!h || !chunk_frames || h->cfg.n != 2048) return USC_ERR_ARGUMENT;
+    if (h->lane_frames == chunk_frames) return USC_OK;
+    for (int i = 0; i < 3; ++i) {
+        cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
+        cudaFree(h->lane_id[i]); cudaFree(h->lane_bit[i]);
+        h->lane_in[i] = nullptr; h->lane_mu[i] = h->lane_md[i] = nullptr; h->lane_iu[i] = h->lane_id[i] = nullptr; h->lane_bit[i] = nullptr;
+    }
+    h->lane_frames = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (!h->lane_stream[i]) CK(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
+        CK(cudaMalloc(&h->lane_in[i], chunk_frames * 2048 * 4));
+        CK(cudaMalloc((void**) &h->lane_mu[i], chunk_frames * 4));
+        CK(cudaMalloc((void**) &h->lane_md[i], chunk_frames * 4));
+        CK(cudaMalloc((void**) &h->lane_iu[i], chunk_frames * 4));
+        CK(cudaMalloc((void**) &h->lane_id[i], chunk_frames * 4));
+        CK(cudaMalloc((void**) &h->lane_bit[i], chunk_frames));
+    }
+    h->lane_frames = chunk_frames;
+    return USC_OK;
+}
+
+int usc_demod_frames_host(usc_handle* h, const void* pcm_host, uint32_t pcm_format, size_t nframes,
+                          float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
+    if (!h || !pcm_host || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    if (!h->lane_frames) {
+        int rc = usc_host_workspace(h, 4096);
+        if (rc) return rc;
+    }
+    const size_t cf = h->lane_frames;
+    const char* src = (const char*) pcm_host;
+    size_t chunk = 0;
+    for (size_t f0 = 0; f0 < nframes; f0 += cf, ++chunk) {
+        const int l = (int) (chunk % 3);
+        const size_t nf = nframes - f0 < cf ? nframes - f0 : cf;
+        cudaStream_t st = h->lane_stream[l];
+        CK(cudaMemcpyAsync(h->lane_in[l], src + f0 * 2048 * 4, nf * 2048 * 4, cudaMemcpyHostToDevice, st));
+        demod_params p;
+        fill_common(h, &p);
+        p.pcm = h->lane_in[l];
+        p.nframes = nf;
+        p.mag_up = h->lane_mu[l]; p.idx_up = h->lane_iu[l]; p.mag_down = h->lane_md[l]; p.idx_down = h->lane_id[l];
+        p.bit = h->lane_bit[l];
+        LAUNCHED(h, launch_demod2048(p, pcm_format, h->num_sms, st));
+        if (mag_up) CK(cudaMemcpyAsync(mag_up + f0, h->lane_mu[l], nf * 4, cudaMemcpyDeviceToHost, st));
+        if (idx_up) CK(cudaMemcpyAsync(idx_up + f0, h->lane_iu[l], nf * 4, cudaMemcpyDeviceToHost, st));
+        if (mag_down) CK(cudaMemcpyAsync(mag_down + f0, h->lane_md[l], nf * 4, cudaMemcpyDeviceToHost, st));
+        if (idx_down) CK(cudaMemcpyAsync(idx_down + f0, h->lane_id[l], nf * 4, cudaMemcpyDeviceToHost, st));
+        if (bit) CK(cudaMemcpyAsync(bit + f0, h->lane_bit[l], nf, cudaMemcpyDeviceToHost, st));
+    }
+    for (int l = 0; l < 3; ++l) CK(cudaStreamSynchronize(h->lane_stream[l]));
     return USC_OK;
 }
 

@@ -40,7 +40,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -241,6 +241,22 @@ class Handle:
                      bit=None):
         _ck(load().usc_demod_frames(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes), _ptr(mag_up),
                                     _ptr(idx_up), _ptr(mag_down), _ptr(idx_down), _ptr(bit)))
+
+    def host_workspace(self, chunk_frames):
+        _ck(load().usc_host_workspace(self._h, C.c_size_t(chunk_frames)))
+
+    def demod_frames_hostbuf(self, pcm_host_ptr, pcm_format, nframes, mag_up, idx_up, mag_down, idx_down, bit):
+        """usc_demod_frames_host on raw HOST addresses (ints / numpy arrays / pinned torch tensors)."""
+        def hp(x):
+            if x is None:
+                return C.c_void_p(0)
+            if isinstance(x, int):
+                return C.c_void_p(x)
+            if isinstance(x, np.ndarray):
+                return C.c_void_p(x.ctypes.data)
+            return C.c_void_p(x.data_ptr())
+        _ck(load().usc_demod_frames_host(self._h, hp(pcm_host_ptr), C.c_uint32(pcm_format), C.c_size_t(nframes),
+                                         hp(mag_up), hp(idx_up), hp(mag_down), hp(idx_down), hp(bit)))
 
     def pipeline(self, frames, mags, updown, batch):
         _ck(load().usc_pipeline(self._h, _ptr(frames), _ptr(mags), C.c_int(updown), C.c_uint32(batch)))
