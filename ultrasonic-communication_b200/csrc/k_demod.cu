@@ -18,7 +18,7 @@
 //           Z[1024 - k] sit in lane (32 - d0) & 31 at register 31 - d1 (32 - d1 on lane 0):
 //           one shuffle pair per bin.  The pass-2 outputs nobody reads (d1 in [NB, 32 - NB))
 //           are dead code, so the compiler prunes the last FFT stages.
-// Both hypotheses (up / down) share the PCM load and the Hann load.
+// Both hypotheses (up / down) share the PCM load, the Hann load and the twiddle loads (f32x2 halves).
 #include "usc_kernels.cuh"
 #include "usc_launch.h"
 
@@ -87,11 +87,50 @@ __device__ __forceinline__ void peak_right(const float (&re)[32], const float (&
     }
 }
 
+// ---- dual-hypothesis kernel: both hypotheses ride in the halves of f32x2 registers ---------------
+// (.x = up-chirp, .y = down-chirp).  The PCM, the Hann table and the inter-pass twiddles are loaded
+// once for both; the two 32-point register FFTs issue as FADD2/FFMA2.  The L1/shared-memory data
+// path (1 wavefront = 128 B per clock per SM) is the scarcest resource of this kernel, so the point
+// of the layout is bytes through L1 per frame: PCM 8 KB + (up,down) table 16 KB + Hann 8 KB +
+// exchange tile 2 x 16 KB + twiddles 8 KB = 72 KB, against 103 KB for two single-hypothesis passes.
+constexpr int kDualWarps = 4;
+constexpr int kTile4Stride = 33;                      // float4 units; odd stride: conflict-free LDS.128
+constexpr int kTile4 = 32 * kTile4Stride;
+
+template <int NB, int HALF>
+__device__ __forceinline__ void peak_right2(const float2 (&re)[32], const float2 (&im)[32],
+                                            const float2 (&ws)[NB], int lane, uint32_t bw2,
+                                            float& best, uint32_t& best_idx) {
+    auto half = [](const float2& v) -> float { return HALF == 0 ? v.x : v.y; };
+    best = -INFINITY;
+    best_idx = 0xffffffffu;
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        float sr = lane == 0 ? half(re[(32 - d1) & 31]) : half(re[31 - d1]);
+        float si = lane == 0 ? half(im[(32 - d1) & 31]) : half(im[31 - d1]);
+        float zcr = __shfl_sync(0xffffffffu, sr, src);
+        float zci = __shfl_sync(0xffffffffu, si, src);
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        float xr, xi;
+        if (d1 == 0 && lane == 0) {
+            xr = __fadd_rn(half(re[0]), half(im[0]));
+            xi = __fsub_rn(half(re[0]), half(im[0]));
+        } else {
+            rfft_split(half(re[d1]), half(im[d1]), zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
+        }
+        float m = cmag(xr, xi);
+        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
+    }
+}
+
 template <typename PCM, int NB>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_demod2048(demod_params p) {
-    __shared__ float2 s_tw[32 * 32];
-    __shared__ float2 s_tile[kWarpsPerCta][kTileFloat2];
+__global__ void __launch_bounds__(kDualWarps * 32, 2) k_demod2048(demod_params p) {
+    extern __shared__ float4 s_dyn[];
+    float2* s_tw = reinterpret_cast<float2*>(s_dyn);                  // 32x32 float2 = 8 KB
+    float4* s_tile_all = s_dyn + 512;                                 // kDualWarps x 32x33 float4
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* tile = s_tile_all + warp * kTile4;
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_tw[i] = p.tw_pass[i];
     float2 ws[NB];
 #pragma unroll
@@ -99,28 +138,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_demod2048(demod_params
     __syncthreads();
 
     using V2 = typename vec2<PCM>::type;
-    const size_t nwarps = (size_t) gridDim.x * kWarpsPerCta;
-    for (size_t f = (size_t) blockIdx.x * kWarpsPerCta + warp; f < p.nframes; f += nwarps) {
+    const float4* __restrict__ chirp_ud = reinterpret_cast<const float4*>(p.chirp_ud);
+    const size_t nwarps = (size_t) gridDim.x * kDualWarps;
+    for (size_t f = (size_t) blockIdx.x * kDualWarps + warp; f < p.nframes; f += nwarps) {
         const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * 2048);
-        float ur[32], ui[32], dr[32], di[32];
+        float2 re[32], im[32];                                        // (.x, .y) = (up, down)
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
             const int m = lane + 32 * b;
             V2 raw = src[m];
             float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
-            float2 cu = __ldg(p.chirp_up + m), cd = __ldg(p.chirp_down + m), w = __ldg(p.hann + m);
-            ur[b] = __fmul_rn(__fmul_rn(x0, cu.x), w.x);
-            ui[b] = __fmul_rn(__fmul_rn(x1, cu.y), w.y);
-            dr[b] = __fmul_rn(__fmul_rn(x0, cd.x), w.x);
-            di[b] = __fmul_rn(__fmul_rn(x1, cd.y), w.y);
+            float4 c = __ldg(chirp_ud + m);                           // (up[2m], down[2m], up[2m+1], down[2m+1])
+            float2 w = __ldg(p.hann + m);
+            re[b] = make_float2(__fmul_rn(__fmul_rn(x0, c.x), w.x), __fmul_rn(__fmul_rn(x0, c.y), w.x));
+            im[b] = make_float2(__fmul_rn(__fmul_rn(x1, c.z), w.y), __fmul_rn(__fmul_rn(x1, c.w), w.y));
         }
+        fft_base2<32>(re, im);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+            float4 v = make_float4(re[d].x, re[d].y, im[d].x, im[d].y);
+            if (d != 0) {
+                float2 w = s_tw[d * 32 + lane];
+                cmul(re[d].x, im[d].x, w.x, w.y, v.x, v.z);
+                cmul(re[d].y, im[d].y, w.x, w.y, v.y, v.w);
+            }
+            tile[d * kTile4Stride + lane] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+            float4 v = tile[lane * kTile4Stride + a];
+            re[a] = make_float2(v.x, v.y);
+            im[a] = make_float2(v.z, v.w);
+        }
+        __syncwarp();
+        fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
-        fft1024_warp(ur, ui, s_tile[warp], s_tw, lane);
-        peak_right<NB>(ur, ui, ws, lane, p.bandwidth2, mu, iu);
+        peak_right2<NB, 0>(re, im, ws, lane, p.bandwidth2, mu, iu);
+        peak_right2<NB, 1>(re, im, ws, lane, p.bandwidth2, md, id);
         warp_argmax(mu, iu);
-        fft1024_warp(dr, di, s_tile[warp], s_tw, lane);
-        peak_right<NB>(dr, di, ws, lane, p.bandwidth2, md, id);
         warp_argmax(md, id);
         if (lane == 0) {
             if (p.mag_up) p.mag_up[f] = mu;
@@ -136,7 +193,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_demod2048(demod_params
 // The receiver variant's "left" window reads the zero upper half (hazard H1, defined): its maximum
 // is 0 at relative index 0, so the right window wins unless its own maximum is negative (never).
 template <int NB>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_dsp2048(demod_params p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_dsp2048(demod_params p) {
     __shared__ float2 s_tw[32 * 32];
     __shared__ float2 s_tile[kWarpsPerCta][kTileFloat2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -188,7 +245,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_dsp2048(demod_params p
 
 static int grid_for(size_t nwork, int num_sms) {
     size_t ctas = (nwork + kWarpsPerCta - 1) / kWarpsPerCta;
-    size_t cap = (size_t) num_sms * 2 * 4;             // persistent-ish: a few waves of resident CTAs
+    size_t cap = (size_t) num_sms * 4 * 4;             // persistent-ish: a few waves of resident CTAs
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     return (int) ctas;
@@ -196,9 +253,26 @@ static int grid_for(size_t nwork, int num_sms) {
 
 template <int NB>
 static cudaError_t launch_demod_nb(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
-    int grid = grid_for(p.nframes, num_sms);
-    if (pcm_format == 1u) k_demod2048<int32_t, NB><<<grid, kWarpsPerCta * 32, 0, st>>>(p);
-    else k_demod2048<float, NB><<<grid, kWarpsPerCta * 32, 0, st>>>(p);
+    size_t ctas = (p.nframes + kDualWarps - 1) / kDualWarps;
+    const size_t cap = (size_t) num_sms * 2 * 4;
+    if (ctas > cap) ctas = cap;
+    const size_t smem = 8192 + sizeof(float4) * kTile4 * kDualWarps;
+    static bool configured[2] = {false, false};
+    if (pcm_format == 1u) {
+        if (!configured[1]) {
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048<int32_t, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) return e;
+            configured[1] = true;
+        }
+        k_demod2048<int32_t, NB><<<(int) ctas, kDualWarps * 32, smem, st>>>(p);
+    } else {
+        if (!configured[0]) {
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) return e;
+            configured[0] = true;
+        }
+        k_demod2048<float, NB><<<(int) ctas, kDualWarps * 32, smem, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -25,7 +25,7 @@ struct usc_handle {
     cudaStream_t stream;
     uint32_t bandwidth, bandwidth2, idx_left_zero;
     std::vector<float> hann, up, down, H_up, H_down;
-    float *d_hann, *d_up, *d_down, *d_H_up, *d_H_down;
+    float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
     float2 *d_tw_pass, *d_tw_split;
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
@@ -120,7 +120,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->device = device;
     h->stream = 0;
     h->launches = 0;
-    h->d_hann = h->d_up = h->d_down = h->d_H_up = h->d_H_down = nullptr;
+    h->d_hann = h->d_up = h->d_down = h->d_ud = h->d_H_up = h->d_H_down = nullptr;
     h->d_tw_pass = h->d_tw_split = nullptr;
     h->d_fir_coeffs = nullptr;
     h->lane_frames = 0;
@@ -146,6 +146,11 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     if ((rc = upload(h->hann.data(), h->hann.size() * 4, (void**) &h->d_hann))) { usc_destroy(h); return rc; }
     if ((rc = upload(h->up.data(), h->up.size() * 4, (void**) &h->d_up))) { usc_destroy(h); return rc; }
     if ((rc = upload(h->down.data(), h->down.size() * 4, (void**) &h->d_down))) { usc_destroy(h); return rc; }
+    if (!cplx) {
+        std::vector<float> ud(2 * (size_t) n);
+        for (uint32_t i = 0; i < n; ++i) { ud[2 * i] = h->up[i]; ud[2 * i + 1] = h->down[i]; }
+        if ((rc = upload(ud.data(), ud.size() * 4, (void**) &h->d_ud))) { usc_destroy(h); return rc; }
+    }
     if (cudaMalloc((void**) &h->d_fir_coeffs, 256 * sizeof(float)) != cudaSuccess) { usc_destroy(h); return USC_ERR_CUDA_BASE - (int) cudaErrorMemoryAllocation; }
     cudaError_t e = fft_generic_prepare();
     if (e != cudaSuccess) { usc_destroy(h); return cuda_rc(e); }
@@ -193,7 +198,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
 
 void usc_destroy(usc_handle* h) {
     if (!h) return;
-    cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
+    cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
     cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) {
@@ -379,6 +384,7 @@ static void fill_common(const usc_handle* h, demod_params* p) {
     memset(p, 0, sizeof *p);
     p->chirp_up = (const float2*) h->d_up;
     p->chirp_down = (const float2*) h->d_down;
+    p->chirp_ud = (const float2*) h->d_ud;
     p->hann = (const float2*) h->d_hann;
     p->tw_pass = h->d_tw_pass;
     p->tw_split = h->d_tw_split;

@@ -101,6 +101,62 @@ __device__ __forceinline__ void fft_base(float (&re)[R], float (&im)[R]) {
     }
 }
 
+// ---- packed (f32x2) twin of the base kernel -------------------------------------------------------
+// Blackwell executes add/mul/fma.f32x2 (SASS FADD2/FMUL2/FFMA2) on register pairs with immediate
+// and negated operands.  Each half is an independent IEEE round-to-nearest operation, so running
+// two transforms side by side in the halves of a float2 gives bit-identical results to two scalar
+// runs while halving the issue slots; the fused demodulator carries the up-chirp hypothesis in .x
+// and the down-chirp hypothesis in .y.
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 bc2(float c) { return make_float2(c, c); }
+
+__device__ __forceinline__ void bfly2_one(float2& er, float2& ei, float2& or_, float2& oi) {
+    float2 sr = __fadd2_rn(er, or_), si = __fadd2_rn(ei, oi);
+    float2 dr = __fadd2_rn(er, neg2(or_)), di = __fadd2_rn(ei, neg2(oi));
+    er = sr; ei = si; or_ = dr; oi = di;
+}
+__device__ __forceinline__ void bfly2_mj(float2& er, float2& ei, float2& or_, float2& oi) {
+    float2 sr = __fadd2_rn(er, oi), si = __fadd2_rn(ei, neg2(or_));
+    float2 dr = __fadd2_rn(er, neg2(oi)), di = __fadd2_rn(ei, or_);
+    er = sr; ei = si; or_ = dr; oi = di;
+}
+__device__ __forceinline__ void bfly2_gen(float2& er, float2& ei, float2& or_, float2& oi, float wr, float wi) {
+    float2 sr = __ffma2_rn(or_, bc2(wr), __ffma2_rn(neg2(oi), bc2(wi), er));
+    float2 si = __ffma2_rn(or_, bc2(wi), __ffma2_rn(oi, bc2(wr), ei));
+    float2 dr = __ffma2_rn(bc2(2.0f), er, neg2(sr));
+    float2 di = __ffma2_rn(bc2(2.0f), ei, neg2(si));
+    er = sr; ei = si; or_ = dr; oi = di;
+}
+
+template <int R>
+__device__ __forceinline__ void fft_base2(float2 (&re)[R], float2 (&im)[R]) {
+    constexpr int BITS = ilog2(R);
+    float2 tr[R], ti[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        tr[i] = re[brev(i, BITS)];
+        ti[i] = im[brev(i, BITS)];
+    }
+#pragma unroll
+    for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * h) {
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+                const int a = blk + j, b = blk + j + h;
+                if (j == 0) bfly2_one(tr[a], ti[a], tr[b], ti[b]);
+                else if (2 * j == h) bfly2_mj(tr[a], ti[a], tr[b], ti[b]);
+                else bfly2_gen(tr[a], ti[a], tr[b], ti[b], w32_re(j * (16 / h)), w32_im(j * (16 / h)));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        re[i] = tr[i];
+        im[i] = ti[i];
+    }
+}
+
 // Forward real-FFT split for one bin k in [1, N/2): Zk = Z[k], Zc = Z[N/2-k], W_N^k = cr - j*si.
 //   2X = (Zk + conj Zc) + W_N^k * (Zk - conj Zc)/j ;  X = 0.5 * 2X
 __device__ __forceinline__ void rfft_split(float zkr, float zki, float zcr, float zci, float cr, float si,

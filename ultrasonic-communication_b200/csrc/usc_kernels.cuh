@@ -52,6 +52,7 @@ struct demod_params {
     size_t nframes;
     const float2* chirp_up;     // 1024 float2 = 2048 floats
     const float2* chirp_down;
+    const float2* chirp_ud;     // interleaved (up[i], down[i]) pairs, 2048 float2
     const float2* hann;
     const float2* tw_pass;      // [d][a] layout: W_1024^(a*d), 32x32 float2
     const float2* tw_split;     // (cos, sin)(2*pi*k/2048), k < 1024
