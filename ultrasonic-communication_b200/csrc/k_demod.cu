@@ -89,69 +89,165 @@ __device__ __forceinline__ void peak_right(const float (&re)[32], const float (&
 
 // ---- dual-hypothesis kernel: both hypotheses ride in the halves of f32x2 registers ---------------
 // (.x = up-chirp, .y = down-chirp).  The PCM, the Hann table and the inter-pass twiddles are loaded
-// once for both; the two 32-point register FFTs issue as FADD2/FFMA2.  The L1/shared-memory data
-// path (1 wavefront = 128 B per clock per SM) is the scarcest resource of this kernel, so the point
-// of the layout is bytes through L1 per frame: PCM 8 KB + (up,down) table 16 KB + Hann 8 KB +
-// exchange tile 2 x 16 KB + twiddles 8 KB = 72 KB, against 103 KB for two single-hypothesis passes.
-constexpr int kDualWarps = 4;
-constexpr int kTile4Stride = 33;                      // float4 units; odd stride: conflict-free LDS.128
-constexpr int kTile4 = 32 * kTile4Stride;
+// once for both; the two 32-point register FFTs issue as FADD2/FFMA2.
+//
+// Persistent: ONE CTA of 8 warps per SM, every warp loops over frames.  Shared memory (224 KB):
+//   twiddles 8 KB | (up,down) chirp table 16 KB | Hann 8 KB | per warp: exchange tile 16 KB + PCM stage 8 KB
+// The PCM of a warp's NEXT frame is fetched by a 1-D TMA bulk copy (cp.async.bulk, mbarrier
+// completion) issued right after the current frame has been pulled into registers, so DRAM latency
+// is hidden behind a whole frame of arithmetic; tables sit in shared memory so every operand of
+// the front end is one LDS away.  The L1/shared data path (128 B per clock per SM) carries, per
+// frame, PCM 8 KB + table 16 KB + Hann 8 KB + exchange 2 x 16 KB + twiddles 8 KB = 72 KB.
+constexpr int kDualWarps = 8;
+constexpr int kTile4 = 32 * 32;                       // float4 units, XOR-swizzled 32x32 tile (16 KB)
+constexpr int kSmemTw = 0;                            // byte offsets into dynamic shared memory
+constexpr int kSmemUd = 8192;
+constexpr int kSmemHann = kSmemUd + 16384;
+constexpr int kSmemWarp = kSmemHann + 8192;
+constexpr int kWarpBytes = 16384 + 8192;              // tile + PCM stage
+constexpr int kSmemBar = kSmemWarp + kDualWarps * kWarpBytes;
+constexpr int kSmemTotal = kSmemBar + kDualWarps * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Exact arm_max_f32 over sqrt(p_k) without taking 2*NB square roots per frame.  sqrt is monotone,
+// so max_k sqrt(p_k) = sqrt(max_k p_k); the first index attaining it is the first k whose p_k rounds
+// to the same square root.  Any such k other than the first arg-max of p must satisfy
+// p_k >= pmax*(1 - 2^-20) (a gap of two ulps of the root guarantees a smaller rounded root), so the
+// fast path only has to rule that out; otherwise the rare slow path takes every root.
+template <int NB>
+__device__ __noinline__ void peak_slow(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
+    best = -INFINITY;
+    best_idx = 0xffffffffu;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        float m = __fsqrt_rn(pw[d1]);
+        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
+    }
+    warp_argmax(best, best_idx);
+}
 
 template <int NB, int HALF>
 __device__ __forceinline__ void peak_right2(const float2 (&re)[32], const float2 (&im)[32],
                                             const float2 (&ws)[NB], int lane, uint32_t bw2,
                                             float& best, uint32_t& best_idx) {
     auto half = [](const float2& v) -> float { return HALF == 0 ? v.x : v.y; };
-    best = -INFINITY;
-    best_idx = 0xffffffffu;
     const int src = (32 - lane) & 31;
+    float pw[NB];                                      // squared magnitudes of this lane's bins
 #pragma unroll
     for (int d1 = 0; d1 < NB; ++d1) {
         float sr = lane == 0 ? half(re[(32 - d1) & 31]) : half(re[31 - d1]);
         float si = lane == 0 ? half(im[(32 - d1) & 31]) : half(im[31 - d1]);
         float zcr = __shfl_sync(0xffffffffu, sr, src);
         float zci = __shfl_sync(0xffffffffu, si, src);
-        const uint32_t k = (uint32_t) lane + 32u * d1;
         float xr, xi;
-        if (d1 == 0 && lane == 0) {
-            xr = __fadd_rn(half(re[0]), half(im[0]));
-            xi = __fsub_rn(half(re[0]), half(im[0]));
-        } else {
-            rfft_split(half(re[d1]), half(im[d1]), zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
+        rfft_split(half(re[d1]), half(im[d1]), zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
+        if (d1 == 0) {                                 // packed bin 0 = (X[0], X[N/2]) on lane 0
+            float dr = __fadd_rn(half(re[0]), half(im[0])), di = __fsub_rn(half(re[0]), half(im[0]));
+            xr = lane == 0 ? dr : xr;
+            xi = lane == 0 ? di : xi;
         }
-        float m = cmag(xr, xi);
-        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
+        pw[d1] = __fmaf_rn(xr, xr, __fmul_rn(xi, xi));
+    }
+    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
+    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
+#pragma unroll
+    for (int d1 = 1; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
+    }
+    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
+    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
+    bool risky = false;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        risky |= (k < kmin) && (pw[d1] >= thr);        // an earlier bin that might round to the same root
+    }
+    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
+        peak_slow<NB>(pw, lane, bw2, best, best_idx);
+    } else {
+        best = __fsqrt_rn(pmax);
+        best_idx = kmin;
     }
 }
 
 template <typename PCM, int NB>
-__global__ void __launch_bounds__(kDualWarps * 32, 2) k_demod2048(demod_params p) {
-    extern __shared__ float4 s_dyn[];
-    float2* s_tw = reinterpret_cast<float2*>(s_dyn);                  // 32x32 float2 = 8 KB
-    float4* s_tile_all = s_dyn + 512;                                 // kDualWarps x 32x33 float4
+__global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(s_raw + kSmemTw);
+    float4* s_ud = reinterpret_cast<float4*>(s_raw + kSmemUd);
+    float2* s_hann = reinterpret_cast<float2*>(s_raw + kSmemHann);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* tile = s_tile_all + warp * kTile4;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_tw[i] = p.tw_pass[i];
+    float4* tile = reinterpret_cast<float4*>(s_raw + kSmemWarp + warp * kWarpBytes);
+    using V2 = typename vec2<PCM>::type;
+    V2* xstage = reinterpret_cast<V2*>(s_raw + kSmemWarp + warp * kWarpBytes + 16384);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + kSmemBar) + warp;
+
+    const size_t nwarps = (size_t) gridDim.x * kDualWarps;
+    size_t f = (size_t) blockIdx.x * kDualWarps + warp;
+    const PCM* pcm = static_cast<const PCM*>(p.pcm);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (f < p.nframes) {
+            mbar_expect_tx(bar, 8192);
+            bulk_g2s(xstage, pcm + f * 2048, 8192, bar);
+        }
+    }
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        s_tw[i] = p.tw_pass[i];
+        s_ud[i] = reinterpret_cast<const float4*>(p.chirp_ud)[i];
+        s_hann[i] = p.hann[i];
+    }
     float2 ws[NB];
 #pragma unroll
     for (int d1 = 0; d1 < NB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
     __syncthreads();
 
-    using V2 = typename vec2<PCM>::type;
-    const float4* __restrict__ chirp_ud = reinterpret_cast<const float4*>(p.chirp_ud);
-    const size_t nwarps = (size_t) gridDim.x * kDualWarps;
-    for (size_t f = (size_t) blockIdx.x * kDualWarps + warp; f < p.nframes; f += nwarps) {
-        const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * 2048);
+    uint32_t parity = 0;
+    for (; f < p.nframes; f += nwarps) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
         float2 re[32], im[32];                                        // (.x, .y) = (up, down)
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
             const int m = lane + 32 * b;
-            V2 raw = src[m];
+            V2 raw = xstage[m];
             float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
-            float4 c = __ldg(chirp_ud + m);                           // (up[2m], down[2m], up[2m+1], down[2m+1])
-            float2 w = __ldg(p.hann + m);
+            float4 c = s_ud[m];                                       // (up[2m], down[2m], up[2m+1], down[2m+1])
+            float2 w = s_hann[m];
             re[b] = make_float2(__fmul_rn(__fmul_rn(x0, c.x), w.x), __fmul_rn(__fmul_rn(x0, c.y), w.x));
             im[b] = make_float2(__fmul_rn(__fmul_rn(x1, c.z), w.y), __fmul_rn(__fmul_rn(x1, c.w), w.y));
+        }
+        __syncwarp();                                                 // every lane has consumed the stage
+        if (lane == 0 && f + nwarps < p.nframes) {                    // refill it with this warp's next frame
+            mbar_expect_tx(bar, 8192);
+            bulk_g2s(xstage, pcm + (f + nwarps) * 2048, 8192, bar);
         }
         fft_base2<32>(re, im);
 #pragma unroll
@@ -162,12 +258,12 @@ __global__ void __launch_bounds__(kDualWarps * 32, 2) k_demod2048(demod_params p
                 cmul(re[d].x, im[d].x, w.x, w.y, v.x, v.z);
                 cmul(re[d].y, im[d].y, w.x, w.y, v.y, v.w);
             }
-            tile[d * kTile4Stride + lane] = v;
+            tile[d * 32 + (lane ^ d)] = v;
         }
         __syncwarp();
 #pragma unroll
         for (int a = 0; a < 32; ++a) {
-            float4 v = tile[lane * kTile4Stride + a];
+            float4 v = tile[lane * 32 + (a ^ lane)];
             re[a] = make_float2(v.x, v.y);
             im[a] = make_float2(v.z, v.w);
         }
@@ -177,8 +273,6 @@ __global__ void __launch_bounds__(kDualWarps * 32, 2) k_demod2048(demod_params p
         uint32_t iu, id;
         peak_right2<NB, 0>(re, im, ws, lane, p.bandwidth2, mu, iu);
         peak_right2<NB, 1>(re, im, ws, lane, p.bandwidth2, md, id);
-        warp_argmax(mu, iu);
-        warp_argmax(md, id);
         if (lane == 0) {
             if (p.mag_up) p.mag_up[f] = mu;
             if (p.idx_up) p.idx_up[f] = iu;
@@ -254,24 +348,22 @@ static int grid_for(size_t nwork, int num_sms) {
 template <int NB>
 static cudaError_t launch_demod_nb(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
     size_t ctas = (p.nframes + kDualWarps - 1) / kDualWarps;
-    const size_t cap = (size_t) num_sms * 2 * 4;
-    if (ctas > cap) ctas = cap;
-    const size_t smem = 8192 + sizeof(float4) * kTile4 * kDualWarps;
+    if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;            // persistent: one CTA per SM
     static bool configured[2] = {false, false};
     if (pcm_format == 1u) {
         if (!configured[1]) {
-            cudaError_t e = cudaFuncSetAttribute(k_demod2048<int32_t, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048<int32_t, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
             if (e != cudaSuccess) return e;
             configured[1] = true;
         }
-        k_demod2048<int32_t, NB><<<(int) ctas, kDualWarps * 32, smem, st>>>(p);
+        k_demod2048<int32_t, NB><<<(int) ctas, kDualWarps * 32, kSmemTotal, st>>>(p);
     } else {
         if (!configured[0]) {
-            cudaError_t e = cudaFuncSetAttribute(k_demod2048<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
             if (e != cudaSuccess) return e;
             configured[0] = true;
         }
-        k_demod2048<float, NB><<<(int) ctas, kDualWarps * 32, smem, st>>>(p);
+        k_demod2048<float, NB><<<(int) ctas, kDualWarps * 32, kSmemTotal, st>>>(p);
     }
     return cudaGetLastError();
 }

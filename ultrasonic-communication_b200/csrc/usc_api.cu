@@ -398,7 +398,7 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
     if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
-    if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;      /* frames are read as 8-byte pairs */
+    if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;     /* frames are fetched by 16-byte-aligned bulk copies */
     if (!nframes) return USC_OK;
     demod_params p;
     fill_common(h, &p);
