@@ -169,6 +169,31 @@ int usc_pipeline(usc_handle *h, const float *frames, float *mags, int updown, ui
  * mag_mean[s].  hist: batch usc_history records on the device. */
 int usc_dsp(usc_handle *h, const float *fifo, size_t fifo_stride, const uint32_t *sync_position,
             const float *mag_mean, int updown, usc_history *hist, uint32_t batch);
+/* Result of the receiver state machine for one stream. 32 bytes. */
+typedef struct usc_rx_result {
+    uint32_t state;          /* final enum state: 0 IDLE, 1 SYNCHRONIZING, 2 SYNCHRONIZED, 3 DATA_RECEIVING
+                                (receiver/Src/main.c:108-111) */
+    uint32_t sync_position;  /* final sync_position */
+    int32_t lock_frame;      /* frame index of the first transition to SYNCHRONIZED, -1 if none */
+    uint32_t lock_position;  /* sync_position chosen then: N/2 + max_idx*N/8 (main.c:483) */
+    uint32_t nbytes;         /* UART bytes produced (may exceed the capacity given; excess is dropped) */
+    uint32_t frames_seen;
+    uint32_t turn, sync_cnt;
+} usc_rx_result;
+
+/* K7.  The receiver's whole main loop (receiver/Src/main.c:417-580) over `nstreams` independent
+ * streams of `nframes` frames each (stream s starts at pcm + s*stream_stride samples; stride even):
+ * 3-frame FIFO, 8-offset sliding-correlation search with the mag_stat noise floor, 3-in-a-row lock,
+ * up/down symbol decision, resync, MSB-first bit packing.  uart: nstreams*uart_cap bytes receiving
+ * what the firmware would printf (decoded chars, '\n' at the end of each message).  Hazards
+ * H1/H3/H4/H5 are defined as in DESIGN.md §3.4. */
+int usc_receiver_run(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                     size_t stream_stride, uint8_t *uart, uint32_t uart_cap, usc_rx_result *results);
+/* K4.  The sliding-correlation search grid alone (main.c:447-451) for every frame of every stream:
+ * 4 x dsp(UP) at N/2 + (t&1)*N/8 + i*N/4 on the FIFO of frame t, after synchronous addition of
+ * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */
+int usc_sync_search(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                    size_t stream_stride, uint32_t sync_add, float *mag, uint32_t *idx);
 /* K2.  compress_chirp() of experiments/chirp_compression_time_domain/Src/chirp.c:78-83 followed
  * by the signed arm_max_f32 over all n lags (.../Src/main.c:189) on `nframes` frames; the handle
  * must be created with chirp_variant T and the symmetric window.  out_frames (nframes*n floats)

@@ -336,3 +336,34 @@ class RefCompressor:
             lib().ref_compressor_free(C.byref(self.c))
         except Exception:
             pass
+
+
+# ---- receiver state machine ---------------------------------------------------------------------
+class RxState(C.Structure):
+    _fields_ = [("state", C.c_uint32), ("turn", C.c_uint32), ("sync_cnt", C.c_uint32),
+                ("sync_position", C.c_uint32), ("max_idx", C.c_uint32), ("mag_stat", C.c_float * 12),
+                ("mag_mean", C.c_float), ("history", History * 8), ("msg", C.c_uint32), ("msg_cnt", C.c_uint32),
+                ("lock_frame", C.c_int32), ("lock_position", C.c_uint32), ("frames_seen", C.c_uint32)]
+
+
+def receiver_run(rxobj, pcm, snr_threshold=2.0, cap=4096):
+    """Whole-stream state machine (receiver/Src/main.c:417-580): -> (uart bytes, final RxState)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    nframes = pcm.size // rxobj.n
+    out = np.zeros(cap, np.uint8)
+    nout = C.c_uint32(0)
+    st = RxState()
+    lib().ref_receiver_run_i32(C.byref(rxobj.rx), C.c_float(snr_threshold), pcm.ctypes.data_as(i32p),
+                               C.c_uint32(nframes), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nout),
+                               C.c_uint32(cap), C.byref(st))
+    return bytes(out[:min(nout.value, cap)]), st
+
+
+def sync_search(rxobj, pcm, sync_add=1):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    nframes = pcm.size // rxobj.n
+    mag = np.empty((nframes, 4), np.float32)
+    idx = np.empty((nframes, 4), np.uint32)
+    lib().ref_sync_search_i32(C.byref(rxobj.rx), pcm.ctypes.data_as(i32p), C.c_uint32(nframes), C.c_uint32(sync_add),
+                              _fp(mag), _up(idx))
+    return mag, idx

@@ -503,6 +503,169 @@ void ref_demod_frames_i32(const ref_receiver *rx, const int32_t *pcm, size_t nfr
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* receiver state machine — receiver/Src/main.c:233-273, 311-339, 417-580                      */
+/* ------------------------------------------------------------------------------------------ */
+void ref_rx_state_init(ref_rx_state *st, const ref_receiver *rx) {
+    memset(st, 0, sizeof *st);
+    st->state = REF_IDLE;                                   /* main.c:111 */
+    st->sync_position = rx->n / 2;                          /* main.c:330 */
+    for (int i = 0; i < 12; ++i) st->mag_stat[i] = 1E37f;   /* main.c:321-322 */
+    st->lock_frame = -1;
+}
+
+/* symbol_snr (main.c:233-236) with hazards H3/H5 defined: a probe outside [0, 2n] reads outside
+ * fifo_queue in the reference; here it yields snr = -inf and leaves the history slot untouched. */
+static float symbol_snr(const ref_receiver *rx, const float *fifo, int64_t pos, ref_history *h, int up) {
+    if (pos < 0 || pos > (int64_t) 2 * rx->n) return -INFINITY;
+    ref_dsp(rx, fifo, (uint32_t) pos, h, h->mag_mean, up);
+    return h->snr;
+}
+
+/* resync (main.c:243-273) */
+static void resync(const ref_receiver *rx, const float *fifo, float snr, ref_history *hist, uint32_t offset,
+                   uint32_t *sync_position, int up) {
+    int64_t l = (int64_t) *sync_position - offset, r = (int64_t) *sync_position + offset;
+    float snr_l = symbol_snr(rx, fifo, l, &hist[2], up);
+    float snr_r = symbol_snr(rx, fifo, r, &hist[3], up);
+    if ((snr > snr_l) && (snr > snr_r)) {
+        hist[2].rank = '-'; hist[3].rank = '-';
+    } else if (snr_l >= snr_r) {
+        if (l >= 0) *sync_position = (uint32_t) l;
+    } else if (snr_l < snr_r) {
+        if (r <= (int64_t) 2 * rx->n) *sync_position = (uint32_t) r;
+    }
+}
+
+static void emit(uint8_t *out, uint32_t *nout, uint32_t cap, uint8_t c) {
+    if (*nout < cap) out[*nout] = c;
+    (*nout)++;
+}
+
+void ref_receiver_step(const ref_receiver *rx, ref_rx_state *st, float thr, const float *fifo,
+                       uint8_t *out, uint32_t *nout, uint32_t cap) {
+    const uint32_t n = rx->n, offset = n / 8, shift = n / 4;               /* main.c:406-407 */
+    uint32_t prev = st->state;
+    switch (st->state) {
+    case REF_IDLE:
+        st->sync_cnt = 0;
+        ref_arm_mean_f32(&st->mag_stat[4], 8, &st->mag_mean);              /* main.c:431 */
+        /* fall through (main.c:434) */
+    case REF_SYNCHRONIZING:
+        for (uint32_t i = 0; i < 4; ++i) {                                  /* main.c:447-451 */
+            st->sync_position = n / 2 + st->turn * offset + shift * i;
+            ref_dsp(rx, fifo, st->sync_position, &st->history[i * 2 + st->turn], st->mag_mean, 1);
+        }
+        st->turn = st->turn == 0 ? 1 : 0;
+        if (st->turn == 1) {
+            for (int i = 10; i >= 0; --i) st->mag_stat[i + 1] = st->mag_stat[i];   /* main.c:458-460 */
+            float mag_max_max = 0.0f;
+            for (uint32_t i = 0; i < 8; ++i) {                              /* main.c:463-471 */
+                st->history[i].rank = '-';
+                if (st->history[i].mag_max > mag_max_max) { mag_max_max = st->history[i].mag_max; st->max_idx = i; }
+            }
+            st->mag_stat[0] = mag_max_max;
+            st->history[st->max_idx].rank = '+';
+            float snr = (mag_max_max - st->mag_mean) / st->mag_mean;        /* main.c:477 */
+            if (snr >= thr) {
+                st->state = REF_SYNCHRONIZING;
+                if (++st->sync_cnt >= 3) {
+                    st->state = REF_SYNCHRONIZED;
+                    st->sync_position = n / 2 + st->max_idx * offset;       /* main.c:483 */
+                }
+            } else {
+                st->state = REF_IDLE;
+            }
+        }
+        break;
+    case REF_SYNCHRONIZED: {
+        float up = symbol_snr(rx, fifo, st->sync_position, &st->history[0], 1);    /* main.c:493-494 */
+        float down = symbol_snr(rx, fifo, st->sync_position, &st->history[1], 0);
+        if (up >= thr || down >= thr) {
+            if (down > up) {                                                /* the delimiter */
+                resync(rx, fifo, down, st->history, offset, &st->sync_position, 0);
+                st->state = REF_DATA_RECEIVING;
+            } else {
+                resync(rx, fifo, up, st->history, offset, &st->sync_position, 1);
+            }
+        } else {
+            st->state = REF_IDLE;
+        }
+        break;
+    }
+    case REF_DATA_RECEIVING: {
+        float up = symbol_snr(rx, fifo, st->sync_position, &st->history[0], 1);    /* main.c:518-519 */
+        float down = symbol_snr(rx, fifo, st->sync_position, &st->history[1], 0);
+        if (up >= thr || down >= thr) {
+            if (down > up) {
+                st->msg = ((st->msg << 1) + 0) & 0xffu;                     /* main.c:525 */
+                resync(rx, fifo, down, st->history, offset, &st->sync_position, 0);
+            } else {
+                st->msg = ((st->msg << 1) + 1) & 0xffu;                     /* main.c:529 */
+                resync(rx, fifo, up, st->history, offset, &st->sync_position, 1);
+            }
+            if (++st->msg_cnt >= 8) {                                       /* main.c:532-537 */
+                emit(out, nout, cap, (uint8_t) st->msg);
+                st->msg = 0; st->msg_cnt = 0;
+            }
+        } else {                                                            /* main.c:539-549 */
+            emit(out, nout, cap, (uint8_t) '\n');
+            st->state = REF_IDLE;
+            st->msg = 0; st->msg_cnt = 0;
+        }
+        break;
+    }
+    }
+    if (prev != REF_SYNCHRONIZED && st->state == REF_SYNCHRONIZED && st->lock_frame < 0) {
+        st->lock_frame = (int32_t) st->frames_seen;
+        st->lock_position = st->sync_position;
+    }
+    st->frames_seen++;
+}
+
+void ref_receiver_run_i32(const ref_receiver *rx, float thr, const int32_t *pcm, uint32_t nframes,
+                          uint8_t *out, uint32_t *nout, uint32_t cap, ref_rx_state *final_state) {
+    const uint32_t n = rx->n;
+    float *fifo = (float *) calloc(3 * (size_t) n, sizeof(float));
+    ref_rx_state st;
+    ref_rx_state_init(&st, rx);
+    *nout = 0;
+    for (uint32_t t = 0; t < nframes; ++t) {
+        memmove(fifo, fifo + n, sizeof(float) * 2 * n);                     /* main.c:662 */
+        for (uint32_t i = 0; i < n; ++i) fifo[2 * n + i] = (float) pcm[(size_t) t * n + i];   /* main.c:663-665 */
+        ref_receiver_step(rx, &st, thr, fifo, out, nout, cap);
+    }
+    if (final_state) *final_state = st;
+    free(fifo);
+}
+
+void ref_sync_search_i32(const ref_receiver *rx, const int32_t *pcm, uint32_t nframes, uint32_t sync_add,
+                         float *mag, uint32_t *idx) {
+    const uint32_t n = rx->n, offset = n / 8, shift = n / 4;
+    if (sync_add < 1) sync_add = 1;
+    float *acc = (float *) malloc(sizeof(float) * 3 * n);
+    for (uint32_t t = 0; t < nframes; ++t) {
+        /* FIFO at frame t = frames t-2, t-1, t (zeros before the stream starts); synchronous
+         * addition sums the FIFOs of frames t, t-1, ..., t-sync_add+1 sample by sample, oldest first */
+        for (uint32_t i = 0; i < 3 * n; ++i) acc[i] = 0.0f;
+        for (uint32_t j = sync_add; j-- > 0;) {
+            for (uint32_t i = 0; i < 3 * n; ++i) {
+                int64_t g = ((int64_t) t - (int64_t) j - 2) * n + i;
+                float v = g >= 0 ? (float) pcm[g] : 0.0f;
+                acc[i] = (j == sync_add - 1) ? v : acc[i] + v;
+            }
+        }
+        ref_history h;
+        for (uint32_t i = 0; i < 4; ++i) {
+            uint32_t pos = n / 2 + (t & 1u) * offset + shift * i;
+            ref_dsp(rx, acc, pos, &h, 1.0f, 1);
+            mag[(size_t) t * 4 + i] = h.mag_max;
+            idx[(size_t) t * 4 + i] = h.max_idx;
+        }
+    }
+    free(acc);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* frequency-domain compression chain                                                          */
 /* ------------------------------------------------------------------------------------------ */
 /* experiments/chirp_compression_time_domain/Src/chirp.c:52-75 */

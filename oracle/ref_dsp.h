@@ -156,6 +156,37 @@ void ref_demod_frames_f32(const ref_receiver *rx, const float *pcm, size_t nfram
                           float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
                           int nthreads);
 
+/* ---- receiver state machine (receiver/Src/main.c:417-580) ---- */
+enum { REF_IDLE = 0, REF_SYNCHRONIZING = 1, REF_SYNCHRONIZED = 2, REF_DATA_RECEIVING = 3 };   /* main.c:108-111 */
+
+typedef struct {
+    uint32_t state, turn, sync_cnt, sync_position, max_idx;
+    float mag_stat[12];                      /* main.c:321-322: starts at 1e37 */
+    float mag_mean;
+    ref_history history[8];                  /* hazard H4 defined: zero-initialised */
+    uint32_t msg, msg_cnt;
+    int32_t lock_frame;                      /* frame index of the first IDLE/SYNCHRONIZING -> SYNCHRONIZED, -1 if none */
+    uint32_t lock_position;                  /* sync_position chosen at that moment */
+    uint32_t frames_seen;
+} ref_rx_state;
+
+void ref_rx_state_init(ref_rx_state *st, const ref_receiver *rx);
+/* One pass of the while(1) body with new_pcm_data set (main.c:422-577).  fifo: 3n floats, already
+ * shifted (main.c:659-668).  UART bytes (decoded chars and the '\n' that ends a message,
+ * main.c:533,540) are appended to out[*nout], up to cap. */
+void ref_receiver_step(const ref_receiver *rx, ref_rx_state *st, float snr_threshold, const float *fifo,
+                       uint8_t *out, uint32_t *nout, uint32_t cap);
+/* A whole stream: nframes frames of int32 PCM pushed through the 3-frame FIFO (zeros before the
+ * first frame) and the state machine. */
+void ref_receiver_run_i32(const ref_receiver *rx, float snr_threshold, const int32_t *pcm, uint32_t nframes,
+                          uint8_t *out, uint32_t *nout, uint32_t cap, ref_rx_state *final_state);
+/* The sliding-correlation search grid alone (main.c:447-451), optionally after synchronous addition
+ * of `sync_add` frame-aligned windows (misc/Formula.ipynb cell 9, SynchronousAddition.ipynb cell 6):
+ * for frame t and i < 4: dsp(UP) at N/2 + (t&1)*N/8 + i*N/4 on the sum over j < sync_add of the
+ * FIFO as it stood at frame t-j.  mag/idx: nframes*4. */
+void ref_sync_search_i32(const ref_receiver *rx, const int32_t *pcm, uint32_t nframes, uint32_t sync_add,
+                         float *mag, uint32_t *idx);
+
 /* ---- frequency-domain compression chain (experiments/chirp_compression_time_domain) ---- */
 typedef struct {
     uint32_t n;

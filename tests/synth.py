@@ -42,3 +42,49 @@ def make_frames(nframes, snr_db=-5.0, amp=2.0e4, seed_bits=2, seed_noise=3, n=N,
     if dtype == np.float32:
         return out.astype(np.float32), bits
     return out, bits
+
+
+# ---- transmitter (generator/ChirpGenerator.ipynb cells 1-3) -----------------------------------------
+TX_T = 0.0262          # ChirpGenerator.ipynb cell 1: TIME_FRAME of the transmitter
+
+
+def orth_symbol(tau, kind, f0=F0, f1=F1, T=TX_T):
+    """chirp_orth law (simulation/signal.py:45-53) in continuous time; kind in 'H' (up), 'L' (down), 'G' (gap)."""
+    if kind == "G":
+        return np.zeros_like(tau)
+    k = (f1 - f0) / T
+    f = f0 + k * tau / 2.0 if kind == "H" else f1 - k * tau / 2.0
+    arg = 2.0 * np.pi * f * tau - np.pi / 2.0
+    return np.cos(arg) + np.sin(arg)
+
+
+def frame_symbols(message, lead_in=40, guard=12):
+    """G*lead_in + 7xH preamble + 1xL delimiter + bits MSB-first (H=1, L=0) + guard x G
+    (ChirpGenerator.ipynb cell 2; the long lead-in covers the 24-frame mag_stat warm-up)."""
+    syms = ["G"] * lead_in + ["H"] * 7 + ["L"]
+    for byte in message:
+        for b in range(7, -1, -1):
+            syms.append("H" if (byte >> b) & 1 else "L")
+    return syms + ["G"] * guard
+
+
+def make_stream(message, snr_db=26.0, amp=2.0e4, start_offset=0, seed=11, lead_in=40, guard=12, nframes=None,
+                fs=FS, n=N, tx_T=TX_T):
+    """One receiver stream: the transmitter's frame rendered at the receiver's fs (symbols last
+    TX_T = 26.2 ms = 2046.875 samples, so the lock drifts and resync has work to do), delayed by
+    start_offset samples, plus Gaussian noise; int32 multiples of 256."""
+    syms = frame_symbols(message, lead_in, guard)
+    total = nframes * n if nframes else int(np.ceil((len(syms) * tx_T * fs + start_offset) / n)) * n
+    t = (np.arange(total) - start_offset) / fs
+    k = np.floor(t / tx_T).astype(np.int64)
+    tau = t - k * tx_T
+    x = np.zeros(total)
+    valid = (k >= 0) & (k < len(syms))
+    kinds = np.array([{"G": 0, "H": 1, "L": 2}[s] for s in syms])
+    kk = np.where(valid, k, 0)
+    kind = np.where(valid, kinds[kk], 0)
+    x = np.where(kind == 1, orth_symbol(tau, "H", T=tx_T), np.where(kind == 2, orth_symbol(tau, "L", T=tx_T), 0.0)) * amp
+    sig_pow = amp * amp            # mean of (cos+sin)^2 = 1
+    sigma = np.sqrt(sig_pow / (10.0 ** (snr_db / 10.0)))
+    x = x + np.random.default_rng(seed).standard_normal(total) * sigma
+    return (np.rint(x).astype(np.int64) * 256).astype(np.int32).reshape(-1, n)

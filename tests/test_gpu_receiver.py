@@ -1,0 +1,122 @@
+"""T4 (GPU): the receiver's whole main loop (K7) and the sliding-correlation search grid (K4)
+against the oracle's restatement of receiver/Src/main.c:417-580 — decoded UART bytes, lock frame
+and sync offsets are integers and must be exact."""
+import numpy as np
+import pytest
+
+import synth
+import usc
+from oracle import pyref as R
+
+pytestmark = pytest.mark.gpu
+N = 2048
+
+
+@pytest.fixture(scope="module")
+def h():
+    hnd = usc.Handle()
+    yield hnd
+    hnd.close()
+
+
+@pytest.fixture(scope="module")
+def rx():
+    return R.RefReceiver()
+
+
+def _streams():
+    msgs = [b"Hello World!", b"B200", b"\x00\xff\x55\xaa", b"ultrasonic", b"A", b""]
+    cfgs = [(26.0, 0), (26.0, 700), (10.0, 1234), (0.0, 300), (20.0, 2047), (26.0, 1024), (-5.0, 17), (15.0, 1800)]
+    out = []
+    for i, (snr, off) in enumerate(cfgs):
+        out.append(synth.make_stream(msgs[i % len(msgs)], snr_db=snr, start_offset=off, seed=100 + i, nframes=160))
+    return np.stack(out)
+
+
+def test_hello_world_loopback(h, rx):
+    """generator/ChirpGenerator.ipynb frame -> receiver: 'Hello World!' (experiments/EXPERIMENT4.md:29)."""
+    pcm = synth.make_stream(b"Hello World!", snr_db=26.0, nframes=160)[None]
+    uart, res = h.receiver_run_host(pcm)
+    assert uart[0] == b"Hello World!\n"
+    assert res["lock_frame"][0] == 44 and res["lock_position"][0] == 2304      # SURVEY §4 validation (3)
+    assert res["state"][0] == 0
+
+
+def test_receiver_run_matches_oracle(h, rx):
+    pcm = _streams()
+    uart, res = h.receiver_run_host(pcm)
+    decoded = 0
+    for s in range(pcm.shape[0]):
+        want, st = R.receiver_run(rx, pcm[s])
+        assert uart[s] == want, s
+        assert (res["state"][s], res["sync_position"][s], res["lock_frame"][s], res["lock_position"][s]) == \
+               (st.state, st.sync_position, st.lock_frame, st.lock_position), s
+        assert (res["turn"][s], res["sync_cnt"][s], res["frames_seen"][s]) == (st.turn, st.sync_cnt, st.frames_seen)
+        decoded += len(want)
+    assert decoded > 20
+
+
+def test_receiver_noise_only_never_locks(h, rx):
+    rng = np.random.default_rng(3)
+    pcm = (np.rint(rng.standard_normal((4, 100, N)) * 3000).astype(np.int64) * 256).astype(np.int32)
+    uart, res = h.receiver_run_host(pcm)
+    for s in range(4):
+        want, st = R.receiver_run(rx, pcm[s])
+        assert uart[s] == want == b""
+        assert res["lock_frame"][s] == st.lock_frame == -1
+
+
+def test_receiver_many_streams_and_uart_cap(h, rx):
+    """130 streams (more than resident warps per CTA wave, ragged) with a tiny UART capacity: the
+    byte count keeps counting, the stored prefix is exact."""
+    base = synth.make_stream(b"Hello World!", snr_db=20.0, nframes=160)
+    pcm = np.stack([np.roll(base.reshape(-1), 64 * s).reshape(160, N) for s in range(130)])
+    pcm[:, 0, :] = 0                                               # wrapped tail -> silence
+    uart, res = h.receiver_run_host(pcm, uart_cap=5)
+    for s in (0, 1, 37, 129):
+        want, st = R.receiver_run(rx, pcm[s])
+        assert res["nbytes"][s] == len(want)
+        assert uart[s] == want[:5]
+
+
+@pytest.mark.parametrize("sync_add", [1, 2, 4])
+def test_sync_search_matches_oracle(h, rx, sync_add):
+    pcm = _streams()[:3, :60]
+    S, F = pcm.shape[:2]
+    d = h.buffer(pcm)
+    d_m, d_i = h.empty(4 * S * F * 4), h.empty(4 * S * F * 4)
+    h.sync_search(d, usc.PCM_I32, S, F, F * N, sync_add, d_m, d_i)
+    h.sync()
+    mag = d_m.to_numpy(np.float32).reshape(S, F, 4)
+    idx = d_i.to_numpy(np.uint32).reshape(S, F, 4)
+    for s in range(S):
+        wm, wi = R.sync_search(rx, pcm[s], sync_add)
+        assert np.array_equal(idx[s], wi)
+        assert np.array_equal(mag[s].view(np.uint32), wm.view(np.uint32))
+
+
+def test_synchronous_addition_raises_the_peak(h):
+    """SynchronousAddition.ipynb cells 5-6: adding K frame-aligned preamble frames grows the
+    de-chirped peak ~K-fold while noise grows ~sqrt(K).  Needs a transmitter whose symbol period is
+    exactly one frame (N/fs), otherwise successive frames are not phase-coherent."""
+    pcm = synth.make_stream(b"", snr_db=-3.0, lead_in=4, guard=30, nframes=40, seed=5, tx_T=N / 78125.0)[None]
+    d = h.buffer(pcm)
+    peaks = []
+    for K in (1, 2, 4):
+        d_m, d_i = h.empty(4 * 40 * 4), h.empty(4 * 40 * 4)
+        h.sync_search(d, usc.PCM_I32, 1, 40, 40 * N, K, d_m, d_i)
+        h.sync()
+        peaks.append(d_m.to_numpy(np.float32).reshape(40, 4)[8:11].max())
+    assert peaks[1] > 1.6 * peaks[0] and peaks[2] > 2.8 * peaks[0]
+
+
+def test_receiver_argument_errors(h):
+    d = h.empty(2 * N * 4)
+    r = h.empty(64)
+    with pytest.raises(usc.UscError) as e:
+        h.receiver_run(d, usc.PCM_I32, 1, 2, N, None, 0, r)         # stride shorter than the stream
+    assert e.value.code == usc.USC_ERR_ARGUMENT
+    with pytest.raises(usc.UscError):
+        h.receiver_run(d, usc.PCM_I32, 1, 2, 2 * N, None, 0, None)   # nothing to write
+    with pytest.raises(usc.UscError):
+        h.sync_search(d, usc.PCM_I32, 1, 2, 2 * N, 0, r, r)          # sync_add >= 1

@@ -171,3 +171,43 @@ def test_compress_in_place_aliasing_defined():
     buf = x.copy()
     R.lib().ref_arm_rfft_fast_f32(__import__("ctypes").byref(r.S), buf.ctypes.data_as(R.f32p), buf.ctypes.data_as(R.f32p), 0)
     assert np.array_equal(buf, y)
+
+
+# ---- state machine (receiver/Src/main.c:417-580) -------------------------------------------------
+def test_state_machine_decodes_hello_world(rx):
+    """SURVEY §4 validation (3): 40xG lead-in (24-frame mag_stat warm-up), 7xH, L, bits, 12xG at
+    +26 dB decodes b'Hello World!' locking at frame 44 with sync_position 2304."""
+    pcm = synth.make_stream(b"Hello World!", snr_db=26.0)
+    out, st = R.receiver_run(rx, pcm)
+    assert out == b"Hello World!\n"
+    assert (st.lock_frame, st.lock_position, st.state) == (44, 2304, 0)
+
+
+def test_state_machine_warmup_blocks_early_detection(rx):
+    """mag_stat starts at 1e37 (main.c:321-322): nothing can lock before 12 decisions = 24 frames."""
+    pcm = synth.make_stream(b"Hi", snr_db=30.0, lead_in=2)
+    out, st = R.receiver_run(rx, pcm)
+    assert out == b"" and st.lock_frame == -1
+
+
+def test_state_machine_offsets_and_noise(rx):
+    for off in (0, 256, 700, 1999):
+        out, st = R.receiver_run(rx, synth.make_stream(b"OK", snr_db=24.0, start_offset=off))
+        assert out == b"OK\n", off
+        assert st.lock_position % 256 == 0 and 1024 <= st.lock_position <= 1024 + 7 * 256   # N/2 + k*N/8
+    rng = np.random.default_rng(1)
+    noise = (np.rint(rng.standard_normal((80, N)) * 5000).astype(np.int64) * 256).astype(np.int32)
+    out, st = R.receiver_run(rx, noise)
+    assert out == b"" and st.lock_frame == -1
+
+
+def test_sync_search_grid_matches_dsp(rx):
+    """ref_sync_search == dsp(UP) on the 3-frame FIFO at N/2 + turn*N/8 + i*N/4 (main.c:447-451)."""
+    pcm = synth.make_stream(b"x", snr_db=10.0, lead_in=3, nframes=12)
+    mag, idx = R.sync_search(rx, pcm, 1)
+    flat = np.concatenate([np.zeros(2 * N, np.float32), pcm.reshape(-1).astype(np.float32)])
+    for t in (0, 1, 5, 8):
+        fifo = flat[t * N:(t + 3) * N]
+        for i in range(4):
+            h = rx.dsp(fifo, N // 2 + (t & 1) * (N // 8) + i * (N // 4), 1.0, up=True)
+            assert (mag[t, i], idx[t, i]) == (h.mag_max, h.max_idx)

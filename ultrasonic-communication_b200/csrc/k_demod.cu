@@ -21,72 +21,11 @@
 // Both hypotheses (up / down) share the PCM load, the Hann load and the twiddle loads (f32x2 halves).
 #include "usc_kernels.cuh"
 #include "usc_launch.h"
+#include "usc_warpfft.cuh"
 
 namespace usc {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kTileStride = 33;                       // float2 units, 32x33 padded tile
-constexpr int kTileFloat2 = 32 * kTileStride;
-
-__device__ __forceinline__ float pcm_to_float(int32_t v) { return __int2float_rn(v); }
-__device__ __forceinline__ float pcm_to_float(float v) { return v; }
-
-template <typename T> struct vec2;
-template <> struct vec2<float> { using type = float2; };
-template <> struct vec2<int32_t> { using type = int2; };
-
-// pass 1 + twiddle + exchange + pass 2 for one hypothesis; on return lane d0 holds Z[d0 + 32*d1].
-__device__ __forceinline__ void fft1024_warp(float (&re)[32], float (&im)[32], float2* tile,
-                                             const float2* __restrict__ tw_pass, int lane) {
-    fft_base<32>(re, im);
-#pragma unroll
-    for (int d = 0; d < 32; ++d) {
-        float xr = re[d], xi = im[d];
-        if (d != 0) {
-            float2 w = tw_pass[d * 32 + lane];
-            cmul(re[d], im[d], w.x, w.y, xr, xi);
-        }
-        tile[d * kTileStride + lane] = make_float2(xr, xi);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int a = 0; a < 32; ++a) {
-        float2 v = tile[lane * kTileStride + a];
-        re[a] = v.x;
-        im[a] = v.y;
-    }
-    __syncwarp();
-    fft_base<32>(re, im);
-}
-
-// split + magnitude + per-lane running arg-max over this lane's bins k = lane + 32*d1, d1 < NB.
-template <int NB>
-__device__ __forceinline__ void peak_right(const float (&re)[32], const float (&im)[32],
-                                           const float2 (&ws)[NB], int lane, uint32_t bw2,
-                                           float& best, uint32_t& best_idx) {
-    best = -INFINITY;
-    best_idx = 0xffffffffu;
-    const int src = (32 - lane) & 31;
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        // partner Z[1024 - k]: provided by lane `src`; lane 0 serves itself from register 32 - d1
-        float sr = lane == 0 ? re[(32 - d1) & 31] : re[31 - d1];
-        float si = lane == 0 ? im[(32 - d1) & 31] : im[31 - d1];
-        float zcr = __shfl_sync(0xffffffffu, sr, src);
-        float zci = __shfl_sync(0xffffffffu, si, src);
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        float xr, xi;
-        if (d1 == 0 && lane == 0) {          // packed bin 0 = (X[0], X[N/2])  [arm_math.h:2246-2249]
-            xr = __fadd_rn(re[0], im[0]);
-            xi = __fsub_rn(re[0], im[0]);
-        } else {
-            rfft_split(re[d1], im[d1], zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
-        }
-        float m = cmag(xr, xi);
-        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
-    }
-}
-
 // ---- dual-hypothesis kernel: both hypotheses ride in the halves of f32x2 registers ---------------
 // (.x = up-chirp, .y = down-chirp).  The PCM, the Hann table and the inter-pass twiddles are loaded
 // once for both; the two 32-point register FFTs issue as FADD2/FFMA2.
@@ -130,70 +69,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-// Exact arm_max_f32 over sqrt(p_k) without taking 2*NB square roots per frame.  sqrt is monotone,
-// so max_k sqrt(p_k) = sqrt(max_k p_k); the first index attaining it is the first k whose p_k rounds
-// to the same square root.  Any such k other than the first arg-max of p must satisfy
-// p_k >= pmax*(1 - 2^-20) (a gap of two ulps of the root guarantees a smaller rounded root), so the
-// fast path only has to rule that out; otherwise the rare slow path takes every root.
-template <int NB>
-__device__ __noinline__ void peak_slow(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
-    best = -INFINITY;
-    best_idx = 0xffffffffu;
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        float m = __fsqrt_rn(pw[d1]);
-        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
-    }
-    warp_argmax(best, best_idx);
-}
-
-template <int NB, int HALF>
-__device__ __forceinline__ void peak_right2(const float2 (&re)[32], const float2 (&im)[32],
-                                            const float2 (&ws)[NB], int lane, uint32_t bw2,
-                                            float& best, uint32_t& best_idx) {
-    auto half = [](const float2& v) -> float { return HALF == 0 ? v.x : v.y; };
-    const int src = (32 - lane) & 31;
-    float pw[NB];                                      // squared magnitudes of this lane's bins
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        float sr = lane == 0 ? half(re[(32 - d1) & 31]) : half(re[31 - d1]);
-        float si = lane == 0 ? half(im[(32 - d1) & 31]) : half(im[31 - d1]);
-        float zcr = __shfl_sync(0xffffffffu, sr, src);
-        float zci = __shfl_sync(0xffffffffu, si, src);
-        float xr, xi;
-        rfft_split(half(re[d1]), half(im[d1]), zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
-        if (d1 == 0) {                                 // packed bin 0 = (X[0], X[N/2]) on lane 0
-            float dr = __fadd_rn(half(re[0]), half(im[0])), di = __fsub_rn(half(re[0]), half(im[0]));
-            xr = lane == 0 ? dr : xr;
-            xi = lane == 0 ? di : xi;
-        }
-        pw[d1] = __fmaf_rn(xr, xr, __fmul_rn(xi, xi));
-    }
-    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
-    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
-#pragma unroll
-    for (int d1 = 1; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
-    }
-    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
-    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
-    bool risky = false;
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        risky |= (k < kmin) && (pw[d1] >= thr);        // an earlier bin that might round to the same root
-    }
-    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
-        peak_slow<NB>(pw, lane, bw2, best, best_idx);
-    } else {
-        best = __fsqrt_rn(pmax);
-        best_idx = kmin;
-    }
 }
 
 template <typename PCM, int NB>
@@ -271,8 +146,15 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p
         fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
-        peak_right2<NB, 0>(re, im, ws, lane, p.bandwidth2, mu, iu);
-        peak_right2<NB, 1>(re, im, ws, lane, p.bandwidth2, md, id);
+        {
+            float zr[32], zi[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { zr[i] = re[i].x; zi[i] = im[i].x; }
+            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, mu, iu);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { zr[i] = re[i].y; zi[i] = im[i].y; }
+            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, md, id);
+        }
         if (lane == 0) {
             if (p.mag_up) p.mag_up[f] = mu;
             if (p.idx_up) p.idx_up[f] = iu;
@@ -312,8 +194,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_dsp2048(demod_params p
         float mr;
         uint32_t ir;
         fft1024_warp(vr, vi, s_tile[warp], s_tw, lane);
-        peak_right<NB>(vr, vi, ws, lane, p.bandwidth2, mr, ir);
-        warp_argmax(mr, ir);
+        peak_window<NB>(vr, vi, ws, lane, p.bandwidth2, mr, ir);
         if (lane == 0) {
             const float ml = 0.0f;
             const uint32_t il = p.idx_left_zero;

@@ -17,6 +17,7 @@
 using namespace usc;
 
 static_assert(sizeof(usc_history) == sizeof(history_rec), "usc_history layout");
+static_assert(sizeof(usc_rx_result) == sizeof(rx_result_rec), "usc_rx_result layout");
 
 struct usc_handle {
     usc_config cfg;
@@ -482,6 +483,45 @@ int usc_dsp(usc_handle* h, const float* fifo, size_t fifo_stride, const uint32_t
     p.hist = (history_rec*) hist;
     p.updown = updown ? 1 : 0;
     LAUNCHED(h, launch_dsp2048(p, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+static int fill_rx(usc_handle* h, rx_launch* a, const void* pcm, uint32_t pcm_format, uint32_t nstreams,
+                   uint32_t nframes, size_t stream_stride) {
+    if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    if (h->bandwidth2 == 0 || h->bandwidth2 > 160) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 7u) != 0 || (stream_stride & 1u) != 0 || stream_stride < (size_t) nframes * 2048) return USC_ERR_ARGUMENT;
+    memset(a, 0, sizeof *a);
+    a->pcm = pcm; a->pcm_format = pcm_format; a->nstreams = nstreams; a->nframes = nframes; a->stream_stride = stream_stride;
+    a->up = (const float2*) h->d_up; a->down = (const float2*) h->d_down; a->hann = (const float2*) h->d_hann;
+    a->tw_pass = h->d_tw_pass; a->tw_split = h->d_tw_split;
+    a->bandwidth2 = h->bandwidth2; a->snr_threshold = h->cfg.snr_threshold;
+    a->sync_add = 1;
+    return USC_OK;
+}
+
+int usc_receiver_run(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                     size_t stream_stride, uint8_t* uart, uint32_t uart_cap, usc_rx_result* results) {
+    rx_launch a;
+    int rc = fill_rx(h, &a, pcm, pcm_format, nstreams, nframes, stream_stride);
+    if (rc) return rc;
+    if (!results && !uart) return USC_ERR_ARGUMENT;
+    if (!nstreams || !nframes) return USC_OK;
+    a.uart = uart; a.uart_cap = uart_cap; a.results = (rx_result_rec*) results;
+    LAUNCHED(h, launch_receiver_run(a, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                    size_t stream_stride, uint32_t sync_add, float* mag, uint32_t* idx) {
+    rx_launch a;
+    int rc = fill_rx(h, &a, pcm, pcm_format, nstreams, nframes, stream_stride);
+    if (rc) return rc;
+    if (!mag || !idx || sync_add < 1 || sync_add > 64) return USC_ERR_ARGUMENT;
+    if (!nstreams || !nframes) return USC_OK;
+    a.sync_add = sync_add; a.ss_mag = mag; a.ss_idx = idx;
+    LAUNCHED(h, launch_sync_search(a, h->num_sms, h->stream));
     return USC_OK;
 }
 

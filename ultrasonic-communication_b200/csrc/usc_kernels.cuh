@@ -13,6 +13,20 @@ struct history_rec {   // == usc_history (include/usc.h)
     uint32_t rank;
 };
 
+struct rx_result_rec {   // == usc_rx_result (include/usc.h)
+    uint32_t state, sync_position;
+    int32_t lock_frame;
+    uint32_t lock_position, nbytes, frames_seen, turn, sync_cnt;
+};
+
+struct rx_launch {       // arguments of K4 / K7
+    const void* pcm; uint32_t pcm_format; uint32_t nstreams; uint32_t nframes; size_t stream_stride;
+    const float2* up; const float2* down; const float2* hann; const float2* tw_pass; const float2* tw_split;
+    uint32_t bandwidth2; float snr_threshold;
+    uint8_t* uart; uint32_t uart_cap; rx_result_rec* results;
+    uint32_t sync_add; float* ss_mag; uint32_t* ss_idx;
+};
+
 // ------------------------------------------------------------------------------------------------
 // element-wise / reduction operators (one HBM pass each; bound: HBM)
 // ------------------------------------------------------------------------------------------------

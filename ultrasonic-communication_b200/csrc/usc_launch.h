@@ -29,5 +29,7 @@ cudaError_t launch_dsp2048(const demod_params& p, int num_sms, cudaStream_t st);
 cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* window,
                                 const float2* H, const float2* tw_pass, const float2* tw_split, float* out_frames,
                                 float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st);
+cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st);
+cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st);
 cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaStream_t st);
 }  // namespace usc

@@ -1,0 +1,111 @@
+// usc_warpfft.cuh — warp-per-frame building blocks shared by the fused kernels (K1, K4, K7):
+// the 1024-point complex FFT of one warp ([32,32] plan, exchange through a padded shared tile) and
+// the exact windowed peak search on the packed real-FFT bins.
+#pragma once
+#include "usc_arith.cuh"
+
+namespace usc {
+
+constexpr int kTileStride = 33;                       // float2 units, 32x33 padded tile
+constexpr int kTileFloat2 = 32 * kTileStride;
+
+__device__ __forceinline__ float pcm_to_float(int32_t v) { return __int2float_rn(v); }
+__device__ __forceinline__ float pcm_to_float(float v) { return v; }
+
+template <typename T> struct vec2;
+template <> struct vec2<float> { using type = float2; };
+template <> struct vec2<int32_t> { using type = int2; };
+
+// pass 1 + twiddle + exchange + pass 2 for one transform; lane a enters with z[a + 32 b] in
+// register b and leaves (as lane d0) with Z[d0 + 32*d1] in register d1.
+__device__ __forceinline__ void fft1024_warp(float (&re)[32], float (&im)[32], float2* tile,
+                                             const float2* __restrict__ tw_pass, int lane) {
+    fft_base<32>(re, im);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        float xr = re[d], xi = im[d];
+        if (d != 0) {
+            float2 w = tw_pass[d * 32 + lane];
+            cmul(re[d], im[d], w.x, w.y, xr, xi);
+        }
+        tile[d * kTileStride + lane] = make_float2(xr, xi);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 32; ++a) {
+        float2 v = tile[lane * kTileStride + a];
+        re[a] = v.x;
+        im[a] = v.y;
+    }
+    __syncwarp();
+    fft_base<32>(re, im);
+}
+
+// Exact arm_max_f32 over sqrt(p_k) without taking NB square roots per lane.  sqrt is monotone,
+// so max_k sqrt(p_k) = sqrt(max_k p_k); the first index attaining it is the first k whose p_k rounds
+// to the same square root.  Any such k other than the first arg-max of p must satisfy
+// p_k >= pmax*(1 - 2^-20) (a gap of two ulps of the root guarantees a smaller rounded root), so the
+// fast path only has to rule that out; otherwise the rare slow path takes every root.
+template <int NB>
+__device__ __noinline__ void peak_slow(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
+    best = -INFINITY;
+    best_idx = 0xffffffffu;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        float m = __fsqrt_rn(pw[d1]);
+        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
+    }
+    warp_argmax(best, best_idx);
+}
+
+// Real-FFT split of this lane's bins k = lane + 32*d1 (d1 < NB), magnitude and arg-max over
+// [0, bw2): the receiver's "right" window (receiver/Src/main.c:208).  zr/zi: lane d0 holds
+// Z[d0 + 32*d1] in element d1; only elements [0, NB) and [32-NB, 32) are read.
+template <int NB>
+__device__ __forceinline__ void peak_window(const float (&zr)[32], const float (&zi)[32],
+                                            const float2 (&ws)[NB], int lane, uint32_t bw2,
+                                            float& best, uint32_t& best_idx) {
+    const int src = (32 - lane) & 31;
+    float pw[NB];                                      // squared magnitudes of this lane's bins
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        // partner Z[1024 - k] lives in lane (32 - lane) & 31, register 31 - d1 (32 - d1 on lane 0)
+        float sr = lane == 0 ? zr[(32 - d1) & 31] : zr[31 - d1];
+        float si = lane == 0 ? zi[(32 - d1) & 31] : zi[31 - d1];
+        float zcr = __shfl_sync(0xffffffffu, sr, src);
+        float zci = __shfl_sync(0xffffffffu, si, src);
+        float xr, xi;
+        rfft_split(zr[d1], zi[d1], zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
+        if (d1 == 0) {                                 // packed bin 0 = (X[0], X[N/2]) on lane 0
+            float dr = __fadd_rn(zr[0], zi[0]), di = __fsub_rn(zr[0], zi[0]);
+            xr = lane == 0 ? dr : xr;
+            xi = lane == 0 ? di : xi;
+        }
+        pw[d1] = __fmaf_rn(xr, xr, __fmul_rn(xi, xi));
+    }
+    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
+    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
+#pragma unroll
+    for (int d1 = 1; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
+    }
+    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
+    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
+    bool risky = false;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        risky |= (k < kmin) && (pw[d1] >= thr);        // an earlier bin that might round to the same root
+    }
+    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
+        peak_slow<NB>(pw, lane, bw2, best, best_idx);
+    } else {
+        best = __fsqrt_rn(pmax);
+        best_idx = kmin;
+    }
+}
+
+}  // namespace usc

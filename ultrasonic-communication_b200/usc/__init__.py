@@ -32,6 +32,9 @@ history_dtype = np.dtype([("mag_max", "f4"), ("mag_max_left", "f4"), ("mag_max_r
                           ("max_idx", "u4"), ("max_idx_left", "u4"), ("max_idx_right", "u4"),
                           ("mag_mean", "f4"), ("snr", "f4"), ("rank", "u4")])
 
+rx_result_dtype = np.dtype([("state", "u4"), ("sync_position", "u4"), ("lock_frame", "i4"), ("lock_position", "u4"),
+                            ("nbytes", "u4"), ("frames_seen", "u4"), ("turn", "u4"), ("sync_cnt", "u4")])
+
 # every symbol include/usc.h declares (tests/test_abi.py checks the .so exports each one)
 SYMBOLS = [
     "usc_default_config", "usc_create", "usc_destroy", "usc_set_stream", "usc_sync", "usc_error_string",
@@ -40,7 +43,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -257,6 +260,26 @@ class Handle:
             return C.c_void_p(x.data_ptr())
         _ck(load().usc_demod_frames_host(self._h, hp(pcm_host_ptr), C.c_uint32(pcm_format), C.c_size_t(nframes),
                                          hp(mag_up), hp(idx_up), hp(mag_down), hp(idx_down), hp(bit)))
+
+    def receiver_run(self, pcm, pcm_format, nstreams, nframes, stream_stride, uart, uart_cap, results):
+        _ck(load().usc_receiver_run(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                    C.c_size_t(stream_stride), _ptr(uart), C.c_uint32(uart_cap), _ptr(results)))
+
+    def sync_search(self, pcm, pcm_format, nstreams, nframes, stream_stride, sync_add, mag, idx):
+        _ck(load().usc_sync_search(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                   C.c_size_t(stream_stride), C.c_uint32(sync_add), _ptr(mag), _ptr(idx)))
+
+    def receiver_run_host(self, pcm, uart_cap=256):
+        """numpy convenience: pcm [nstreams, nframes, n] int32 -> (list of uart byte strings, results array)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        S, F = pcm.shape[0], pcm.shape[1]
+        d = self.buffer(pcm)
+        d_u, d_r = self.empty(S * uart_cap), self.empty(S * rx_result_dtype.itemsize)
+        self.receiver_run(d, PCM_I32, S, F, F * self.n, d_u, uart_cap, d_r)
+        self.sync()
+        res = d_r.to_numpy(rx_result_dtype)
+        u = d_u.to_numpy(np.uint8).reshape(S, uart_cap)
+        return [bytes(u[s, :min(int(res["nbytes"][s]), uart_cap)]) for s in range(S)], res
 
     def pipeline(self, frames, mags, updown, batch):
         _ck(load().usc_pipeline(self._h, _ptr(frames), _ptr(mags), C.c_int(updown), C.c_uint32(batch)))
