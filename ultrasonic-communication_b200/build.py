@@ -64,6 +64,19 @@ def build(force=False, verbose=False):
     if jobs or force or _stale(LIB, objs):
         _run([NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static", "-lm"],
              os.path.join(OBJ, "link.log"))
+    # CMSIS exact-name host-pointer shim (tests / drop-in demonstration), plain C over the C-ABI
+    shim_src = os.path.join(CSRC, "usc_cmsis_shim.c")
+    shim_lib = os.path.join(HERE, "libusc_cmsis.so")
+    if force or _stale(shim_lib, [shim_src, LIB] + headers):
+        _run(["gcc"] + CC_FLAGS + ["-shared", shim_src, "-o", shim_lib, "-L", HERE, "-lusc", "-Wl,-rpath," + HERE,
+                                  "-Wl,-rpath,$ORIGIN"], os.path.join(OBJ, "shim.log"))
+    # the plain-C host driver links against the C-ABI only (no CUDA headers): proves the boundary
+    host_src = os.path.join(HERE, "host", "receiver_host.c")
+    host_bin = os.path.join(HERE, "host", "receiver_host")
+    if force or _stale(host_bin, [host_src, LIB, os.path.join(os.path.dirname(HERE), "include", "usc.h")]):
+        _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-I", os.path.join(os.path.dirname(HERE), "include"), host_src,
+              "-o", host_bin, "-L", HERE, "-lusc", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."],
+             os.path.join(OBJ, "host.log"))
     return LIB
 
 
