@@ -367,3 +367,41 @@ def sync_search(rxobj, pcm, sync_add=1):
     lib().ref_sync_search_i32(C.byref(rxobj.rx), pcm.ctypes.data_as(i32p), C.c_uint32(nframes), C.c_uint32(sync_add),
                               _fp(mag), _up(idx))
     return mag, idx
+
+
+# ---- complex-FFT variant (experiments/synchronization) ---------------------------------------------
+class SyncReceiver(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("fs", C.c_float), ("bandwidth", C.c_uint32), ("bandwidth2", C.c_uint32),
+                ("idx_left_zero", C.c_uint32), ("hann", f32p), ("up_chirp", f32p), ("down_chirp", f32p),
+                ("C", CfftInstance)]
+
+
+class RefSyncReceiver:
+    def __init__(self, n=2048, fs=78125.0, f0=16000.0, f1=19000.0, sweep_T=0.0205):
+        self.rx = SyncReceiver()
+        if lib().ref_sync_receiver_init(C.byref(self.rx), C.c_uint32(n), C.c_float(fs), C.c_float(f0), C.c_float(f1),
+                                        C.c_float(sweep_T)) != 0:
+            raise RuntimeError("ref_sync_receiver_init failed")
+        self.n = n
+
+    def table(self, name):
+        ln = self.n if name == "hann" else 2 * self.n
+        return np.ctypeslib.as_array(getattr(self.rx, name), shape=(ln,)).copy()
+
+    def pipeline(self, cframe, up):
+        s = f32(cframe).copy()
+        lib().ref_sync_pipeline(C.byref(self.rx), _fp(s), C.c_int(1 if up else 0))
+        return s[:self.n].copy()
+
+    def dsp(self, fifo, sync_position, mag_mean, up):
+        fifo = f32(fifo)
+        h = History()
+        lib().ref_sync_dsp(C.byref(self.rx), _fp(fifo), C.c_uint32(sync_position), C.byref(h), C.c_float(mag_mean),
+                           C.c_int(1 if up else 0))
+        return h
+
+    def __del__(self):
+        try:
+            lib().ref_sync_receiver_free(C.byref(self.rx))
+        except Exception:
+            pass

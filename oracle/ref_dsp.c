@@ -503,6 +503,65 @@ void ref_demod_frames_i32(const ref_receiver *rx, const int32_t *pcm, size_t nfr
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* complex-FFT variant — experiments/synchronization/Src/main.c:135-213, Src/chirp.c:16-57      */
+/* ------------------------------------------------------------------------------------------ */
+int ref_sync_receiver_init(ref_sync_receiver *rx, uint32_t n, float fs, float f0, float f1, float sweep_T) {
+    memset(rx, 0, sizeof *rx);
+    rx->n = n; rx->fs = fs;
+    rx->bandwidth = (uint32_t) ((float) ((unsigned long) (int) (f1 - f0) * (unsigned long) n) / fs);   /* main.c:353 */
+    rx->bandwidth2 = rx->bandwidth * 2;
+    rx->idx_left_zero = n - rx->bandwidth2;
+    rx->hann = (float *) malloc(sizeof(float) * n);
+    rx->up_chirp = (float *) malloc(sizeof(float) * 2 * n);
+    rx->down_chirp = (float *) malloc(sizeof(float) * 2 * n);
+    if (!rx->hann || !rx->up_chirp || !rx->down_chirp) return -1;
+    if (ref_arm_cfft_init_f32(&rx->C, n) != REF_MATH_SUCCESS) return -1;
+    ref_chirp_params cp = { n, fs, f0, f1, sweep_T, -90.0f };
+    ref_generate_ref_chirp(REF_CHIRP_S, &cp, 1, rx->up_chirp);                     /* chirp.c:47 */
+    ref_generate_ref_chirp(REF_CHIRP_S, &cp, 0, rx->down_chirp);                   /* chirp.c:48 */
+    ref_hann_window(rx->hann, n, REF_HANN_PERIODIC);
+    return 0;
+}
+void ref_sync_receiver_free(ref_sync_receiver *rx) {
+    free(rx->hann); free(rx->up_chirp); free(rx->down_chirp);
+    ref_arm_cfft_free(&rx->C);
+    memset(rx, 0, sizeof *rx);
+}
+/* main.c:144-158 */
+void ref_sync_pipeline(const ref_sync_receiver *rx, float32_t *pframe, int up) {
+    uint32_t n = rx->n;
+    ref_arm_cmplx_mult_cmplx_f32(pframe, up ? rx->up_chirp : rx->down_chirp, pframe, n);   /* chirp.c:51-57 */
+    ref_arm_cmplx_mult_real_f32(pframe, rx->hann, pframe, n);                      /* main.c:150 */
+    ref_arm_cfft_f32(&rx->C, pframe, 0, 1);                                        /* main.c:153 */
+    float *mag = (float *) malloc(sizeof(float) * n);
+    ref_arm_cmplx_mag_f32(pframe, mag, n);                                         /* main.c:156 */
+    memcpy(pframe, mag, sizeof(float) * n);
+    free(mag);
+}
+/* main.c:161-213 */
+void ref_sync_dsp(const ref_sync_receiver *rx, const float32_t *fifo, uint32_t sync_position, ref_history *h,
+                  float mag_mean, int up) {
+    uint32_t n = rx->n;
+    float *tf = (float *) malloc(sizeof(float) * 2 * n);
+    for (uint32_t i = 0; i < n; ++i) { tf[2 * i] = fifo[sync_position + i]; tf[2 * i + 1] = 0.0f; }   /* main.c:175-180 */
+    ref_sync_pipeline(rx, tf, up);
+    float ml, mr, mm;
+    uint32_t il, ir, im;
+    ref_arm_max_f32(&tf[rx->idx_left_zero], rx->bandwidth2, &ml, &il);             /* main.c:188 */
+    ref_arm_max_f32(&tf[0], rx->bandwidth2, &mr, &ir);                             /* main.c:190 */
+    if (ml > mr) { mm = ml; im = rx->idx_left_zero + il; } else { mm = mr; im = ir; }
+    ref_receiver tmp; memset(&tmp, 0, sizeof tmp); tmp.n = n; tmp.fs = rx->fs;     /* idx2freq is identical (main.c:135-141) */
+    h->mag_max = mm; h->mag_max_left = ml; h->mag_max_right = mr;
+    h->max_idx = im; h->max_idx_left = rx->idx_left_zero + il; h->max_idx_right = ir;
+    h->max_freq = ref_idx2freq(&tmp, im);
+    h->max_freq_left = ref_idx2freq(&tmp, rx->idx_left_zero + il);
+    h->max_freq_right = ref_idx2freq(&tmp, ir);
+    h->mag_mean = mag_mean;
+    h->snr = (mm - mag_mean) / mag_mean;
+    free(tf);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* receiver state machine — receiver/Src/main.c:233-273, 311-339, 417-580                      */
 /* ------------------------------------------------------------------------------------------ */
 void ref_rx_state_init(ref_rx_state *st, const ref_receiver *rx) {

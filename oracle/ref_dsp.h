@@ -156,6 +156,24 @@ void ref_demod_frames_f32(const ref_receiver *rx, const float *pcm, size_t nfram
                           float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
                           int nthreads);
 
+/* ---- complex-FFT variant (experiments/synchronization/Src/main.c:135-213, chirp.c:16-57) ---- */
+typedef struct {
+    uint32_t n;
+    float fs;
+    uint32_t bandwidth, bandwidth2, idx_left_zero;
+    float *hann;                    /* periodic Hann (main.c:77) */
+    float *up_chirp, *down_chirp;   /* variant S: 2n floats, interleaved (cos, sin) */
+    ref_cfft_instance_f32 C;        /* arm_cfft_sR_f32_len2048 */
+} ref_sync_receiver;
+
+int ref_sync_receiver_init(ref_sync_receiver *rx, uint32_t n, float fs, float f0, float f1, float sweep_T);
+void ref_sync_receiver_free(ref_sync_receiver *rx);
+/* main.c:144-158: pframe holds n complex (2n floats) in, n magnitudes out in pframe[0..n) */
+void ref_sync_pipeline(const ref_sync_receiver *rx, float32_t *pframe, int up);
+/* main.c:161-213: real PCM -> complex buffer, pipeline, left/right windowed arg-max, SNR */
+void ref_sync_dsp(const ref_sync_receiver *rx, const float32_t *fifo, uint32_t sync_position, ref_history *h,
+                  float mag_mean, int up);
+
 /* ---- receiver state machine (receiver/Src/main.c:417-580) ---- */
 enum { REF_IDLE = 0, REF_SYNCHRONIZING = 1, REF_SYNCHRONIZED = 2, REF_DATA_RECEIVING = 3 };   /* main.c:108-111 */
 

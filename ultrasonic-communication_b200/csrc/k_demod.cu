@@ -124,26 +124,7 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p
             mbar_expect_tx(bar, 8192);
             bulk_g2s(xstage, pcm + (f + nwarps) * 2048, 8192, bar);
         }
-        fft_base2<32>(re, im);
-#pragma unroll
-        for (int d = 0; d < 32; ++d) {
-            float4 v = make_float4(re[d].x, re[d].y, im[d].x, im[d].y);
-            if (d != 0) {
-                float2 w = s_tw[d * 32 + lane];
-                cmul(re[d].x, im[d].x, w.x, w.y, v.x, v.z);
-                cmul(re[d].y, im[d].y, w.x, w.y, v.y, v.w);
-            }
-            tile[d * 32 + (lane ^ d)] = v;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int a = 0; a < 32; ++a) {
-            float4 v = tile[lane * 32 + (a ^ lane)];
-            re[a] = make_float2(v.x, v.y);
-            im[a] = make_float2(v.z, v.w);
-        }
-        __syncwarp();
-        fft_base2<32>(re, im);
+        fft1024_warp2(re, im, tile, s_tw, lane);
         float mu, md;
         uint32_t iu, id;
         {

@@ -389,6 +389,7 @@ static void fill_common(const usc_handle* h, demod_params* p) {
     p->hann = (const float2*) h->d_hann;
     p->tw_pass = h->d_tw_pass;
     p->tw_split = h->d_tw_split;
+    { auto it = h->tw_cache.find(2048); p->tw_master = it == h->tw_cache.end() ? nullptr : it->second; }
     p->bandwidth2 = h->bandwidth2;
     p->idx_left_zero = h->idx_left_zero;
     p->fs_int = (int32_t) h->cfg.fs;
@@ -470,7 +471,18 @@ int usc_demod_frames_host(usc_handle* h, const void* pcm_host, uint32_t pcm_form
 int usc_dsp(usc_handle* h, const float* fifo, size_t fifo_stride, const uint32_t* sync_position,
             const float* mag_mean, int updown, usc_history* hist, uint32_t batch) {
     if (!h || !fifo || !sync_position || !mag_mean || !hist) return USC_ERR_ARGUMENT;
-    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048) return USC_ERR_ARGUMENT;
+    if (h->cfg.chirp_variant == USC_CHIRP_S) {
+        /* complex-FFT variant (experiments/synchronization/Src/main.c:161-213): both windows are real */
+        if (h->bandwidth2 == 0 || h->bandwidth2 > 192) return USC_ERR_ARGUMENT;
+        if (!batch) return USC_OK;
+        demod_params q;
+        fill_common(h, &q);
+        q.pcm = fifo; q.nframes = batch; q.fifo_stride = fifo_stride; q.sync_position = sync_position;
+        q.mag_mean = mag_mean; q.hist = (history_rec*) hist; q.updown = updown ? 1 : 0;
+        LAUNCHED(h, launch_dsp2048c(q, h->num_sms, h->stream));
+        return USC_OK;
+    }
     if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
     if (!batch) return USC_OK;
     demod_params p;

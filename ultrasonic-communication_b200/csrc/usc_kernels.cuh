@@ -70,6 +70,7 @@ struct demod_params {
     const float2* hann;
     const float2* tw_pass;      // [d][a] layout: W_1024^(a*d), 32x32 float2
     const float2* tw_split;     // (cos, sin)(2*pi*k/2048), k < 1024
+    const float2* tw_master;    // (cos, -sin)(2*pi*j/2048), j < 2048
     uint32_t bandwidth2;        // arg-max window [0, bandwidth2)
     float* mag_up; uint32_t* idx_up; float* mag_down; uint32_t* idx_down; uint8_t* bit;
     // dsp() mode

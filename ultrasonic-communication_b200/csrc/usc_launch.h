@@ -26,6 +26,7 @@ cudaError_t launch_fft_generic(int mode, const fft_plan_dev& plan, const float* 
 cudaError_t fft_generic_prepare();   // opt in to large dynamic shared memory (once)
 cudaError_t launch_demod2048(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
 cudaError_t launch_dsp2048(const demod_params& p, int num_sms, cudaStream_t st);
+cudaError_t launch_dsp2048c(const demod_params& p, int num_sms, cudaStream_t st);
 cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* window,
                                 const float2* H, const float2* tw_pass, const float2* tw_split, float* out_frames,
                                 float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st);

@@ -41,22 +41,72 @@ __device__ __forceinline__ void fft1024_warp(float (&re)[32], float (&im)[32], f
     fft_base<32>(re, im);
 }
 
-// Exact arm_max_f32 over sqrt(p_k) without taking NB square roots per lane.  sqrt is monotone,
+// Packed twin: two transforms side by side in the halves of f32x2 registers (K1: up/down hypothesis
+// of one frame; K3: the even/odd halves of a 2048-point complex FFT).  tile: XOR-swizzled 32x32
+// float4 (16 KB), conflict-free for the 128-bit stores and loads.
+__device__ __forceinline__ void fft1024_warp2(float2 (&re)[32], float2 (&im)[32], float4* tile,
+                                              const float2* __restrict__ tw_pass, int lane) {
+    fft_base2<32>(re, im);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        float4 v = make_float4(re[d].x, re[d].y, im[d].x, im[d].y);
+        if (d != 0) {
+            float2 w = tw_pass[d * 32 + lane];
+            cmul(re[d].x, im[d].x, w.x, w.y, v.x, v.z);
+            cmul(re[d].y, im[d].y, w.x, w.y, v.y, v.w);
+        }
+        tile[d * 32 + (lane ^ d)] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 32; ++a) {
+        float4 v = tile[lane * 32 + (a ^ lane)];
+        re[a] = make_float2(v.x, v.y);
+        im[a] = make_float2(v.z, v.w);
+    }
+    __syncwarp();
+    fft_base2<32>(re, im);
+}
+
+// Exact arm_max_f32 over sqrt(p_k) without taking a square root per candidate.  sqrt is monotone,
 // so max_k sqrt(p_k) = sqrt(max_k p_k); the first index attaining it is the first k whose p_k rounds
 // to the same square root.  Any such k other than the first arg-max of p must satisfy
 // p_k >= pmax*(1 - 2^-20) (a gap of two ulps of the root guarantees a smaller rounded root), so the
 // fast path only has to rule that out; otherwise the rare slow path takes every root.
-template <int NB>
-__device__ __noinline__ void peak_slow(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
+// Each lane passes NC candidates (squared magnitude p >= 0, index k, validity) in ascending k.
+template <int NC>
+__device__ __noinline__ void argmax_slow(const float (&p)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
+                                         float& best, uint32_t& best_idx) {
     best = -INFINITY;
     best_idx = 0xffffffffu;
 #pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        float m = __fsqrt_rn(pw[d1]);
-        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
+    for (int c = 0; c < NC; ++c) {
+        float m = __fsqrt_rn(p[c]);
+        if (ok[c] && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k[c]; }
     }
     warp_argmax(best, best_idx);
+}
+
+template <int NC>
+__device__ __forceinline__ void argmax_exact(const float (&p)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
+                                             float& best, uint32_t& best_idx) {
+    float pb = ok[0] ? p[0] : 0.0f;
+    uint32_t kb = ok[0] ? k[0] : 0xffffffffu;
+#pragma unroll
+    for (int c = 1; c < NC; ++c)
+        if (ok[c] && (p[c] > pb || kb == 0xffffffffu)) { pb = p[c]; kb = k[c]; }
+    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
+    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
+    bool risky = false;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) risky |= ok[c] && (k[c] < kmin) && (p[c] >= thr);
+    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
+        argmax_slow<NC>(p, k, ok, best, best_idx);
+    } else {
+        best = __fsqrt_rn(pmax);
+        best_idx = kmin;
+    }
 }
 
 // Real-FFT split of this lane's bins k = lane + 32*d1 (d1 < NB), magnitude and arg-max over
@@ -84,28 +134,14 @@ __device__ __forceinline__ void peak_window(const float (&zr)[32], const float (
         }
         pw[d1] = __fmaf_rn(xr, xr, __fmul_rn(xi, xi));
     }
-    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
-    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
-#pragma unroll
-    for (int d1 = 1; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
-    }
-    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
-    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
-    bool risky = false;
+    uint32_t kk[NB];
+    bool ok[NB];
 #pragma unroll
     for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        risky |= (k < kmin) && (pw[d1] >= thr);        // an earlier bin that might round to the same root
+        kk[d1] = (uint32_t) lane + 32u * d1;
+        ok[d1] = kk[d1] < bw2;
     }
-    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
-        peak_slow<NB>(pw, lane, bw2, best, best_idx);
-    } else {
-        best = __fsqrt_rn(pmax);
-        best_idx = kmin;
-    }
+    argmax_exact<NB>(pw, kk, ok, best, best_idx);
 }
 
 }  // namespace usc
