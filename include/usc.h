@@ -52,7 +52,7 @@ extern "C" {
 /* Compile-time constants of the reference gathered in one POD (receiver/Inc/main.h:97-98,
  * receiver/Inc/chirp.h:16-19, receiver/Src/dfsdm.c:59-61,69). */
 typedef struct usc_config {
-    uint32_t n;             /* NN / PCM_SAMPLES: samples per frame, power of two, 32..4096        */
+    uint32_t n;             /* NN / PCM_SAMPLES: samples per frame, power of two, 32..65536       */
     float fs;               /* sampling rate as the firmware computes it (78125.0f)               */
     float f0, f1;           /* sweep range F0,F1 (receiver) or F1,F2 (experiments)                */
     float sweep_T;          /* TIME_FRAME (0.0205f) for variants R,S; T,F use n/fs                */
@@ -131,12 +131,13 @@ int usc_arm_max_f32_batch(usc_handle *h, const float *src, size_t stride_src, ui
 /* arm_mean_f32, arm_math.h:6192: sequential sum / block_size */
 int usc_arm_mean_f32_batch(usc_handle *h, const float *src, size_t stride_src, uint32_t block_size,
                            float *result, uint32_t batch);
-/* arm_rfft_fast_f32, arm_math.h:2246-2249.  fft_len real points per vector (32..8192, power of two);
+/* arm_rfft_fast_f32, arm_math.h:2246-2249.  fft_len real points per vector (power of two; 32..65536 forward, ..16384 inverse);
  * in == out allowed (hazard H2 is defined away: the result is always the mathematically right one). */
 int usc_arm_rfft_fast_f32_batch(usc_handle *h, uint32_t fft_len, const float *in, float *out, uint8_t ifft_flag,
                                 uint32_t batch);
 /* arm_cfft_f32, arm_math.h:2149-2153 with bitReverseFlag = 1: in place, fft_len complex points
- * (16..4096); forward unscaled, inverse scaled by 1/fft_len. */
+ * (16..32768 forward, ..8192 inverse); forward unscaled, inverse scaled by 1/fft_len.  Lengths
+ * beyond CMSIS's 4096 (arm_const_structs.h:49-57) exist for the long-frame sweep (BASELINE config 5). */
 int usc_arm_cfft_f32_batch(usc_handle *h, uint32_t fft_len, float *data, uint8_t ifft_flag, uint32_t batch);
 /* arm_fir_f32, arm_math.h:1194-1214.  coeffs (host pointer) in CMSIS time-reversed order; state:
  * batch x (num_taps-1) floats on the device carrying the filter history between calls (zero it to

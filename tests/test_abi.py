@@ -59,7 +59,7 @@ def test_create_argument_errors_mirror_arm_status():
     """arm_rfft_fast_init_f32 returns ARM_MATH_ARGUMENT_ERROR (-1) for unsupported lengths
     (arm_math.h:373-382, 2242-2244); usc_create does the same before touching CUDA."""
     L = usc.load()
-    for bad_n in (0, 31, 1000, 8192 * 2):
+    for bad_n in (0, 31, 1000, 65536 * 2):
         cfg = usc.default_config(n=bad_n)
         hnd = C.c_void_p()
         assert L.usc_create(C.byref(cfg), 0, C.byref(hnd)) == usc.USC_ERR_ARGUMENT

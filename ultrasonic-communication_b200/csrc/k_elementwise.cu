@@ -139,6 +139,16 @@ __global__ void k_fir(const float* __restrict__ coeffs, uint32_t taps, float* st
     }
 }
 
+// symbol decision of the receiver (receiver/Src/main.c:523): down only if strictly greater
+__global__ void k_decide(const float* __restrict__ mu, const float* __restrict__ md, uint8_t* __restrict__ bit, size_t n) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        bit[i] = md[i] > mu[i] ? 0 : 1;
+}
+cudaError_t launch_decide(const float* mu, const float* md, uint8_t* bit, size_t n, cudaStream_t st) {
+    k_decide<<<blocks_for(n, 256), 256, 0, st>>>(mu, md, bit, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st) {
     k_i32_to_f32<<<blocks_for(count / 4 + 1, 256), 256, 0, st>>>(src, dst, count);
     return cudaGetLastError();

@@ -136,8 +136,102 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_generic(fft_plan_dev plan, 
     }
 }
 
+// ---- transforms too large for one CTA's shared memory (complex length 16384 / 32768) ---------------
+// Level 0 of the canonical plan runs in global memory (one thread per (vector, a): gather B elements
+// at stride A — coalesced across a —, base FFT, twiddle, scatter), the B sub-transforms of length
+// A <= 1024... 8192 then run through k_fft_generic in place, and a last pass undoes the digit
+// reversal of level 0 (k = B c + d) and, for real input, applies the split.
+template <int B>
+__global__ void k_fft_level0(fft_plan_dev plan, const float2* __restrict__ in, float2* __restrict__ work, uint32_t batch) {
+    const uint32_t A = plan.n / B;
+    const size_t items = (size_t) batch * A;
+    const uint32_t tw_step = plan.tw_n / plan.n;
+    for (size_t it = (size_t) blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (size_t) gridDim.x * blockDim.x) {
+        const size_t v = it / A;
+        const uint32_t a = (uint32_t) (it - v * A);
+        const float2* src = in + v * plan.n + a;
+        float2* dst = work + v * plan.n + a;
+        float re[B], im[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            float2 x = src[(size_t) A * b];
+            re[b] = x.x;
+            im[b] = x.y;
+        }
+        fft_base<B>(re, im);
+#pragma unroll
+        for (int d = 0; d < B; ++d) {
+            float xr = re[d], xi = im[d];
+            if (d != 0) {
+                float2 w = plan.tw[(size_t) a * d * tw_step];
+                cmul(re[d], im[d], w.x, w.y, xr, xi);
+            }
+            dst[(size_t) A * d] = make_float2(xr, xi);
+        }
+    }
+}
+
+// work holds, per vector, B sub-spectra of length A in natural order: Z[B c + d] = work[d A + c]
+template <int MODE>
+__global__ void k_fft_final(fft_plan_dev plan, const float2* __restrict__ work, float2* __restrict__ out, uint32_t batch) {
+    const uint32_t n = plan.n, B = plan.rad[0], A = n / B;
+    const size_t total = (size_t) batch * n;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const size_t v = i / n;
+        const uint32_t k = (uint32_t) (i - v * n);
+        const float2* w = work + v * n;
+        const float2 zk = w[(size_t) (k % B) * A + k / B];
+        if (MODE == FFT_C2C_FWD) {
+            out[i] = zk;
+        } else {   // FFT_R2C
+            float xr, xi;
+            if (k == 0) {
+                xr = __fadd_rn(zk.x, zk.y);
+                xi = __fsub_rn(zk.x, zk.y);
+            } else {
+                const uint32_t kc = n - k;
+                const float2 zc = w[(size_t) (kc % B) * A + kc / B];
+                const float2 t = plan.tw[k];
+                rfft_split(zk.x, zk.y, zc.x, zc.y, t.x, -t.y, xr, xi);
+            }
+            out[i] = make_float2(xr, xi);
+        }
+    }
+}
+
+cudaError_t launch_fft_large(int mode, const fft_plan_dev& plan, const float* in, float* out, float* work,
+                             uint32_t batch, cudaStream_t st) {
+    if (mode != FFT_C2C_FWD && mode != FFT_R2C) return cudaErrorInvalidValue;
+    const uint32_t B = plan.rad[0], A = plan.n / B;
+    const size_t items = (size_t) batch * A;
+    int grid = (int) ((items + 255) / 256 < 148u * 16u ? (items + 255) / 256 : 148u * 16u);
+    if (grid < 1) grid = 1;
+    const float2* src = reinterpret_cast<const float2*>(in);
+    float2* w = reinterpret_cast<float2*>(work);
+    switch (B) {
+        case 2: k_fft_level0<2><<<grid, 256, 0, st>>>(plan, src, w, batch); break;
+        case 4: k_fft_level0<4><<<grid, 256, 0, st>>>(plan, src, w, batch); break;
+        case 8: k_fft_level0<8><<<grid, 256, 0, st>>>(plan, src, w, batch); break;
+        case 16: k_fft_level0<16><<<grid, 256, 0, st>>>(plan, src, w, batch); break;
+        default: k_fft_level0<32><<<grid, 256, 0, st>>>(plan, src, w, batch); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    fft_plan_dev sub = plan;                      // B*batch sub-transforms of length A, same master table
+    sub.n = A;
+    sub.nrad = plan.nrad - 1;
+    for (uint32_t i = 0; i + 1 < plan.nrad; ++i) sub.rad[i] = plan.rad[i + 1];
+    e = launch_fft_generic(FFT_C2C_FWD, sub, work, work, batch * B, st);
+    if (e != cudaSuccess) return e;
+    const size_t total = (size_t) batch * plan.n;
+    int g2 = (int) ((total + 255) / 256 < 148u * 32u ? (total + 255) / 256 : 148u * 32u);
+    if (mode == FFT_R2C) k_fft_final<FFT_R2C><<<g2, 256, 0, st>>>(plan, w, reinterpret_cast<float2*>(out), batch);
+    else k_fft_final<FFT_C2C_FWD><<<g2, 256, 0, st>>>(plan, w, reinterpret_cast<float2*>(out), batch);
+    return cudaGetLastError();
+}
+
 cudaError_t fft_generic_prepare() {
-    const int max_smem = 200 * 1024;
+    const int max_smem = 128 * 1024;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2C_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
     if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2C_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
@@ -149,7 +243,7 @@ cudaError_t fft_generic_prepare() {
 cudaError_t launch_fft_generic(int mode, const fft_plan_dev& plan, const float* in, float* out, uint32_t batch,
                                cudaStream_t st) {
     const size_t smem = sizeof(float2) * 2 * (size_t) plan.n;
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 128 * 1024) return cudaErrorInvalidValue;
     int grid = batch < 148u * 16u ? (int) batch : 148 * 16;
     if (grid < 1) grid = 1;
     switch (mode) {

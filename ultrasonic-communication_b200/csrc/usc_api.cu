@@ -29,6 +29,8 @@ struct usc_handle {
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
     float2 *d_tw_pass, *d_tw_split;
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
+    float* d_work;                                    // grow-on-demand scratch (large FFTs, generic demod)
+    size_t work_bytes;
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
     std::map<uint32_t, std::vector<float>> tw_host;
     uint64_t launches;
@@ -72,6 +74,18 @@ static int get_twiddles(usc_handle* h, uint32_t len, float2** out) {
     return USC_OK;
 }
 
+// scratch owned by the handle; grows (with a stream sync) only when a call needs more than before
+static int reserve_work(usc_handle* h, size_t bytes) {
+    if (h->work_bytes >= bytes) return USC_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_work);
+    h->d_work = nullptr;
+    h->work_bytes = 0;
+    CK(cudaMalloc((void**) &h->d_work, bytes));
+    h->work_bytes = bytes;
+    return USC_OK;
+}
+
 static int make_plan(usc_handle* h, uint32_t n_complex, uint32_t tw_len, fft_plan_dev* plan) {
     plan->n = n_complex;
     plan->nrad = usc_host_radices(n_complex, plan->rad);
@@ -109,7 +123,7 @@ const char* usc_error_string(int code) {
 int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     if (!cfg || !out) return USC_ERR_ARGUMENT;
     *out = nullptr;
-    if (!pow2(cfg->n) || cfg->n < 32 || cfg->n > 4096) return USC_ERR_ARGUMENT;
+    if (!pow2(cfg->n) || cfg->n < 32 || cfg->n > 65536) return USC_ERR_ARGUMENT;
     if (!(cfg->fs > 0.0f) || cfg->chirp_variant > USC_CHIRP_F || cfg->window > USC_HANN_SYMMETRIC) return USC_ERR_ARGUMENT;
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));                    // no device -> error: there is no CPU fallback
@@ -124,6 +138,8 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->d_hann = h->d_up = h->d_down = h->d_ud = h->d_H_up = h->d_H_down = nullptr;
     h->d_tw_pass = h->d_tw_split = nullptr;
     h->d_fir_coeffs = nullptr;
+    h->d_work = nullptr;
+    h->work_bytes = 0;
     h->lane_frames = 0;
     for (int i = 0; i < 3; ++i) { h->lane_stream[i] = nullptr; h->lane_in[i] = nullptr; h->lane_mu[i] = h->lane_md[i] = nullptr; h->lane_iu[i] = h->lane_id[i] = nullptr; h->lane_bit[i] = nullptr; }
     cudaDeviceProp prop;
@@ -200,7 +216,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
 void usc_destroy(usc_handle* h) {
     if (!h) return;
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
-    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs);
+    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) {
         cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
@@ -352,20 +368,34 @@ int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in
                                 uint32_t batch) {
     /* supported lengths: CMSIS's 32..4096 (arm_math.h:2242-2244 returns ARM_MATH_ARGUMENT_ERROR
      * otherwise) extended to 8192 while one transform fits shared memory */
-    if (!h || !in || !out || !pow2(fft_len) || fft_len < 32 || fft_len > 8192) return USC_ERR_ARGUMENT;
+    if (!h || !in || !out || !pow2(fft_len) || fft_len < 32 || fft_len > 65536) return USC_ERR_ARGUMENT;
+    if (ifft_flag && fft_len > 16384) return USC_ERR_ARGUMENT;      /* inverse: shared-memory sizes only */
     if (!batch) return USC_OK;
     fft_plan_dev plan;
     int rc = make_plan(h, fft_len / 2, fft_len, &plan);
     if (rc) return rc;
+    if (fft_len > 16384) {                                          /* 32768 / 65536: level 0 in global memory */
+        if ((rc = reserve_work(h, (size_t) batch * fft_len * sizeof(float)))) return rc;
+        CK(launch_fft_large(FFT_R2C, plan, in, out, h->d_work, batch, h->stream));
+        h->launches += 3;
+        return USC_OK;
+    }
     LAUNCHED(h, launch_fft_generic(ifft_flag ? FFT_C2R : FFT_R2C, plan, in, out, batch, h->stream));
     return USC_OK;
 }
 int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t ifft_flag, uint32_t batch) {
-    if (!h || !data || !pow2(fft_len) || fft_len < 16 || fft_len > 4096) return USC_ERR_ARGUMENT;
+    if (!h || !data || !pow2(fft_len) || fft_len < 16 || fft_len > 32768) return USC_ERR_ARGUMENT;
+    if (ifft_flag && fft_len > 8192) return USC_ERR_ARGUMENT;
     if (!batch) return USC_OK;
     fft_plan_dev plan;
     int rc = make_plan(h, fft_len, fft_len, &plan);
     if (rc) return rc;
+    if (fft_len > 8192) {
+        if ((rc = reserve_work(h, (size_t) batch * fft_len * 2 * sizeof(float)))) return rc;
+        CK(launch_fft_large(FFT_C2C_FWD, plan, data, data, h->d_work, batch, h->stream));
+        h->launches += 3;
+        return USC_OK;
+    }
     LAUNCHED(h, launch_fft_generic(ifft_flag ? FFT_C2C_INV : FFT_C2C_FWD, plan, data, data, batch, h->stream));
     return USC_OK;
 }
@@ -395,13 +425,52 @@ static void fill_common(const usc_handle* h, demod_params* p) {
     p->fs_int = (int32_t) h->cfg.fs;
 }
 
+// Any frame length (32..65536): the same chain operator by operator on handle-owned scratch
+// (cast, de-chirp, window, RFFT, magnitude, arg-max), once per hypothesis.  Used for the long-frame
+// sweep (BASELINE config 5) and for geometries the fused 2048-point kernel does not cover.
+static int demod_generic(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, float* mag_up,
+                         uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
+    const uint32_t n = h->cfg.n;
+    if (nframes > 0xffffffffu || h->bandwidth2 == 0 || h->bandwidth2 > n / 2) return USC_ERR_ARGUMENT;
+    const uint32_t B = (uint32_t) nframes;
+    const size_t W = nframes * n;
+    int rc = reserve_work(h, (3 * W + 2 * nframes) * sizeof(float));
+    if (rc) return rc;
+    float *fA = h->d_work, *fB = fA + W, *fC = fB + W, *tmp_mag = fC + W;
+    const float* x = (const float*) pcm;
+    if (pcm_format == USC_PCM_I32) {
+        LAUNCHED(h, launch_i32_to_f32((const int32_t*) pcm, fC, W, h->stream));
+        x = fC;
+    }
+    fft_plan_dev plan;
+    if ((rc = make_plan(h, n / 2, n, &plan))) return rc;
+    float* mags[2] = {mag_up ? mag_up : tmp_mag, mag_down ? mag_down : tmp_mag + nframes};
+    uint32_t* idxs[2] = {idx_up, idx_down};
+    const float* chirps[2] = {h->d_up, h->d_down};
+    for (int hyp = 0; hyp < 2; ++hyp) {
+        LAUNCHED(h, launch_mult(x, n, chirps[hyp], 0, fA, n, n, B, h->stream));
+        LAUNCHED(h, launch_mult(fA, n, h->d_hann, 0, fA, n, n, B, h->stream));
+        if (n > 16384) {
+            CK(launch_fft_large(FFT_R2C, plan, fA, fA, fB, B, h->stream));
+            h->launches += 3;
+        } else {
+            LAUNCHED(h, launch_fft_generic(FFT_R2C, plan, fA, fA, B, h->stream));
+        }
+        LAUNCHED(h, launch_cmag(fA, n, fB, n / 2, n / 2, B, h->stream));
+        LAUNCHED(h, launch_max(fB, n / 2, h->bandwidth2, mags[hyp], idxs[hyp], B, h->stream));
+    }
+    if (bit) LAUNCHED(h, launch_decide(mags[0], mags[1], bit, nframes, h->stream));
+    return USC_OK;
+}
+
 int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, float* mag_up,
                      uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
     if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
-    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
-    if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
+    if (h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;     /* frames are fetched by 16-byte-aligned bulk copies */
     if (!nframes) return USC_OK;
+    if (h->cfg.n != 2048 || h->bandwidth2 == 0 || h->bandwidth2 > 512)
+        return demod_generic(h, pcm, pcm_format, nframes, mag_up, idx_up, mag_down, idx_down, bit);
     demod_params p;
     fill_common(h, &p);
     p.pcm = pcm;

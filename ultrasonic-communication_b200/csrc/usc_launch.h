@@ -5,6 +5,7 @@
 
 namespace usc {
 cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st);
+cudaError_t launch_decide(const float* mu, const float* md, uint8_t* bit, size_t n, cudaStream_t st);
 cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
                         uint32_t len, uint32_t batch, cudaStream_t st);
 cudaError_t launch_scale(const float* src, float scale, float* dst, size_t total, cudaStream_t st);
@@ -23,6 +24,8 @@ cudaError_t launch_fir(const float* coeffs_dev, uint32_t taps, float* state, con
 // mode: fft_mode.  in/out: batch vectors of 2n floats (C2C) or 2n floats real (R2C/C2R, n = N/2).
 cudaError_t launch_fft_generic(int mode, const fft_plan_dev& plan, const float* in, float* out, uint32_t batch,
                                cudaStream_t st);
+cudaError_t launch_fft_large(int mode, const fft_plan_dev& plan, const float* in, float* out, float* work,
+                             uint32_t batch, cudaStream_t st);
 cudaError_t fft_generic_prepare();   // opt in to large dynamic shared memory (once)
 cudaError_t launch_demod2048(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
 cudaError_t launch_dsp2048(const demod_params& p, int num_sms, cudaStream_t st);
