@@ -195,6 +195,20 @@ int usc_receiver_run(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32
  * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */
 int usc_sync_search(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                     size_t stream_stride, uint32_t sync_add, float *mag, uint32_t *idx);
+/* K5.  I/Q baseband path (experiments/iq_modulation/Src/iq_modem.c:34-66, Src/main.c:117-134, with the
+ * semantics of simulation/IQ_modulation.ipynb cells 16-31 and BASELINE config 3's decimation by 2).
+ * usc_iq_init builds the carrier tables (init_iq_modem), the baseband reference chirp -bw/2..+bw/2
+ * at fs/2 and the n/2-point Hann, and stores the FIR taps (CMSIS time-reversed order, e.g. the 27
+ * taps of iq_modem.c:18).  usc_iq_demod, per frame of every stream: x*cos, x*sin -> FIR on each (state
+ * carried from the previous frame of the stream, zero at its start) -> every 2nd sample -> R = I + jQ
+ * -> up: R x conj(chirp), down: R x chirp -> Hann -> n/2-point complex FFT -> magnitude -> arg-max
+ * over window_bins bins on either side of DC (left wins only if strictly greater).  Outputs have
+ * nstreams*nframes entries (any may be NULL); bit = !(mag_down > mag_up). */
+int usc_iq_init(usc_handle *h, float carrier_hz, float bw_hz, const float *fir_coeffs_host, uint32_t num_taps,
+                uint32_t window_bins);
+int usc_iq_demod(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                 size_t stream_stride, float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
+                 uint8_t *bit);
 /* K2.  compress_chirp() of experiments/chirp_compression_time_domain/Src/chirp.c:78-83 followed
  * by the signed arm_max_f32 over all n lags (.../Src/main.c:189) on `nframes` frames; the handle
  * must be created with chirp_variant T and the symmetric window.  out_frames (nframes*n floats)

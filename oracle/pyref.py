@@ -405,3 +405,39 @@ class RefSyncReceiver:
             lib().ref_sync_receiver_free(C.byref(self.rx))
         except Exception:
             pass
+
+
+# ---- I/Q baseband path ---------------------------------------------------------------------------
+class Iq(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("fs", C.c_float), ("window_bins", C.c_uint32), ("carrier_cos", f32p),
+                ("carrier_sin", f32p), ("chirp", f32p), ("chirp_conj", f32p), ("hann", f32p), ("taps", C.c_float * 64),
+                ("num_taps", C.c_uint32), ("C", CfftInstance)]
+
+
+class RefIq:
+    def __init__(self, taps_reversed, n=2048, fs=78125.0, carrier=18000.0, bw=3000.0, sweep_T=0.0205, window_bins=32):
+        self.q = Iq()
+        t = f32(taps_reversed)
+        if lib().ref_iq_init(C.byref(self.q), C.c_uint32(n), C.c_float(fs), C.c_float(carrier), C.c_float(bw),
+                             C.c_float(sweep_T), _fp(t), C.c_uint32(t.size), C.c_uint32(window_bins)) != 0:
+            raise RuntimeError("ref_iq_init failed")
+        self.n = n
+
+    def table(self, name):
+        ln = {"carrier_cos": self.n, "carrier_sin": self.n, "chirp": self.n, "chirp_conj": self.n, "hann": self.n // 2}[name]
+        return np.ctypeslib.as_array(getattr(self.q, name), shape=(ln,)).copy()
+
+    def demod(self, pcm):
+        """pcm: [nframes, n] int32 of ONE stream -> (mag_up, idx_up, mag_down, idx_down)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        nf = pcm.size // self.n
+        mu, md = np.empty(nf, np.float32), np.empty(nf, np.float32)
+        iu, idn = np.empty(nf, np.uint32), np.empty(nf, np.uint32)
+        lib().ref_iq_demod_i32(C.byref(self.q), pcm.ctypes.data_as(i32p), C.c_uint32(nf), _fp(mu), _up(iu), _fp(md), _up(idn))
+        return mu, iu, md, idn
+
+    def __del__(self):
+        try:
+            lib().ref_iq_free(C.byref(self.q))
+        except Exception:
+            pass

@@ -562,6 +562,73 @@ void ref_sync_dsp(const ref_sync_receiver *rx, const float32_t *fifo, uint32_t s
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* I/Q baseband path — experiments/iq_modulation/Src/iq_modem.c, IQ_modulation.ipynb           */
+/* ------------------------------------------------------------------------------------------ */
+int ref_iq_init(ref_iq *q, uint32_t n, float fs, float carrier, float bw, float sweep_T, const float *taps,
+                uint32_t num_taps, uint32_t window_bins) {
+    memset(q, 0, sizeof *q);
+    if (num_taps < 1 || num_taps > 64) return -1;
+    q->n = n; q->fs = fs; q->window_bins = window_bins; q->num_taps = num_taps;
+    memcpy(q->taps, taps, sizeof(float) * num_taps);
+    q->carrier_cos = (float *) malloc(sizeof(float) * n);
+    q->carrier_sin = (float *) malloc(sizeof(float) * n);
+    q->chirp = (float *) malloc(sizeof(float) * n);
+    q->chirp_conj = (float *) malloc(sizeof(float) * n);
+    q->hann = (float *) malloc(sizeof(float) * (n / 2));
+    if (ref_arm_cfft_init_f32(&q->C, n / 2) != REF_MATH_SUCCESS) return -1;
+    /* iq_modem.c:34-46 */
+    float delta_t = sweep_T / (sweep_T * fs), t = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float theta = (float) (360.0 * (double) carrier * (double) t);
+        ref_arm_sin_cos_f32(theta, &q->carrier_sin[i], &q->carrier_cos[i]);
+        t = t + delta_t;
+    }
+    /* baseband chirp -bw/2 .. +bw/2 over one frame at the decimated rate (IQ_modulation.ipynb cells 2-3,10) */
+    ref_chirp_params cp = { n / 2, fs / 2.0f, -bw / 2.0f, bw / 2.0f, (float) n / fs, 0.0f };
+    ref_generate_ref_chirp(REF_CHIRP_S, &cp, 1, q->chirp);
+    for (uint32_t m = 0; m < n / 2; ++m) { q->chirp_conj[2 * m] = q->chirp[2 * m]; q->chirp_conj[2 * m + 1] = -q->chirp[2 * m + 1]; }
+    ref_hann_window(q->hann, n / 2, REF_HANN_PERIODIC);
+    return 0;
+}
+void ref_iq_free(ref_iq *q) {
+    free(q->carrier_cos); free(q->carrier_sin); free(q->chirp); free(q->chirp_conj); free(q->hann);
+    ref_arm_cfft_free(&q->C);
+    memset(q, 0, sizeof *q);
+}
+void ref_iq_demod_i32(const ref_iq *q, const int32_t *pcm, uint32_t nframes, float *mag_up, uint32_t *idx_up,
+                      float *mag_down, uint32_t *idx_down) {
+    const uint32_t n = q->n, h = n / 2, W = q->window_bins;
+    float *x = (float *) malloc(sizeof(float) * n), *I = (float *) malloc(sizeof(float) * n), *Q = (float *) malloc(sizeof(float) * n);
+    float *R = (float *) malloc(sizeof(float) * n), *P = (float *) malloc(sizeof(float) * n), *mag = (float *) malloc(sizeof(float) * h);
+    float *si = (float *) malloc(sizeof(float) * (q->num_taps + n)), *sq = (float *) malloc(sizeof(float) * (q->num_taps + n));
+    ref_fir_instance_f32 SI, SQ;
+    ref_arm_fir_init_f32(&SI, (uint16_t) q->num_taps, q->taps, si, n);             /* iq_modem.c:48-49 */
+    ref_arm_fir_init_f32(&SQ, (uint16_t) q->num_taps, q->taps, sq, n);
+    for (uint32_t t = 0; t < nframes; ++t) {
+        for (uint32_t i = 0; i < n; ++i) x[i] = (float) pcm[(size_t) t * n + i];
+        ref_arm_mult_f32(x, q->carrier_sin, Q, n);                                 /* iq_modem.c:59 */
+        ref_arm_mult_f32(x, q->carrier_cos, I, n);                                 /* iq_modem.c:60 */
+        ref_arm_fir_f32(&SI, I, I, n);                                             /* iq_modem.c:63 */
+        ref_arm_fir_f32(&SQ, Q, Q, n);                                             /* iq_modem.c:64 */
+        for (uint32_t m = 0; m < h; ++m) { R[2 * m] = I[2 * m]; R[2 * m + 1] = Q[2 * m]; }   /* R = I + jQ, every 2nd sample */
+        for (int hyp = 0; hyp < 2; ++hyp) {
+            /* up: R x conj(chirp) (notebook cell 29); down: R x chirp (cell 30) */
+            ref_arm_cmplx_mult_cmplx_f32(R, hyp == 0 ? q->chirp_conj : q->chirp, P, h);
+            ref_arm_cmplx_mult_real_f32(P, q->hann, P, h);
+            ref_arm_cfft_f32(&q->C, P, 0, 1);
+            ref_arm_cmplx_mag_f32(P, mag, h);
+            float ml, mr; uint32_t il, ir;
+            ref_arm_max_f32(&mag[h - W], W, &ml, &il);
+            ref_arm_max_f32(&mag[0], W, &mr, &ir);
+            float mm = mr; uint32_t im = ir;
+            if (ml > mr) { mm = ml; im = h - W + il; }
+            if (hyp == 0) { mag_up[t] = mm; idx_up[t] = im; } else { mag_down[t] = mm; idx_down[t] = im; }
+        }
+    }
+    free(x); free(I); free(Q); free(R); free(P); free(mag); free(si); free(sq);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* receiver state machine — receiver/Src/main.c:233-273, 311-339, 417-580                      */
 /* ------------------------------------------------------------------------------------------ */
 void ref_rx_state_init(ref_rx_state *st, const ref_receiver *rx) {

@@ -174,6 +174,28 @@ void ref_sync_pipeline(const ref_sync_receiver *rx, float32_t *pframe, int up);
 void ref_sync_dsp(const ref_sync_receiver *rx, const float32_t *fifo, uint32_t sync_position, ref_history *h,
                   float mag_mean, int up);
 
+/* ---- I/Q baseband path (experiments/iq_modulation/Src/iq_modem.c:16-66, main.c:117-134; semantics of
+ * simulation/IQ_modulation.ipynb cells 16-31; BASELINE config 3: decimate by 2 -> 1024-pt complex FFT) ---- */
+typedef struct {
+    uint32_t n;                 /* real samples per frame (2048) */
+    float fs;
+    uint32_t window_bins;       /* search window [0,W) and [n/2-W, n/2) around DC */
+    float *carrier_cos, *carrier_sin;     /* n each, iq_modem.c:34-46 */
+    float *chirp, *chirp_conj;  /* n/2 complex each: baseband chirp at fs/2 and its conjugate */
+    float *hann;                /* periodic Hann, n/2 */
+    float taps[64];             /* CMSIS order (time-reversed) */
+    uint32_t num_taps;
+    ref_cfft_instance_f32 C;    /* arm_cfft_sR_f32_len1024 */
+} ref_iq;
+
+int ref_iq_init(ref_iq *q, uint32_t n, float fs, float carrier, float bw, float sweep_T, const float *taps,
+                uint32_t num_taps, uint32_t window_bins);
+void ref_iq_free(ref_iq *q);
+/* One stream of nframes frames (FIR state carried frame to frame, zero at the start).
+ * Outputs nframes each. */
+void ref_iq_demod_i32(const ref_iq *q, const int32_t *pcm, uint32_t nframes, float *mag_up, uint32_t *idx_up,
+                      float *mag_down, uint32_t *idx_down);
+
 /* ---- receiver state machine (receiver/Src/main.c:417-580) ---- */
 enum { REF_IDLE = 0, REF_SYNCHRONIZING = 1, REF_SYNCHRONIZED = 2, REF_DATA_RECEIVING = 3 };   /* main.c:108-111 */
 

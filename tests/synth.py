@@ -88,3 +88,21 @@ def make_stream(message, snr_db=26.0, amp=2.0e4, start_offset=0, seed=11, lead_i
     sigma = np.sqrt(sig_pow / (10.0 ** (snr_db / 10.0)))
     x = x + np.random.default_rng(seed).standard_normal(total) * sigma
     return (np.rint(x).astype(np.int64) * 256).astype(np.int32).reshape(-1, n)
+
+
+# ---- I/Q path input (simulation/IQ_modulation.ipynb cell 4: chirp_x_carrier) -----------------------
+def make_iq_stream(nframes, carrier=18000.0, bw=3000.0, snr_db=10.0, amp=2.0e4, seed_bits=5, seed_noise=6, fs=FS, n=N):
+    """Frames of A*cos(2*pi*(fc - fb(t))*t), fb the baseband up/down chirp -bw/2..+bw/2 over one frame
+    (bit 1 = up), plus Gaussian noise, int32 x256.  -> (pcm [nframes, n], bits)."""
+    t = np.arange(n) / fs
+    T = n / fs
+    k = bw / T
+    waves = []
+    for updown in ("up", "down"):
+        f = -bw / 2 + k * t / 2.0 if updown == "up" else bw / 2 - k * t / 2.0
+        waves.append(np.cos(2.0 * np.pi * (carrier - f) * t))
+    bits = np.random.default_rng(seed_bits).integers(0, 2, nframes, dtype=np.uint8)
+    sigma = np.sqrt(0.5 * amp * amp / (10.0 ** (snr_db / 10.0)))
+    x = np.where(bits[:, None] == 1, waves[0][None, :], waves[1][None, :]) * amp
+    x = x + np.random.default_rng(seed_noise).standard_normal((nframes, n)) * sigma
+    return (np.rint(x).astype(np.int64) * 256).astype(np.int32), bits

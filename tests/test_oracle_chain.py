@@ -211,3 +211,28 @@ def test_sync_search_grid_matches_dsp(rx):
         for i in range(4):
             h = rx.dsp(fifo, N // 2 + (t & 1) * (N // 8) + i * (N // 4), 1.0, up=True)
             assert (mag[t, i], idx[t, i]) == (h.mag_max, h.max_idx)
+
+
+# ---- I/Q baseband path (config 3) -----------------------------------------------------------------
+def test_iq_chain_decides_symbols_and_peaks_at_dc(fir_taps):
+    """IQ_modulation.ipynb cells 28-31: the right hypothesis collapses to ~0 Hz, the wrong one to a
+    double peak near +-1.6 kHz (outside the +-32-bin window), so up/down is decided by the larger peak."""
+    q = R.RefIq(fir_taps.astype(np.float32)[::-1].copy())
+    pcm, bits = synth.make_iq_stream(24, snr_db=10.0)
+    mu, iu, md, idn = q.demod(pcm)
+    assert np.array_equal((~(md > mu)).astype(np.uint8), bits)
+    right = np.where(bits == 1, iu, idn)
+    assert np.all((right <= 5) | (right >= 1019))
+    ratio = np.where(bits == 1, mu / md, md / mu)
+    assert ratio.min() > 3.0
+
+
+def test_iq_fir_state_carries_across_frames(fir_taps):
+    """arm_fir_f32 keeps numTaps-1 samples of history between calls (arm_math.h:1194-1214): frame t's
+    result depends on the tail of frame t-1."""
+    q = R.RefIq(fir_taps.astype(np.float32)[::-1].copy())
+    pcm, _ = synth.make_iq_stream(2, snr_db=20.0)
+    both = q.demod(pcm)
+    alone = q.demod(pcm[1:2])
+    assert both[0][1] != alone[0][0]
+    assert abs(both[0][1] - alone[0][0]) < 0.05 * both[0][1]

@@ -29,6 +29,10 @@ struct usc_handle {
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
     float2 *d_tw_pass, *d_tw_split;
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
+    // I/Q path (usc_iq_init): carrier tables, baseband chirp and its conjugate, half-length Hann, FIR taps
+    std::vector<float> iq_cos, iq_sin, iq_chirp, iq_hann;
+    float *d_iq_cos, *d_iq_sin, *d_iq_chirp, *d_iq_conj, *d_iq_hann, *d_iq_taps;
+    uint32_t iq_ntaps, iq_window;
     float* d_work;                                    // grow-on-demand scratch (large FFTs, generic demod)
     size_t work_bytes;
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
@@ -140,6 +144,8 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->d_fir_coeffs = nullptr;
     h->d_work = nullptr;
     h->work_bytes = 0;
+    h->d_iq_cos = h->d_iq_sin = h->d_iq_chirp = h->d_iq_conj = h->d_iq_hann = h->d_iq_taps = nullptr;
+    h->iq_ntaps = h->iq_window = 0;
     h->lane_frames = 0;
     for (int i = 0; i < 3; ++i) { h->lane_stream[i] = nullptr; h->lane_in[i] = nullptr; h->lane_mu[i] = h->lane_md[i] = nullptr; h->lane_iu[i] = h->lane_id[i] = nullptr; h->lane_bit[i] = nullptr; }
     cudaDeviceProp prop;
@@ -217,6 +223,7 @@ void usc_destroy(usc_handle* h) {
     if (!h) return;
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
     cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
+    cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) {
         cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
@@ -603,6 +610,75 @@ int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_
     if (!nstreams || !nframes) return USC_OK;
     a.sync_add = sync_add; a.ss_mag = mag; a.ss_idx = idx;
     LAUNCHED(h, launch_sync_search(a, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_iq_init(usc_handle* h, float carrier_hz, float bw_hz, const float* fir_coeffs_host, uint32_t num_taps,
+                uint32_t window_bins) {
+    if (!h || !fir_coeffs_host || num_taps < 1 || num_taps > 64) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n, half = n / 2;
+    if (n < 64 || n > 4096 || window_bins < 1 || window_bins > half / 2) return USC_ERR_ARGUMENT;
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
+    h->d_iq_cos = h->d_iq_sin = h->d_iq_chirp = h->d_iq_conj = h->d_iq_hann = h->d_iq_taps = nullptr;
+    h->iq_cos.resize(n); h->iq_sin.resize(n); h->iq_chirp.resize(n); h->iq_hann.resize(half);
+    /* carrier: experiments/iq_modulation/Src/iq_modem.c:34-46 (degrees, float-accumulated t) */
+    const float sweep_T = h->cfg.sweep_T, fs = h->cfg.fs;
+    float dt = sweep_T / (sweep_T * fs), t = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float theta = (float) (360.0 * (double) carrier_hz * (double) t);
+        usc_host_arm_sin_cos_f32(theta, &h->iq_sin[i], &h->iq_cos[i]);
+        t = t + dt;
+    }
+    /* baseband chirp -bw/2..+bw/2 over one frame at fs/2 (simulation/IQ_modulation.ipynb cells 2-3, 10) */
+    usc_host_ref_chirp(USC_CHIRP_S, half, fs / 2.0f, -bw_hz / 2.0f, bw_hz / 2.0f, (float) n / fs, 0.0f, 1, h->iq_chirp.data());
+    std::vector<float> conj(n);
+    for (uint32_t m = 0; m < half; ++m) { conj[2 * m] = h->iq_chirp[2 * m]; conj[2 * m + 1] = -h->iq_chirp[2 * m + 1]; }
+    usc_host_hann(h->iq_hann.data(), half, USC_HANN_PERIODIC);
+    int rc;
+    if ((rc = upload(h->iq_cos.data(), n * 4, (void**) &h->d_iq_cos))) return rc;
+    if ((rc = upload(h->iq_sin.data(), n * 4, (void**) &h->d_iq_sin))) return rc;
+    if ((rc = upload(h->iq_chirp.data(), n * 4, (void**) &h->d_iq_chirp))) return rc;
+    if ((rc = upload(conj.data(), n * 4, (void**) &h->d_iq_conj))) return rc;
+    if ((rc = upload(h->iq_hann.data(), half * 4, (void**) &h->d_iq_hann))) return rc;
+    if ((rc = upload(fir_coeffs_host, num_taps * 4, (void**) &h->d_iq_taps))) return rc;
+    h->iq_ntaps = num_taps;
+    h->iq_window = window_bins;
+    return USC_OK;
+}
+
+int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                 size_t stream_stride, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                 uint8_t* bit) {
+    if (!h || !pcm || pcm_format > USC_PCM_I32 || !h->d_iq_taps) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n, half = n / 2, W = h->iq_window;
+    if (stream_stride < (size_t) nframes * n) return USC_ERR_ARGUMENT;
+    const size_t F = (size_t) nstreams * nframes;
+    if (!F) return USC_OK;
+    if (F > 0xffffffffu) return USC_ERR_ARGUMENT;
+    /* scratch: R (F*n) | P (F*n) | mags (F*half) | 4 result vectors + 2 spare magnitude vectors */
+    int rc = reserve_work(h, (2 * F * n + F * half + 8 * F) * sizeof(float));
+    if (rc) return rc;
+    float *R = h->d_work, *P = R + F * n, *M = P + F * n;
+    float *mr = M + F * half, *ml = mr + F, *spare_u = ml + F, *spare_d = spare_u + F;
+    uint32_t *ir = (uint32_t*) (spare_d + F), *il = ir + F;
+    fft_plan_dev plan;
+    if ((rc = make_plan(h, half, half, &plan))) return rc;
+    LAUNCHED(h, launch_iq_frontend(pcm, pcm_format, nstreams, nframes, stream_stride, n, h->d_iq_cos, h->d_iq_sin,
+                                   h->d_iq_taps, h->iq_ntaps, R, h->stream));
+    float* mags[2] = {mag_up ? mag_up : spare_u, mag_down ? mag_down : spare_d};
+    uint32_t* idxs[2] = {idx_up, idx_down};
+    const float* refs[2] = {h->d_iq_conj, h->d_iq_chirp};       /* up: R x conj(chirp); down: R x chirp */
+    for (int hyp = 0; hyp < 2; ++hyp) {
+        LAUNCHED(h, launch_cmul(R, n, refs[hyp], 0, P, n, half, (uint32_t) F, h->stream));
+        LAUNCHED(h, launch_cmul_real(P, n, h->d_iq_hann, 0, P, n, half, (uint32_t) F, h->stream));
+        LAUNCHED(h, launch_fft_generic(FFT_C2C_FWD, plan, P, P, (uint32_t) F, h->stream));
+        LAUNCHED(h, launch_cmag(P, n, M, half, half, (uint32_t) F, h->stream));
+        LAUNCHED(h, launch_max(M, half, W, mr, ir, (uint32_t) F, h->stream));
+        LAUNCHED(h, launch_max(M + (half - W), half, W, ml, il, (uint32_t) F, h->stream));
+        LAUNCHED(h, launch_iq_pick(mr, ir, ml, il, half - W, mags[hyp], idxs[hyp], F, h->stream));
+    }
+    if (bit) LAUNCHED(h, launch_decide(mags[0], mags[1], bit, F, h->stream));
     return USC_OK;
 }
 

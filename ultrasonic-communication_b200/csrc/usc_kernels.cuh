@@ -13,6 +13,9 @@ struct history_rec {   // == usc_history (include/usc.h)
     uint32_t rank;
 };
 
+__device__ __forceinline__ float pcm_cast(int32_t v) { return __int2float_rn(v); }
+__device__ __forceinline__ float pcm_cast(float v) { return v; }
+
 struct rx_result_rec {   // == usc_rx_result (include/usc.h)
     uint32_t state, sync_position;
     int32_t lock_frame;

@@ -35,5 +35,10 @@ cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nfr
                                 float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st);
 cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st);
 cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st);
+cudaError_t launch_iq_frontend(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                               size_t stream_stride, uint32_t n, const float* car_cos, const float* car_sin,
+                               const float* taps, uint32_t ntaps, float* out, cudaStream_t st);
+cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t left0,
+                           float* mag, uint32_t* idx, size_t count, cudaStream_t st);
 cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaStream_t st);
 }  // namespace usc

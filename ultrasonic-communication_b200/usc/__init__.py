@@ -43,7 +43,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -280,6 +280,17 @@ class Handle:
         res = d_r.to_numpy(rx_result_dtype)
         u = d_u.to_numpy(np.uint8).reshape(S, uart_cap)
         return [bytes(u[s, :min(int(res["nbytes"][s]), uart_cap)]) for s in range(S)], res
+
+    def iq_init(self, carrier_hz, bw_hz, fir_coeffs, window_bins=32):
+        c = np.ascontiguousarray(fir_coeffs, np.float32)
+        _ck(load().usc_iq_init(self._h, C.c_float(carrier_hz), C.c_float(bw_hz), c.ctypes.data_as(C.POINTER(C.c_float)),
+                               C.c_uint32(c.size), C.c_uint32(window_bins)))
+
+    def iq_demod(self, pcm, pcm_format, nstreams, nframes, stream_stride, mag_up=None, idx_up=None, mag_down=None,
+                 idx_down=None, bit=None):
+        _ck(load().usc_iq_demod(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                C.c_size_t(stream_stride), _ptr(mag_up), _ptr(idx_up), _ptr(mag_down), _ptr(idx_down),
+                                _ptr(bit)))
 
     def pipeline(self, frames, mags, updown, batch):
         _ck(load().usc_pipeline(self._h, _ptr(frames), _ptr(mags), C.c_int(updown), C.c_uint32(batch)))
