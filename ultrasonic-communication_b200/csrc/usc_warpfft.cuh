@@ -75,7 +75,7 @@ __device__ __forceinline__ void fft1024_warp2(float2 (&re)[32], float2 (&im)[32]
 // fast path only has to rule that out; otherwise the rare slow path takes every root.
 // Each lane passes NC candidates (squared magnitude p >= 0, index k, validity) in ascending k.
 template <int NC>
-__device__ __noinline__ void argmax_slow(const float (&p)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
+__device__ __forceinline__ void argmax_slow(const float (&p)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
                                          float& best, uint32_t& best_idx) {
     best = -INFINITY;
     best_idx = 0xffffffffu;
@@ -109,6 +109,20 @@ __device__ __forceinline__ void argmax_exact(const float (&p)[NC], const uint32_
     }
 }
 
+// rare path of peak_window: every root, then the first-occurrence arg-max
+template <int NB>
+__device__ __noinline__ void peak_slow(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
+    best = -INFINITY;
+    best_idx = 0xffffffffu;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        float m = __fsqrt_rn(pw[d1]);
+        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
+    }
+    warp_argmax(best, best_idx);
+}
+
 // Real-FFT split of this lane's bins k = lane + 32*d1 (d1 < NB), magnitude and arg-max over
 // [0, bw2): the receiver's "right" window (receiver/Src/main.c:208).  zr/zi: lane d0 holds
 // Z[d0 + 32*d1] in element d1; only elements [0, NB) and [32-NB, 32) are read.
@@ -134,14 +148,28 @@ __device__ __forceinline__ void peak_window(const float (&zr)[32], const float (
         }
         pw[d1] = __fmaf_rn(xr, xr, __fmul_rn(xi, xi));
     }
-    uint32_t kk[NB];
-    bool ok[NB];
+    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
+    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
+#pragma unroll
+    for (int d1 = 1; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
+    }
+    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
+    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
+    bool risky = false;
 #pragma unroll
     for (int d1 = 0; d1 < NB; ++d1) {
-        kk[d1] = (uint32_t) lane + 32u * d1;
-        ok[d1] = kk[d1] < bw2;
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        risky |= (k < kmin) && (pw[d1] >= thr);        // an earlier bin that might round to the same root
     }
-    argmax_exact<NB>(pw, kk, ok, best, best_idx);
+    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
+        peak_slow<NB>(pw, lane, bw2, best, best_idx);
+    } else {
+        best = __fsqrt_rn(pmax);
+        best_idx = kmin;
+    }
 }
 
 }  // namespace usc

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libusc.so")
+LIB_PATH = os.environ.get("USC_LIB") or os.path.join(_PKG, "libusc.so")   # USC_LIB: A/B a build of the same ABI
 
 USC_OK = 0
 USC_ERR_ARGUMENT = -1
@@ -60,8 +60,9 @@ def load():
         L.usc_error_string.restype = C.c_char_p
         L.usc_launch_count.restype = C.c_uint64
         L.usc_launch_count.argtypes = [C.c_void_p]
-        for name in SYMBOLS:
-            getattr(L, name)
+        if not os.environ.get("USC_LIB"):          # an A/B build may predate newer entry points
+            for name in SYMBOLS:
+                getattr(L, name)
         _lib = L
     return _lib
 
