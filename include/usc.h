@@ -150,7 +150,9 @@ int usc_arm_fir_f32_batch(usc_handle *h, const float *coeffs_host, uint32_t num_
  * frame): de-chirp x Hann x RFFT x |.| x arg-max over bins [0, bandwidth2) in ONE pass over the
  * PCM.  pcm: nframes*n samples of pcm_format.  Outputs (device, nframes each; any may be NULL):
  * peak magnitude and bin per hypothesis, and the symbol decision bit = !(mag_down > mag_up)
- * (receiver/Src/main.c:523: down wins only if strictly greater). */
+ * (receiver/Src/main.c:523: down wins only if strictly greater).  When only one hypothesis' outputs
+ * are requested (the other pair and `bit` NULL) only that hypothesis is computed — dsp(.., UP) or
+ * dsp(.., DOWN) alone — at half the cost per frame. */
 int usc_demod_frames(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, float *mag_up,
                      uint32_t *idx_up, float *mag_down, uint32_t *idx_down, uint8_t *bit);
 /* The same chain on HOST buffers (the call a firmware-style host makes once per capture): frames are

@@ -27,6 +27,19 @@ def timeit(fn, reps=30):
     return e0.elapsed_time(e1) / reps
 ms = timeit(lambda: h.demod_frames(big, usc.PCM_I32, F, o[0], o[1], o[2], o[3], b))
 print("K1 dual   : %.3f ms  %.1f Msym/s  %.0f GB/s (%.1f%% of 6552)" % (ms, F / ms / 1e3, F * 8208 / ms / 1e6, F * 8208 / ms / 1e6 / 65.52))
+# single hypothesis (pair-mode kernel)
+for nf in (1, 2, 7, 2048):
+    d = h.buffer(pcm[:nf]); a, b2 = h.empty(4 * nf), h.empty(4 * nf)
+    ok = True
+    for up in (True, False):
+        if up: h.demod_frames(d, usc.PCM_I32, nf, mag_up=a, idx_up=b2)
+        else: h.demod_frames(d, usc.PCM_I32, nf, mag_down=a, idx_down=b2)
+        h.sync()
+        wm, wi = (want[0], want[1]) if up else (want[2], want[3])
+        ok &= np.array_equal(a.to_numpy(np.float32).view(np.uint32), wm[:nf].view(np.uint32)) and np.array_equal(b2.to_numpy(np.uint32), wi[:nf])
+    print("K1 single parity nf=%d:" % nf, ok)
+ms = timeit(lambda: h.demod_frames(big, usc.PCM_I32, F, o[0], o[1]))
+print("K1 single : %.3f ms  %.1f Mframes/s  %.0f GB/s (%.1f%% of 6552)" % (ms, F / ms / 1e3, F * 8200 / ms / 1e6, F * 8200 / ms / 1e6 / 65.52))
 if "--compress" in sys.argv:
     hc = usc.Handle(usc.default_config(fs=100000.0, f0=17000.0, f1=18000.0, chirp_variant=usc.CHIRP_T, window=usc.HANN_SYMMETRIC))
     hc.set_stream(st.cuda_stream)

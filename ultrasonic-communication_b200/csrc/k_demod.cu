@@ -146,6 +146,127 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p
     }
 }
 
+// ---- single-hypothesis kernel: TWO FRAMES ride in the halves of the f32x2 registers ----------------
+// dsp() for one hypothesis (receiver/Src/main.c:183-215) on aligned frames.  Same packed core as the
+// dual kernel, but .x / .y carry frames 2i and 2i+1, so one chirp table serves both and each frame
+// costs half of a dual-hypothesis frame: this is the fused "window + FFT + compression + peak" kernel
+// whose time per 8 KB frame is closest to the HBM roofline.  The 16 KB of PCM for a warp's next
+// frame pair arrive by one TMA bulk copy; to stay inside 227 KB of shared memory with 8 warps the
+// exchange goes through an 8 KB tile in two rounds (one per half).
+constexpr int kPairSmemTabs = 3 * 8192;               // twiddles | chirp | Hann
+constexpr int kPairWarpBytes = kTileFloat2 * 8 + 16384;   // padded 32x33 float2 tile + 2-frame PCM stage
+constexpr int kPairSmemBar = kPairSmemTabs + kDualWarps * kPairWarpBytes;
+constexpr int kPairSmemTotal = kPairSmemBar + kDualWarps * 8;
+
+template <typename PCM, int NB>
+__global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_params p) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(s_raw);
+    float2* s_chirp = reinterpret_cast<float2*>(s_raw + 8192);
+    float2* s_hann = reinterpret_cast<float2*>(s_raw + 16384);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = s_raw + kPairSmemTabs + warp * kPairWarpBytes;
+    using V2 = typename vec2<PCM>::type;
+    V2* xstage = reinterpret_cast<V2*>(wbase);                       // 2 x 1024 pairs (16-byte aligned)
+    float2* tile = reinterpret_cast<float2*>(wbase + 16384);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + kPairSmemBar) + warp;
+
+    const size_t npairs = (p.nframes + 1) / 2;
+    const size_t nwarps = (size_t) gridDim.x * kDualWarps;
+    size_t q = (size_t) blockIdx.x * kDualWarps + warp;
+    const PCM* pcm = static_cast<const PCM*>(p.pcm);
+    auto pair_bytes = [&](size_t pr) -> uint32_t { return 2 * pr + 1 < p.nframes ? 16384u : 8192u; };
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (q < npairs) {
+            mbar_expect_tx(bar, pair_bytes(q));
+            bulk_g2s(xstage, pcm + q * 4096, pair_bytes(q), bar);
+        }
+    }
+    const float2* chirp = p.updown ? p.chirp_up : p.chirp_down;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        s_tw[i] = p.tw_pass[i];
+        s_chirp[i] = chirp[i];
+        s_hann[i] = p.hann[i];
+    }
+    float2 ws[NB];
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
+    __syncthreads();
+
+    uint32_t parity = 0;
+    for (; q < npairs; q += nwarps) {
+        const bool two = 2 * q + 1 < p.nframes;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        float2 re[32], im[32];                                        // (.x, .y) = (frame 2q, frame 2q+1)
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int m = lane + 32 * b;
+            const V2 ra = xstage[m];
+            const V2 rb = two ? xstage[1024 + m] : ra;
+            const float2 c = s_chirp[m], w = s_hann[m];
+            re[b] = make_float2(__fmul_rn(__fmul_rn(pcm_to_float(ra.x), c.x), w.x), __fmul_rn(__fmul_rn(pcm_to_float(rb.x), c.x), w.x));
+            im[b] = make_float2(__fmul_rn(__fmul_rn(pcm_to_float(ra.y), c.y), w.y), __fmul_rn(__fmul_rn(pcm_to_float(rb.y), c.y), w.y));
+        }
+        __syncwarp();
+        if (lane == 0 && q + nwarps < npairs) {
+            mbar_expect_tx(bar, pair_bytes(q + nwarps));
+            bulk_g2s(xstage, pcm + (q + nwarps) * 4096, pair_bytes(q + nwarps), bar);
+        }
+        fft_base2<32>(re, im);
+#pragma unroll
+        for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both halves
+            const float2 w = s_tw[d * 32 + lane];
+            float ar, ai, br, bi;
+            cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
+            cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
+            re[d] = make_float2(ar, br);
+            im[d] = make_float2(ai, bi);
+        }
+#pragma unroll
+        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = make_float2(re[d].x, im[d].x);
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+            const float2 v = tile[lane * kTileStride + a];
+            re[a].x = v.x;
+            im[a].x = v.y;
+        }
+        __syncwarp();
+        // second round: the .y halves (frame 2q+1) still hold their pass-1 values
+#pragma unroll
+        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = make_float2(re[d].y, im[d].y);
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+            const float2 v = tile[lane * kTileStride + a];
+            re[a].y = v.x;
+            im[a].y = v.y;
+        }
+        __syncwarp();
+        fft_base2<32>(re, im);
+        float ma, mb;
+        uint32_t ia, ib;
+        {
+            float zr[32], zi[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { zr[i] = re[i].x; zi[i] = im[i].x; }
+            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, ma, ia);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { zr[i] = re[i].y; zi[i] = im[i].y; }
+            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, mb, ib);
+        }
+        if (lane == 0) {
+            float* mag = p.updown ? p.mag_up : p.mag_down;
+            uint32_t* idx = p.updown ? p.idx_up : p.idx_down;
+            if (mag) { mag[2 * q] = ma; if (two) mag[2 * q + 1] = mb; }
+            if (idx) { idx[2 * q] = ia; if (two) idx[2 * q + 1] = ib; }
+        }
+    }
+}
+
 // dsp() for one hypothesis with a per-stream gather offset (receiver/Src/main.c:183-231).
 // The receiver variant's "left" window reads the zero upper half (hazard H1, defined): its maximum
 // is 0 at relative index 0, so the right window wins unless its own maximum is negative (never).
@@ -228,6 +349,36 @@ static cudaError_t launch_demod_nb(const demod_params& p, uint32_t pcm_format, i
         k_demod2048<float, NB><<<(int) ctas, kDualWarps * 32, kSmemTotal, st>>>(p);
     }
     return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_pair_nb(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
+    size_t ctas = ((p.nframes + 1) / 2 + kDualWarps - 1) / kDualWarps;
+    if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
+    static bool configured[2] = {false, false};
+    if (pcm_format == 1u) {
+        if (!configured[1]) {
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048_pair<int32_t, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal);
+            if (e != cudaSuccess) return e;
+            configured[1] = true;
+        }
+        k_demod2048_pair<int32_t, NB><<<(int) ctas, kDualWarps * 32, kPairSmemTotal, st>>>(p);
+    } else {
+        if (!configured[0]) {
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048_pair<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal);
+            if (e != cudaSuccess) return e;
+            configured[0] = true;
+        }
+        k_demod2048_pair<float, NB><<<(int) ctas, kDualWarps * 32, kPairSmemTotal, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// one hypothesis only (p.updown): frames are processed in pairs
+cudaError_t launch_demod2048_single(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
+    const uint32_t nb = (p.bandwidth2 + 31) / 32;
+    if (nb <= 5) return launch_pair_nb<5>(p, pcm_format, num_sms, st);
+    return launch_pair_nb<16>(p, pcm_format, num_sms, st);
 }
 
 cudaError_t launch_demod2048(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {

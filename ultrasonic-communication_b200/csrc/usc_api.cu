@@ -483,6 +483,14 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     p.pcm = pcm;
     p.nframes = nframes;
     p.mag_up = mag_up; p.idx_up = idx_up; p.mag_down = mag_down; p.idx_down = idx_down; p.bit = bit;
+    const bool want_up = mag_up || idx_up, want_down = mag_down || idx_down;
+    if (!bit && want_up != want_down) {
+        /* only one hypothesis asked for: dsp(pos, .., UP) or dsp(pos, .., DOWN) alone — frames go
+         * through the packed core two at a time */
+        p.updown = want_up ? 1 : 0;
+        LAUNCHED(h, launch_demod2048_single(p, pcm_format, h->num_sms, h->stream));
+        return USC_OK;
+    }
     LAUNCHED(h, launch_demod2048(p, pcm_format, h->num_sms, h->stream));
     return USC_OK;
 }

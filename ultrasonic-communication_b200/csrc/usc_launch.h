@@ -28,6 +28,7 @@ cudaError_t launch_fft_large(int mode, const fft_plan_dev& plan, const float* in
                              uint32_t batch, cudaStream_t st);
 cudaError_t fft_generic_prepare();   // opt in to large dynamic shared memory (once)
 cudaError_t launch_demod2048(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
+cudaError_t launch_demod2048_single(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
 cudaError_t launch_dsp2048(const demod_params& p, int num_sms, cudaStream_t st);
 cudaError_t launch_dsp2048c(const demod_params& p, int num_sms, cudaStream_t st);
 cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* window,
