@@ -27,3 +27,9 @@ elif which == "compress":
         h.compress_chirp(pcm, usc.PCM_I32, F, False, None, o[0], o[1])
 torch.cuda.synchronize()
 print("done", which, reps)
+if which == "single":
+    h = usc.Handle()
+    for _ in range(reps):
+        h.demod_frames(pcm, usc.PCM_I32, F, o[0], o[1])
+    torch.cuda.synchronize()
+    print("done single", reps)

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p
 // costs half of a dual-hypothesis frame: this is the fused "window + FFT + compression + peak" kernel
 // whose time per 8 KB frame is closest to the HBM roofline.  The 16 KB of PCM for a warp's next
 // frame pair arrive by one TMA bulk copy; to stay inside 227 KB of shared memory with 8 warps the
-// exchange goes through an 8 KB tile in two rounds (one per half).
+// exchange goes through an 8 KB tile in two rounds (real parts, then imaginary parts).
 constexpr int kPairSmemTabs = 3 * 8192;               // twiddles | chirp | Hann
 constexpr int kPairWarpBytes = kTileFloat2 * 8 + 16384;   // padded 32x33 float2 tile + 2-frame PCM stage
 constexpr int kPairSmemBar = kPairSmemTabs + kDualWarps * kPairWarpBytes;
@@ -225,26 +225,19 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
             re[d] = make_float2(ar, br);
             im[d] = make_float2(ai, bi);
         }
+        // exchange in two rounds through the 8 KB tile, one per component: each 64-bit word is a
+        // (frame 2q, frame 2q+1) register pair, so values land in place with no repacking moves
 #pragma unroll
-        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = make_float2(re[d].x, im[d].x);
+        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = re[d];
         __syncwarp();
 #pragma unroll
-        for (int a = 0; a < 32; ++a) {
-            const float2 v = tile[lane * kTileStride + a];
-            re[a].x = v.x;
-            im[a].x = v.y;
-        }
-        __syncwarp();
-        // second round: the .y halves (frame 2q+1) still hold their pass-1 values
-#pragma unroll
-        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = make_float2(re[d].y, im[d].y);
+        for (int a = 0; a < 32; ++a) re[a] = tile[lane * kTileStride + a];
         __syncwarp();
 #pragma unroll
-        for (int a = 0; a < 32; ++a) {
-            const float2 v = tile[lane * kTileStride + a];
-            re[a].y = v.x;
-            im[a].y = v.y;
-        }
+        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = im[d];
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) im[a] = tile[lane * kTileStride + a];
         __syncwarp();
         fft_base2<32>(re, im);
         float ma, mb;
