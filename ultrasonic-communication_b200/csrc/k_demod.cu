@@ -37,15 +37,8 @@ constexpr int kWarpsPerCta = 4;
 // is hidden behind a whole frame of arithmetic; tables sit in shared memory so every operand of
 // the front end is one LDS away.  The L1/shared data path (128 B per clock per SM) carries, per
 // frame, PCM 8 KB + table 16 KB + Hann 8 KB + exchange 2 x 16 KB + twiddles 8 KB = 72 KB.
-constexpr int kDualWarps = 8;
-constexpr int kTile4 = 32 * 32;                       // float4 units, XOR-swizzled 32x32 tile (16 KB)
-constexpr int kSmemTw = 0;                            // byte offsets into dynamic shared memory
-constexpr int kSmemUd = 8192;
-constexpr int kSmemHann = kSmemUd + 16384;
-constexpr int kSmemWarp = kSmemHann + 8192;
-constexpr int kWarpBytes = 16384 + 8192;              // tile + PCM stage
-constexpr int kSmemBar = kSmemWarp + kDualWarps * kWarpBytes;
-constexpr int kSmemTotal = kSmemBar + kDualWarps * 8;
+constexpr int kDualWarps = 8;                         // warps per CTA of the pair kernel below
+constexpr int kTile4 = 32 * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -71,20 +64,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <typename PCM, int NB>
-__global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p) {
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    float2* s_tw = reinterpret_cast<float2*>(s_raw + kSmemTw);
-    float4* s_ud = reinterpret_cast<float4*>(s_raw + kSmemUd);
-    float2* s_hann = reinterpret_cast<float2*>(s_raw + kSmemHann);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* tile = reinterpret_cast<float4*>(s_raw + kSmemWarp + warp * kWarpBytes);
-    using V2 = typename vec2<PCM>::type;
-    V2* xstage = reinterpret_cast<V2*>(s_raw + kSmemWarp + warp * kWarpBytes + 16384);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + kSmemBar) + warp;
+// Shared memory of the dual kernel with W warps: twiddles 8 KB | (up,down) table 16 KB | Hann 8 KB |
+// per warp: XOR-swizzled 32x32 float2 tile 8 KB + PCM stage 8 KB | mbarriers.
+template <int W> struct dual_smem {
+    static constexpr int tw = 0, ud = 8192, hann = ud + 16384, warp = hann + 8192, warp_bytes = 8192 + 8192,
+                         bar = warp + W * warp_bytes, total = bar + W * 8;
+};
 
-    const size_t nwarps = (size_t) gridDim.x * kDualWarps;
-    size_t f = (size_t) blockIdx.x * kDualWarps + warp;
+template <typename PCM, int NB, int W>
+__global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
+    using L = dual_smem<W>;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
+    float4* s_ud = reinterpret_cast<float4*>(s_raw + L::ud);
+    float2* s_hann = reinterpret_cast<float2*>(s_raw + L::hann);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = reinterpret_cast<float2*>(s_raw + L::warp + warp * L::warp_bytes);
+    using V2 = typename vec2<PCM>::type;
+    V2* xstage = reinterpret_cast<V2*>(s_raw + L::warp + warp * L::warp_bytes + 8192);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + L::bar) + warp;
+
+    const size_t nwarps = (size_t) gridDim.x * W;
+    size_t f = (size_t) blockIdx.x * W + warp;
     const PCM* pcm = static_cast<const PCM*>(p.pcm);
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -124,7 +125,31 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048(demod_params p
             mbar_expect_tx(bar, 8192);
             bulk_g2s(xstage, pcm + (f + nwarps) * 2048, 8192, bar);
         }
-        fft1024_warp2(re, im, tile, s_tw, lane);
+        fft_base2<32>(re, im);
+#pragma unroll
+        for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both hypotheses
+            const float2 w = s_tw[d * 32 + lane];
+            float ar, ai, br, bi;
+            cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
+            cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
+            re[d] = make_float2(ar, br);
+            im[d] = make_float2(ai, bi);
+        }
+        // exchange in two rounds (real parts, then imaginary parts): each 64-bit word is an (up, down)
+        // register pair, so values land in place; XOR swizzle keeps both directions conflict-free
+#pragma unroll
+        for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) re[a] = tile[lane * 32 + (a ^ lane)];
+        __syncwarp();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = im[d];
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
+        __syncwarp();
+        fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
         {
@@ -321,25 +346,30 @@ static int grid_for(size_t nwork, int num_sms) {
     return (int) ctas;
 }
 
+#ifndef USC_DUAL_WARPS
+#define USC_DUAL_WARPS 8
+#endif
 template <int NB>
 static cudaError_t launch_demod_nb(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
-    size_t ctas = (p.nframes + kDualWarps - 1) / kDualWarps;
+    constexpr int W = USC_DUAL_WARPS;
+    size_t ctas = (p.nframes + W - 1) / W;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;            // persistent: one CTA per SM
     static bool configured[2] = {false, false};
+    const int smem = dual_smem<W>::total;
     if (pcm_format == 1u) {
         if (!configured[1]) {
-            cudaError_t e = cudaFuncSetAttribute(k_demod2048<int32_t, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048<int32_t, NB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
             configured[1] = true;
         }
-        k_demod2048<int32_t, NB><<<(int) ctas, kDualWarps * 32, kSmemTotal, st>>>(p);
+        k_demod2048<int32_t, NB, W><<<(int) ctas, W * 32, smem, st>>>(p);
     } else {
         if (!configured[0]) {
-            cudaError_t e = cudaFuncSetAttribute(k_demod2048<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+            cudaError_t e = cudaFuncSetAttribute(k_demod2048<float, NB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
             configured[0] = true;
         }
-        k_demod2048<float, NB><<<(int) ctas, kDualWarps * 32, kSmemTotal, st>>>(p);
+        k_demod2048<float, NB, W><<<(int) ctas, W * 32, smem, st>>>(p);
     }
     return cudaGetLastError();
 }

@@ -80,8 +80,6 @@ struct demod_params {
     size_t fifo_stride; const uint32_t* sync_position; const float* mag_mean; history_rec* hist;
     uint32_t idx_left_zero; int32_t fs_int; int updown;
 };
-template <typename PCM, int NB>
-__global__ void k_demod2048(demod_params p);
 template <int NB>
 __global__ void k_dsp2048(demod_params p);
 
