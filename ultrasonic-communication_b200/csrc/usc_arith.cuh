@@ -178,6 +178,31 @@ __device__ __forceinline__ void rfft_merge(float xkr, float xki, float xcr, floa
     zi = __fmaf_rn(qr, cr, __fmaf_rn(-qi, si, pi));
 }
 
+// ---- packed forms with a scalar (per-lane) second operand broadcast to both halves ------------------
+// (SASS: FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2 — no repacking moves).  Half by half identical to the
+// scalar functions above.
+__device__ __forceinline__ void cmul2(float2 ar, float2 ai, float br, float bi, float2& re, float2& im) {
+    const float2 t0 = __fmul2_rn(ai, bc2(bi)), t1 = __fmul2_rn(ai, bc2(br));
+    re = __ffma2_rn(ar, bc2(br), neg2(t0));
+    im = __ffma2_rn(ar, bc2(bi), t1);
+}
+__device__ __forceinline__ void rfft_split2(float2 zkr, float2 zki, float2 zcr, float2 zci, float cr, float si,
+                                            float2& xr, float2& xi) {
+    const float2 pr = __fadd2_rn(zkr, zcr), pi = __fadd2_rn(zki, neg2(zci));
+    const float2 qr = __fadd2_rn(zki, zci), qi = __fadd2_rn(zcr, neg2(zkr));
+    const float2 tr = __ffma2_rn(qr, bc2(cr), __ffma2_rn(qi, bc2(si), pr));
+    const float2 ti = __ffma2_rn(qi, bc2(cr), __ffma2_rn(neg2(qr), bc2(si), pi));
+    xr = __fmul2_rn(bc2(0.5f), tr);
+    xi = __fmul2_rn(bc2(0.5f), ti);
+}
+__device__ __forceinline__ void rfft_merge2(float2 xkr, float2 xki, float2 xcr, float2 xci, float cr, float si,
+                                            float2& zr, float2& zi) {
+    const float2 pr = __fadd2_rn(xkr, xcr), pi = __fadd2_rn(xki, neg2(xci));
+    const float2 qr = __fadd2_rn(xkr, neg2(xcr)), qi = __fadd2_rn(xki, xci);
+    zr = __ffma2_rn(neg2(qi), bc2(cr), __ffma2_rn(neg2(qr), bc2(si), pr));
+    zi = __ffma2_rn(qr, bc2(cr), __ffma2_rn(neg2(qi), bc2(si), pi));
+}
+
 // arm_max_f32 combine: keep the larger value; on equal values keep the lower index.
 __device__ __forceinline__ void argmax_combine(float& v, uint32_t& i, float ov, uint32_t oi) {
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
