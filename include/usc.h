@@ -197,6 +197,12 @@ int usc_receiver_run(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32
  * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */
 int usc_sync_search(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                     size_t stream_stride, uint32_t sync_add, float *mag, uint32_t *idx);
+/* The audio spectrum analyser fft() of experiments/basic/Src/main.c:107-142 (the producer of the
+ * reference's captured .raw/.flt/.fft files): PCM x Hann -> RFFT -> magnitude * 1/sqrt(N) -> bins below
+ * ac_coupling_hz (FFT_AC_COUPLING_HZ = 1000) forced to 1.0 -> dB = 10*log10 -> arg-max.  Uses the
+ * handle's window and fs.  mag/db: nframes*n/2 floats, peak/peak_idx: nframes (any may be NULL). */
+int usc_spectrum_analyzer(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nframes, float ac_coupling_hz,
+                          float *mag, float *db, float *peak, uint32_t *peak_idx);
 /* K5.  I/Q baseband path (experiments/iq_modulation/Src/iq_modem.c:34-66, Src/main.c:117-134, with the
  * semantics of simulation/IQ_modulation.ipynb cells 16-31 and BASELINE config 3's decimation by 2).
  * usc_iq_init builds the carrier tables (init_iq_modem), the baseband reference chirp -bw/2..+bw/2

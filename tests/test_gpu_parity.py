@@ -296,3 +296,82 @@ def test_full_size_properties(h, rx):
     assert np.array_equal(mu[:4096].view(np.uint32), wmu.view(np.uint32))
     assert np.array_equal(md[:4096].view(np.uint32), wmd.view(np.uint32))
     assert (bit[:4096] == bits).mean() > 0.9
+
+
+def test_spectrum_analyzer_reproduces_device_captures(device_triples):
+    """experiments/basic fft() end to end on the GPU (usc_spectrum_analyzer) vs the Cortex-M4 captures:
+    every printed magnitude (AC-coupled bins = 1.0 included) within 1e-4 relative (+1e-6 print
+    resolution) and the same peak bin, at the three sampling rates the captures were taken with
+    (fs = 80 MHz / divider / 32 in integer arithmetic, experiments/basic*/Src/main.c:240-243)."""
+    ok = device_triples["consistent"]
+    names = device_triples["names"][ok]
+    raw, dev_mag, freq = device_triples["raw"][ok], device_triples["fft_mag"][ok], device_triples["fft_freq"][ok]
+    checked = 0
+    for fs in (100000.0, 48076.0, 41666.0):
+        sel = np.array([abs(f[1000] * 2048 / 1000 - fs) < 30 for f in freq])
+        if not sel.any():
+            continue
+        h = usc.Handle(usc.default_config(fs=fs))
+        B = int(sel.sum())
+        d = h.buffer(raw[sel])
+        d_mag, d_db, d_pk, d_pi = h.empty(4 * B * 1024), h.empty(4 * B * 1024), h.empty(4 * B), h.empty(4 * B)
+        h.spectrum_analyzer(d, usc.PCM_I32, B, 1000.0, d_mag, d_db, d_pk, d_pi)
+        h.sync()
+        mag = d_mag.to_numpy(np.float32).reshape(B, 1024)
+        db = d_db.to_numpy(np.float32).reshape(B, 1024)
+        pi = d_pi.to_numpy(np.uint32)
+        want = dev_mag[sel]
+        fr = freq[sel]
+        for i in range(B):
+            ac = fr[i] < 1000.0 - 0.05                      # printed with one decimal
+            edge = np.abs(fr[i] - 1000.0) <= 0.05
+            assert np.all(mag[i][ac] == 1.0)
+            body = ~ac & ~edge
+            big = body & (want[i] >= 0.01 * want[i][body].max())
+            assert (np.abs(mag[i][big] - want[i][big]) / want[i][big]).max() < 1e-4, names[sel][i]
+            assert np.abs(mag[i][body] - want[i][body]).max() <= 1e-4 * want[i][body].max() + 1e-6
+            assert int(pi[i]) == int(np.argmax(np.where(edge, 0, want[i])))
+            assert np.abs(db[i] - 10.0 * np.log10(mag[i].astype(np.float64))).max() < 1e-4
+            checked += 1
+        h.close()
+    assert checked == 23
+
+
+@pytest.mark.parametrize("nframes", [1, 2, 3, 8, 255, 4099])
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+def test_single_hypothesis_pair_kernel_bit_exact(h, rx, nframes, dtype):
+    """usc_demod_frames with only one hypothesis' outputs requested = dsp(.., UP) or dsp(.., DOWN) alone
+    (receiver/Src/main.c:183-215); frames go through the packed core two at a time (odd counts too)."""
+    pcm, _ = synth.make_frames(nframes, seed_noise=77 + nframes, dtype=dtype)
+    want = rx.demod_frames(pcm, nthreads=8)
+    fmt = usc.PCM_I32 if dtype == np.int32 else usc.PCM_F32
+    d = h.buffer(pcm)
+    m, i = h.empty(4 * nframes), h.empty(4 * nframes)
+    h.demod_frames(d, fmt, nframes, mag_up=m, idx_up=i)
+    h.sync()
+    assert np.array_equal(m.to_numpy(np.float32).view(np.uint32), want[0].view(np.uint32))
+    assert np.array_equal(i.to_numpy(np.uint32), want[1])
+    h.demod_frames(d, fmt, nframes, mag_down=m, idx_down=i)
+    h.sync()
+    assert np.array_equal(m.to_numpy(np.float32).view(np.uint32), want[2].view(np.uint32))
+    assert np.array_equal(i.to_numpy(np.uint32), want[3])
+    h.demod_frames(d, fmt, nframes, idx_up=i)                   # indices only
+    h.sync()
+    assert np.array_equal(i.to_numpy(np.uint32), want[1])
+
+
+def test_host_buffer_path_matches_device_path(h, rx):
+    """usc_demod_frames_host (chunked H2D / K1 / D2H through three stream lanes) on pageable numpy memory,
+    with a chunk size that does not divide the frame count."""
+    nframes = 1000
+    pcm, _ = synth.make_frames(nframes, seed_noise=5)
+    want = rx.demod_frames(pcm, nthreads=8)
+    h.host_workspace(96)
+    mu, md = np.empty(nframes, np.float32), np.empty(nframes, np.float32)
+    iu, idn = np.empty(nframes, np.uint32), np.empty(nframes, np.uint32)
+    bit = np.empty(nframes, np.uint8)
+    h.demod_frames_hostbuf(pcm, usc.PCM_I32, nframes, mu, iu, md, idn, bit)
+    for g, w in zip((mu, iu, md, idn), want):
+        assert np.array_equal(g.view(np.uint32), w.view(np.uint32))
+    assert np.array_equal(bit, (~(want[2] > want[0])).astype(np.uint8))
+    h.host_workspace(4096)

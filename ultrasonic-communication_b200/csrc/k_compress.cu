@@ -27,34 +27,6 @@ constexpr int kCWarpBytes = 8192 + 16384;             // XOR-swizzled float2 til
 constexpr int kCSmemBar = kCSmemTabs + kCWarps * kCWarpBytes;
 constexpr int kCSmemTotal = kCSmemBar + kCWarps * 8;
 
-// pass 1, inter-pass twiddle, two-round exchange (real parts, imaginary parts), pass 2 — on pairs
-__device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32], float2* tile,
-                                             const float2* __restrict__ s_tw, int lane) {
-    fft_base2<32>(re, im);
-#pragma unroll
-    for (int d = 1; d < 32; ++d) {
-        const float2 w = s_tw[d * 32 + lane];
-        float ar, ai, br, bi;
-        cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
-        cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
-        re[d] = make_float2(ar, br);
-        im[d] = make_float2(ai, bi);
-    }
-#pragma unroll
-    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
-    __syncwarp();
-#pragma unroll
-    for (int a = 0; a < 32; ++a) re[a] = tile[lane * 32 + (a ^ lane)];
-    __syncwarp();
-#pragma unroll
-    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = im[d];
-    __syncwarp();
-#pragma unroll
-    for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
-    __syncwarp();
-    fft_base2<32>(re, im);
-}
-
 __device__ __forceinline__ float2 shfl2(float2 v, int src) {
     return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }

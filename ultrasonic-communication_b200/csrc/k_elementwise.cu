@@ -139,6 +139,40 @@ __global__ void k_fir(const float* __restrict__ coeffs, uint32_t taps, float* st
     }
 }
 
+// Tail of the spectrum analyser fft() (experiments/basic/Src/main.c:117-142): packed spectrum ->
+// magnitude * 1/sqrt(N), bins below the AC-coupling frequency forced to 1.0, dB = 10*log10f(mag),
+// arg-max of the magnitudes.  One warp per frame.  mag/db: n/2 floats per frame (either may be NULL).
+__global__ void k_spectrum_tail(const float* __restrict__ spec, uint32_t n, float inv_sqrt_n, uint32_t ac_bins,
+                                float* __restrict__ mag, float* __restrict__ db, float* __restrict__ peak,
+                                uint32_t* __restrict__ peak_idx, uint32_t batch) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    const uint32_t half = n / 2;
+    for (size_t v = warp; v < batch; v += nwarps) {
+        const float* p = spec + v * n;
+        float best = -INFINITY;
+        uint32_t bi = 0xffffffffu;
+        for (uint32_t e = lane; e < half; e += 32) {
+            float m = __fmul_rn(cmag(p[2 * e], p[2 * e + 1]), inv_sqrt_n);     // arm_cmplx_mag_f32 + arm_scale_f32
+            if (e < ac_bins) m = 1.0f;                                          // main.c:126-131
+            if (mag) mag[v * half + e] = m;
+            if (db) db[v * half + e] = 10.0f * log10f(m);                       // main.c:133-135
+            if (bi == 0xffffffffu || best < m) { best = m; bi = e; }
+        }
+        warp_argmax(best, bi);
+        if (lane == 0) {
+            if (peak) peak[v] = best;
+            if (peak_idx) peak_idx[v] = bi;
+        }
+    }
+}
+cudaError_t launch_spectrum_tail(const float* spec, uint32_t n, float inv_sqrt_n, uint32_t ac_bins, float* mag, float* db,
+                                 float* peak, uint32_t* peak_idx, uint32_t batch, cudaStream_t st) {
+    k_spectrum_tail<<<blocks_for((size_t) batch * 32, 256), 256, 0, st>>>(spec, n, inv_sqrt_n, ac_bins, mag, db, peak, peak_idx, batch);
+    return cudaGetLastError();
+}
+
 // symbol decision of the receiver (receiver/Src/main.c:523): down only if strictly greater
 __global__ void k_decide(const float* __restrict__ mu, const float* __restrict__ md, uint8_t* __restrict__ bit, size_t n) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)

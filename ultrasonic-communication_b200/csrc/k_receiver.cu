@@ -17,9 +17,9 @@
 
 namespace usc {
 
-constexpr int kRxWarps = 4;
+constexpr int kRxWarps = 8;
 constexpr int kRxNB = 5;
-constexpr int kRxSmem = (4096 + kRxWarps * kTileFloat2) * (int) sizeof(float2);
+constexpr int kRxSmem = 4 * 8192 + kRxWarps * 8192 + kRxWarps * 128;   // tables | per-warp 8 KB tile | per-warp state
 
 struct rx_tables {
     const float2* up;       // shared-memory copies
@@ -27,33 +27,6 @@ struct rx_tables {
     const float2* hann;
     const float2* tw;
 };
-
-// dsp() for one hypothesis on the FIFO of frame t at sync_position pos: returns mag_max (the right
-// window always wins in the receiver variant, hazard H1) and its bin.
-template <typename PCM>
-__device__ __forceinline__ void dsp_fifo(const PCM* __restrict__ stream, int64_t nsamples, int64_t g0,
-                                         const rx_tables& tb, bool up, float2* tile, const float2 (&ws)[kRxNB],
-                                         int lane, uint32_t bw2, float& mag, uint32_t& idx) {
-    using V2 = typename vec2<PCM>::type;
-    const float2* chirp = up ? tb.up : tb.down;
-    float re[32], im[32];
-#pragma unroll
-    for (int b = 0; b < 32; ++b) {
-        const int m = lane + 32 * b;
-        const int64_t g = g0 + 2 * m;                        // g0 is a multiple of N/8: pairs never straddle 0
-        float x0 = 0.0f, x1 = 0.0f;
-        if (g >= 0 && g + 1 < nsamples) {
-            V2 raw = *reinterpret_cast<const V2*>(stream + g);
-            x0 = pcm_to_float(raw.x);
-            x1 = pcm_to_float(raw.y);
-        }
-        float2 c = chirp[m], w = tb.hann[m];
-        re[b] = __fmul_rn(__fmul_rn(x0, c.x), w.x);
-        im[b] = __fmul_rn(__fmul_rn(x1, c.y), w.y);
-    }
-    fft1024_warp(re, im, tile, tb.tw, lane);
-    peak_window<kRxNB>(re, im, ws, lane, bw2, mag, idx);
-}
 
 struct rx_params {
     const void* pcm; uint32_t nstreams; uint32_t nframes; size_t stream_stride;
@@ -63,6 +36,70 @@ struct rx_params {
     // sync search
     uint32_t sync_add; float* ss_mag; uint32_t* ss_idx;
 };
+
+template <typename PCM>
+__device__ __forceinline__ float2 load_pair(const PCM* __restrict__ stream, int64_t nsamples, int64_t g) {
+    using V2 = typename vec2<PCM>::type;
+    if (g >= 0 && g + 1 < nsamples) {                  // g is even (window starts are multiples of N/8)
+        const V2 raw = *reinterpret_cast<const V2*>(stream + g);
+        return make_float2(pcm_to_float(raw.x), pcm_to_float(raw.y));
+    }
+    return make_float2(0.0f, 0.0f);                    // before the stream starts the FIFO holds zeros
+}
+
+// TWO dsp() calls at once (halves .x / .y of the packed core): windows starting at stream samples gA
+// and gB, de-chirped by chirpA / chirpB (the same table for two offsets of one hypothesis, the up
+// and down tables for the two hypotheses of one position).  Returns the right-window peaks (the
+// right window always wins in the receiver variant, hazard H1).  sync_add > 1 sums that many
+// frame-aligned windows, oldest first, before the de-chirp (synchronous addition).
+template <typename PCM, bool MULTI>
+__device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t nsamples, int64_t gA, int64_t gB,
+                                         const float2* chirpA, const float2* chirpB, const rx_tables& tb,
+                                         uint32_t sync_add, float2* tile, const float2 (&ws)[kRxNB], int lane,
+                                         uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB) {
+    float2 re[32], im[32];
+    if (!MULTI) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int m = lane + 32 * b;
+            const float2 xa = load_pair<PCM>(stream, nsamples, gA + 2 * m), xb = load_pair<PCM>(stream, nsamples, gB + 2 * m);
+            re[b] = make_float2(xa.x, xb.x);
+            im[b] = make_float2(xa.y, xb.y);
+        }
+    } else {
+        for (uint32_t j = sync_add; j-- > 0;) {        // oldest FIFO first
+            const int64_t back = (int64_t) j * 2048;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const int m = lane + 32 * b;
+                const float2 xa = load_pair<PCM>(stream, nsamples, gA - back + 2 * m);
+                const float2 xb = load_pair<PCM>(stream, nsamples, gB - back + 2 * m);
+                if (j == sync_add - 1) {
+                    re[b] = make_float2(xa.x, xb.x);
+                    im[b] = make_float2(xa.y, xb.y);
+                } else {
+                    re[b] = make_float2(__fadd_rn(re[b].x, xa.x), __fadd_rn(re[b].y, xb.x));
+                    im[b] = make_float2(__fadd_rn(im[b].x, xa.y), __fadd_rn(im[b].y, xb.y));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+        const int m = lane + 32 * b;
+        const float2 ca = chirpA[m], cb = chirpB[m], w = tb.hann[m];
+        re[b] = make_float2(__fmul_rn(__fmul_rn(re[b].x, ca.x), w.x), __fmul_rn(__fmul_rn(re[b].y, cb.x), w.x));
+        im[b] = make_float2(__fmul_rn(__fmul_rn(im[b].x, ca.y), w.y), __fmul_rn(__fmul_rn(im[b].y, cb.y), w.y));
+    }
+    fft1024_pair(re, im, tile, tb.tw, lane);
+    float zr[32], zi[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { zr[i] = re[i].x; zi[i] = im[i].x; }
+    peak_window<kRxNB>(zr, zi, ws, lane, bw2, magA, idxA);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { zr[i] = re[i].y; zi[i] = im[i].y; }
+    peak_window<kRxNB>(zr, zi, ws, lane, bw2, magB, idxB);
+}
 
 __device__ __forceinline__ void load_tables(const rx_params& p, float2* s_up, float2* s_down, float2* s_hann, float2* s_tw) {
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -74,10 +111,9 @@ __device__ __forceinline__ void load_tables(const rx_params& p, float2* s_up, fl
 }
 
 template <typename PCM>
-__global__ void __launch_bounds__(kRxWarps * 32, 3) k_receiver_run(rx_params p) {
+__global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) {
     extern __shared__ float2 s_rx[];
     float2 *s_up = s_rx, *s_down = s_rx + 1024, *s_hann = s_rx + 2048, *s_tw = s_rx + 3072;
-    float2* s_tile_base = s_rx + 4096;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(p, s_up, s_down, s_hann, s_tw);
     float2 ws[kRxNB];
@@ -85,7 +121,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 3) k_receiver_run(rx_params p) 
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
     __syncthreads();
     const rx_tables tb{s_up, s_down, s_hann, s_tw};
-    float2* tile = s_tile_base + warp * kTileFloat2;
+    float2* tile = s_rx + 4096 + warp * 1024;
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const float thr = p.snr_threshold;
     const uint32_t bw2 = p.bandwidth2;
@@ -100,75 +136,114 @@ __global__ void __launch_bounds__(kRxWarps * 32, 3) k_receiver_run(rx_params p) 
         int32_t lock_frame = -1;
         uint32_t lock_pos = 0;
         float mag_mean = 0.0f;
-        float mag_stat[12], hmag[8], hmean[4];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) mag_stat[i] = 1E37f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hmag[i] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hmean[i] = 0.0f;
+        // mag_stat[12] | history mag_max[8] | history mag_mean[4] live in shared memory (the packed core
+        // needs the registers); every lane reads them (broadcast), lane 0 writes
+        float* mag_stat = reinterpret_cast<float*>(s_rx + 4096 + kRxWarps * 1024) + warp * 32;
+        float* hmag = mag_stat + 12;
+        float* hmean = mag_stat + 20;
+        __syncwarp();
+        if (lane < 12) mag_stat[lane] = 1E37f;
+        else if (lane < 24) mag_stat[lane] = 0.0f;
+        __syncwarp();
 
         auto emit = [&](uint32_t c) {
             if (lane == 0 && uart && nout < p.uart_cap) uart[nout] = (uint8_t) c;
             nout++;
         };
-        // symbol_snr (main.c:233-236): dsp into history slot `slot` (< 4) using the slot's own mag_mean
-        auto symbol_snr = [&](int64_t fifo0, int64_t q, int slot, bool up) -> float {
-            if (q < 0 || q > (int64_t) 2 * N) return -INFINITY;          // hazards H3/H5 defined
-            float m;
-            uint32_t k;
-            dsp_fifo<PCM>(stream, nsamples, fifo0 + q, tb, up, tile, ws, lane, bw2, m, k);
-            float mean = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mean = slot == i ? hmean[i] : mean;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hmag[i] = slot == i ? m : hmag[i];
-            return __fdiv_rn(__fsub_rn(m, mean), mean);                   // main.c:229
-        };
-        // resync (main.c:243-273)
-        auto resync = [&](int64_t fifo0, float snr, bool up) {
-            const int64_t l = (int64_t) pos - offset, r = (int64_t) pos + offset;
-            const float snr_l = symbol_snr(fifo0, l, 2, up);
-            const float snr_r = symbol_snr(fifo0, r, 3, up);
-            if ((snr > snr_l) && (snr > snr_r)) {
-            } else if (snr_l >= snr_r) {
-                if (l >= 0) pos = (uint32_t) l;
-            } else if (snr_l < snr_r) {
-                if (r <= (int64_t) 2 * N) pos = (uint32_t) r;
-            }
-        };
-
         for (uint32_t t = 0; t < p.nframes; ++t) {
             const int64_t fifo0 = ((int64_t) t - 2) * N;                  // stream index of fifo_queue[0]
+            if (t + 1 < p.nframes) {                                      // pull the next frame towards L2
+                const char* nxt = reinterpret_cast<const char*>(stream + (size_t) (t + 1) * N);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 4096 + lane * 128));
+            }
             const uint32_t prev = state;
-            if (state == 0 || state == 1) {
-                if (state == 0) {                                         // IDLE (main.c:428-434)
-                    sync_cnt = 0;
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int i = 4; i < 12; ++i) sum = __fadd_rn(sum, mag_stat[i]);
-                    mag_mean = __fdiv_rn(sum, 8.0f);
+            const bool searching = state == 0 || state == 1;
+            if (state == 0) {                                             // IDLE (main.c:428-434)
+                sync_cnt = 0;
+                float sum = 0.0f;
+                for (int i = 4; i < 12; ++i) sum = __fadd_rn(sum, mag_stat[i]);
+                mag_mean = __fdiv_rn(sum, 8.0f);
+            }
+            // Every frame costs two packed passes through ONE inlined copy of the chain:
+            //   searching: offsets (0,1) then (2,3) of the grid, up-chirp            main.c:447-451
+            //   locked:    (UP, DOWN) at sync_position, then the two resync probes    main.c:493-494, 243-249
+            float up = 0.0f, down = 0.0f;
+            bool is_down = false, symbol = false;
+            for (int pass = 0; pass < 2; ++pass) {
+                int64_t qa, qb;
+                const float2 *ca, *cb;
+                bool a_ok = true, b_ok = true;
+                if (searching) {
+                    qa = N / 2 + turn * offset + shift * (2 * pass);
+                    qb = qa + shift;
+                    ca = cb = tb.up;
+                } else if (pass == 0) {
+                    qa = qb = pos;
+                    ca = tb.up;
+                    cb = tb.down;
+                } else {
+                    if (!symbol) break;                                   // neither SNR reached the threshold
+                    qa = (int64_t) pos - offset;                          // resync (main.c:246-249); probes outside
+                    qb = (int64_t) pos + offset;                          // [0, 2N] are hazards H3/H5: snr = -inf
+                    a_ok = qa >= 0 && qa <= (int64_t) 2 * N;
+                    b_ok = qb >= 0 && qb <= (int64_t) 2 * N;
+                    ca = cb = is_down ? tb.down : tb.up;
                 }
-                for (uint32_t i = 0; i < 4; ++i) {                        // main.c:447-451
-                    pos = N / 2 + turn * offset + shift * i;
-                    float m;
-                    uint32_t k;
-                    dsp_fifo<PCM>(stream, nsamples, fifo0 + pos, tb, true, tile, ws, lane, bw2, m, k);
-                    const uint32_t slot = i * 2 + turn;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) hmag[j] = slot == (uint32_t) j ? m : hmag[j];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) hmean[j] = slot == (uint32_t) j ? mag_mean : hmean[j];
+                float ma, mb;
+                uint32_t ka, kb;
+                dsp_pair<PCM, false>(stream, nsamples, fifo0 + (a_ok ? qa : (int64_t) pos), fifo0 + (b_ok ? qb : (int64_t) pos), ca, cb, tb,
+                              1, tile, ws, lane, bw2, ma, ka, mb, kb);
+                if (searching) {
+                    const int sa = (int) (4 * pass + turn), sb = sa + 2;  // history[i*2 + turn]
+                    __syncwarp();
+                    if (lane == 0) {
+                        hmag[sa] = ma;
+                        hmag[sb] = mb;
+                        if (sa < 4) hmean[sa] = mag_mean;
+                        if (sb < 4) hmean[sb] = mag_mean;
+                    }
+                    __syncwarp();
+                    pos = (uint32_t) qb;
+                } else if (pass == 0) {
+                    const float mean0 = hmean[0], mean1 = hmean[1];
+                    __syncwarp();
+                    if (lane == 0) { hmag[0] = ma; hmag[1] = mb; }
+                    __syncwarp();
+                    up = __fdiv_rn(__fsub_rn(ma, mean0), mean0);          // main.c:229
+                    down = __fdiv_rn(__fsub_rn(mb, mean1), mean1);
+                    symbol = up >= thr || down >= thr;
+                    is_down = down > up;
+                } else {
+                    float snr_l = -INFINITY, snr_r = -INFINITY;
+                    const float mean2 = hmean[2], mean3 = hmean[3];
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (a_ok) hmag[2] = ma;
+                        if (b_ok) hmag[3] = mb;
+                    }
+                    __syncwarp();
+                    if (a_ok) snr_l = __fdiv_rn(__fsub_rn(ma, mean2), mean2);
+                    if (b_ok) snr_r = __fdiv_rn(__fsub_rn(mb, mean3), mean3);
+                    const float snr = is_down ? down : up;
+                    if ((snr > snr_l) && (snr > snr_r)) {                 // main.c:252-270
+                    } else if (snr_l >= snr_r) {
+                        if (qa >= 0) pos = (uint32_t) qa;
+                    } else if (snr_l < snr_r) {
+                        if (qb <= (int64_t) 2 * N) pos = (uint32_t) qb;
+                    }
                 }
+            }
+            if (searching) {
                 turn ^= 1u;
                 if (turn == 1u) {
-#pragma unroll
-                    for (int i = 10; i >= 0; --i) mag_stat[i + 1] = mag_stat[i];     // main.c:458-460
                     float mmm = 0.0f;
-#pragma unroll
                     for (int i = 0; i < 8; ++i)
                         if (hmag[i] > mmm) { mmm = hmag[i]; max_idx = i; }           // main.c:463-471
-                    mag_stat[0] = mmm;
+                    const float shifted = lane >= 1 && lane < 12 ? mag_stat[lane - 1] : mmm;
+                    __syncwarp();
+                    if (lane < 12) mag_stat[lane] = shifted;                         // main.c:458-460, 473
+                    __syncwarp();
                     const float snr = __fdiv_rn(__fsub_rn(mmm, mag_mean), mag_mean);  // main.c:477
                     if (snr >= thr) {
                         state = 1;
@@ -180,28 +255,22 @@ __global__ void __launch_bounds__(kRxWarps * 32, 3) k_receiver_run(rx_params p) 
                         state = 0;
                     }
                 }
-            } else {
-                const float up = symbol_snr(fifo0, pos, 0, true);         // main.c:493-494 / 518-519
-                const float down = symbol_snr(fifo0, pos, 1, false);
-                if (up >= thr || down >= thr) {
-                    const bool is_down = down > up;
-                    if (state == 3) msg = ((msg << 1) + (is_down ? 0u : 1u)) & 0xffu;   // main.c:525,529
-                    resync(fifo0, is_down ? down : up, !is_down);
-                    if (state == 2) {
-                        if (is_down) state = 3;                           // the delimiter (main.c:500)
-                    } else if (++msg_cnt >= 8) {                          // main.c:532-537
-                        emit(msg);
-                        msg = 0;
-                        msg_cnt = 0;
-                    }
-                } else {
-                    if (state == 3) {                                     // end of message (main.c:539-549)
-                        emit((uint32_t) '\n');
-                        msg = 0;
-                        msg_cnt = 0;
-                    }
-                    state = 0;
+            } else if (symbol) {
+                if (state == 3) msg = ((msg << 1) + (is_down ? 0u : 1u)) & 0xffu;     // main.c:525,529
+                if (state == 2) {
+                    if (is_down) state = 3;                               // the delimiter (main.c:500)
+                } else if (++msg_cnt >= 8) {                              // main.c:532-537
+                    emit(msg);
+                    msg = 0;
+                    msg_cnt = 0;
                 }
+            } else {
+                if (state == 3) {                                         // end of message (main.c:539-549)
+                    emit((uint32_t) '\n');
+                    msg = 0;
+                    msg_cnt = 0;
+                }
+                state = 0;
             }
             if (prev != 2 && state == 2 && lock_frame < 0) {
                 lock_frame = (int32_t) t;
@@ -218,20 +287,20 @@ __global__ void __launch_bounds__(kRxWarps * 32, 3) k_receiver_run(rx_params p) 
 }
 
 // K4: the search grid of main.c:447-451 for every (stream, frame), after optional synchronous
-// addition of sync_add frame-aligned FIFOs (oldest first).  One warp per (stream, frame).
-template <typename PCM>
-__global__ void __launch_bounds__(kRxWarps * 32, 3) k_sync_search(rx_params p) {
+// addition of sync_add frame-aligned FIFOs (oldest first).  One warp per (stream, frame), two packed
+// passes of two offsets each.
+template <typename PCM, bool MULTI>
+__global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
     extern __shared__ float2 s_rx[];
     float2 *s_up = s_rx, *s_down = s_rx + 1024, *s_hann = s_rx + 2048, *s_tw = s_rx + 3072;
-    float2* s_tile_base = s_rx + 4096;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(p, s_up, s_down, s_hann, s_tw);
     float2 ws[kRxNB];
 #pragma unroll
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
     __syncthreads();
-    float2* tile = s_tile_base + warp * kTileFloat2;
-    using V2 = typename vec2<PCM>::type;
+    const rx_tables tb{s_up, s_down, s_hann, s_tw};
+    float2* tile = s_rx + 4096 + warp * 1024;
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const size_t total = (size_t) p.nstreams * p.nframes;
     const size_t nwarps = (size_t) gridDim.x * kRxWarps;
@@ -239,35 +308,16 @@ __global__ void __launch_bounds__(kRxWarps * 32, 3) k_sync_search(rx_params p) {
         const uint32_t s = (uint32_t) (w / p.nframes), t = (uint32_t) (w - (size_t) s * p.nframes);
         const PCM* stream = static_cast<const PCM*>(p.pcm) + (size_t) s * p.stream_stride;
         const int64_t nsamples = (int64_t) p.nframes * N;
-        for (uint32_t i = 0; i < 4; ++i) {
-            const uint32_t pos = N / 2 + (t & 1u) * offset + shift * i;
-            float re[32], im[32];
-#pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const int m = lane + 32 * b;
-                float x0 = 0.0f, x1 = 0.0f;
-                for (uint32_t j = p.sync_add; j-- > 0;) {                 // oldest FIFO first
-                    const int64_t g = ((int64_t) t - (int64_t) j - 2) * N + pos + 2 * m;
-                    float v0 = 0.0f, v1 = 0.0f;
-                    if (g >= 0 && g + 1 < nsamples) {
-                        V2 raw = *reinterpret_cast<const V2*>(stream + g);
-                        v0 = pcm_to_float(raw.x);
-                        v1 = pcm_to_float(raw.y);
-                    }
-                    if (j == p.sync_add - 1) { x0 = v0; x1 = v1; }
-                    else { x0 = __fadd_rn(x0, v0); x1 = __fadd_rn(x1, v1); }
-                }
-                float2 c = s_up[m], wn = s_hann[m];
-                re[b] = __fmul_rn(__fmul_rn(x0, c.x), wn.x);
-                im[b] = __fmul_rn(__fmul_rn(x1, c.y), wn.y);
-            }
-            fft1024_warp(re, im, tile, s_tw, lane);
-            float mag;
-            uint32_t idx;
-            peak_window<kRxNB>(re, im, ws, lane, p.bandwidth2, mag, idx);
+        const int64_t fifo0 = ((int64_t) t - 2) * N;
+        for (uint32_t i = 0; i < 4; i += 2) {
+            const uint32_t pa = N / 2 + (t & 1u) * offset + shift * i, pb = pa + shift;
+            float ma, mb;
+            uint32_t ka, kb;
+            dsp_pair<PCM, MULTI>(stream, nsamples, fifo0 + pa, fifo0 + pb, tb.up, tb.up, tb, p.sync_add, tile, ws, lane, p.bandwidth2,
+                          ma, ka, mb, kb);
             if (lane == 0) {
-                p.ss_mag[w * 4 + i] = mag;
-                p.ss_idx[w * 4 + i] = idx;
+                p.ss_mag[w * 4 + i] = ma; p.ss_idx[w * 4 + i] = ka;
+                p.ss_mag[w * 4 + i + 1] = mb; p.ss_idx[w * 4 + i + 1] = kb;
             }
         }
     }
@@ -289,8 +339,10 @@ static cudaError_t rx_prepare() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_receiver_run<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_receiver_run<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
     done = true;
     return cudaSuccess;
 }
@@ -298,7 +350,7 @@ static cudaError_t rx_prepare() {
 cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st) {
     rx_params p = make_params(a);
     size_t ctas = ((size_t) a.nstreams + kRxWarps - 1) / kRxWarps;
-    const size_t cap = (size_t) num_sms * 3;
+    const size_t cap = (size_t) num_sms;                 // persistent: one CTA of 8 warps per SM
     if (ctas > cap) ctas = cap;
     cudaError_t e = rx_prepare();
     if (e != cudaSuccess) return e;
@@ -310,12 +362,18 @@ cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st
 cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st) {
     rx_params p = make_params(a);
     size_t ctas = ((size_t) a.nstreams * a.nframes + kRxWarps - 1) / kRxWarps;
-    const size_t cap = (size_t) num_sms * 3 * 2;
+    const size_t cap = (size_t) num_sms * 2;
     if (ctas > cap) ctas = cap;
     cudaError_t e = rx_prepare();
     if (e != cudaSuccess) return e;
-    if (a.pcm_format == 1u) k_sync_search<int32_t><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
-    else k_sync_search<float><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+    const bool multi = p.sync_add > 1;
+    if (a.pcm_format == 1u) {
+        if (multi) k_sync_search<int32_t, true><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+        else k_sync_search<int32_t, false><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+    } else {
+        if (multi) k_sync_search<float, true><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+        else k_sync_search<float, false><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // launches.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -618,6 +619,33 @@ int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_
     if (!nstreams || !nframes) return USC_OK;
     a.sync_add = sync_add; a.ss_mag = mag; a.ss_idx = idx;
     LAUNCHED(h, launch_sync_search(a, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_spectrum_analyzer(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nframes, float ac_coupling_hz,
+                          float* mag, float* db, float* peak, uint32_t* peak_idx) {
+    /* fft() of experiments/basic/Src/main.c:107-142: window, RFFT, magnitude/sqrt(N), AC coupling, dB, arg-max */
+    if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n;
+    if (n > 16384) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    const size_t W = (size_t) nframes * n;
+    int rc = reserve_work(h, W * sizeof(float));
+    if (rc) return rc;
+    float* x = h->d_work;
+    if (pcm_format == USC_PCM_I32) {
+        LAUNCHED(h, launch_i32_to_f32((const int32_t*) pcm, x, W, h->stream));
+        LAUNCHED(h, launch_mult(x, n, h->d_hann, 0, x, n, n, nframes, h->stream));
+    } else {
+        LAUNCHED(h, launch_mult((const float*) pcm, n, h->d_hann, 0, x, n, n, nframes, h->stream));
+    }
+    fft_plan_dev plan;
+    if ((rc = make_plan(h, n / 2, n, &plan))) return rc;
+    LAUNCHED(h, launch_fft_generic(FFT_R2C, plan, x, x, nframes, h->stream));
+    /* fft_frequency[i] = i*fs/N < FFT_AC_COUPLING_HZ (main.c:127,250): count of leading bins forced to 1.0 */
+    uint32_t ac_bins = 0;
+    while (ac_bins < n / 2 && (float) ac_bins * h->cfg.fs / (float) n < ac_coupling_hz) ++ac_bins;
+    LAUNCHED(h, launch_spectrum_tail(x, n, 1.0f / sqrtf((float) n), ac_bins, mag, db, peak, peak_idx, nframes, h->stream));
     return USC_OK;
 }
 

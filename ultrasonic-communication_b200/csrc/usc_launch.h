@@ -5,6 +5,8 @@
 
 namespace usc {
 cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st);
+cudaError_t launch_spectrum_tail(const float* spec, uint32_t n, float inv_sqrt_n, uint32_t ac_bins, float* mag, float* db,
+                                 float* peak, uint32_t* peak_idx, uint32_t batch, cudaStream_t st);
 cudaError_t launch_decide(const float* mu, const float* md, uint8_t* bit, size_t n, cudaStream_t st);
 cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
                         uint32_t len, uint32_t batch, cudaStream_t st);

@@ -93,6 +93,34 @@ __device__ __forceinline__ void fft1024_warp2(float2 (&re)[32], float2 (&im)[32]
     fft_base2<32>(re, im);
 }
 
+// pass 1, inter-pass twiddle, two-round exchange (real parts, imaginary parts), pass 2 — on pairs
+__device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32], float2* tile /* 32x32 float2, XOR-swizzled, 8 KB */,
+                                             const float2* __restrict__ s_tw, int lane) {
+    fft_base2<32>(re, im);
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        const float2 w = s_tw[d * 32 + lane];
+        float ar, ai, br, bi;
+        cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
+        cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
+        re[d] = make_float2(ar, br);
+        im[d] = make_float2(ai, bi);
+    }
+#pragma unroll
+    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 32; ++a) re[a] = tile[lane * 32 + (a ^ lane)];
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = im[d];
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
+    __syncwarp();
+    fft_base2<32>(re, im);
+}
+
 // Exact arm_max_f32 over sqrt(p_k) without taking a square root per candidate.  sqrt is monotone,
 // so max_k sqrt(p_k) = sqrt(max_k p_k); the first index attaining it is the first k whose p_k rounds
 // to the same square root.  Any such k other than the first arg-max of p must satisfy
