@@ -45,34 +45,20 @@ UNIT = "symbols/s"
 WORKLOAD = "receiver chain (Hanning + 2048-pt RFFT + chirp compression + peak), 4096 streams x 1 s"
 
 
-def symbol_waves():
-    """chirp_orth of simulation/signal.py:45-53 at the receiver's fs with T = N/fs (N samples)."""
-    t = np.linspace(0.0, N / FS, N)
-    k = (F1 - F0) / (N / FS)
-    out = []
-    for updown in ("up", "down"):
-        f = F0 + k * t / 2.0 if updown == "up" else F1 - k * t / 2.0
-        arg = 2.0 * np.pi * f * t - np.pi / 2.0
-        out.append(np.cos(arg) + np.sin(arg))
-    return out
+SEED = 20261017
+AMP = 2.0e4                                  # symbol amplitude before the x256 (|cos+sin| <= sqrt(2))
+SNR_DB = -5.0
+NOISE_SIGMA = AMP / (10.0 ** (SNR_DB / 20.0))    # chirp_orth has unit mean power
 
 
-def make_device_frames(torch, nframes, device, seed, snr_db=-5.0, amp=2.0e4):
-    """Synthetic PCM generated on the device: A*chirp_orth(bit) + Gaussian noise, x256 int32."""
-    up, down = symbol_waves()
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    t_up = torch.tensor(up, dtype=torch.float32, device=device) * amp
-    t_dn = torch.tensor(down, dtype=torch.float32, device=device) * amp
-    sigma = float(np.sqrt(np.mean(up ** 2) * amp * amp / (10.0 ** (snr_db / 10.0))))
+def make_device_frames(torch, h, nframes, device, first_frame):
+    """Synthetic PCM generated ON THE DEVICE by the library's counter-based generator (usc_synth_frames:
+    chirp_orth symbol chosen by a random bit + noise, int32 x256).  Frames are indexed globally, so
+    rank r generates frames [r*nframes, (r+1)*nframes) of one reproducible dataset."""
     pcm = torch.empty((nframes, N), dtype=torch.int32, device=device)
-    bits = torch.randint(0, 2, (nframes,), generator=g, device=device, dtype=torch.uint8)
-    chunk = 8192
-    for s in range(0, nframes, chunk):
-        e = min(nframes, s + chunk)
-        b = bits[s:e, None].bool()
-        x = torch.where(b, t_up[None, :], t_dn[None, :]) + torch.randn((e - s, N), generator=g, device=device) * sigma
-        pcm[s:e] = torch.round(x).to(torch.int32) * 256
+    bits = torch.empty(nframes, dtype=torch.uint8, device=device)
+    h.synth_frames(SEED, first_frame, nframes, AMP, NOISE_SIGMA, pcm, bits)
+    h.sync()
     return pcm, bits
 
 
@@ -149,12 +135,7 @@ def cpu_port(nframes_sample, threads, budget_s=12.0, seed=7):
     """The CPU oracle port (test infrastructure) timed as the reported baseline."""
     from oracle import pyref
     rx = pyref.RefReceiver()
-    up, down = symbol_waves()
-    rng = np.random.default_rng(seed)
-    bits = rng.integers(0, 2, nframes_sample)
-    sigma = float(np.sqrt(np.mean(up ** 2) * 2.0e4 ** 2 / (10.0 ** (-0.5))))
-    x = np.where(bits[:, None] == 1, up[None, :], down[None, :]) * 2.0e4 + rng.standard_normal((nframes_sample, N)) * sigma
-    pcm = (np.rint(x).astype(np.int64) * 256).astype(np.int32)
+    pcm, _ = pyref.synth_frames(SEED, 0, nframes_sample, AMP, NOISE_SIGMA)      # the same dataset, first frames
     rx.demod_frames(pcm[:256], nthreads=threads)                # warm the threads
     # about 12 s of CPU work in total: passes over the sample until the budget is spent
     t_start = time.perf_counter()
@@ -176,12 +157,7 @@ def run_reference(args, rank):
     sample = 32768
     from oracle import pyref
     rx = pyref.RefReceiver()
-    up, down = symbol_waves()
-    rng = np.random.default_rng(7)
-    bits = rng.integers(0, 2, sample)
-    sigma = float(np.sqrt(np.mean(up ** 2) * 2.0e4 ** 2 / (10.0 ** (-0.5))))
-    x = np.where(bits[:, None] == 1, up[None, :], down[None, :]) * 2.0e4 + rng.standard_normal((sample, N)) * sigma
-    pcm = (np.rint(x).astype(np.int64) * 256).astype(np.int32)
+    pcm, _ = pyref.synth_frames(SEED, 0, sample, AMP, NOISE_SIGMA)
     for _ in range(max(args.warmup, 1)):
         rx.demod_frames(pcm[:4096], nthreads=threads)
     t0 = time.perf_counter()
@@ -240,7 +216,7 @@ def main():
     h.set_stream(stream.cuda_stream)
 
     # this rank's shard of the streams (weak scaling: every GPU gets the config-2 batch)
-    pcm, bits = make_device_frames(torch, NFRAMES, dev, seed=1000 + rank)
+    pcm, bits = make_device_frames(torch, h, NFRAMES, dev, first_frame=rank * NFRAMES)
     mag_up = torch.empty(NFRAMES, dtype=torch.float32, device=dev)
     mag_dn = torch.empty(NFRAMES, dtype=torch.float32, device=dev)
     idx_up = torch.empty(NFRAMES, dtype=torch.int32, device=dev)
@@ -328,7 +304,7 @@ def main():
             "msamples_per_s": value * N / 1e6,
             "config": {"workload": WORKLOAD, "streams_per_gpu": STREAMS, "frames_per_stream": FRAMES_PER_STREAM,
                        "frames_per_step_per_gpu": NFRAMES, "n": N, "fs": FS, "pcm": "int32 (x256 DFSDM words)",
-                       "hypotheses": 2, "snr_db": -5.0, "parallelism": "streams sharded, no collective",
+                       "hypotheses": 2, "snr_db": SNR_DB, "generator": "usc_synth_frames (Philox-4x32-10, CPU twin in oracle)", "parallelism": "streams sharded, no collective",
                        "l2": "input 1.275 GB per step >> 126 MB L2 (no flush needed)",
                        "symbol_accuracy_vs_tx_bits": accuracy},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -197,6 +197,15 @@ int usc_receiver_run(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32
  * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */
 int usc_sync_search(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                     size_t stream_stride, uint32_t sync_add, float *mag, uint32_t *idx);
+/* Synthetic receiver input generated on the device (the step before the path):
+ * frame f (global index first_frame + i, so shards on different GPUs are disjoint and reproducible)
+ * = the transmitter's up- or down-chirp symbol (chirp_orth, generator/ChirpGenerator.ipynb cell 1 +
+ * simulation/signal.py:45-53, amplitude amp) chosen by a counter-based random bit, plus noise of
+ * standard deviation noise_sigma, as int32 words with the 24-bit sample in bits 31:8 (x256,
+ * receiver/Src/dfsdm.c:78).  Integer-only arithmetic on Philox-4x32-10 keyed by (seed, frame, sample):
+ * the oracle regenerates any frame bit for bit on the CPU.  bits (nframes, may be NULL): 1 = up. */
+int usc_synth_frames(usc_handle *h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp,
+                     double noise_sigma, int32_t *pcm, uint8_t *bits);
 /* The audio spectrum analyser fft() of experiments/basic/Src/main.c:107-142 (the producer of the
  * reference's captured .raw/.flt/.fft files): PCM x Hann -> RFFT -> magnitude * 1/sqrt(N) -> bins below
  * ac_coupling_hz (FFT_AC_COUPLING_HZ = 1000) forced to 1.0 -> dB = 10*log10 -> arg-max.  Uses the

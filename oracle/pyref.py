@@ -441,3 +441,13 @@ class RefIq:
             lib().ref_iq_free(C.byref(self.q))
         except Exception:
             pass
+
+
+def synth_frames(seed, first_frame, nframes, amp, noise_sigma, n=2048, fs=78125.0, f0=16000.0, f1=19000.0):
+    """CPU twin of usc_synth_frames -> (pcm [nframes, n] int32, bits)."""
+    pcm = np.empty((nframes, n), np.int32)
+    bits = np.empty(nframes, np.uint8)
+    lib().ref_synth_frames(C.c_uint64(seed), C.c_uint64(first_frame), C.c_size_t(nframes), C.c_uint32(n), C.c_float(fs),
+                           C.c_float(f0), C.c_float(f1), C.c_double(amp), C.c_double(noise_sigma),
+                           pcm.ctypes.data_as(i32p), bits.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return pcm, bits

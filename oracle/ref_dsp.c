@@ -840,3 +840,48 @@ void ref_compress_frames_i32(const ref_compressor *c, const int32_t *pcm, size_t
         free(fr);
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* twin of the device-side synthetic generator (Philox-4x32-10, integer arithmetic only)       */
+/* ------------------------------------------------------------------------------------------ */
+static void philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t) p1;
+        uint32_t n2 = (uint32_t) (p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t) p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
+                      double amp, double noise_sigma, int32_t *pcm, uint8_t *bits) {
+    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
+    const double T = (double) n / (double) fs, k = ((double) f1 - (double) f0) / T;
+    for (int down = 0; down < 2; ++down)
+        for (uint32_t i = 0; i < n; ++i) {          /* chirp_orth, simulation/signal.py:45-53 */
+            double t = T * (double) i / (double) (n - 1);
+            double f = down ? (double) f1 - k * t / 2.0 : (double) f0 + k * t / 2.0;
+            double arg = 2.0 * M_PI * f * t - M_PI / 2.0;
+            tab[(size_t) down * n + i] = (int32_t) llround(amp * (cos(arg) + sin(arg)));
+        }
+    const int32_t gain = (int32_t) llround(noise_sigma / sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0) * 65536.0);
+    const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
+    for (size_t fl = 0; fl < nframes; ++fl) {
+        uint64_t f = first_frame + fl;
+        uint32_t r[4];
+        philox(k0, k1, (uint32_t) f, (uint32_t) (f >> 32), 0xB175u, 0u, r);
+        uint32_t bit = r[0] & 1u;
+        if (bits) bits[fl] = (uint8_t) bit;
+        for (uint32_t blk = 0; blk < n / 2; ++blk) {
+            philox(k0, k1, (uint32_t) f, (uint32_t) (f >> 32), blk, 1u, r);
+            const int32_t *t2 = tab + (size_t) (bit ? 0 : 1) * n + 2 * blk;
+            int32_t s0 = (int32_t) ((r[0] & 0xffffu) + (r[0] >> 16) + (r[1] & 0xffffu) + (r[1] >> 16)) - 131070;
+            int32_t s1 = (int32_t) ((r[2] & 0xffffu) + (r[2] >> 16) + (r[3] & 0xffffu) + (r[3] >> 16)) - 131070;
+            pcm[fl * n + 2 * blk] = (t2[0] + (int32_t) (((int64_t) s0 * gain) / 65536)) * 256;
+            pcm[fl * n + 2 * blk + 1] = (t2[1] + (int32_t) (((int64_t) s1 * gain) / 65536)) * 256;
+        }
+    }
+    free(tab);
+}

@@ -196,6 +196,10 @@ void ref_iq_free(ref_iq *q);
 void ref_iq_demod_i32(const ref_iq *q, const int32_t *pcm, uint32_t nframes, float *mag_up, uint32_t *idx_up,
                       float *mag_down, uint32_t *idx_down);
 
+/* ---- twin of the device-side synthetic generator (usc_synth_frames): regenerates any frame on the CPU ---- */
+void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
+                      double amp, double noise_sigma, int32_t *pcm, uint8_t *bits);
+
 /* ---- receiver state machine (receiver/Src/main.c:417-580) ---- */
 enum { REF_IDLE = 0, REF_SYNCHRONIZING = 1, REF_SYNCHRONIZED = 2, REF_DATA_RECEIVING = 3 };   /* main.c:108-111 */
 

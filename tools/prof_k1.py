@@ -12,7 +12,8 @@ import bench  # noqa: E402
 which = sys.argv[1] if len(sys.argv) > 1 else "demod"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
-pcm, bits = bench.make_device_frames(torch, bench.NFRAMES, dev, seed=1000)
+_h0 = usc.Handle()
+pcm, bits = bench.make_device_frames(torch, _h0, bench.NFRAMES, dev, 0)
 F = bench.NFRAMES
 o = [torch.empty(F, dtype=torch.float32, device=dev) for _ in range(4)]
 b = torch.empty(F, dtype=torch.uint8, device=dev)

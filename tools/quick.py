@@ -13,7 +13,7 @@ want = R.RefReceiver().demod_frames(pcm, nthreads=8)
 got = h.demod_frames_host(pcm)
 print("K1 parity:", all(np.array_equal(g.view(np.uint32), w.view(np.uint32)) for g, w in zip(got[:4], want)))
 dev = torch.device("cuda", 0)
-big, _ = bench.make_device_frames(torch, bench.NFRAMES, dev, seed=1000)
+big, _ = bench.make_device_frames(torch, h, bench.NFRAMES, dev, 0)
 F = bench.NFRAMES
 o = [torch.empty(F, dtype=torch.float32, device=dev) for _ in range(4)]
 b = torch.empty(F, dtype=torch.uint8, device=dev)

@@ -1,0 +1,30 @@
+"""Small workload touching every fused kernel once, for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "ultrasonic-communication_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np
+import usc, synth
+
+N = 2048
+h = usc.Handle()
+pcm, _ = synth.make_frames(37)
+out = h.demod_frames_host(pcm)                                   # K1 dual
+d = h.buffer(pcm); m, i = h.empty(4 * 37), h.empty(4 * 37)
+h.demod_frames(d, usc.PCM_I32, 37, mag_up=m, idx_up=i); h.sync()  # K1 pair
+st = synth.make_stream(b"Hi", snr_db=20.0, nframes=70)[None]
+print(h.receiver_run_host(np.repeat(st, 3, 0))[0])                # K7
+dm, di = h.empty(4 * 70 * 4), h.empty(4 * 70 * 4)
+ds = h.buffer(st)
+for K in (1, 3):
+    h.sync_search(ds, usc.PCM_I32, 1, 70, 70 * N, K, dm, di); h.sync()   # K4
+f = h.buffer(pcm[:3].astype(np.float32).reshape(1, -1)); pos = h.buffer(np.array([300], np.uint32)); mean = h.buffer(np.array([1e8], np.float32))
+hh = h.empty(48); h.dsp(f, 3 * N, pos, mean, usc.UP, hh, 1); h.sync()     # k_dsp2048
+hc = usc.Handle(usc.default_config(fs=100000.0, f0=17000.0, f1=18000.0, chirp_variant=usc.CHIRP_T, window=usc.HANN_SYMMETRIC))
+dc = hc.buffer(pcm); o = hc.empty(4 * 37 * N)
+hc.compress_chirp(dc, usc.PCM_I32, 37, False, o, m, i); hc.sync()  # K2
+hs = usc.Handle(usc.default_config(chirp_variant=usc.CHIRP_S))
+hs.dsp(f, 3 * N, pos, mean, usc.DOWN, hh, 1); hs.sync()            # K3
+x = h.buffer(np.random.default_rng(0).standard_normal((2, 65536)).astype(np.float32)); y = h.empty(2 * 65536 * 4)
+h.arm_rfft_fast_f32(65536, x, y, 0, 2); h.arm_rfft_fast_f32(4096, x, y, 0, 2); h.arm_rfft_fast_f32(4096, y, y, 1, 2); h.sync()
+print("sanitize workload done")

@@ -1,0 +1,65 @@
+// k_synth.cu — counter-based synthetic receiver input on the device (SURVEY §8d "input generation",
+// §8f row f2): frame f carries the transmitter's up- or down-chirp symbol (chirp_orth law of
+// simulation/signal.py:45-53, as integer tables) plus noise, as int32 DFSDM-style words (x256).
+// Everything is integer arithmetic on Philox-4x32-10 output keyed by (seed, frame, sample block), so
+// any frame can be regenerated bit for bit on the CPU (the oracle has a twin) without storing the
+// dataset: full-size runs are checked by re-creating sampled frames on the host.
+//   bit[f]      = philox(seed; f, 0, 0xB175, 0).x & 1
+//   noise[f][n] = ((u0 + u1 + u2 + u3 - 131070) * gain) / 65536      (four 16-bit uniforms: Irwin-Hall)
+//   pcm[f][n]   = (table[bit][n] + noise) * 256
+#include "usc_kernels.cuh"
+#include "usc_launch.h"
+
+namespace usc {
+
+__host__ __device__ inline void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t) p1;
+        const uint32_t n2 = (uint32_t) (p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t) p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void k_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, const int32_t* __restrict__ table,
+                               int32_t gain, int32_t* __restrict__ pcm, uint8_t* __restrict__ bits) {
+    const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
+    const size_t pairs = (size_t) n / 2;
+    const size_t total = nframes * pairs;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const size_t fl = i / pairs;
+        const uint32_t blk = (uint32_t) (i - fl * pairs);
+        const uint64_t f = first_frame + fl;
+        uint32_t r[4];
+        philox4x32_10(k0, k1, (uint32_t) f, (uint32_t) (f >> 32), 0xB175u, 0u, r);
+        const uint32_t bit = r[0] & 1u;
+        if (blk == 0 && bits) bits[fl] = (uint8_t) bit;
+        philox4x32_10(k0, k1, (uint32_t) f, (uint32_t) (f >> 32), blk, 1u, r);
+        const int32_t* tab = table + (size_t) (bit ? 0u : 1u) * n + 2 * blk;      // bit 1 = up symbol (table 0)
+        int2 o;
+        {
+            const int32_t s = (int32_t) ((r[0] & 0xffffu) + (r[0] >> 16) + (r[1] & 0xffffu) + (r[1] >> 16)) - 131070;
+            o.x = (tab[0] + (int32_t) (((int64_t) s * gain) / 65536)) * 256;
+        }
+        {
+            const int32_t s = (int32_t) ((r[2] & 0xffffu) + (r[2] >> 16) + (r[3] & 0xffffu) + (r[3] >> 16)) - 131070;
+            o.y = (tab[1] + (int32_t) (((int64_t) s * gain) / 65536)) * 256;
+        }
+        reinterpret_cast<int2*>(pcm)[i] = o;
+    }
+}
+
+cudaError_t launch_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, const int32_t* table,
+                                int32_t gain, int32_t* pcm, uint8_t* bits, cudaStream_t st) {
+    const size_t total = nframes * (n / 2);
+    size_t b = (total + 255) / 256;
+    if (b > 148u * 32u) b = 148u * 32u;
+    k_synth_frames<<<(int) (b ? b : 1), 256, 0, st>>>(seed, first_frame, nframes, n, table, gain, pcm, bits);
+    return cudaGetLastError();
+}
+
+}  // namespace usc

@@ -34,6 +34,8 @@ struct usc_handle {
     std::vector<float> iq_cos, iq_sin, iq_chirp, iq_hann;
     float *d_iq_cos, *d_iq_sin, *d_iq_chirp, *d_iq_conj, *d_iq_hann, *d_iq_taps;
     uint32_t iq_ntaps, iq_window;
+    int32_t* d_sym_table;                             // synthetic generator: up/down symbol tables (2n int32)
+    double sym_amp;
     float* d_work;                                    // grow-on-demand scratch (large FFTs, generic demod)
     size_t work_bytes;
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
@@ -145,6 +147,8 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->d_fir_coeffs = nullptr;
     h->d_work = nullptr;
     h->work_bytes = 0;
+    h->d_sym_table = nullptr;
+    h->sym_amp = 0.0;
     h->d_iq_cos = h->d_iq_sin = h->d_iq_chirp = h->d_iq_conj = h->d_iq_hann = h->d_iq_taps = nullptr;
     h->iq_ntaps = h->iq_window = 0;
     h->lane_frames = 0;
@@ -225,6 +229,7 @@ void usc_destroy(usc_handle* h) {
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
     cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
+    cudaFree(h->d_sym_table);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) {
         cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
@@ -619,6 +624,27 @@ int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_
     if (!nstreams || !nframes) return USC_OK;
     a.sync_add = sync_add; a.ss_mag = mag; a.ss_idx = idx;
     LAUNCHED(h, launch_sync_search(a, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp, double noise_sigma,
+                     int32_t* pcm, uint8_t* bits) {
+    if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    const uint32_t n = h->cfg.n;
+    if (!h->d_sym_table || h->sym_amp != amp) {
+        std::vector<int32_t> tab(2 * (size_t) n);
+        usc_host_symbol_tables(n, h->cfg.fs, h->cfg.f0, h->cfg.f1, amp, tab.data());
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_sym_table);
+        h->d_sym_table = nullptr;
+        int rc = upload(tab.data(), tab.size() * sizeof(int32_t), (void**) &h->d_sym_table);
+        if (rc) return rc;
+        h->sym_amp = amp;
+    }
+    LAUNCHED(h, launch_synth_frames(seed, first_frame, nframes, n, h->d_sym_table, usc_host_noise_gain(noise_sigma), pcm, bits,
+                                    h->stream));
     return USC_OK;
 }
 

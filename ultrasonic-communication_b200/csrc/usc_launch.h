@@ -43,5 +43,7 @@ cudaError_t launch_iq_frontend(const void* pcm, uint32_t pcm_format, uint32_t ns
                                const float* taps, uint32_t ntaps, float* out, cudaStream_t st);
 cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t left0,
                            float* mag, uint32_t* idx, size_t count, cudaStream_t st);
+cudaError_t launch_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, const int32_t* table,
+                                int32_t gain, int32_t* pcm, uint8_t* bits, cudaStream_t st);
 cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaStream_t st);
 }  // namespace usc

@@ -108,3 +108,20 @@ uint32_t usc_host_bandwidth(uint32_t n, float fs, float f0, float f1) {
     unsigned long span = (unsigned long) (int) (f1 - f0) * (unsigned long) n;
     return (uint32_t) ((float) span / fs);
 }
+
+void usc_host_symbol_tables(uint32_t n, float fs, float f0, float f1, double amp, int32_t *out) {
+    const double T = (double) n / (double) fs, k = ((double) f1 - (double) f0) / T;
+    for (int down = 0; down < 2; ++down)
+        for (uint32_t i = 0; i < n; ++i) {
+            const double t = T * (double) i / (double) (n - 1);
+            const double f = down ? (double) f1 - k * t / 2.0 : (double) f0 + k * t / 2.0;
+            const double arg = 2.0 * M_PI * f * t - M_PI / 2.0;
+            out[(size_t) down * n + i] = (int32_t) llround(amp * (cos(arg) + sin(arg)));
+        }
+}
+
+int32_t usc_host_noise_gain(double sigma) {
+    /* sum of four independent 16-bit uniforms: variance 4 * (65536^2 - 1) / 12 */
+    const double unit = sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0);
+    return (int32_t) llround(sigma / unit * 65536.0);
+}

@@ -24,6 +24,12 @@ void usc_host_ref_chirp(uint32_t variant, uint32_t n, float fs, float f0, float 
 void usc_host_twiddles(float *tw, uint32_t n);
 /* Radix list of the canonical mixed-radix plan. Returns the count, 0 if bad. */
 uint32_t usc_host_radices(uint32_t n, uint32_t *rad);
+/* Transmitter symbol tables for the synthetic generator: round(amp * (cos(arg) + sin(arg))) with the
+ * chirp_orth law of simulation/signal.py:45-53 (t = linspace(0, T, n), T = n/fs, phase -pi/2), evaluated
+ * in double.  out: 2n int32 — the up symbol then the down symbol. */
+void usc_host_symbol_tables(uint32_t n, float fs, float f0, float f1, double amp, int32_t *out);
+/* noise gain of the integer generator for a target standard deviation (PCM units before the x256) */
+int32_t usc_host_noise_gain(double sigma);
 /* (F1 - F0) * NN / fs truncated to uint32 (receiver/Src/main.c:372). */
 uint32_t usc_host_bandwidth(uint32_t n, float fs, float f0, float f1);
 

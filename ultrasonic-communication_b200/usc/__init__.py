@@ -43,7 +43,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -281,6 +281,10 @@ class Handle:
         res = d_r.to_numpy(rx_result_dtype)
         u = d_u.to_numpy(np.uint8).reshape(S, uart_cap)
         return [bytes(u[s, :min(int(res["nbytes"][s]), uart_cap)]) for s in range(S)], res
+
+    def synth_frames(self, seed, first_frame, nframes, amp, noise_sigma, pcm, bits=None):
+        _ck(load().usc_synth_frames(self._h, C.c_uint64(seed), C.c_uint64(first_frame), C.c_size_t(nframes), C.c_double(amp),
+                                    C.c_double(noise_sigma), _ptr(pcm), _ptr(bits)))
 
     def spectrum_analyzer(self, pcm, pcm_format, nframes, ac_coupling_hz, mag=None, db=None, peak=None, peak_idx=None):
         _ck(load().usc_spectrum_analyzer(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nframes),
