@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
             float4 c = s_ud[m];                                       // (up[2m], down[2m], up[2m+1], down[2m+1])
             float2 w = s_hann[m];
-            re[b] = make_float2(__fmul_rn(__fmul_rn(x0, c.x), w.x), __fmul_rn(__fmul_rn(x0, c.y), w.x));
-            im[b] = make_float2(__fmul_rn(__fmul_rn(x1, c.z), w.y), __fmul_rn(__fmul_rn(x1, c.w), w.y));
+            re[b] = __fmul2_rn(__fmul2_rn(make_float2(c.x, c.y), bc2(x0)), bc2(w.x));     // ((x*c)*w), both hypotheses
+            im[b] = __fmul2_rn(__fmul2_rn(make_float2(c.z, c.w), bc2(x1)), bc2(w.y));
         }
         __syncwarp();                                                 // every lane has consumed the stage
         if (lane == 0 && f + nwarps < p.nframes) {                    // refill it with this warp's next frame
@@ -105,11 +105,10 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
 #pragma unroll
         for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both hypotheses
             const float2 w = s_tw[d * 32 + lane];
-            float ar, ai, br, bi;
-            cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
-            cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
-            re[d] = make_float2(ar, br);
-            im[d] = make_float2(ai, bi);
+            float2 tr, ti;
+            cmul2(re[d], im[d], w.x, w.y, tr, ti);
+            re[d] = tr;
+            im[d] = ti;
         }
         // exchange in two rounds (real parts, then imaginary parts): each 64-bit word is an (up, down)
         // register pair, so values land in place; XOR swizzle keeps both directions conflict-free
@@ -128,15 +127,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
         fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
-        {
-            float zr[32], zi[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { zr[i] = re[i].x; zi[i] = im[i].x; }
-            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, mu, iu);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { zr[i] = re[i].y; zi[i] = im[i].y; }
-            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, md, id);
-        }
+        peak_window_pair<NB>(re, im, ws, lane, p.bandwidth2, mu, iu, md, id);
         if (lane == 0) {
             if (p.mag_up) p.mag_up[f] = mu;
             if (p.idx_up) p.idx_up[f] = iu;
@@ -208,8 +199,9 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
             const V2 ra = xstage[m];
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 c = s_chirp[m], w = s_hann[m];
-            re[b] = make_float2(__fmul_rn(__fmul_rn(pcm_to_float(ra.x), c.x), w.x), __fmul_rn(__fmul_rn(pcm_to_float(rb.x), c.x), w.x));
-            im[b] = make_float2(__fmul_rn(__fmul_rn(pcm_to_float(ra.y), c.y), w.y), __fmul_rn(__fmul_rn(pcm_to_float(rb.y), c.y), w.y));
+            // ((x*c)*w) on both frames at once: the per-lane table values broadcast to the two halves
+            re[b] = __fmul2_rn(__fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(c.x)), bc2(w.x));
+            im[b] = __fmul2_rn(__fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(c.y)), bc2(w.y));
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {
@@ -220,11 +212,10 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
 #pragma unroll
         for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both halves
             const float2 w = s_tw[d * 32 + lane];
-            float ar, ai, br, bi;
-            cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
-            cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
-            re[d] = make_float2(ar, br);
-            im[d] = make_float2(ai, bi);
+            float2 tr, ti;
+            cmul2(re[d], im[d], w.x, w.y, tr, ti);
+            re[d] = tr;
+            im[d] = ti;
         }
         // exchange in two rounds through the 8 KB tile, one per component: each 64-bit word is a
         // (frame 2q, frame 2q+1) register pair, so values land in place with no repacking moves
@@ -243,15 +234,7 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
         fft_base2<32>(re, im);
         float ma, mb;
         uint32_t ia, ib;
-        {
-            float zr[32], zi[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { zr[i] = re[i].x; zi[i] = im[i].x; }
-            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, ma, ia);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { zr[i] = re[i].y; zi[i] = im[i].y; }
-            peak_window<NB>(zr, zi, ws, lane, p.bandwidth2, mb, ib);
-        }
+        peak_window_pair<NB>(re, im, ws, lane, p.bandwidth2, ma, ia, mb, ib);
         if (lane == 0) {
             float* mag = p.updown ? p.mag_up : p.mag_down;
             uint32_t* idx = p.updown ? p.idx_up : p.idx_down;

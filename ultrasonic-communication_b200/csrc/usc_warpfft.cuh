@@ -225,4 +225,60 @@ __device__ __forceinline__ void peak_window(const float (&zr)[32], const float (
     }
 }
 
+
+// peak_window on both halves of the packed registers at once: the split and the squared magnitudes
+// are f32x2 operations with the per-lane split twiddle broadcast; the two arg-max searches stay scalar.
+template <int NB>
+__device__ __forceinline__ void peak_tail(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
+    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
+    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
+#pragma unroll
+    for (int d1 = 1; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
+    }
+    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
+    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
+    bool risky = false;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        risky |= (k < kmin) && (pw[d1] >= thr);
+    }
+    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
+        peak_slow<NB>(pw, lane, bw2, best, best_idx);
+    } else {
+        best = __fsqrt_rn(pmax);
+        best_idx = kmin;
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void peak_window_pair(const float2 (&zr)[32], const float2 (&zi)[32], const float2 (&ws)[NB],
+                                                 int lane, uint32_t bw2, float& bestA, uint32_t& idxA, float& bestB,
+                                                 uint32_t& idxB) {
+    const int src = (32 - lane) & 31;
+    float pa[NB], pb[NB];
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const float2 sr = lane == 0 ? zr[(32 - d1) & 31] : zr[31 - d1];
+        const float2 si = lane == 0 ? zi[(32 - d1) & 31] : zi[31 - d1];
+        const float2 zcr = make_float2(__shfl_sync(0xffffffffu, sr.x, src), __shfl_sync(0xffffffffu, sr.y, src));
+        const float2 zci = make_float2(__shfl_sync(0xffffffffu, si.x, src), __shfl_sync(0xffffffffu, si.y, src));
+        float2 xr, xi;
+        rfft_split2(zr[d1], zi[d1], zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
+        if (d1 == 0) {                                 // packed bin 0 = (X[0], X[N/2]) on lane 0
+            const float2 dr = __fadd2_rn(zr[0], zi[0]), di = __fadd2_rn(zr[0], neg2(zi[0]));
+            xr = lane == 0 ? dr : xr;
+            xi = lane == 0 ? di : xi;
+        }
+        const float2 p = __ffma2_rn(xr, xr, __fmul2_rn(xi, xi));
+        pa[d1] = p.x;
+        pb[d1] = p.y;
+    }
+    peak_tail<NB>(pa, lane, bw2, bestA, idxA);
+    peak_tail<NB>(pb, lane, bw2, bestB, idxB);
+}
+
 }  // namespace usc
