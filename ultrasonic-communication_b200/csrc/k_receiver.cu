@@ -92,13 +92,7 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
         im[b] = make_float2(__fmul_rn(__fmul_rn(im[b].x, ca.y), w.y), __fmul_rn(__fmul_rn(im[b].y, cb.y), w.y));
     }
     fft1024_pair(re, im, tile, tb.tw, lane);
-    float zr[32], zi[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { zr[i] = re[i].x; zi[i] = im[i].x; }
-    peak_window<kRxNB>(zr, zi, ws, lane, bw2, magA, idxA);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { zr[i] = re[i].y; zi[i] = im[i].y; }
-    peak_window<kRxNB>(zr, zi, ws, lane, bw2, magB, idxB);
+    peak_window_pair<kRxNB>(re, im, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 
 __device__ __forceinline__ void load_tables(const rx_params& p, float2* s_up, float2* s_down, float2* s_hann, float2* s_tw) {

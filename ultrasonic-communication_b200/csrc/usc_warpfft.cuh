@@ -100,11 +100,10 @@ __device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32],
 #pragma unroll
     for (int d = 1; d < 32; ++d) {
         const float2 w = s_tw[d * 32 + lane];
-        float ar, ai, br, bi;
-        cmul(re[d].x, im[d].x, w.x, w.y, ar, ai);
-        cmul(re[d].y, im[d].y, w.x, w.y, br, bi);
-        re[d] = make_float2(ar, br);
-        im[d] = make_float2(ai, bi);
+        float2 tr, ti;
+        cmul2(re[d], im[d], w.x, w.y, tr, ti);
+        re[d] = tr;
+        im[d] = ti;
     }
 #pragma unroll
     for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
