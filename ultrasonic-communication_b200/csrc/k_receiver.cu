@@ -59,12 +59,24 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
                                          uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB) {
     float2 re[32], im[32];
     if (!MULTI) {
+        if (gA >= 0 && gB >= 0 && gA + 2048 <= nsamples && gB + 2048 <= nsamples) {    // both windows inside the stream
+            using V2 = typename vec2<PCM>::type;
+            const V2* pa = reinterpret_cast<const V2*>(stream + gA) + lane;
+            const V2* pb = reinterpret_cast<const V2*>(stream + gB) + lane;
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const int m = lane + 32 * b;
-            const float2 xa = load_pair<PCM>(stream, nsamples, gA + 2 * m), xb = load_pair<PCM>(stream, nsamples, gB + 2 * m);
-            re[b] = make_float2(xa.x, xb.x);
-            im[b] = make_float2(xa.y, xb.y);
+            for (int b = 0; b < 32; ++b) {
+                const V2 ra = pa[32 * b], rb = pb[32 * b];
+                re[b] = make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x));
+                im[b] = make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y));
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const int m = lane + 32 * b;
+                const float2 xa = load_pair<PCM>(stream, nsamples, gA + 2 * m), xb = load_pair<PCM>(stream, nsamples, gB + 2 * m);
+                re[b] = make_float2(xa.x, xb.x);
+                im[b] = make_float2(xa.y, xb.y);
+            }
         }
     } else {
         for (uint32_t j = sync_add; j-- > 0;) {        // oldest FIFO first
@@ -303,6 +315,19 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
         const PCM* stream = static_cast<const PCM*>(p.pcm) + (size_t) s * p.stream_stride;
         const int64_t nsamples = (int64_t) p.nframes * N;
         const int64_t fifo0 = ((int64_t) t - 2) * N;
+        {   // pull the next work item's window union (1.75 N samples = 14 KB) towards L2 while this one computes
+            const size_t wn = w + nwarps;
+            if (wn < total) {
+                const uint32_t sn = (uint32_t) (wn / p.nframes), tn = (uint32_t) (wn - (size_t) sn * p.nframes);
+                const int64_t gn = ((int64_t) tn - 2) * N + N / 2 + (tn & 1u) * offset;
+                if (gn >= 0) {
+                    const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (size_t) sn * p.stream_stride + gn);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q * 4096 + lane * 128 < 14336) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + q * 4096 + lane * 128));
+                }
+            }
+        }
         for (uint32_t i = 0; i < 4; i += 2) {
             const uint32_t pa = N / 2 + (t & 1u) * offset + shift * i, pb = pa + shift;
             float ma, mb;
