@@ -309,7 +309,7 @@ def main():
                        "symbol_accuracy_vs_tx_bits": accuracy},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "kernel": "k_demod2048<int,5>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL * NFRAMES,
+                         "kernel": "k_demod2048<int,5,8>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL * NFRAMES,
                          "note": "dual-hypothesis kernel is fp32-pipe bound (see DESIGN.md §5); frac is vs HBM"},
             "e2e": {"value": NFRAMES * world * args.e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": NFRAMES * N * 4, "d2h_bytes_per_step": NFRAMES * 17,
