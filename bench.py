@@ -259,6 +259,34 @@ def main():
     s1.record(stream)
     torch.cuda.synchronize()
     ms_single = s0.elapsed_time(s1) / args.steps
+    # reported comparison only (never on the product path): the same chain on library kernels — torch
+    # element-wise ops + cuFFT (torch.fft.rfft) + abs + arg-max, >= 6 HBM passes per hypothesis
+    cufft_ms = None
+    if rank == 0:
+        try:
+            t_up = torch.from_numpy(h.table("up")).to(dev)
+            t_dn = torch.from_numpy(h.table("down")).to(dev)
+            t_w = torch.from_numpy(h.table("hann")).to(dev)
+            sub = 16384                                      # frames per library batch (134 MB of PCM)
+
+            def lib_chain():
+                for f0 in range(0, NFRAMES, sub):
+                    x = pcm[f0:f0 + sub].to(torch.float32)
+                    for tab in (t_up, t_dn):
+                        m = torch.fft.rfft(x * tab * t_w, dim=1)[:, :156].abs()
+                        m.max(dim=1)
+            lib_chain()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(3):
+                lib_chain()
+            c1.record(stream)
+            torch.cuda.synchronize()
+            cufft_ms = c0.elapsed_time(c1) / 3
+        except Exception as exc:                             # comparison is optional
+            cufft_ms = None
+            sys.stderr.write("cuFFT comparison skipped: %r\n" % (exc,))
     for _ in range(2):                                   # leave the dual-hypothesis results in the buffers
         step()
     torch.cuda.synchronize()
@@ -319,6 +347,10 @@ def main():
                 "frac": (N * 4 + 8) * NFRAMES / (ms_single * 1e-3) / 1e9 / peak, "kernel": "k_demod2048_pair<int,5>",
                 "ms_per_launch": ms_single, "frames_per_s": NFRAMES / (ms_single * 1e-3),
                 "note": "dsp() for one hypothesis (window + 2048-pt RFFT + compression + peak), two frames per warp"},
+            "cufft_comparison": (None if cufft_ms is None else {
+                "value": NFRAMES / (cufft_ms * 1e-3), "unit": UNIT, "ms_per_step": cufft_ms,
+                "what": "torch elementwise + torch.fft.rfft (cuFFT) + abs + max per hypothesis on the same device data; "
+                        "reported comparison, not the product path"}),
             "gpu_launches": launches,
             "clocks": clocks,
         }
