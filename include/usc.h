@@ -197,6 +197,17 @@ int usc_receiver_run(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32
  * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */
 int usc_sync_search(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                     size_t stream_stride, uint32_t sync_add, float *mag, uint32_t *idx);
+/* One entry of the 4-offset scan history (experiments/chirp_compression_freq_domain/Src/main.c:95-104). */
+typedef struct usc_scan_entry {
+    float mag_max_right, mag_max_left;
+    uint32_t max_idx_right, max_idx_left;
+} usc_scan_entry;
+/* The 4-offset sliding scan of experiments/chirp_compression_freq_domain/Src/main.c:113-160, 245-251 on
+ * `batch` 2n-sample buffers (device floats, stride 2n): for offsets 0, n/4, n/2, 3n/4: x down-chirp
+ * (handle variant F or T) x Hann -> in-place RFFT -> n/2 magnitudes -> arm_max over [0, 8*bandwidth) and
+ * over the last 8*bandwidth floats of the in-place buffer (which still hold packed-spectrum values, as
+ * in the reference).  out: batch x 4 entries. */
+int usc_scan4(usc_handle *h, const float *pcm2n, uint32_t batch, usc_scan_entry *out);
 /* Synthetic receiver input generated on the device (the step before the path):
  * frame f (global index first_frame + i, so shards on different GPUs are disjoint and reproducible)
  * = the transmitter's up- or down-chirp symbol (chirp_orth, generator/ChirpGenerator.ipynb cell 1 +

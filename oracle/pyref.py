@@ -451,3 +451,20 @@ def synth_frames(seed, first_frame, nframes, amp, noise_sigma, n=2048, fs=78125.
                            C.c_float(f0), C.c_float(f1), C.c_double(amp), C.c_double(noise_sigma),
                            pcm.ctypes.data_as(i32p), bits.ctypes.data_as(C.POINTER(C.c_uint8)))
     return pcm, bits
+
+
+class ScanEntry(C.Structure):
+    _fields_ = [("mag_max_right", C.c_float), ("mag_max_left", C.c_float), ("max_idx_right", C.c_uint32),
+                ("max_idx_left", C.c_uint32)]
+
+
+def scan4(pcm2n, n=2048, fs=100000.0, f1=17000.0, f2=18000.0):
+    """experiments/chirp_compression_freq_domain 4-offset scan on one 2n-sample buffer -> 4 ScanEntry."""
+    r = Rfft(n)
+    hann = hann_window(n)
+    chirp = generate_ref_chirp("F", n, fs, f1, f2, 0.0, 0.0, 0)
+    bandwidth = int(np.float32((int(f2 - f1) * n)) / np.float32(fs))
+    buf = f32(pcm2n)
+    out = (ScanEntry * 4)()
+    lib().ref_scan4(C.byref(r.S), _fp(hann), _fp(chirp), C.c_uint32(n), C.c_uint32(bandwidth), _fp(buf), out)
+    return [(e.mag_max_right, e.max_idx_right, e.mag_max_left, e.max_idx_left) for e in out]

@@ -842,6 +842,30 @@ void ref_compress_frames_i32(const ref_compressor *c, const int32_t *pcm, size_t
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* 4-offset scan — experiments/chirp_compression_freq_domain/Src/main.c:113-160, 245-251         */
+/* ------------------------------------------------------------------------------------------ */
+void ref_scan4(const ref_rfft_fast_instance_f32 *S, const float *hann, const float *chirp, uint32_t n, uint32_t bandwidth,
+               const float *pcm2n, ref_scan_entry *out) {
+    float *buf = (float *) malloc(sizeof(float) * n), *mag = (float *) malloc(sizeof(float) * (n / 2));
+    const uint32_t bw8 = bandwidth * 8;
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t pos = (n / 4) * i;                                           /* main.c:246 */
+        for (uint32_t j = 0; j < n; ++j) buf[j] = pcm2n[j + pos];                  /* main.c:247-249 */
+        ref_arm_mult_f32(buf, chirp, buf, n);                                       /* chirp.c:42-44 */
+        ref_arm_mult_f32(buf, hann, buf, n);                                        /* main.c:123 */
+        ref_arm_rfft_fast_f32(S, buf, buf, 0);                                      /* main.c:126, in place */
+        ref_arm_cmplx_mag_f32(buf, mag, n / 2);                                     /* main.c:129, in place: */
+        memcpy(buf, mag, sizeof(float) * (n / 2));                                  /* lower half only */
+        uint32_t ir, il;
+        ref_arm_max_f32(&buf[0], bw8, &out[i].mag_max_right, &ir);                  /* main.c:146 */
+        ref_arm_max_f32(&buf[n - bw8], bw8, &out[i].mag_max_left, &il);             /* main.c:147 */
+        out[i].max_idx_right = ir;
+        out[i].max_idx_left = bw8 - il;                                             /* main.c:157 */
+    }
+    free(buf); free(mag);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* twin of the device-side synthetic generator (Philox-4x32-10, integer arithmetic only)       */
 /* ------------------------------------------------------------------------------------------ */
 static void philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {

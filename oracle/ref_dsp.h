@@ -196,6 +196,15 @@ void ref_iq_free(ref_iq *q);
 void ref_iq_demod_i32(const ref_iq *q, const int32_t *pcm, uint32_t nframes, float *mag_up, uint32_t *idx_up,
                       float *mag_down, uint32_t *idx_down);
 
+/* ---- 4-offset scan of experiments/chirp_compression_freq_domain/Src/main.c:113-160, 245-251 ---- */
+typedef struct { float mag_max_right, mag_max_left; uint32_t max_idx_right, max_idx_left; } ref_scan_entry;
+/* pcm2n: 2n floats (the 2-frame buffer, main.c:385-394).  hann: periodic; chirp: variant F down-chirp.
+ * out: 4 entries (SYNC_RESOLUTION), offsets 0, n/4, n/2, 3n/4.  The "left" window reads the upper half of
+ * the in-place buffer, which still holds packed-spectrum floats after the n/2 magnitudes were written
+ * (main.c:126-147); max_idx_left = bandwidth*8 - index (main.c:157). */
+void ref_scan4(const ref_rfft_fast_instance_f32 *S, const float *hann, const float *chirp, uint32_t n, uint32_t bandwidth,
+               const float *pcm2n, ref_scan_entry *out);
+
 /* ---- twin of the device-side synthetic generator (usc_synth_frames): regenerates any frame on the CPU ---- */
 void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
                       double amp, double noise_sigma, int32_t *pcm, uint8_t *bits);

@@ -375,3 +375,32 @@ def test_host_buffer_path_matches_device_path(h, rx):
         assert np.array_equal(g.view(np.uint32), w.view(np.uint32))
     assert np.array_equal(bit, (~(want[2] > want[0])).astype(np.uint8))
     h.host_workspace(4096)
+
+
+def test_scan4_freq_domain_experiment_bit_exact():
+    """experiments/chirp_compression_freq_domain: 4-offset scan (offsets 0, N/4, N/2, 3N/4 over a 2N buffer),
+    real down-chirp (variant F), right window on the magnitudes, left window on the leftover packed
+    spectrum floats of the in-place buffer."""
+    cfg = usc.default_config(fs=100000.0, f0=17000.0, f1=18000.0, chirp_variant=usc.CHIRP_F)
+    hf = usc.Handle(cfg)
+    assert hf.geometry()[0] == 20                                # (F2-F1)*N/fs = 20.48 -> 20
+    rng = np.random.default_rng(17)
+    B = 9
+    up = R.generate_ref_chirp("F", N, 100000.0, 17000.0, 18000.0, 0.0, 0.0, 1)
+    bufs = np.zeros((B, 2 * N), np.float32)
+    for b in range(B):
+        off = int(rng.integers(0, N))
+        bufs[b, off:off + N] += up * 20000
+        bufs[b] += rng.standard_normal(2 * N).astype(np.float32) * 3000
+    d, o = hf.buffer(bufs), hf.empty(B * 4 * 16)
+    hf.scan4(d, B, o)
+    hf.sync()
+    got = o.to_numpy(usc.scan_entry_dtype).reshape(B, 4)
+    for b in range(B):
+        want = R.scan4(bufs[b])
+        for i in range(4):
+            g = got[b, i]
+            assert (g["max_idx_right"], g["max_idx_left"]) == (want[i][1], want[i][3])
+            assert np.float32(g["mag_max_right"]).view(np.uint32) == np.float32(want[i][0]).view(np.uint32)
+            assert np.float32(g["mag_max_left"]).view(np.uint32) == np.float32(want[i][2]).view(np.uint32)
+    hf.close()

@@ -223,19 +223,21 @@ cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nfr
 
 // tail of pipeline(): packed spectrum (n floats) -> n/2 magnitudes + n/2 zeros, in place, one CTA
 // per vector staged through shared memory (receiver/Src/main.c:178 with hazard H1 defined).
-__global__ void k_pipeline_tail(float* data, uint32_t n, uint32_t batch) {
+__global__ void k_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zero_upper) {
     extern __shared__ float s_vec[];
     for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
         float* p = data + (size_t) v * n;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_vec[i] = p[i];
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-            p[i] = i < n / 2 ? cmag(s_vec[2 * i], s_vec[2 * i + 1]) : 0.0f;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            if (i < n / 2) p[i] = cmag(s_vec[2 * i], s_vec[2 * i + 1]);
+            else if (zero_upper) p[i] = 0.0f;          // otherwise the packed-spectrum floats stay (in-place semantics)
+        }
         __syncthreads();
     }
 }
 
-cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaStream_t st) {
+cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zero_upper, cudaStream_t st) {
     int grid = batch < 148u * 16u ? (int) batch : 148 * 16;
     static bool configured = false;
     if (!configured && n * sizeof(float) > 48 * 1024) {
@@ -243,7 +245,7 @@ cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaSt
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_pipeline_tail<<<grid, 256, n * sizeof(float), st>>>(data, n, batch);
+    k_pipeline_tail<<<grid, 256, n * sizeof(float), st>>>(data, n, batch, zero_upper);
     return cudaGetLastError();
 }
 

@@ -173,6 +173,23 @@ cudaError_t launch_spectrum_tail(const float* spec, uint32_t n, float inv_sqrt_n
     return cudaGetLastError();
 }
 
+// history[] entry of the 4-offset scan (experiments/chirp_compression_freq_domain/Src/main.c:152-157)
+__global__ void k_scan_pack(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t bw8,
+                            float* out, uint32_t slot, uint32_t batch) {
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < batch; v += gridDim.x * blockDim.x) {
+        float* e = out + ((size_t) v * 4 + slot) * 4;
+        e[0] = mr[v];
+        e[1] = ml[v];
+        reinterpret_cast<uint32_t*>(e)[2] = ir[v];
+        reinterpret_cast<uint32_t*>(e)[3] = bw8 - il[v];
+    }
+}
+cudaError_t launch_scan_pack(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t bw8,
+                             float* out, uint32_t slot, uint32_t batch, cudaStream_t st) {
+    k_scan_pack<<<blocks_for(batch, 128), 128, 0, st>>>(mr, ir, ml, il, bw8, out, slot, batch);
+    return cudaGetLastError();
+}
+
 // symbol decision of the receiver (receiver/Src/main.c:523): down only if strictly greater
 __global__ void k_decide(const float* __restrict__ mu, const float* __restrict__ md, uint8_t* __restrict__ bit, size_t n) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)

@@ -627,6 +627,32 @@ int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_
     return USC_OK;
 }
 
+int usc_scan4(usc_handle* h, const float* pcm2n, uint32_t batch, usc_scan_entry* out) {
+    /* experiments/chirp_compression_freq_domain/Src/main.c:113-160, 245-251 on `batch` 2n-sample buffers */
+    if (!h || !pcm2n || !out || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n, bw8 = h->bandwidth * 8;
+    if (n > 16384 || bw8 == 0 || bw8 > n / 2) return USC_ERR_ARGUMENT;
+    if (!batch) return USC_OK;
+    int rc = reserve_work(h, ((size_t) batch * n + 4 * (size_t) batch) * sizeof(float));
+    if (rc) return rc;
+    float* w = h->d_work;
+    float *mr = w + (size_t) batch * n, *ml = mr + batch;
+    uint32_t *ir = (uint32_t*) (ml + batch), *il = ir + batch;
+    fft_plan_dev plan;
+    if ((rc = make_plan(h, n / 2, n, &plan))) return rc;
+    for (uint32_t i = 0; i < 4; ++i) {
+        const float* src = pcm2n + (size_t) (n / 4) * i;                               /* main.c:246-249 */
+        LAUNCHED(h, launch_mult(src, 2 * (size_t) n, h->d_down, 0, w, n, n, batch, h->stream));   /* mult_ref_chirp (down-chirp) */
+        LAUNCHED(h, launch_mult(w, n, h->d_hann, 0, w, n, n, batch, h->stream));
+        LAUNCHED(h, launch_fft_generic(FFT_R2C, plan, w, w, batch, h->stream));
+        LAUNCHED(h, launch_pipeline_tail(w, n, batch, 0, h->stream));                  /* in-place magnitudes, upper half kept */
+        LAUNCHED(h, launch_max(w, n, bw8, mr, ir, batch, h->stream));
+        LAUNCHED(h, launch_max(w + (n - bw8), n, bw8, ml, il, batch, h->stream));
+        LAUNCHED(h, launch_scan_pack(mr, ir, ml, il, bw8, (float*) out, i, batch, h->stream));
+    }
+    return USC_OK;
+}
+
 int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp, double noise_sigma,
                      int32_t* pcm, uint8_t* bits) {
     if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
@@ -755,7 +781,7 @@ int usc_pipeline(usc_handle* h, const float* frames, float* mags, int updown, ui
     if ((rc = usc_arm_mult_f32_batch(h, frames, n, updown ? h->d_up : h->d_down, 0, mags, n, n, batch))) return rc;
     if ((rc = usc_arm_mult_f32_batch(h, mags, n, h->d_hann, 0, mags, n, n, batch))) return rc;
     if ((rc = usc_arm_rfft_fast_f32_batch(h, n, mags, mags, 0, batch))) return rc;
-    LAUNCHED(h, launch_pipeline_tail(mags, n, batch, h->stream));
+    LAUNCHED(h, launch_pipeline_tail(mags, n, batch, 1, h->stream));
     return USC_OK;
 }
 

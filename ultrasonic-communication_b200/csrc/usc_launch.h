@@ -7,6 +7,8 @@ namespace usc {
 cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st);
 cudaError_t launch_spectrum_tail(const float* spec, uint32_t n, float inv_sqrt_n, uint32_t ac_bins, float* mag, float* db,
                                  float* peak, uint32_t* peak_idx, uint32_t batch, cudaStream_t st);
+cudaError_t launch_scan_pack(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t bw8,
+                             float* out, uint32_t slot, uint32_t batch, cudaStream_t st);
 cudaError_t launch_decide(const float* mu, const float* md, uint8_t* bit, size_t n, cudaStream_t st);
 cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
                         uint32_t len, uint32_t batch, cudaStream_t st);
@@ -45,5 +47,5 @@ cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml,
                            float* mag, uint32_t* idx, size_t count, cudaStream_t st);
 cudaError_t launch_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, const int32_t* table,
                                 int32_t gain, int32_t* pcm, uint8_t* bits, cudaStream_t st);
-cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, cudaStream_t st);
+cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zero_upper, cudaStream_t st);
 }  // namespace usc

@@ -35,6 +35,8 @@ history_dtype = np.dtype([("mag_max", "f4"), ("mag_max_left", "f4"), ("mag_max_r
 rx_result_dtype = np.dtype([("state", "u4"), ("sync_position", "u4"), ("lock_frame", "i4"), ("lock_position", "u4"),
                             ("nbytes", "u4"), ("frames_seen", "u4"), ("turn", "u4"), ("sync_cnt", "u4")])
 
+scan_entry_dtype = np.dtype([("mag_max_right", "f4"), ("mag_max_left", "f4"), ("max_idx_right", "u4"), ("max_idx_left", "u4")])
+
 # every symbol include/usc.h declares (tests/test_abi.py checks the .so exports each one)
 SYMBOLS = [
     "usc_default_config", "usc_create", "usc_destroy", "usc_set_stream", "usc_sync", "usc_error_string",
@@ -43,7 +45,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -285,6 +287,9 @@ class Handle:
     def synth_frames(self, seed, first_frame, nframes, amp, noise_sigma, pcm, bits=None):
         _ck(load().usc_synth_frames(self._h, C.c_uint64(seed), C.c_uint64(first_frame), C.c_size_t(nframes), C.c_double(amp),
                                     C.c_double(noise_sigma), _ptr(pcm), _ptr(bits)))
+
+    def scan4(self, pcm2n, batch, out):
+        _ck(load().usc_scan4(self._h, _ptr(pcm2n), C.c_uint32(batch), _ptr(out)))
 
     def spectrum_analyzer(self, pcm, pcm_format, nframes, ac_coupling_hz, mag=None, db=None, peak=None, peak_idx=None):
         _ck(load().usc_spectrum_analyzer(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nframes),
