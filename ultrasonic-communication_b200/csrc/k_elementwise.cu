@@ -190,6 +190,52 @@ cudaError_t launch_scan_pack(const float* mr, const uint32_t* ir, const float* m
     return cudaGetLastError();
 }
 
+// Front end of the receiver chain for any frame length: (float) pcm -> x chirp -> x Hann in one pass
+// (receiver/Src/main.c:663-665, chirp.c:47-53, main.c:171).  Tables are broadcast over the batch.
+template <typename PCM>
+__global__ void k_prep(const PCM* __restrict__ pcm, const float* __restrict__ chirp, const float* __restrict__ hann,
+                       float* __restrict__ dst, uint32_t n, size_t total) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const uint32_t e = (uint32_t) (i % n);
+        dst[i] = __fmul_rn(__fmul_rn(pcm_cast(pcm[i]), chirp[e]), hann[e]);
+    }
+}
+cudaError_t launch_prep(const void* pcm, uint32_t pcm_format, const float* chirp, const float* hann, float* dst, uint32_t n,
+                        size_t total, cudaStream_t st) {
+    if (pcm_format == 1u) k_prep<int32_t><<<blocks_for(total, 256), 256, 0, st>>>((const int32_t*) pcm, chirp, hann, dst, n, total);
+    else k_prep<float><<<blocks_for(total, 256), 256, 0, st>>>((const float*) pcm, chirp, hann, dst, n, total);
+    return cudaGetLastError();
+}
+
+// Tail of the receiver chain for any frame length: magnitudes of the packed bins [0, window) and their
+// first-occurrence arg-max (arm_cmplx_mag_f32 + arm_max_f32, main.c:178, 208).  One warp per frame.
+__global__ void k_mag_max(const float* __restrict__ spec, size_t stride, uint32_t window, float* __restrict__ result,
+                          uint32_t* __restrict__ index, uint32_t batch) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    for (size_t v = warp; v < batch; v += nwarps) {
+        const float2* p = reinterpret_cast<const float2*>(spec + v * stride);
+        float best = -INFINITY;
+        uint32_t bi = 0xffffffffu;
+        for (uint32_t e = lane; e < window; e += 32) {
+            const float2 z = p[e];
+            const float m = cmag(z.x, z.y);
+            if (bi == 0xffffffffu || best < m) { best = m; bi = e; }
+        }
+        warp_argmax(best, bi);
+        if (lane == 0) {
+            result[v] = best;
+            if (index) index[v] = bi;
+        }
+    }
+}
+cudaError_t launch_mag_max(const float* spec, size_t stride, uint32_t window, float* result, uint32_t* index, uint32_t batch,
+                           cudaStream_t st) {
+    k_mag_max<<<blocks_for((size_t) batch * 32, 256), 256, 0, st>>>(spec, stride, window, result, index, batch);
+    return cudaGetLastError();
+}
+
 // symbol decision of the receiver (receiver/Src/main.c:523): down only if strictly greater
 __global__ void k_decide(const float* __restrict__ mu, const float* __restrict__ md, uint8_t* __restrict__ bit, size_t n) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)

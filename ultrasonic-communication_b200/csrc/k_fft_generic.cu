@@ -14,19 +14,24 @@ namespace usc {
 
 constexpr int kFftThreads = 256;
 
+// one float2 of padding per 32 keeps the last level (each thread owns 32 CONTIGUOUS points, i.e. a
+// stride of 32 float2 between lanes) free of shared-memory bank conflicts
+__device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 5); }
+
 template <int B>
 __device__ __forceinline__ void level_items(float2* s, uint32_t n_total, uint32_t n_l, const float2* tw,
                                             uint32_t tw_n, bool last) {
     const uint32_t A = n_l / B;
     const uint32_t items = n_total / B;
     const uint32_t tw_step = tw_n / n_l;
+    const uint32_t la = 31u - (uint32_t) __clz(A);          // all lengths are powers of two
     for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
-        const uint32_t blk = it / A, a = it - blk * A;
-        float2* base = s + (size_t) blk * n_l + a;
+        const uint32_t blk = it >> la, a = it & (A - 1u);
+        const uint32_t base = blk * n_l + a;
         float re[B], im[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-            float2 v = base[(size_t) A * b];
+            float2 v = s[pad(base + A * b)];
             re[b] = v.x;
             im[b] = v.y;
         }
@@ -38,7 +43,7 @@ __device__ __forceinline__ void level_items(float2* s, uint32_t n_total, uint32_
                 float2 w = tw[(size_t) a * d * tw_step];
                 cmul(re[d], im[d], w.x, w.y, xr, xi);
             }
-            base[(size_t) A * d] = make_float2(xr, xi);
+            s[pad(base + A * d)] = make_float2(xr, xi);
         }
     }
 }
@@ -61,13 +66,12 @@ __device__ __forceinline__ void run_levels(float2* s, const fft_plan_dev& plan) 
 
 // position in the level buffer of output index k
 __device__ __forceinline__ uint32_t out_position(const fft_plan_dev& plan, uint32_t k) {
-    uint32_t pos = 0, n_l = plan.n;
+    uint32_t pos = 0, ln = 31u - (uint32_t) __clz(plan.n);
     for (uint32_t l = 0; l < plan.nrad; ++l) {
-        const uint32_t B = plan.rad[l], A = n_l / B;
-        const uint32_t d = k % B;
-        k /= B;
-        pos += d * A;
-        n_l = A;
+        const uint32_t B = plan.rad[l], lb = 31u - (uint32_t) __clz(B);
+        ln -= lb;                                      // log2(A)
+        pos += (k & (B - 1u)) << ln;
+        k >>= lb;
     }
     return pos;
 }
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_generic(fft_plan_dev plan, 
                                                              uint32_t batch) {
     extern __shared__ float2 s_fft[];
     float2* work = s_fft;
-    float2* nat = s_fft + plan.n;
+    float2* nat = s_fft + pad(plan.n) + 1;
     const uint32_t n = plan.n;
     for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
         const float2* src = reinterpret_cast<const float2*>(in) + (size_t) v * n;
@@ -96,17 +100,17 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_generic(fft_plan_dev plan, 
                     float2 w = plan.tw[k];                   // master table has 2n entries: W_N^k
                     rfft_merge(xk.x, xk.y, xc.x, xc.y, w.x, -w.y, zr, zi);
                 }
-                work[k] = make_float2(zi, zr);
+                work[pad(k)] = make_float2(zi, zr);
             }
         } else {
             for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
                 float2 x = src[k];
-                work[k] = MODE == FFT_C2C_INV ? make_float2(x.y, x.x) : x;
+                work[pad(k)] = MODE == FFT_C2C_INV ? make_float2(x.y, x.x) : x;
             }
         }
         __syncthreads();
         run_levels(work, plan);
-        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) nat[k] = work[out_position(plan, k)];
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) nat[k] = work[pad(out_position(plan, k))];
         __syncthreads();
         if (MODE == FFT_C2C_FWD) {
             for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) dst[k] = nat[k];
@@ -231,7 +235,7 @@ cudaError_t launch_fft_large(int mode, const fft_plan_dev& plan, const float* in
 }
 
 cudaError_t fft_generic_prepare() {
-    const int max_smem = 128 * 1024;
+    const int max_smem = 136 * 1024;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2C_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
     if ((e = cudaFuncSetAttribute(k_fft_generic<FFT_C2C_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))) return e;
@@ -242,8 +246,8 @@ cudaError_t fft_generic_prepare() {
 
 cudaError_t launch_fft_generic(int mode, const fft_plan_dev& plan, const float* in, float* out, uint32_t batch,
                                cudaStream_t st) {
-    const size_t smem = sizeof(float2) * 2 * (size_t) plan.n;
-    if (smem > 128 * 1024) return cudaErrorInvalidValue;
+    const size_t smem = sizeof(float2) * (2 * (size_t) plan.n + plan.n / 32 + 2);
+    if (smem > 136 * 1024) return cudaErrorInvalidValue;
     int grid = batch < 148u * 16u ? (int) batch : 148 * 16;
     if (grid < 1) grid = 1;
     switch (mode) {

@@ -447,30 +447,24 @@ static int demod_generic(usc_handle* h, const void* pcm, uint32_t pcm_format, si
     if (nframes > 0xffffffffu || h->bandwidth2 == 0 || h->bandwidth2 > n / 2) return USC_ERR_ARGUMENT;
     const uint32_t B = (uint32_t) nframes;
     const size_t W = nframes * n;
-    int rc = reserve_work(h, (3 * W + 2 * nframes) * sizeof(float));
+    int rc = reserve_work(h, (2 * W + 2 * nframes) * sizeof(float));
     if (rc) return rc;
-    float *fA = h->d_work, *fB = fA + W, *fC = fB + W, *tmp_mag = fC + W;
-    const float* x = (const float*) pcm;
-    if (pcm_format == USC_PCM_I32) {
-        LAUNCHED(h, launch_i32_to_f32((const int32_t*) pcm, fC, W, h->stream));
-        x = fC;
-    }
+    float *fA = h->d_work, *fB = fA + W, *tmp_mag = fB + W;
     fft_plan_dev plan;
     if ((rc = make_plan(h, n / 2, n, &plan))) return rc;
     float* mags[2] = {mag_up ? mag_up : tmp_mag, mag_down ? mag_down : tmp_mag + nframes};
     uint32_t* idxs[2] = {idx_up, idx_down};
     const float* chirps[2] = {h->d_up, h->d_down};
     for (int hyp = 0; hyp < 2; ++hyp) {
-        LAUNCHED(h, launch_mult(x, n, chirps[hyp], 0, fA, n, n, B, h->stream));
-        LAUNCHED(h, launch_mult(fA, n, h->d_hann, 0, fA, n, n, B, h->stream));
+        /* cast, de-chirp and window in one pass; RFFT; magnitude + windowed arg-max in one pass */
+        LAUNCHED(h, launch_prep(pcm, pcm_format, chirps[hyp], h->d_hann, fA, n, W, h->stream));
         if (n > 16384) {
             CK(launch_fft_large(FFT_R2C, plan, fA, fA, fB, B, h->stream));
             h->launches += 3;
         } else {
             LAUNCHED(h, launch_fft_generic(FFT_R2C, plan, fA, fA, B, h->stream));
         }
-        LAUNCHED(h, launch_cmag(fA, n, fB, n / 2, n / 2, B, h->stream));
-        LAUNCHED(h, launch_max(fB, n / 2, h->bandwidth2, mags[hyp], idxs[hyp], B, h->stream));
+        LAUNCHED(h, launch_mag_max(fA, n, h->bandwidth2, mags[hyp], idxs[hyp], B, h->stream));
     }
     if (bit) LAUNCHED(h, launch_decide(mags[0], mags[1], bit, nframes, h->stream));
     return USC_OK;

@@ -9,6 +9,10 @@ cudaError_t launch_spectrum_tail(const float* spec, uint32_t n, float inv_sqrt_n
                                  float* peak, uint32_t* peak_idx, uint32_t batch, cudaStream_t st);
 cudaError_t launch_scan_pack(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t bw8,
                              float* out, uint32_t slot, uint32_t batch, cudaStream_t st);
+cudaError_t launch_prep(const void* pcm, uint32_t pcm_format, const float* chirp, const float* hann, float* dst, uint32_t n,
+                        size_t total, cudaStream_t st);
+cudaError_t launch_mag_max(const float* spec, size_t stride, uint32_t window, float* result, uint32_t* index, uint32_t batch,
+                           cudaStream_t st);
 cudaError_t launch_decide(const float* mu, const float* md, uint8_t* bit, size_t n, cudaStream_t st);
 cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
                         uint32_t len, uint32_t batch, cudaStream_t st);
