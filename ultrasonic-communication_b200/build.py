@@ -15,12 +15,12 @@ OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libusc.so")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v",
               "--expt-relaxed-constexpr"]
 CC_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-Wall"]
 
-CU = ["usc_api.cu", "k_demod.cu", "k_receiver.cu", "k_sync.cu", "k_iq.cu", "k_synth.cu", "k_compress.cu", "k_fft_generic.cu", "k_elementwise.cu"]
+CU = ["usc_api.cu", "k_demod.cu", "k_receiver.cu", "k_sync.cu", "k_iq.cu", "k_synth.cu", "k_long.cu", "k_compress.cu", "k_fft_generic.cu", "k_elementwise.cu"]
 C = ["usc_tables.c"]
 
 

@@ -166,8 +166,9 @@ __global__ void __launch_bounds__(kCWarps * 32, 1) k_compress2048(compress_param
             const V2 ra = xstage[m];
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 w = s_win[m];
-            re[b] = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(w.x));
-            im[b] = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(w.y));
+            // scalar multiplies: a packed mul.rn.f32x2 feeding the first butterfly's add would be contracted by ptxas
+            re[b] = make_float2(__fmul_rn(pcm_to_float(ra.x), w.x), __fmul_rn(pcm_to_float(rb.x), w.x));
+            im[b] = make_float2(__fmul_rn(pcm_to_float(ra.y), w.y), __fmul_rn(pcm_to_float(rb.y), w.y));
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {

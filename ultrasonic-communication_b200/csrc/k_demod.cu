@@ -93,8 +93,12 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
             float4 c = s_ud[m];                                       // (up[2m], down[2m], up[2m+1], down[2m+1])
             float2 w = s_hann[m];
-            re[b] = __fmul2_rn(__fmul2_rn(make_float2(c.x, c.y), bc2(x0)), bc2(w.x));     // ((x*c)*w), both hypotheses
-            im[b] = __fmul2_rn(__fmul2_rn(make_float2(c.z, c.w), bc2(x1)), bc2(w.y));
+            // ((x*c)*w) for both hypotheses.  The window multiply stays SCALAR on purpose: ptxas 12.9 contracts
+            // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would fuse this product
+            // into the first butterfly's additions and break bit-parity; scalar mul.rn is never contracted.
+            const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
+            re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));
+            im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
         }
         __syncwarp();                                                 // every lane has consumed the stage
         if (lane == 0 && f + nwarps < p.nframes) {                    // refill it with this warp's next frame
@@ -200,8 +204,11 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 c = s_chirp[m], w = s_hann[m];
             // ((x*c)*w) on both frames at once: the per-lane table values broadcast to the two halves
-            re[b] = __fmul2_rn(__fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(c.x)), bc2(w.x));
-            im[b] = __fmul2_rn(__fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(c.y)), bc2(w.y));
+            // (window multiply scalar: see the note in k_demod2048 about ptxas contracting packed mul + add)
+            const float2 tr = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(c.x));
+            const float2 ti = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(c.y));
+            re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));
+            im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {

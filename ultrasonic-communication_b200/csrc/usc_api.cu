@@ -186,22 +186,27 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     // master table W_n (n entries) serves the n-point real FFT (n/2 complex) and its split stage
     float2* d_master = nullptr;
     if ((rc = get_twiddles(h, n, &d_master))) { usc_destroy(h); return rc; }
-    if (n == 2048) {
-        // fused-kernel tables: pass twiddles W_1024^(a d) laid out [d][a]; split table (cos, sin)(2 pi k / 2048)
+    if (n >= 2048) {
+        // fused-kernel tables: pass twiddles W_1024^(a d) laid out [d][a] (identical values for every master
+        // length: the double argument 2*pi*j/1024 is reproduced exactly); split table (cos, sin)(2 pi k / 2048)
         const std::vector<float>& tw = h->tw_host[n];
-        std::vector<float> pass(2 * 1024), split(2 * 1024);
+        std::vector<float> pass(2 * 1024);
+        const uint32_t step = n / 1024;
         for (uint32_t d = 0; d < 32; ++d)
             for (uint32_t a = 0; a < 32; ++a) {
-                const uint32_t j = a * d * 2;                    // W_1024^(ad) = W_2048^(2ad)
+                const uint32_t j = a * d * step;                 // W_1024^(ad) = W_n^(ad * n/1024)
                 pass[2 * (d * 32 + a)] = tw[2 * j];
                 pass[2 * (d * 32 + a) + 1] = tw[2 * j + 1];
             }
-        for (uint32_t k = 0; k < 1024; ++k) {
-            split[2 * k] = tw[2 * k];
-            split[2 * k + 1] = -tw[2 * k + 1];
-        }
         if ((rc = upload(pass.data(), pass.size() * 4, (void**) &h->d_tw_pass))) { usc_destroy(h); return rc; }
-        if ((rc = upload(split.data(), split.size() * 4, (void**) &h->d_tw_split))) { usc_destroy(h); return rc; }
+        if (n == 2048) {
+            std::vector<float> split(2 * 1024);
+            for (uint32_t k = 0; k < 1024; ++k) {
+                split[2 * k] = tw[2 * k];
+                split[2 * k + 1] = -tw[2 * k + 1];
+            }
+            if ((rc = upload(split.data(), split.size() * 4, (void**) &h->d_tw_split))) { usc_destroy(h); return rc; }
+        }
     }
     if (cfg->chirp_variant == USC_CHIRP_T) {
         // init_ref_chirp of experiments/chirp_compression_time_domain/Src/chirp.c:52-75:
@@ -476,6 +481,16 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     if (h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;     /* frames are fetched by 16-byte-aligned bulk copies */
     if (!nframes) return USC_OK;
+    if ((h->cfg.n == 8192 || h->cfg.n == 16384) && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u)) {
+        /* long frames: one CTA per frame, level 0 from global memory, packed 1024-point cores (k_long.cu) */
+        float2* master = nullptr;
+        int rc = get_twiddles(h, h->cfg.n, &master);
+        if (rc) return rc;
+        LAUNCHED(h, launch_demod_long(pcm, pcm_format, nframes, h->cfg.n, (const float2*) h->d_ud, (const float2*) h->d_hann,
+                                      master, h->d_tw_pass, h->bandwidth2, mag_up, idx_up, mag_down, idx_down, bit,
+                                      h->num_sms, h->stream));
+        return USC_OK;
+    }
     if (h->cfg.n != 2048 || h->bandwidth2 == 0 || h->bandwidth2 > 512)
         return demod_generic(h, pcm, pcm_format, nframes, mag_up, idx_up, mag_down, idx_down, bit);
     demod_params p;

@@ -107,6 +107,10 @@ __device__ __forceinline__ void fft_base(float (&re)[R], float (&im)[R]) {
 // two transforms side by side in the halves of a float2 gives bit-identical results to two scalar
 // runs while halving the issue slots; the fused demodulator carries the up-chirp hypothesis in .x
 // and the down-chirp hypothesis in .y.
+// CAVEAT (ptxas 12.9): a mul.rn.f32x2 whose only consumer is an add.rn.f32x2 is contracted into FFMA2 even
+// with -fmad=false (scalar mul.rn/add.rn never are).  Every packed multiply here therefore feeds an FMA
+// addend/multiplicand or a scalar operation, never a packed add; products that must reach a packed add
+// (front-end window multiplies) are done with scalar __fmul_rn.  tools/microbench shows the reproducer.
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 bc2(float c) { return make_float2(c, c); }
 
