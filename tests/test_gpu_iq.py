@@ -49,3 +49,33 @@ def test_iq_requires_init_and_checks_arguments(fir_taps):
     with pytest.raises(usc.UscError):
         h.iq_init(18000.0, 3000.0, np.zeros(100, np.float32), 32)
     h.close()
+
+
+@pytest.mark.parametrize("ntaps,window,unfused", [(27, 32, True), (5, 8, False), (16, 32, False), (32, 20, False),
+                                                  (1, 32, False), (33, 32, False), (27, 48, False)])
+def test_iq_variants_match_oracle(fir_taps, monkeypatch, ntaps, window, unfused):
+    """Tap counts either side of the register-blocked FIR's limit (32), odd and even history lengths,
+    narrower and wider peak windows, and the operator-chain form (USC_IQ_UNFUSED) — all exact."""
+    if unfused:
+        monkeypatch.setenv("USC_IQ_UNFUSED", "1")
+    rng = np.random.default_rng(ntaps)
+    taps = np.resize(fir_taps.astype(np.float32)[::-1], ntaps).copy() if ntaps != 27 else fir_taps.astype(np.float32)[::-1].copy()
+    taps *= rng.uniform(0.5, 1.5, ntaps).astype(np.float32)
+    h = usc.Handle()
+    h.iq_init(18000.0, 3000.0, taps, window)
+    q = R.RefIq(taps, window_bins=window)
+    S, F = 3, 11
+    pcm = np.stack([synth.make_iq_stream(F, snr_db=snr, seed_bits=70 + s, seed_noise=80 + s)[0]
+                    for s, snr in enumerate((15.0, 0.0, -8.0))])
+    d = h.buffer(pcm)
+    o = [h.empty(4 * S * F) for _ in range(4)]
+    b = h.empty(S * F)
+    h.iq_demod(d, usc.PCM_I32, S, F, F * N, o[0], o[1], o[2], o[3], b)
+    h.sync()
+    got = [o[0].to_numpy(np.float32).reshape(S, F), o[1].to_numpy(np.uint32).reshape(S, F),
+           o[2].to_numpy(np.float32).reshape(S, F), o[3].to_numpy(np.uint32).reshape(S, F)]
+    for s in range(S):
+        want = q.demod(pcm[s])
+        for g, w in zip(got, want):
+            assert np.array_equal(g[s].view(np.uint32), w.view(np.uint32)), s
+    h.close()

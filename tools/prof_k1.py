@@ -34,3 +34,12 @@ if which == "single":
         h.demod_frames(pcm, usc.PCM_I32, F, o[0], o[1])
     torch.cuda.synchronize()
     print("done single", reps)
+if which == "iq":
+    import numpy as np
+    taps = np.load(os.path.join(ROOT, "tests/golden/fir_taps.npz"))["taps"].astype(np.float32)[::-1].copy()
+    h = usc.Handle()
+    h.iq_init(18000.0, 3000.0, taps, 32)
+    for _ in range(reps):
+        h.iq_demod(pcm, usc.PCM_I32, 4096, 38, 38 * 2048, o[0], o[1], o[2], o[3], b)
+    torch.cuda.synchronize()
+    print("done iq", reps)

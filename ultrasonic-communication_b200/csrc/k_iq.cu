@@ -55,6 +55,76 @@ __global__ void __launch_bounds__(256) k_iq_frontend(const PCM* __restrict__ pcm
     }
 }
 
+// Register-blocked variant for ntaps <= 32: one CTA per frame, each thread owns four consecutive outputs
+// of both rails.  Mixed samples are staged as (even, odd) pairs; output j at tap pair q - j reads pair
+// m0 + q, so one pair load feeds up to four outputs.  The accumulation order per output is the
+// reference's (taps ascending, one FMA each).  Pair index p lives at p + (p >> 2) to spread the
+// 4-pair lane stride over the banks.
+constexpr int kFirTmax = 32, kFirOut = 4, kFirPairs = kFirTmax / 2 + kFirOut - 1;
+
+template <typename PCM>
+__global__ void __launch_bounds__(256) k_iq_frontend_rb(const PCM* __restrict__ pcm, uint32_t nstreams, uint32_t nframes,
+                                                        size_t stream_stride, const float* __restrict__ car_cos,
+                                                        const float* __restrict__ car_sin, const float* __restrict__ taps,
+                                                        uint32_t ntaps, float2* __restrict__ out) {
+    constexpr uint32_t n = 2048, P = n / 2 + kFirPairs + 4, PP = P + (P >> 2) + 1;      // pairs per rail (padded)
+    __shared__ float2 sI[PP], sQ[PP];
+    const uint32_t H = ntaps - 1;
+    float t[kFirTmax];
+#pragma unroll
+    for (int i = 0; i < kFirTmax; ++i) t[i] = (uint32_t) i < ntaps ? taps[i] : 0.0f;
+    const size_t total = (size_t) nstreams * nframes;
+    for (size_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const uint32_t s = (uint32_t) (w / nframes), fr = (uint32_t) (w - (size_t) s * nframes);
+        const PCM* cur = pcm + (size_t) s * stream_stride + (size_t) fr * n;
+        for (uint32_t j = threadIdx.x; j < 2 * P; j += blockDim.x) {
+            float vi = 0.0f, vq = 0.0f;
+            if (j >= H && j < n + H) {
+                const uint32_t k = j - H;
+                const float x = pcm_cast(cur[k]);
+                vi = __fmul_rn(x, car_cos[k]);
+                vq = __fmul_rn(x, car_sin[k]);
+            } else if (j < H && fr > 0) {                    // history: tail of the previous frame
+                const uint32_t k = n - H + j;
+                const float x = pcm_cast(cur[(ptrdiff_t) k - (ptrdiff_t) n]);
+                vi = __fmul_rn(x, car_cos[k]);
+                vq = __fmul_rn(x, car_sin[k]);
+            }
+            const uint32_t pp = j >> 1, slot = pp + (pp >> 2);
+            reinterpret_cast<float*>(sI)[2 * slot + (j & 1)] = vi;
+            reinterpret_cast<float*>(sQ)[2 * slot + (j & 1)] = vq;
+        }
+        __syncthreads();
+        const uint32_t m0 = threadIdx.x * kFirOut;
+        float ai[kFirOut], aq[kFirOut];
+#pragma unroll
+        for (int j = 0; j < kFirOut; ++j) ai[j] = aq[j] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kFirPairs; ++q) {
+            if ((uint32_t) (2 * (q - (kFirOut - 1))) >= ntaps && q >= kFirOut - 1) break;     // past the last tap for every output
+            const uint32_t pp = m0 + q, slot = pp + (pp >> 2);
+            const float2 vi = sI[slot], vq = sQ[slot];
+#pragma unroll
+            for (int j = 0; j < kFirOut; ++j) {
+                const int i0 = 2 * (q - j);
+                if (i0 < 0 || i0 >= kFirTmax) continue;
+                if ((uint32_t) i0 < ntaps) {
+                    ai[j] = __fmaf_rn(vi.x, t[i0], ai[j]);
+                    aq[j] = __fmaf_rn(vq.x, t[i0], aq[j]);
+                }
+                if ((uint32_t) (i0 + 1) < ntaps) {
+                    ai[j] = __fmaf_rn(vi.y, t[i0 + 1], ai[j]);
+                    aq[j] = __fmaf_rn(vq.y, t[i0 + 1], aq[j]);
+                }
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(out + w * (n / 2) + m0);
+        dst[0] = make_float4(ai[0], aq[0], ai[1], aq[1]);
+        dst[1] = make_float4(ai[2], aq[2], ai[3], aq[3]);
+        __syncthreads();
+    }
+}
+
 // left/right choice (strict '>' keeps the right window on ties) and absolute bin of the winner
 __global__ void k_iq_pick(const float* __restrict__ mr, const uint32_t* __restrict__ ir, const float* __restrict__ ml,
                           const uint32_t* __restrict__ il, uint32_t left0, float* __restrict__ mag,
@@ -73,6 +143,16 @@ cudaError_t launch_iq_frontend(const void* pcm, uint32_t pcm_format, uint32_t ns
     const int grid = (int) (total < 148u * 16u ? total : 148u * 16u);
     const size_t smem = sizeof(float) * (2 * ((size_t) n + ntaps - 1) + ntaps);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    if (n == 2048 && ntaps <= (uint32_t) kFirTmax && ntaps >= 1) {
+        const int g2 = (int) (total < 148u * 8u ? total : 148u * 8u);
+        if (pcm_format == 1u)
+            k_iq_frontend_rb<int32_t><<<g2, 256, 0, st>>>((const int32_t*) pcm, nstreams, nframes, stream_stride, car_cos,
+                                                           car_sin, taps, ntaps, (float2*) out);
+        else
+            k_iq_frontend_rb<float><<<g2, 256, 0, st>>>((const float*) pcm, nstreams, nframes, stream_stride, car_cos, car_sin,
+                                                         taps, ntaps, (float2*) out);
+        return cudaGetLastError();
+    }
     if (pcm_format == 1u)
         k_iq_frontend<int32_t><<<grid, 256, smem, st>>>((const int32_t*) pcm, nstreams, nframes, stream_stride, n, car_cos,
                                                          car_sin, taps, ntaps, (float2*) out);
@@ -87,6 +167,286 @@ cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml,
     size_t b = (count + 255) / 256;
     if (b > 148u * 8u) b = 148u * 8u;
     k_iq_pick<<<(int) (b ? b : 1), 256, 0, st>>>(mr, ir, ml, il, left0, mag, idx, count);
+    return cudaGetLastError();
+}
+
+}  // namespace usc
+
+// ---- fused back end of the I/Q path ------------------------------------------------------------------
+// One warp per frame; the halves of the packed core carry the two hypotheses: .x = R x conj(chirp)
+// (up), .y = R x chirp (down).  Hann, the 1024-point complex FFT ([32,32] plan), magnitudes and the two
+// windowed arg-max searches around DC follow.  With window_bins <= 32 only outputs k = d0 (element 0)
+// and k = 992 + d0 (element 31) of the last pass are needed, so 30 of its 32 outputs are pruned.
+#include "usc_warpfft.cuh"
+
+namespace usc {
+
+constexpr int kIqWarps = 8;
+constexpr int kIqSmem = 8192 + 8192 + 4096 + kIqWarps * 8192;     // twiddles | chirp | Hann | per-warp tile
+
+__global__ void __launch_bounds__(kIqWarps * 32, 1) k_iq_backend(const float2* __restrict__ R, size_t nframes,
+                                                                 const float2* __restrict__ chirp,
+                                                                 const float* __restrict__ hann,
+                                                                 const float2* __restrict__ tw_pass, uint32_t W,
+                                                                 float* mag_up, uint32_t* idx_up, float* mag_down,
+                                                                 uint32_t* idx_down, uint8_t* bit) {
+    extern __shared__ __align__(16) unsigned char s_iq2[];
+    float2* s_tw = reinterpret_cast<float2*>(s_iq2);
+    float2* s_c = reinterpret_cast<float2*>(s_iq2 + 8192);
+    float* s_w = reinterpret_cast<float*>(s_iq2 + 16384);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = reinterpret_cast<float2*>(s_iq2 + 20480) + warp * 1024;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        s_tw[i] = tw_pass[i];
+        s_c[i] = chirp[i];
+        s_w[i] = hann[i];
+    }
+    __syncthreads();
+    const size_t nwarps = (size_t) gridDim.x * kIqWarps;
+    for (size_t f = (size_t) blockIdx.x * kIqWarps + warp; f < nframes; f += nwarps) {
+        const float2* src = R + f * 1024;
+        float2 re[32], im[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int m = lane + 32 * b;
+            const float2 r = src[m], c = s_c[m];
+            const float w = s_w[m];
+            float ur, ui, dr, di;
+            cmul(r.x, r.y, c.x, -c.y, ur, ui);           // arm_cmplx_mult_cmplx_f32(R, conj chirp)
+            cmul(r.x, r.y, c.x, c.y, dr, di);            // arm_cmplx_mult_cmplx_f32(R, chirp)
+            re[b] = make_float2(__fmul_rn(ur, w), __fmul_rn(dr, w));     // arm_cmplx_mult_real_f32 (scalar: see usc_arith.cuh)
+            im[b] = make_float2(__fmul_rn(ui, w), __fmul_rn(di, w));
+        }
+        fft1024_pair(re, im, tile, s_tw, lane);
+        // candidates of this lane: right window k = lane (element 0), left window k = 992 + lane (element 31)
+        const float2 pr = __ffma2_rn(re[0], re[0], __fmul2_rn(im[0], im[0]));
+        const float2 pl = __ffma2_rn(re[31], re[31], __fmul2_rn(im[31], im[31]));
+        const bool in_r = (uint32_t) lane < W, in_l = 992u + lane >= 1024u - W;
+        float out_m[2];
+        uint32_t out_i[2];
+#pragma unroll
+        for (int hyp = 0; hyp < 2; ++hyp) {
+            float mr = in_r ? __fsqrt_rn(hyp ? pr.y : pr.x) : -INFINITY, ml = in_l ? __fsqrt_rn(hyp ? pl.y : pl.x) : -INFINITY;
+            uint32_t ir = in_r ? (uint32_t) lane : 0xffffffffu, il = in_l ? 992u + lane : 0xffffffffu;
+            warp_argmax(mr, ir);                           // arm_max_f32 over [0, W)
+            warp_argmax(ml, il);                           // arm_max_f32 over [1024 - W, 1024)
+            const bool left = ml > mr;                     // strict: right wins ties
+            out_m[hyp] = left ? ml : mr;
+            out_i[hyp] = left ? il : ir;
+        }
+        if (lane == 0) {
+            if (mag_up) mag_up[f] = out_m[0];
+            if (idx_up) idx_up[f] = out_i[0];
+            if (mag_down) mag_down[f] = out_m[1];
+            if (idx_down) idx_down[f] = out_i[1];
+            if (bit) bit[f] = out_m[1] > out_m[0] ? 0 : 1;
+        }
+    }
+}
+
+cudaError_t launch_iq_backend(const float* R, size_t nframes, const float* chirp, const float* hann, const float2* tw_pass,
+                              uint32_t window, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                              uint8_t* bit, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_iq_backend, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    size_t ctas = (nframes + kIqWarps - 1) / kIqWarps;
+    if (ctas > (size_t) num_sms * 2) ctas = (size_t) num_sms * 2;
+    k_iq_backend<<<(int) ctas, kIqWarps * 32, kIqSmem, st>>>((const float2*) R, nframes, (const float2*) chirp, hann, tw_pass,
+                                                             window, mag_up, idx_up, mag_down, idx_down, bit);
+    return cudaGetLastError();
+}
+
+}  // namespace usc
+
+// ---- whole I/Q path in one kernel ---------------------------------------------------------------------
+// One warp per frame, persistent CTAs of 8 warps.  Stage: PCM (+ ntaps-1 samples of history) is cast,
+// mixed with the carrier and parked as (I, Q) pairs.  FIR: each lane owns four consecutive decimated
+// outputs per pass (eight passes); both rails ride one FFMA2 with the tap broadcast, taps ascending as in
+// arm_fir_f32.  The baseband frame R goes through the warp's region once (blocked -> strided), then the
+// back end above runs unchanged.  R never touches HBM.
+namespace usc {
+
+constexpr int kIqfWarps = 8;
+#ifndef USC_IQF_ROWS
+#define USC_IQF_ROWS 64
+#endif
+constexpr int kIqfRows = USC_IQF_ROWS;                                       // 32-sample rows loaded per lane before any is used
+constexpr uint32_t kIqfPairs = 1024 + kFirPairs + 4;                          // sample pairs per frame incl. history, zero tail
+constexpr uint32_t kIqfSlots = kIqfPairs + (kIqfPairs >> 2) + 1;              // pair p lives in float4 slot p + (p >> 2)
+constexpr int kIqfRegion = (int) kIqfSlots * 16;
+constexpr int kIqfTables = 8192 + 8192 + 4096 + 16384;                        // twiddles | chirp | Hann | (cos, sin)
+constexpr int kIqfSmem = kIqfTables + kIqfWarps * kIqfRegion;
+
+template <typename PCM>
+__global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __restrict__ pcm, uint32_t nstreams, uint32_t nframes,
+                                                                size_t stream_stride, const float* __restrict__ car_cos,
+                                                                const float* __restrict__ car_sin,
+                                                                const float* __restrict__ taps, uint32_t ntaps,
+                                                                const float2* __restrict__ chirp, const float* __restrict__ hann,
+                                                                const float2* __restrict__ tw_pass, uint32_t W, float* mag_up,
+                                                                uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                                                                uint8_t* bit) {
+    constexpr uint32_t n = 2048;
+    extern __shared__ __align__(16) unsigned char s_f[];
+    float2* s_tw = reinterpret_cast<float2*>(s_f);
+    float2* s_c = reinterpret_cast<float2*>(s_f + 8192);
+    float* s_w = reinterpret_cast<float*>(s_f + 16384);
+    float2* s_cs = reinterpret_cast<float2*>(s_f + 20480);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* region = s_f + kIqfTables + warp * kIqfRegion;
+    float2* smp = reinterpret_cast<float2*>(region);         // sample j at float2 index 2 * slot(j >> 1) + (j & 1)
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        s_tw[i] = tw_pass[i];
+        s_c[i] = chirp[i];
+        s_w[i] = hann[i];
+    }
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_cs[i] = make_float2(car_cos[i], car_sin[i]);
+    __syncthreads();
+    const uint32_t H = ntaps - 1;
+    float t[kFirTmax];
+#pragma unroll
+    for (int i = 0; i < kFirTmax; ++i) t[i] = (uint32_t) i < ntaps ? taps[i] : 0.0f;
+    const size_t total = (size_t) nstreams * nframes, nwarps = (size_t) gridDim.x * kIqfWarps;
+    for (size_t f = (size_t) blockIdx.x * kIqfWarps + warp; f < total; f += nwarps) {
+        const uint32_t s = (uint32_t) (f / nframes), fr = (uint32_t) (f - (size_t) s * nframes);
+        const PCM* cur = pcm + (size_t) s * stream_stride + (size_t) fr * n;
+        if (f + nwarps < total) {                            // pull the next frame of this warp towards L2
+            const size_t g = f + nwarps;
+            const uint32_t s2 = (uint32_t) (g / nframes), f2 = (uint32_t) (g - (size_t) s2 * nframes);
+            const char* nxt = reinterpret_cast<const char*>(pcm + (size_t) s2 * stream_stride + (size_t) f2 * n);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 4096 + lane * 128));
+        }
+        // ---- stage: cast, mix, park as (I, Q) ----
+        // Sample j = k + H of the staged sequence is PCM sample k: no bounds to test in the main part, and
+        // sixteen independent loads are in flight per lane.
+        {
+            const uint32_t jl = lane + H, pl = jl >> 1;
+#pragma unroll 1
+            for (uint32_t r0 = 0; r0 < 64; r0 += kIqfRows) {
+                float x[kIqfRows];
+#pragma unroll
+                for (int u = 0; u < kIqfRows; ++u) x[u] = pcm_cast(cur[(r0 + u) * 32 + lane]);
+                // pair pl + 16 r sits in slot pl + (pl >> 2) + 20 r: a constant 40 float2 per row
+                float2* dst = smp + 2 * (pl + (pl >> 2)) + (jl & 1u) + 40u * r0;
+                const float2* cs = s_cs + r0 * 32 + lane;
+#pragma unroll
+                for (int u0 = 0; u0 < kIqfRows; u0 += 8) {     // carrier values in batches so their loads overlap
+                    float2 c[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) c[u] = cs[32 * (u0 + u)];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) dst[40 * (u0 + u)] = __fmul2_rn(bc2(x[u0 + u]), c[u]);
+                }
+            }
+            if ((uint32_t) lane < H) {                         // history: tail of the previous frame (zeros before frame 0)
+                const uint32_t k = n - H + lane, pp = (uint32_t) lane >> 1;
+                const float xh = fr > 0 ? pcm_cast(cur[(ptrdiff_t) lane - (ptrdiff_t) H]) : 0.0f;
+                smp[2 * (pp + (pp >> 2)) + (lane & 1)] = __fmul2_rn(bc2(xh), s_cs[k]);
+            }
+        }
+        __syncwarp();
+        // ---- FIR + decimation by two; R parked blocked at the head of the region ----
+        // Output m0 + j at tap pair ip reads sample pair m0 + j + ip: a window of four pairs slides one pair
+        // per tap pair.  Per output the taps run in ascending order, one FMA each (arm_fir_f32).
+#pragma unroll 1
+        for (uint32_t pass = 0; pass < 8; ++pass) {
+            const uint32_t m0 = (pass * 32 + lane) * kFirOut;
+            float2 acc[kFirOut];
+#pragma unroll
+            for (int j = 0; j < kFirOut; ++j) acc[j] = make_float2(0.0f, 0.0f);
+            float4 w[kFirTmax / 2 + kFirOut];
+#pragma unroll
+            for (int q = 0; q < kFirOut - 1; ++q) {
+                const uint32_t pp = m0 + q;
+                w[q] = reinterpret_cast<const float4*>(region)[pp + (pp >> 2)];
+            }
+#pragma unroll
+            for (int ip = 0; ip < kFirTmax / 2; ++ip) {
+                // no early exit: predicated in place, so the accumulators keep their registers
+                const bool first = (uint32_t) (2 * ip) < ntaps, second = (uint32_t) (2 * ip + 1) < ntaps;
+                const uint32_t pp = m0 + ip + kFirOut - 1;
+                w[ip + kFirOut - 1] = reinterpret_cast<const float4*>(region)[pp + (pp >> 2)];
+#pragma unroll
+                for (int j = 0; j < kFirOut; ++j) {
+                    const float2 a0 = __ffma2_rn(make_float2(w[ip + j].x, w[ip + j].y), bc2(t[2 * ip]), acc[j]);
+                    acc[j] = first ? a0 : acc[j];
+                    const float2 a1 = __ffma2_rn(make_float2(w[ip + j].z, w[ip + j].w), bc2(t[2 * ip + 1]), acc[j]);
+                    acc[j] = second ? a1 : acc[j];
+                }
+            }
+            __syncwarp();                                    // this pass's samples overlap where R of pass 0 lands
+            float4* dst = reinterpret_cast<float4*>(region + (size_t) m0 * 8);
+            dst[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+            dst[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+        }
+        __syncwarp();
+        // ---- back end: de-chirp both ways, Hann, FFT, windowed peaks ----
+        float2 re[32], im[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int m = lane + 32 * b;
+            const float2 r = reinterpret_cast<const float2*>(region)[m], c = s_c[m];
+            const float w = s_w[m];
+            // cmul(R, conj c) and cmul(R, c) share their two rounded products; the FMAs ride one FFMA2 each
+            const float t0 = __fmul_rn(r.y, c.y), t1 = __fmul_rn(r.y, c.x);
+            const float2 pr2 = __ffma2_rn(bc2(r.x), bc2(c.x), make_float2(t0, -t0));      // (up.re, down.re)
+            const float2 pi2 = __ffma2_rn(bc2(r.x), make_float2(-c.y, c.y), bc2(t1));     // (up.im, down.im)
+            re[b] = make_float2(__fmul_rn(pr2.x, w), __fmul_rn(pr2.y, w));                // scalar: see usc_arith.cuh
+            im[b] = make_float2(__fmul_rn(pi2.x, w), __fmul_rn(pi2.y, w));
+        }
+        __syncwarp();
+        fft1024_pair(re, im, reinterpret_cast<float2*>(region), s_tw, lane);
+        const float2 pr = __ffma2_rn(re[0], re[0], __fmul2_rn(im[0], im[0]));
+        const float2 pl = __ffma2_rn(re[31], re[31], __fmul2_rn(im[31], im[31]));
+        const bool in_r = (uint32_t) lane < W, in_l = 992u + lane >= 1024u - W;
+        float out_m[2];
+        uint32_t out_i[2];
+#pragma unroll
+        for (int hyp = 0; hyp < 2; ++hyp) {
+            float mr = in_r ? __fsqrt_rn(hyp ? pr.y : pr.x) : -INFINITY, ml = in_l ? __fsqrt_rn(hyp ? pl.y : pl.x) : -INFINITY;
+            uint32_t ir = in_r ? (uint32_t) lane : 0xffffffffu, il = in_l ? 992u + lane : 0xffffffffu;
+            warp_argmax(mr, ir);
+            warp_argmax(ml, il);
+            const bool left = ml > mr;
+            out_m[hyp] = left ? ml : mr;
+            out_i[hyp] = left ? il : ir;
+        }
+        if (lane == 0) {
+            if (mag_up) mag_up[f] = out_m[0];
+            if (idx_up) idx_up[f] = out_i[0];
+            if (mag_down) mag_down[f] = out_m[1];
+            if (idx_down) idx_down[f] = out_i[1];
+            if (bit) bit[f] = out_m[1] > out_m[0] ? 0 : 1;
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_iq_fused(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                            const float* car_cos, const float* car_sin, const float* taps, uint32_t ntaps, const float* chirp,
+                            const float* hann, const float2* tw_pass, uint32_t window, float* mag_up, uint32_t* idx_up,
+                            float* mag_down, uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_iq_fused<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqfSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_iq_fused<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqfSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const size_t total = (size_t) nstreams * nframes;
+    size_t ctas = (total + kIqfWarps - 1) / kIqfWarps;
+    if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
+    if (pcm_format == 1u)
+        k_iq_fused<int32_t><<<(int) ctas, kIqfWarps * 32, kIqfSmem, st>>>((const int32_t*) pcm, nstreams, nframes, stream_stride,
+            car_cos, car_sin, taps, ntaps, (const float2*) chirp, hann, tw_pass, window, mag_up, idx_up, mag_down, idx_down, bit);
+    else
+        k_iq_fused<float><<<(int) ctas, kIqfWarps * 32, kIqfSmem, st>>>((const float*) pcm, nstreams, nframes, stream_stride,
+            car_cos, car_sin, taps, ntaps, (const float2*) chirp, hann, tw_pass, window, mag_up, idx_up, mag_down, idx_down, bit);
     return cudaGetLastError();
 }
 

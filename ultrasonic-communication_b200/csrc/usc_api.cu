@@ -753,6 +753,13 @@ int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t n
     const size_t F = (size_t) nstreams * nframes;
     if (!F) return USC_OK;
     if (F > 0xffffffffu) return USC_ERR_ARGUMENT;
+    if (n == 2048 && W <= 32 && h->iq_ntaps <= 32 && h->d_tw_pass && !getenv("USC_IQ_UNFUSED")) {
+        /* whole path in one kernel: mix, FIR, de-chirp both ways, Hann, FFT, windowed peaks (k_iq.cu) */
+        LAUNCHED(h, launch_iq_fused(pcm, pcm_format, nstreams, nframes, stream_stride, h->d_iq_cos, h->d_iq_sin, h->d_iq_taps,
+                                    h->iq_ntaps, h->d_iq_chirp, h->d_iq_hann, h->d_tw_pass, W, mag_up, idx_up, mag_down,
+                                    idx_down, bit, h->num_sms, h->stream));
+        return USC_OK;
+    }
     /* scratch: R (F*n) | P (F*n) | mags (F*half) | 4 result vectors + 2 spare magnitude vectors */
     int rc = reserve_work(h, (2 * F * n + F * half + 8 * F) * sizeof(float));
     if (rc) return rc;
@@ -763,6 +770,12 @@ int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t n
     if ((rc = make_plan(h, half, half, &plan))) return rc;
     LAUNCHED(h, launch_iq_frontend(pcm, pcm_format, nstreams, nframes, stream_stride, n, h->d_iq_cos, h->d_iq_sin,
                                    h->d_iq_taps, h->iq_ntaps, R, h->stream));
+    if (n == 2048 && W <= 32 && h->d_tw_pass) {
+        /* fused back end: both hypotheses in the packed 32x32 core, one warp per frame */
+        LAUNCHED(h, launch_iq_backend(R, F, h->d_iq_chirp, h->d_iq_hann, h->d_tw_pass, W, mag_up, idx_up, mag_down, idx_down,
+                                      bit, h->num_sms, h->stream));
+        return USC_OK;
+    }
     float* mags[2] = {mag_up ? mag_up : spare_u, mag_down ? mag_down : spare_d};
     uint32_t* idxs[2] = {idx_up, idx_down};
     const float* refs[2] = {h->d_iq_conj, h->d_iq_chirp};       /* up: R x conj(chirp); down: R x chirp */

@@ -51,6 +51,13 @@ cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st)
 cudaError_t launch_iq_frontend(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                                size_t stream_stride, uint32_t n, const float* car_cos, const float* car_sin,
                                const float* taps, uint32_t ntaps, float* out, cudaStream_t st);
+cudaError_t launch_iq_backend(const float* R, size_t nframes, const float* chirp, const float* hann, const float2* tw_pass,
+                              uint32_t window, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                              uint8_t* bit, int num_sms, cudaStream_t st);
+cudaError_t launch_iq_fused(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                            const float* car_cos, const float* car_sin, const float* taps, uint32_t ntaps, const float* chirp,
+                            const float* hann, const float2* tw_pass, uint32_t window, float* mag_up, uint32_t* idx_up,
+                            float* mag_down, uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st);
 cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t left0,
                            float* mag, uint32_t* idx, size_t count, cudaStream_t st);
 cudaError_t launch_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, const int32_t* table,
