@@ -43,3 +43,12 @@ if which == "iq":
         h.iq_demod(pcm, usc.PCM_I32, 4096, 38, 38 * 2048, o[0], o[1], o[2], o[3], b)
     torch.cuda.synchronize()
     print("done iq", reps)
+if which == "long32":
+    hh = usc.Handle(usc.default_config(n=65536))
+    nf = 2048
+    x = torch.empty((nf, 65536), dtype=torch.int32, device=dev)
+    hh.synth_frames(2, 0, nf, 2.0e4, 1.0e5, x)
+    for _ in range(reps):
+        hh.demod_frames(x, usc.PCM_I32, nf, o[0], o[1], o[2], o[3], b)
+    torch.cuda.synchronize()
+    print("done long32", reps)

@@ -162,6 +162,204 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
     return cudaGetLastError();
 }
 
+// ---- N = 65536: a cluster of four CTAs owns a frame ---------------------------------------------------
+// Plan [32, 32, 32] over the 32768-point complex sequence.  Sub-sequences no longer fit one SM
+// (32 x 16 KB), so the cluster's distributed shared memory holds them, eight per CTA:
+//   level 0   CTA r, thread t takes a = 256 r + t: gathers z[a + 1024 b], b < 32, from global memory,
+//             de-chirp x Hann for both hypotheses, radix-32 butterfly, x W^(a d) (table [d][a], coalesced),
+//             and stores element d into CTA d/8's copy of sub-sequence d — remote stores over DSMEM
+//   core      after a cluster barrier, warp w of CTA r runs the packed 32x32 core on sub-sequence 8 r + w
+//   split     after a second barrier each CTA takes the bins k = 32 c + d of its own d; the partner
+//             Z[nc - k] sits in sub-sequence (32 - d) mod 32, usually another CTA's: remote loads
+//   result    the four partial arg-max results meet in CTA 0 (remote stores), third barrier, one thread
+//             writes the frame's outputs
+constexpr int kL32Cluster = 4, kL32Warps = 8, kL32Threads = 256;
+struct l32_smem {
+    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + kL32Warps * region, total = red + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void* local, uint32_t rank) {       // shared::cluster address of a peer's copy
+    uint32_t l = (uint32_t) __cvta_generic_to_shared(local), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float2 v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <typename PCM>
+__global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Threads, 1) k_demod_long32(long_params p, const float2* __restrict__ tw_l0) {
+    using L = l32_smem;
+    using V2 = typename vec2<PCM>::type;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cluster_rank();
+    constexpr uint32_t nc = 32768u;
+    for (int i = tid; i < 1024; i += kL32Threads) s_tw[i] = p.tw_pass[i];
+    __syncthreads();
+    const uint32_t bw2 = p.bandwidth2;
+    // peer addresses of the sub-sequence area and of CTA 0's result slots
+    uint32_t peer_sub[kL32Cluster];
+#pragma unroll
+    for (int r = 0; r < kL32Cluster; ++r) peer_sub[r] = map_to_rank(s_raw + L::sub, r);
+    const uint32_t red0 = map_to_rank(s_raw + L::red, 0);
+    cluster_sync_all();                                  // every CTA of the cluster is resident before remote traffic
+
+    for (size_t f = cluster_id_x(); f < p.nframes; f += cluster_count_x()) {
+        const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * 65536u);
+        if (f + cluster_count_x() < p.nframes) {         // next frame of this cluster towards L2 (each CTA a quarter)
+            const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + cluster_count_x()) * 65536u);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * 256 + tid) * 256));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * 256 + tid) * 256 + 128));
+        }
+        // ---- level 0 ----
+        {
+            const uint32_t a = rank * 256u + tid;
+            float2 re[32], im[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const uint32_t m = a + 1024u * b;
+                const V2 raw = src[m];
+                const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
+                const float4 c = __ldg(p.chirp_ud + m);
+                const float2 w = __ldg(p.hann + m);
+                const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
+                re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));      // scalar: see usc_arith.cuh
+                im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
+            }
+            fft_base2<32>(re, im);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                float2 xr = re[d], xi = im[d];
+                if (d != 0) {
+                    const float2 w = __ldg(tw_l0 + d * 1024 + a);                    // W_32768^(a d)
+                    cmul2(re[d], im[d], w.x, w.y, xr, xi);
+                }
+                const uint32_t base = peer_sub[d >> 3] + (uint32_t) (d & 7) * L::region;
+                st_cluster_f4(base + a * 16u, make_float4(xr.x, xr.y, xi.x, xi.y));       // one 16-byte remote store per element
+            }
+        }
+        cluster_sync_all();
+        // ---- 1024-point packed core on sub-sequence 8 rank + warp ----
+        {
+            float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + warp * L::region);
+            float2 re[32], im[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const float4 v = reinterpret_cast<const float4*>(reg)[lane + 32 * b];       // (re pair, im pair)
+                re[b] = make_float2(v.x, v.y);
+                im[b] = make_float2(v.z, v.w);
+            }
+            __syncwarp();
+            fft1024_pair(re, im, reg, s_tw, lane);
+            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + 8192);
+#pragma unroll
+            for (int j = 0; j < kLongNB; ++j) {
+                keep[lane + 32 * j] = make_float4(re[j].x, re[j].y, im[j].x, im[j].y);
+                keep[kLongKeep + lane + 32 * j] = make_float4(re[32 - kLongNB + j].x, re[32 - kLongNB + j].y,
+                                                              im[32 - kLongNB + j].x, im[32 - kLongNB + j].y);
+            }
+        }
+        cluster_sync_all();
+        // ---- split, magnitude, arg-max over the bins of this CTA's sub-sequences ----
+        float bu = -INFINITY, bd = -INFINITY;
+        uint32_t iu = 0xffffffffu, id = 0xffffffffu;
+        // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread
+        for (uint32_t c = tid >> 3; c < (uint32_t) kLongKeep; c += kL32Threads / 8) {
+            const uint32_t dl = tid & 7u, d = rank * 8u + dl, k = 32u * c + d;
+            if (k >= bw2) continue;
+            const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + 8192)[c];
+            float2 xr, xi;
+            if (k == 0) {
+                xr = __fadd2_rn(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w));
+                xi = __fadd2_rn(make_float2(zk.x, zk.y), neg2(make_float2(zk.z, zk.w)));
+            } else {
+                // nc - k = 32 (1024 - c) for d = 0 (c >= 1), else 32 (1023 - c) + (32 - d)
+                const uint32_t d2 = (32u - d) & 31u, c2 = d == 0 ? 1024u - c : 1023u - c;
+                const uint32_t addr = peer_sub[d2 >> 3] + (d2 & 7u) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+                const float4 zc = ld_cluster_f4(addr);
+                const float2 w = __ldg(p.tw_master + k);
+                rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
+                            make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
+            }
+            const float2 pw = __ffma2_rn(xr, xr, __fmul2_rn(xi, xi));
+            const float mu = __fsqrt_rn(pw.x), md = __fsqrt_rn(pw.y);
+            if (iu == 0xffffffffu || bu < mu) { bu = mu; iu = k; }
+            if (id == 0xffffffffu || bd < md) { bd = md; id = k; }
+        }
+        warp_argmax(bu, iu);
+        warp_argmax(bd, id);
+        float* red = reinterpret_cast<float*>(s_raw + L::red);
+        if (lane == 0) {
+            red[128 / 4 + warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(red)[128 / 4 + warp * 4 + 1] = iu;
+            red[128 / 4 + warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(red)[128 / 4 + warp * 4 + 3] = id;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w2 = 1; w2 < kL32Warps; ++w2) {
+                argmax_combine(bu, iu, red[32 + w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 1]);
+                argmax_combine(bd, id, red[32 + w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 3]);
+            }
+            st_cluster_f4(red0 + rank * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
+        }
+        cluster_sync_all();                              // results are in CTA 0; all remote reads of this frame are done
+        if (rank == 0 && tid == 0) {
+            const float4* r4 = reinterpret_cast<const float4*>(s_raw + L::red);
+            float4 v = r4[0];
+            bu = v.x; iu = __float_as_uint(v.y); bd = v.z; id = __float_as_uint(v.w);
+            for (int r = 1; r < kL32Cluster; ++r) {
+                v = r4[r];
+                argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
+                argmax_combine(bd, id, v.z, __float_as_uint(v.w));
+            }
+            if (p.mag_up) p.mag_up[f] = bu;
+            if (p.idx_up) p.idx_up[f] = iu;
+            if (p.mag_down) p.mag_down[f] = bd;
+            if (p.idx_down) p.idx_down[f] = id;
+            if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
+        }
+    }
+    cluster_sync_all();                                  // no CTA leaves while a peer may still address its memory
+}
+
+template <typename PCM>
+static cudaError_t launch_long32_t(const long_params& p, const float2* tw_l0, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_demod_long32<PCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, l32_smem::total);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    size_t clusters = (size_t) num_sms / kL32Cluster;
+    if (clusters > p.nframes) clusters = p.nframes;
+    k_demod_long32<PCM><<<(int) (clusters * kL32Cluster), kL32Threads, l32_smem::total, st>>>(p, tw_l0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* chirp_ud, const float2* hann,
+                                const float2* tw_master, const float2* tw_pass, const float2* tw_l0, uint32_t bandwidth2,
+                                float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit,
+                                int num_sms, cudaStream_t st) {
+    long_params p{pcm, nframes, 65536u, reinterpret_cast<const float4*>(chirp_ud), hann, tw_master, tw_pass, bandwidth2,
+                  mag_up, idx_up, mag_down, idx_down, bit};
+    return pcm_format == 1u ? launch_long32_t<int32_t>(p, tw_l0, num_sms, st) : launch_long32_t<float>(p, tw_l0, num_sms, st);
+}
+
 cudaError_t launch_demod_long(const void* pcm, uint32_t pcm_format, size_t nframes, uint32_t n, const float2* chirp_ud,
                               const float2* hann, const float2* tw_master, const float2* tw_pass, uint32_t bandwidth2,
                               float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit,

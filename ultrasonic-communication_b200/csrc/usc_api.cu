@@ -28,7 +28,7 @@ struct usc_handle {
     uint32_t bandwidth, bandwidth2, idx_left_zero;
     std::vector<float> hann, up, down, H_up, H_down;
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
-    float2 *d_tw_pass, *d_tw_split;
+    float2 *d_tw_pass, *d_tw_split, *d_tw_l0;      // d_tw_l0: W_32768^(a d), [d][a], 65536-point frames only
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
     // I/Q path (usc_iq_init): carrier tables, baseband chirp and its conjugate, half-length Hann, FIR taps
     std::vector<float> iq_cos, iq_sin, iq_chirp, iq_hann;
@@ -143,7 +143,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->stream = 0;
     h->launches = 0;
     h->d_hann = h->d_up = h->d_down = h->d_ud = h->d_H_up = h->d_H_down = nullptr;
-    h->d_tw_pass = h->d_tw_split = nullptr;
+    h->d_tw_pass = h->d_tw_split = h->d_tw_l0 = nullptr;
     h->d_fir_coeffs = nullptr;
     h->d_work = nullptr;
     h->work_bytes = 0;
@@ -199,6 +199,17 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
                 pass[2 * (d * 32 + a) + 1] = tw[2 * j + 1];
             }
         if ((rc = upload(pass.data(), pass.size() * 4, (void**) &h->d_tw_pass))) { usc_destroy(h); return rc; }
+        if (n == 65536) {
+            // level-0 twiddles of the [32, 32, 32] plan: W_32768^(a d) = W_n^(2 a d), laid out [d][a] for coalescing
+            std::vector<float> l0(2 * 32 * 1024);
+            for (uint32_t d = 0; d < 32; ++d)
+                for (uint32_t a = 0; a < 1024; ++a) {
+                    const uint32_t j = 2 * a * d;
+                    l0[2 * (d * 1024 + a)] = tw[2 * j];
+                    l0[2 * (d * 1024 + a) + 1] = tw[2 * j + 1];
+                }
+            if ((rc = upload(l0.data(), l0.size() * 4, (void**) &h->d_tw_l0))) { usc_destroy(h); return rc; }
+        }
         if (n == 2048) {
             std::vector<float> split(2 * 1024);
             for (uint32_t k = 0; k < 1024; ++k) {
@@ -232,7 +243,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
 void usc_destroy(usc_handle* h) {
     if (!h) return;
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
-    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
+    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
     cudaFree(h->d_sym_table);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
@@ -489,6 +500,16 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
         LAUNCHED(h, launch_demod_long(pcm, pcm_format, nframes, h->cfg.n, (const float2*) h->d_ud, (const float2*) h->d_hann,
                                       master, h->d_tw_pass, h->bandwidth2, mag_up, idx_up, mag_down, idx_down, bit,
                                       h->num_sms, h->stream));
+        return USC_OK;
+    }
+    if (h->cfg.n == 65536 && h->d_tw_l0 && h->bandwidth2 > 0 && h->bandwidth2 <= 5120u && !getenv("USC_LONG_UNFUSED")) {
+        /* 65536-point frames: a four-CTA cluster per frame, sub-sequences in distributed shared memory (k_long.cu) */
+        float2* master = nullptr;
+        int rc = get_twiddles(h, h->cfg.n, &master);
+        if (rc) return rc;
+        LAUNCHED(h, launch_demod_long32(pcm, pcm_format, nframes, (const float2*) h->d_ud, (const float2*) h->d_hann, master,
+                                        h->d_tw_pass, h->d_tw_l0, h->bandwidth2, mag_up, idx_up, mag_down, idx_down, bit,
+                                        h->num_sms, h->stream));
         return USC_OK;
     }
     if (h->cfg.n != 2048 || h->bandwidth2 == 0 || h->bandwidth2 > 512)
