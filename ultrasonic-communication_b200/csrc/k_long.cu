@@ -162,20 +162,30 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
     return cudaGetLastError();
 }
 
-// ---- N = 65536: a cluster of four CTAs owns a frame ---------------------------------------------------
+// ---- N = 65536: a cluster of CTAs owns a frame ---------------------------------------------------
 // Plan [32, 32, 32] over the 32768-point complex sequence.  Sub-sequences no longer fit one SM
-// (32 x 16 KB), so the cluster's distributed shared memory holds them, eight per CTA:
-//   level 0   CTA r, thread t takes a = 256 r + t: gathers z[a + 1024 b], b < 32, from global memory,
-//             de-chirp x Hann for both hypotheses, radix-32 butterfly, x W^(a d) (table [d][a], coalesced),
-//             and stores element d into CTA d/8's copy of sub-sequence d — remote stores over DSMEM
-//   core      after a cluster barrier, warp w of CTA r runs the packed 32x32 core on sub-sequence 8 r + w
+// (32 x 16 KB), so the cluster's distributed shared memory holds them: four CTAs of eight warps, eight
+// sub-sequences each (USC_L32_CLUSTER=8 builds the 8 x 4 split with two CTAs per SM; measured 8 % slower).
+// With T threads per CTA:
+//   level 0   CTA r, thread t takes a = T r + t: gathers z[a + 1024 b], b < 32, from global memory,
+//             de-chirp x Hann for both hypotheses, radix-32 butterfly, x W^(a d) (frame-invariant, kept
+//             in shared memory), and stores element d into the owner CTA's copy of sub-sequence d —
+//             16-byte remote stores over DSMEM
+//   core      after a cluster barrier, each warp runs the packed 32x32 core on one local sub-sequence
 //   split     after a second barrier each CTA takes the bins k = 32 c + d of its own d; the partner
 //             Z[nc - k] sits in sub-sequence (32 - d) mod 32, usually another CTA's: remote loads
-//   result    the four partial arg-max results meet in CTA 0 (remote stores), third barrier, one thread
+//   result    the partial arg-max results meet in CTA 0 (remote stores), third barrier, one thread
 //             writes the frame's outputs
-constexpr int kL32Cluster = 4, kL32Warps = 8, kL32Threads = 256;
+#ifndef USC_L32_CLUSTER
+#define USC_L32_CLUSTER 4
+#endif
+constexpr int kL32Cluster = USC_L32_CLUSTER, kL32Warps = 32 / kL32Cluster, kL32Threads = 32 * kL32Warps;
+constexpr int kL32PerSm = kL32Cluster == 8 ? 2 : 1;     // two co-resident CTAs of different clusters overlap their phases
+constexpr int kL32Shift = kL32Cluster == 8 ? 2 : 3;     // sub-sequence d lives in CTA d >> shift, slot d & (warps - 1)
 struct l32_smem {
-    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + kL32Warps * region, total = red + 256;
+    // pass twiddles | 8 sub-sequences | result slots | this CTA's level-0 twiddles W^(a d), [d][thread] (frame-invariant)
+    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + kL32Warps * region, l0 = red + 256,
+                         total = l0 + 32 * kL32Threads * 8;
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -202,7 +212,7 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
 }
 
 template <typename PCM>
-__global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Threads, 1) k_demod_long32(long_params p, const float2* __restrict__ tw_l0) {
+__global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_params p, const float2* __restrict__ tw_l0) {
     using L = l32_smem;
     using V2 = typename vec2<PCM>::type;
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -211,8 +221,16 @@ __global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Thread
     const uint32_t rank = cluster_rank();
     constexpr uint32_t nc = 32768u;
     for (int i = tid; i < 1024; i += kL32Threads) s_tw[i] = p.tw_pass[i];
+    float2* s_l0 = reinterpret_cast<float2*>(s_raw + L::l0);
+    for (int d = 1; d < 32; ++d) s_l0[d * kL32Threads + tid] = tw_l0[d * 1024 + rank * kL32Threads + tid];
     __syncthreads();
     const uint32_t bw2 = p.bandwidth2;
+    float2 w_split[kLongNB];                             // split twiddles of this thread's bins, frame-invariant too
+#pragma unroll
+    for (int j = 0; j < kLongNB; ++j) {
+        const uint32_t k = 32u * ((tid >> kL32Shift) + 32u * j) + rank * kL32Warps + (tid & (kL32Warps - 1u));
+        w_split[j] = p.tw_master[k];
+    }
     // peer addresses of the sub-sequence area and of CTA 0's result slots
     uint32_t peer_sub[kL32Cluster];
 #pragma unroll
@@ -224,12 +242,12 @@ __global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Thread
         const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * 65536u);
         if (f + cluster_count_x() < p.nframes) {         // next frame of this cluster towards L2 (each CTA a quarter)
             const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + cluster_count_x()) * 65536u);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * 256 + tid) * 256));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * 256 + tid) * 256 + 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kL32Threads + tid) * 256));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kL32Threads + tid) * 256 + 128));
         }
         // ---- level 0 ----
         {
-            const uint32_t a = rank * 256u + tid;
+            const uint32_t a = rank * kL32Threads + tid;
             float2 re[32], im[32];
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
@@ -247,10 +265,10 @@ __global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Thread
             for (int d = 0; d < 32; ++d) {
                 float2 xr = re[d], xi = im[d];
                 if (d != 0) {
-                    const float2 w = __ldg(tw_l0 + d * 1024 + a);                    // W_32768^(a d)
+                    const float2 w = s_l0[d * kL32Threads + tid];                    // W_32768^(a d)
                     cmul2(re[d], im[d], w.x, w.y, xr, xi);
                 }
-                const uint32_t base = peer_sub[d >> 3] + (uint32_t) (d & 7) * L::region;
+                const uint32_t base = peer_sub[d >> kL32Shift] + (uint32_t) (d & (kL32Warps - 1)) * L::region;
                 st_cluster_f4(base + a * 16u, make_float4(xr.x, xr.y, xi.x, xi.y));       // one 16-byte remote store per element
             }
         }
@@ -280,8 +298,9 @@ __global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Thread
         float bu = -INFINITY, bd = -INFINITY;
         uint32_t iu = 0xffffffffu, id = 0xffffffffu;
         // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread
-        for (uint32_t c = tid >> 3; c < (uint32_t) kLongKeep; c += kL32Threads / 8) {
-            const uint32_t dl = tid & 7u, d = rank * 8u + dl, k = 32u * c + d;
+#pragma unroll
+        for (int j = 0; j < kLongNB; ++j) {
+            const uint32_t c = (tid >> kL32Shift) + 32u * j, dl = tid & (kL32Warps - 1u), d = rank * kL32Warps + dl, k = 32u * c + d;
             if (k >= bw2) continue;
             const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + 8192)[c];
             float2 xr, xi;
@@ -291,9 +310,9 @@ __global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Thread
             } else {
                 // nc - k = 32 (1024 - c) for d = 0 (c >= 1), else 32 (1023 - c) + (32 - d)
                 const uint32_t d2 = (32u - d) & 31u, c2 = d == 0 ? 1024u - c : 1023u - c;
-                const uint32_t addr = peer_sub[d2 >> 3] + (d2 & 7u) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+                const uint32_t addr = peer_sub[d2 >> kL32Shift] + (d2 & (kL32Warps - 1u)) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
                 const float4 zc = ld_cluster_f4(addr);
-                const float2 w = __ldg(p.tw_master + k);
+                const float2 w = w_split[j];
                 rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
                             make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
             }
@@ -339,16 +358,33 @@ __global__ void __cluster_dims__(kL32Cluster, 1, 1) __launch_bounds__(kL32Thread
 
 template <typename PCM>
 static cudaError_t launch_long32_t(const long_params& p, const float2* tw_l0, int num_sms, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    // The loop inside the kernel strides by the number of clusters launched, so launch exactly as many as
+    // can be resident at once (fewer than SMs / cluster size: clusters do not straddle GPCs) — a cluster
+    // left for a second wave would run its whole share after everyone else has finished.
+    static int max_clusters = 0;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kL32Cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kL32Threads);
+    cfg.dynamicSmemBytes = l32_smem::total;
+    cfg.stream = st;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (!max_clusters) {
         cudaError_t e = cudaFuncSetAttribute(k_demod_long32<PCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, l32_smem::total);
         if (e != cudaSuccess) return e;
-        configured = true;
+        cfg.gridDim = dim3((unsigned) (num_sms * kL32PerSm / kL32Cluster * kL32Cluster));
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, k_demod_long32<PCM>, &cfg);
+        if (e != cudaSuccess) return e;
+        if (n < 1) return cudaErrorLaunchOutOfResources;
+        max_clusters = n;
     }
-    size_t clusters = (size_t) num_sms / kL32Cluster;
+    size_t clusters = (size_t) max_clusters;
     if (clusters > p.nframes) clusters = p.nframes;
-    k_demod_long32<PCM><<<(int) (clusters * kL32Cluster), kL32Threads, l32_smem::total, st>>>(p, tw_l0);
-    return cudaGetLastError();
+    cfg.gridDim = dim3((unsigned) (clusters * kL32Cluster));
+    return cudaLaunchKernelEx(&cfg, k_demod_long32<PCM>, p, tw_l0);
 }
 
 cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* chirp_ud, const float2* hann,
