@@ -27,4 +27,13 @@ hs = usc.Handle(usc.default_config(chirp_variant=usc.CHIRP_S))
 hs.dsp(f, 3 * N, pos, mean, usc.DOWN, hh, 1); hs.sync()            # K3
 x = h.buffer(np.random.default_rng(0).standard_normal((2, 65536)).astype(np.float32)); y = h.empty(2 * 65536 * 4)
 h.arm_rfft_fast_f32(65536, x, y, 0, 2); h.arm_rfft_fast_f32(4096, x, y, 0, 2); h.arm_rfft_fast_f32(4096, y, y, 1, 2); h.sync()
+for n, nf in ((8192, 3), (16384, 2), (65536, 40)):                # K6: fused long frames, cluster kernel at 65536
+    hl = usc.Handle(usc.default_config(n=n))
+    pl, _ = synth.make_frames(nf, n=n, seed_noise=n)
+    hl.demod_frames_host(pl); hl.close()
+taps = np.load(os.path.join(ROOT, "tests/golden/fir_taps.npz"))["taps"].astype(np.float32)[::-1].copy()
+hq = usc.Handle(); hq.iq_init(18000.0, 3000.0, taps, 32)           # K5: whole I/Q path
+pq = np.stack([synth.make_iq_stream(5, seed_bits=s)[0] for s in range(3)])
+dq = hq.buffer(pq); oq = [hq.empty(4 * 15) for _ in range(4)]; bq = hq.empty(15)
+hq.iq_demod(dq, usc.PCM_I32, 3, 5, 5 * N, oq[0], oq[1], oq[2], oq[3], bq); hq.sync()
 print("sanitize workload done")
