@@ -217,6 +217,17 @@ int usc_scan4(usc_handle *h, const float *pcm2n, uint32_t batch, usc_scan_entry 
  * the oracle regenerates any frame bit for bit on the CPU.  bits (nframes, may be NULL): 1 = up. */
 int usc_synth_frames(usc_handle *h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp,
                      double noise_sigma, int32_t *pcm, uint8_t *bits);
+/* Whole synthetic receiver streams in the transmitter's frame format (generator/ChirpGenerator.ipynb
+ * cell 2): stream g (global index first_stream + s) repeats the pattern
+ * lead_in x G (silence), 7 x H (up symbol), 1 x L (down symbol), 8*msg_bytes data symbols (MSB first,
+ * H = 1), guard x G; every symbol lasts n samples; the whole stream is delayed by a per-stream start
+ * offset in [0, n); noise as in usc_synth_frames.  Offsets and message bytes (printable ASCII) come from
+ * Philox keyed by (seed, g), so shards are disjoint and any stream can be regenerated on the CPU by the
+ * oracle's twin.  Stream s starts at pcm + s*stream_stride samples (stride even, >= nframes*n).
+ * offsets (nstreams) and messages (nstreams*msg_bytes) may be NULL. */
+int usc_synth_streams(usc_handle *h, uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes,
+                      size_t stream_stride, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp,
+                      double noise_sigma, int32_t *pcm, uint32_t *offsets, uint8_t *messages);
 /* The audio spectrum analyser fft() of experiments/basic/Src/main.c:107-142 (the producer of the
  * reference's captured .raw/.flt/.fft files): PCM x Hann -> RFFT -> magnitude * 1/sqrt(N) -> bins below
  * ac_coupling_hz (FFT_AC_COUPLING_HZ = 1000) forced to 1.0 -> dB = 10*log10 -> arg-max.  Uses the

@@ -453,6 +453,19 @@ def synth_frames(seed, first_frame, nframes, amp, noise_sigma, n=2048, fs=78125.
     return pcm, bits
 
 
+def synth_streams(seed, first_stream, nstreams, nframes, lead_in, msg_bytes, guard, amp, noise_sigma, n=2048, fs=78125.0,
+                  f0=16000.0, f1=19000.0):
+    """CPU twin of usc_synth_streams -> (pcm [nstreams, nframes, n] int32, offsets, messages [nstreams, msg_bytes])."""
+    pcm = np.empty((nstreams, nframes, n), np.int32)
+    offs = np.empty(nstreams, np.uint32)
+    msgs = np.empty((nstreams, max(msg_bytes, 1)), np.uint8)
+    lib().ref_synth_streams(C.c_uint64(seed), C.c_uint64(first_stream), C.c_uint32(nstreams), C.c_uint32(nframes), C.c_uint32(n),
+                            C.c_float(fs), C.c_float(f0), C.c_float(f1), C.c_uint32(lead_in), C.c_uint32(msg_bytes),
+                            C.c_uint32(guard), C.c_double(amp), C.c_double(noise_sigma), pcm.ctypes.data_as(i32p), _up(offs),
+                            msgs.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return pcm, offs, msgs[:, :msg_bytes]
+
+
 class ScanEntry(C.Structure):
     _fields_ = [("mag_max_right", C.c_float), ("mag_max_left", C.c_float), ("max_idx_right", C.c_uint32),
                 ("max_idx_left", C.c_uint32)]

@@ -879,9 +879,7 @@ static void philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
-                      double amp, double noise_sigma, int32_t *pcm, uint8_t *bits) {
-    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
+static void synth_tables(uint32_t n, float fs, float f0, float f1, double amp, int32_t *tab) {
     const double T = (double) n / (double) fs, k = ((double) f1 - (double) f0) / T;
     for (int down = 0; down < 2; ++down)
         for (uint32_t i = 0; i < n; ++i) {          /* chirp_orth, simulation/signal.py:45-53 */
@@ -890,6 +888,69 @@ void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint3
             double arg = 2.0 * M_PI * f * t - M_PI / 2.0;
             tab[(size_t) down * n + i] = (int32_t) llround(amp * (cos(arg) + sin(arg)));
         }
+}
+
+static uint32_t synth_msg_byte(uint32_t k0, uint32_t k1, uint64_t g, uint32_t m) {
+    uint32_t r[4];
+    philox(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), 0x4D5347u, m >> 4, r);
+    return 0x20u + ((r[(m >> 2) & 3u] >> (8u * (m & 3u))) & 0xffu) % 95u;
+}
+
+/* Twin of usc_synth_streams: whole streams in the transmitter's frame format (generator/ChirpGenerator.ipynb
+ * cell 2): lead_in x G, 7 x H, L, message bits MSB first, guard x G, repeated; per-stream start offset. */
+void ref_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, uint32_t n, float fs, float f0,
+                       float f1, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp, double noise_sigma,
+                       int32_t *pcm, uint32_t *offsets, uint8_t *messages) {
+    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
+    synth_tables(n, fs, f0, f1, amp, tab);
+    const int32_t gain = (int32_t) llround(noise_sigma / sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0) * 65536.0);
+    const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
+    const uint32_t pattern = lead_in + 8u + 8u * msg_bytes + guard;
+    uint8_t *msg = (uint8_t *) malloc(msg_bytes ? msg_bytes : 1);
+    for (uint32_t s = 0; s < nstreams; ++s) {
+        const uint64_t g = first_stream + s;
+        uint32_t r[4];
+        philox(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), 0x0FF5E7u, 0u, r);
+        const uint32_t off = r[0] % n;
+        if (offsets) offsets[s] = off;
+        for (uint32_t m = 0; m < msg_bytes; ++m) {
+            msg[m] = (uint8_t) synth_msg_byte(k0, k1, g, m);
+            if (messages) messages[(size_t) s * msg_bytes + m] = msg[m];
+        }
+        int32_t *dst = pcm + (size_t) s * nframes * n;
+        const size_t total = (size_t) nframes * n;
+        for (size_t blk = 0; blk < total / 2; ++blk) {
+            philox(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), (uint32_t) blk, 2u, r);
+            int32_t sn[2];
+            sn[0] = (int32_t) ((r[0] & 0xffffu) + (r[0] >> 16) + (r[1] & 0xffffu) + (r[1] >> 16)) - 131070;
+            sn[1] = (int32_t) ((r[2] & 0xffffu) + (r[2] >> 16) + (r[3] & 0xffffu) + (r[3] >> 16)) - 131070;
+            for (int e = 0; e < 2; ++e) {
+                const size_t i = 2 * blk + e;
+                int32_t v = (int32_t) (((int64_t) sn[e] * gain) / 65536);
+                if (i >= off) {
+                    const size_t t = i - off;
+                    const uint32_t k = (uint32_t) ((t / n) % pattern), tau = (uint32_t) (t % n);
+                    int kind = 0;
+                    if (k >= lead_in && k < lead_in + 7u) kind = 1;
+                    else if (k == lead_in + 7u) kind = 2;
+                    else if (k > lead_in + 7u && k < lead_in + 8u + 8u * msg_bytes) {
+                        const uint32_t b = k - (lead_in + 8u);
+                        kind = ((msg[b >> 3] >> (7u - (b & 7u))) & 1u) ? 1 : 2;
+                    }
+                    if (kind) v += tab[(size_t) (kind - 1) * n + tau];
+                }
+                dst[i] = v * 256;
+            }
+        }
+    }
+    free(msg);
+    free(tab);
+}
+
+void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
+                      double amp, double noise_sigma, int32_t *pcm, uint8_t *bits) {
+    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
+    synth_tables(n, fs, f0, f1, amp, tab);
     const int32_t gain = (int32_t) llround(noise_sigma / sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0) * 65536.0);
     const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
     for (size_t fl = 0; fl < nframes; ++fl) {

@@ -206,6 +206,9 @@ void ref_scan4(const ref_rfft_fast_instance_f32 *S, const float *hann, const flo
                const float *pcm2n, ref_scan_entry *out);
 
 /* ---- twin of the device-side synthetic generator (usc_synth_frames): regenerates any frame on the CPU ---- */
+void ref_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, uint32_t n, float fs, float f0,
+                       float f1, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp, double noise_sigma,
+                       int32_t *pcm, uint32_t *offsets, uint8_t *messages);
 void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
                       double amp, double noise_sigma, int32_t *pcm, uint8_t *bits);
 

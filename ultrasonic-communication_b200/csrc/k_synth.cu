@@ -53,6 +53,78 @@ __global__ void k_synth_frames(uint64_t seed, uint64_t first_frame, size_t nfram
     }
 }
 
+// Whole streams in the transmitter's frame format (usc_synth_streams).  Per stream g:
+//   offset[g]  = philox(seed; g, 0x0FF5E7, 0).x mod n
+//   msg[g][m]  = 0x20 + (byte (m & 3) of word ((m >> 2) & 3) of philox(seed; g, 0x4D5347, m >> 4)) mod 95
+//   symbol k of the pattern: G for k < lead_in, H for the next 7, L, then the message bits MSB first, then G
+//   pcm[g][i]  = (table[kind][(i - offset) mod n] + noise(seed; g, block i/2, 2)) * 256, silence before the offset
+__host__ __device__ inline uint32_t stream_offset(uint32_t k0, uint32_t k1, uint64_t g, uint32_t n) {
+    uint32_t r[4];
+    philox4x32_10(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), 0x0FF5E7u, 0u, r);
+    return r[0] % n;
+}
+__host__ __device__ inline uint32_t stream_msg_byte(uint32_t k0, uint32_t k1, uint64_t g, uint32_t m) {
+    uint32_t r[4];
+    philox4x32_10(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), 0x4D5347u, m >> 4, r);
+    return 0x20u + ((r[(m >> 2) & 3u] >> (8u * (m & 3u))) & 0xffu) % 95u;
+}
+
+__global__ void k_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                                uint32_t n, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard,
+                                const int32_t* __restrict__ table, int32_t gain, int32_t* __restrict__ pcm,
+                                uint32_t* __restrict__ offsets, uint8_t* __restrict__ messages) {
+    const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
+    const uint32_t pattern = lead_in + 8u + 8u * msg_bytes + guard;
+    const size_t pairs = (size_t) nframes * (n / 2);
+    for (uint32_t s = blockIdx.y; s < nstreams; s += gridDim.y) {
+        const uint64_t g = first_stream + s;
+        const uint32_t off = stream_offset(k0, k1, g, n);
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0 && offsets) offsets[s] = off;
+            if (messages)
+                for (uint32_t m = threadIdx.x; m < msg_bytes; m += blockDim.x) messages[(size_t) s * msg_bytes + m] = (uint8_t) stream_msg_byte(k0, k1, g, m);
+        }
+        int32_t* dst = pcm + (size_t) s * stream_stride;
+        for (size_t blk = (size_t) blockIdx.x * blockDim.x + threadIdx.x; blk < pairs; blk += (size_t) gridDim.x * blockDim.x) {
+            uint32_t r[4];
+            philox4x32_10(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), (uint32_t) blk, 2u, r);
+            const int32_t s0 = (int32_t) ((r[0] & 0xffffu) + (r[0] >> 16) + (r[1] & 0xffffu) + (r[1] >> 16)) - 131070;
+            const int32_t s1 = (int32_t) ((r[2] & 0xffffu) + (r[2] >> 16) + (r[3] & 0xffffu) + (r[3] >> 16)) - 131070;
+            int32_t v[2] = {(int32_t) (((int64_t) s0 * gain) / 65536), (int32_t) (((int64_t) s1 * gain) / 65536)};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const size_t i = 2 * blk + e;
+                if (i >= off) {
+                    const size_t t = i - off;
+                    const uint32_t k = (uint32_t) ((t / n) % pattern), tau = (uint32_t) (t % n);
+                    int kind = 0;                                     // 0 G, 1 H, 2 L
+                    if (k >= lead_in && k < lead_in + 7u) kind = 1;
+                    else if (k == lead_in + 7u) kind = 2;
+                    else if (k > lead_in + 7u && k < lead_in + 8u + 8u * msg_bytes) {
+                        const uint32_t b = k - (lead_in + 8u);
+                        kind = ((stream_msg_byte(k0, k1, g, b >> 3) >> (7u - (b & 7u))) & 1u) ? 1 : 2;
+                    }
+                    if (kind) v[e] += table[(size_t) (kind - 1) * n + tau];
+                }
+                v[e] *= 256;
+            }
+            reinterpret_cast<int2*>(dst)[blk] = make_int2(v[0], v[1]);
+        }
+    }
+}
+
+cudaError_t launch_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                                 uint32_t n, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, const int32_t* table,
+                                 int32_t gain, int32_t* pcm, uint32_t* offsets, uint8_t* messages, cudaStream_t st) {
+    const size_t pairs = (size_t) nframes * (n / 2);
+    size_t bx = (pairs + 255) / 256;
+    if (bx > 64) bx = 64;
+    const uint32_t by = nstreams < 8192u ? nstreams : 8192u;
+    k_synth_streams<<<dim3((unsigned) bx, by), 256, 0, st>>>(seed, first_stream, nstreams, nframes, stream_stride, n, lead_in,
+                                                              msg_bytes, guard, table, gain, pcm, offsets, messages);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, const int32_t* table,
                                 int32_t gain, int32_t* pcm, uint8_t* bits, cudaStream_t st) {
     const size_t total = nframes * (n / 2);

@@ -683,11 +683,7 @@ int usc_scan4(usc_handle* h, const float* pcm2n, uint32_t batch, usc_scan_entry*
     return USC_OK;
 }
 
-int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp, double noise_sigma,
-                     int32_t* pcm, uint8_t* bits) {
-    if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
-    if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;
-    if (!nframes) return USC_OK;
+static int ensure_symbol_table(usc_handle* h, double amp) {
     const uint32_t n = h->cfg.n;
     if (!h->d_sym_table || h->sym_amp != amp) {
         std::vector<int32_t> tab(2 * (size_t) n);
@@ -699,6 +695,32 @@ int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t 
         if (rc) return rc;
         h->sym_amp = amp;
     }
+    return USC_OK;
+}
+
+int usc_synth_streams(usc_handle* h, uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes,
+                      size_t stream_stride, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp,
+                      double noise_sigma, int32_t* pcm, uint32_t* offsets, uint8_t* messages) {
+    if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n;
+    if (((uintptr_t) pcm & 7u) != 0 || (stream_stride & 1u) || stream_stride < (size_t) nframes * n) return USC_ERR_ARGUMENT;
+    if (msg_bytes > 4096u || lead_in > 65536u || guard > 65536u || (size_t) nframes * (n / 2) > 0xffffffffu) return USC_ERR_ARGUMENT;
+    if (!nstreams || !nframes) return USC_OK;
+    int rc = ensure_symbol_table(h, amp);
+    if (rc) return rc;
+    LAUNCHED(h, launch_synth_streams(seed, first_stream, nstreams, nframes, stream_stride, n, lead_in, msg_bytes, guard,
+                                     h->d_sym_table, usc_host_noise_gain(noise_sigma), pcm, offsets, messages, h->stream));
+    return USC_OK;
+}
+
+int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp, double noise_sigma,
+                     int32_t* pcm, uint8_t* bits) {
+    if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    const uint32_t n = h->cfg.n;
+    int rc = ensure_symbol_table(h, amp);
+    if (rc) return rc;
     LAUNCHED(h, launch_synth_frames(seed, first_frame, nframes, n, h->d_sym_table, usc_host_noise_gain(noise_sigma), pcm, bits,
                                     h->stream));
     return USC_OK;

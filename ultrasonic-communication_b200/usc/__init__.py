@@ -45,7 +45,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -283,6 +283,13 @@ class Handle:
         res = d_r.to_numpy(rx_result_dtype)
         u = d_u.to_numpy(np.uint8).reshape(S, uart_cap)
         return [bytes(u[s, :min(int(res["nbytes"][s]), uart_cap)]) for s in range(S)], res
+
+    def synth_streams(self, seed, first_stream, nstreams, nframes, stream_stride, lead_in, msg_bytes, guard, amp, noise_sigma,
+                      pcm, offsets=None, messages=None):
+        _ck(load().usc_synth_streams(self._h, C.c_uint64(seed), C.c_uint64(first_stream), C.c_uint32(nstreams),
+                                     C.c_uint32(nframes), C.c_size_t(stream_stride), C.c_uint32(lead_in), C.c_uint32(msg_bytes),
+                                     C.c_uint32(guard), C.c_double(amp), C.c_double(noise_sigma), _ptr(pcm), _ptr(offsets),
+                                     _ptr(messages)))
 
     def synth_frames(self, seed, first_frame, nframes, amp, noise_sigma, pcm, bits=None):
         _ck(load().usc_synth_frames(self._h, C.c_uint64(seed), C.c_uint64(first_frame), C.c_size_t(nframes), C.c_double(amp),
