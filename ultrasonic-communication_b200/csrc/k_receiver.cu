@@ -78,6 +78,31 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
                 im[b] = make_float2(xa.y, xb.y);
             }
         }
+    } else if (gA - (int64_t) (sync_add - 1) * 2048 >= 0 && gB - (int64_t) (sync_add - 1) * 2048 >= 0 &&
+               gA + 2048 <= nsamples && gB + 2048 <= nsamples) {   // every summed window inside the stream: unchecked loads
+        using V2 = typename vec2<PCM>::type;
+        {
+            const int64_t back = (int64_t) (sync_add - 1) * 2048;          // oldest FIFO first
+            const V2* pa = reinterpret_cast<const V2*>(stream + gA - back) + lane;
+            const V2* pb = reinterpret_cast<const V2*>(stream + gB - back) + lane;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const V2 ra = pa[32 * b], rb = pb[32 * b];
+                re[b] = make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x));
+                im[b] = make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y));
+            }
+        }
+        for (uint32_t j = sync_add - 1; j-- > 0;) {
+            const int64_t back = (int64_t) j * 2048;
+            const V2* pa = reinterpret_cast<const V2*>(stream + gA - back) + lane;
+            const V2* pb = reinterpret_cast<const V2*>(stream + gB - back) + lane;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const V2 ra = pa[32 * b], rb = pb[32 * b];
+                re[b] = __fadd2_rn(re[b], make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)));
+                im[b] = __fadd2_rn(im[b], make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)));
+            }
+        }
     } else {
         for (uint32_t j = sync_add; j-- > 0;) {        // oldest FIFO first
             const int64_t back = (int64_t) j * 2048;
