@@ -228,6 +228,44 @@ int usc_synth_frames(usc_handle *h, uint64_t seed, uint64_t first_frame, size_t 
 int usc_synth_streams(usc_handle *h, uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes,
                       size_t stream_stride, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp,
                       double noise_sigma, int32_t *pcm, uint32_t *offsets, uint8_t *messages);
+/* ---- the reference's two earlier detectors, n = 2048 only ------------------------
+ * Both share the analyser's front half: (float) pcm x Hann -> RFFT -> magnitude * 1/sqrt(N)
+ * (experiments/chirp/Src/main.c:200-216, experiments/ultracom/Src/main.c:115-128), computed for bins
+ * [0, 512).  Streams are `nframes` consecutive frames each; stream_stride == nframes*n is required
+ * (frames of all streams are contiguous).  Every output pointer may be NULL. */
+typedef struct usc_onoff_config {
+    float f1_hz, f2_hz;            /* CHIRP_F1 / CHIRP_F2 (17000 / 18000, Inc/main.h:79-80); the counted band is
+                                      [F1, F1 + 2 (F2 - F1)] (Src/main.c:372-383) */
+    float magnitude_threshold;     /* CHIRP_MAGNITUDE_THRESHOLD 3000 (Inc/main.h:83) */
+    float high_frac, low_frac;     /* CHIRP_SIGNAL_THRESHOLD_HIGH / LOW 0.1 / 0.05 (Inc/main.h:86-87) */
+    uint32_t frame_start, frame_bit, sync_threshold, sampling_offset;   /* 3, 2, 2, 1 (Inc/main.h:95-98) */
+} usc_onoff_config;
+void usc_onoff_default_config(usc_onoff_config *cfg);
+/* On/off chirp detector: strength[f] = number of band bins above the threshold (Src/main.c:237-242),
+ * level[f] = 1 HIGH / -1 LOW / 0 UNKNOWN (:276-286); decode() (:119-198) then runs per stream over the
+ * levels: chars (nstreams*cap) receive the byte of every completed frame, nchars the count (may exceed
+ * cap), sync_errors the number of "Sync error!" resets.  As in the firmware, a sync error does not
+ * reset the bit counter. */
+int usc_onoff_detect(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                     const usc_onoff_config *cfg, uint16_t *strength, int8_t *level, uint8_t *chars, uint32_t cap,
+                     uint32_t *nchars, uint32_t *sync_errors);
+typedef struct usc_fsk_config {
+    uint32_t sof_bin, eof_bin, hex0_bin, hex_step;   /* 340, 344, 348, 4 (ultracom/Inc/main.h:84-101) */
+    uint32_t tolerance;                              /* TOLERANCE 0 (:109) */
+    uint32_t tq_n;                                   /* TQ_N 2 (:120) */
+    float magnitude_threshold;                       /* MAGNITUDE_THRESHOLD 5000 (:111) */
+} usc_fsk_config;
+void usc_fsk_default_config(usc_fsk_config *cfg);
+/* FSK 18-tone detector: code[f] = 0xF0 start of frame, 0xF1 end of frame, 0..15 hex digit, 0xFF nothing
+ * (ultracom/Src/main.c:130-168; first hit in that order, tolerance window scanned upwards), with the
+ * magnitude of the hit bin j and frequency[j + 1] (sic, :137); parser() (:175-236) then runs per stream:
+ * a code must repeat tq_n times after its first sighting, start-of-frame arms, nibble pairs make chars.
+ * nsof / neof count the accepted start / end markers. */
+int usc_fsk_detect(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                   const usc_fsk_config *cfg, uint8_t *code, float *magnitude, float *frequency, uint8_t *chars,
+                   uint32_t cap, uint32_t *nchars, uint32_t *nsof, uint32_t *neof);
+/* The front half alone: nframes x 512 magnitudes (bins 0..511). */
+int usc_band_magnitudes(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, float *mag);
 /* The audio spectrum analyser fft() of experiments/basic/Src/main.c:107-142 (the producer of the
  * reference's captured .raw/.flt/.fft files): PCM x Hann -> RFFT -> magnitude * 1/sqrt(N) -> bins below
  * ac_coupling_hz (FFT_AC_COUPLING_HZ = 1000) forced to 1.0 -> dB = 10*log10 -> arg-max.  Uses the

@@ -453,6 +453,56 @@ def synth_frames(seed, first_frame, nframes, amp, noise_sigma, n=2048, fs=78125.
     return pcm, bits
 
 
+def legacy_magnitudes(pcm, nthreads=4):
+    """[nframes, n] int32 -> [nframes, n/2] magnitudes of the legacy detectors' shared front half."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    nf, n = pcm.shape
+    mag = np.empty((nf, n // 2), np.float32)
+    lib().ref_legacy_magnitudes_i32(pcm.ctypes.data_as(i32p), C.c_size_t(nf), C.c_uint32(n), _fp(mag), C.c_int(nthreads))
+    return mag
+
+
+def onoff_detect(mag, fs=78125.0, f1=17000.0, f2=18000.0, mag_threshold=3000.0, high_frac=0.1, low_frac=0.05):
+    nf, half = mag.shape
+    lo, hi = C.c_uint32(0), C.c_uint32(0)
+    lib().ref_onoff_band(C.c_uint32(2 * half), C.c_float(fs), C.c_float(f1), C.c_float(f2), C.byref(lo), C.byref(hi))
+    strength, level = np.empty(nf, np.uint16), np.empty(nf, np.int8)
+    lib().ref_onoff_levels(_fp(mag), C.c_size_t(nf), C.c_uint32(half), lo, hi, C.c_float(mag_threshold), C.c_float(high_frac),
+                           C.c_float(low_frac), strength.ctypes.data_as(C.POINTER(C.c_uint16)),
+                           level.ctypes.data_as(C.POINTER(C.c_int8)))
+    return strength, level, (lo.value, hi.value)
+
+
+def onoff_decode(level, frame_start=3, frame_bit=2, sync_threshold=2, sampling_offset=1, cap=64):
+    level = np.ascontiguousarray(level, dtype=np.int8)
+    chars = np.zeros(cap, np.uint8)
+    errs = C.c_uint32(0)
+    lib().ref_onoff_decode.restype = C.c_uint32
+    n = lib().ref_onoff_decode(level.ctypes.data_as(C.POINTER(C.c_int8)), C.c_uint32(level.size), C.c_uint32(frame_start),
+                               C.c_uint32(frame_bit), C.c_uint32(sync_threshold), C.c_uint32(sampling_offset),
+                               chars.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint32(cap), C.byref(errs))
+    return bytes(chars[:min(n, cap)]), n, errs.value
+
+
+def fsk_codes(mag, fs=78125.0, sof_bin=340, eof_bin=344, hex0_bin=348, hex_step=4, tolerance=0, mag_threshold=5000.0):
+    nf, half = mag.shape
+    code, m, fr = np.empty(nf, np.uint8), np.empty(nf, np.float32), np.empty(nf, np.float32)
+    lib().ref_fsk_codes(_fp(mag), C.c_size_t(nf), C.c_uint32(half), C.c_float(fs), C.c_uint32(2 * half), C.c_uint32(sof_bin),
+                        C.c_uint32(eof_bin), C.c_uint32(hex0_bin), C.c_uint32(hex_step), C.c_uint32(tolerance),
+                        C.c_float(mag_threshold), code.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(m), _fp(fr))
+    return code, m, fr
+
+
+def fsk_parse(code, tq_n=2, cap=64):
+    code = np.ascontiguousarray(code, dtype=np.uint8)
+    chars = np.zeros(cap, np.uint8)
+    sof, eof = C.c_uint32(0), C.c_uint32(0)
+    lib().ref_fsk_parse.restype = C.c_uint32
+    n = lib().ref_fsk_parse(code.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint32(code.size), C.c_uint32(tq_n),
+                            chars.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint32(cap), C.byref(sof), C.byref(eof))
+    return bytes(chars[:min(n, cap)]), n, sof.value, eof.value
+
+
 def synth_streams(seed, first_stream, nstreams, nframes, lead_in, msg_bytes, guard, amp, noise_sigma, n=2048, fs=78125.0,
                   f0=16000.0, f1=19000.0):
     """CPU twin of usc_synth_streams -> (pcm [nstreams, nframes, n] int32, offsets, messages [nstreams, msg_bytes])."""

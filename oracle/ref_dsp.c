@@ -879,6 +879,150 @@ static void philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* ---- the two earlier detectors ------------------------------------------------------------------------ */
+void ref_legacy_magnitudes_i32(const int32_t *pcm, size_t nframes, uint32_t n, float *mag, int nthreads) {
+    /* experiments/chirp/Src/main.c:200-216 == experiments/ultracom/Src/main.c:115-128 == experiments/basic fft() */
+    float *hann = (float *) malloc(sizeof(float) * n);
+    ref_hann_window(hann, n, REF_HANN_PERIODIC);
+    const float inv = 1.0f / sqrtf((float) n);
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+        ref_rfft_fast_instance_f32 S;
+        ref_arm_rfft_fast_init_f32(&S, (uint16_t) n);
+        float *in = (float *) malloc(sizeof(float) * n), *out = (float *) malloc(sizeof(float) * n);
+#pragma omp for schedule(static)
+        for (long f = 0; f < (long) nframes; ++f) {
+            for (uint32_t i = 0; i < n; ++i) in[i] = (float) pcm[(size_t) f * n + i];
+            ref_arm_mult_f32(in, hann, in, n);
+            ref_arm_rfft_fast_f32(&S, in, out, 0);
+            ref_arm_cmplx_mag_f32(out, mag + (size_t) f * (n / 2), n / 2);
+            ref_arm_scale_f32(mag + (size_t) f * (n / 2), inv, mag + (size_t) f * (n / 2), n / 2);
+        }
+        free(in); free(out);
+        ref_arm_rfft_fast_free(&S);
+    }
+    free(hann);
+}
+
+void ref_onoff_band(uint32_t n, float fs, float f1, float f2, uint32_t *lo, uint32_t *hi) {
+    const float freq1 = f1, freq2 = (float) ((double) f1 + 2.0 * ((double) f2 - (double) f1));   /* main.c:372-373 */
+    uint32_t b1 = 0, b2 = 0;
+    for (uint32_t i = 0; i < n / 2; ++i) {
+        float f = (float) i * fs / (float) n;                                                   /* main.c:376 */
+        if (b1 == 0 && f >= freq1) b1 = i;
+        if (b2 == 0 && f >= freq2) b2 = i;
+    }
+    *lo = b1; *hi = b2;
+}
+
+void ref_onoff_levels(const float *mag, size_t nframes, uint32_t half, uint32_t lo, uint32_t hi, float mag_threshold,
+                      float high_frac, float low_frac, uint16_t *strength, int8_t *level) {
+    const uint16_t th = (uint16_t) ((float) (hi - lo + 1) * high_frac), tl = (uint16_t) ((float) (hi - lo + 1) * low_frac);
+    for (size_t f = 0; f < nframes; ++f) {
+        uint16_t c = 0;
+        for (uint32_t i = lo; i <= hi; ++i)
+            if (mag[f * half + i] > mag_threshold) c += 1;                                       /* main.c:238-242 */
+        if (strength) strength[f] = c;
+        if (level) level[f] = c >= th ? 1 : (c <= tl ? -1 : 0);                                  /* main.c:276-286 */
+    }
+}
+
+uint32_t ref_onoff_decode(const int8_t *level, uint32_t nframes, uint32_t frame_start, uint32_t frame_bit, uint32_t sync_threshold,
+                          uint32_t sampling_offset, uint8_t *chars, uint32_t cap, uint32_t *sync_errors) {
+    /* decode(), main.c:119-198; the statics become locals of one stream */
+    uint16_t count = 0, n = 0, high_count = 0;
+    uint8_t bits = 0;
+    uint32_t out = 0, errs = 0;
+    const uint16_t offset = (uint16_t) (frame_start + sampling_offset), max_length = (uint16_t) (offset + frame_bit * 8);
+    for (uint32_t t = 0; t < nframes; ++t) {
+        const int lv = level[t];
+        const int sampling_point = count == offset + frame_bit * n;
+        if (lv > 0) {                                   /* CHIRP_HIGH */
+            if (count < offset) high_count++;
+            else if (sampling_point) { bits = (uint8_t) (bits | (n < 8 ? (0x80 >> n) : 0)); n++; }
+            count++;
+        } else if (lv == 0) {                           /* CHIRP_UNKNOWN */
+            if (sampling_point) n++;
+            count++;
+        } else {                                        /* CHIRP_LOW */
+            if (count > 0) {
+                count++;
+                if (sampling_point) n++;
+            }
+        }
+        if (count >= frame_start && high_count < sync_threshold) {   /* Sync error: n and bits stay */
+            errs++;
+            count = 0;
+            high_count = 0;
+        }
+        if (count >= max_length) {                      /* frame receiving completed */
+            count = 0; n = 0; high_count = 0;
+            if (chars && out < cap) chars[out] = bits;
+            out++;
+            bits = 0;
+        }
+    }
+    if (sync_errors) *sync_errors = errs;
+    return out;
+}
+
+void ref_fsk_codes(const float *mag, size_t nframes, uint32_t half, float fs, uint32_t n, uint32_t sof_bin, uint32_t eof_bin,
+                   uint32_t hex0_bin, uint32_t hex_step, uint32_t tolerance, float mag_threshold, uint8_t *code, float *magnitude,
+                   float *frequency) {
+    for (size_t f = 0; f < nframes; ++f) {
+        const float *m = mag + f * half;
+        int found = 0;
+        uint8_t data = 0xFF;
+        uint32_t jj = 0;
+        for (int c = 0; c < 18 && !found; ++c) {        /* start of frame, end of frame, then symbols[0..15] (main.c:130-166) */
+            const uint32_t centre = c == 0 ? sof_bin : (c == 1 ? eof_bin : hex0_bin + (uint32_t) (c - 2) * hex_step);
+            for (uint32_t j = centre - tolerance; j <= centre + tolerance; ++j)
+                if (m[j] > mag_threshold) {
+                    found = 1;
+                    data = c == 0 ? 0xF0 : (c == 1 ? 0xF1 : (uint8_t) (c - 2));
+                    jj = j;
+                    break;
+                }
+        }
+        code[f] = data;
+        if (magnitude) magnitude[f] = found ? m[jj] : 0.0f;
+        if (frequency) frequency[f] = found ? (float) (jj + 1) * fs / (float) n : 0.0f;          /* frequency[j + 1], main.c:137 */
+    }
+}
+
+uint32_t ref_fsk_parse(const uint8_t *code, uint32_t nframes, uint32_t tq_n, uint8_t *chars, uint32_t cap, uint32_t *nsof,
+                       uint32_t *neof) {
+    /* parser(), ultracom/Src/main.c:175-236 */
+    enum { IDLE, DATA_MSB, DATA_LSB } recv_state = IDLE;
+    uint8_t hex_data_n = 0xFF, data_cnt = 0, data_msb = 0;
+    uint32_t out = 0, sof = 0, eof = 0;
+    for (uint32_t t = 0; t < nframes; ++t) {
+        const uint8_t data = code[t];
+        int output_result = 0;
+        if (data != hex_data_n) { data_cnt = 0; hex_data_n = data; }
+        else if (data_cnt == tq_n) { }
+        else if (++data_cnt == tq_n && hex_data_n != 0xFF) output_result = 1;
+        if (!output_result) continue;
+        switch (hex_data_n) {
+        case 0xF0: recv_state = DATA_MSB; sof++; break;
+        case 0xF1: recv_state = IDLE; eof++; break;
+        default:
+            if (recv_state == DATA_MSB) { data_msb = (uint8_t) (hex_data_n << 4); recv_state = DATA_LSB; }
+            else if (recv_state == DATA_LSB) {
+                if (chars && out < cap) chars[out] = (uint8_t) (data_msb + hex_data_n);
+                out++;
+                data_msb = 0;
+                recv_state = DATA_MSB;
+            }
+            break;
+        }
+    }
+    if (nsof) *nsof = sof;
+    if (neof) *neof = eof;
+    return out;
+}
+
 static void synth_tables(uint32_t n, float fs, float f0, float f1, double amp, int32_t *tab) {
     const double T = (double) n / (double) fs, k = ((double) f1 - (double) f0) / T;
     for (int down = 0; down < 2; ++down)

@@ -206,6 +206,23 @@ void ref_scan4(const ref_rfft_fast_instance_f32 *S, const float *hann, const flo
                const float *pcm2n, ref_scan_entry *out);
 
 /* ---- twin of the device-side synthetic generator (usc_synth_frames): regenerates any frame on the CPU ---- */
+/* ---- the two earlier detectors (experiments/chirp, experiments/ultracom), n = 2048 ---- */
+/* front half shared with the analyser: (float) pcm x Hann (periodic) -> RFFT -> magnitude * 1/sqrt(N); mag: nframes x n/2 */
+void ref_legacy_magnitudes_i32(const int32_t *pcm, size_t nframes, uint32_t n, float *mag, int nthreads);
+/* experiments/chirp/Src/main.c:237-286, 372-387: band indices from (fs, F1, F2), strength, level (1 / -1 / 0) */
+void ref_onoff_band(uint32_t n, float fs, float f1, float f2, uint32_t *lo, uint32_t *hi);
+void ref_onoff_levels(const float *mag, size_t nframes, uint32_t half, uint32_t lo, uint32_t hi, float mag_threshold,
+                      float high_frac, float low_frac, uint16_t *strength, int8_t *level);
+/* decode(), :119-198, over one stream's levels; returns the number of completed frames (bytes), writes min(that, cap) */
+uint32_t ref_onoff_decode(const int8_t *level, uint32_t nframes, uint32_t frame_start, uint32_t frame_bit, uint32_t sync_threshold,
+                          uint32_t sampling_offset, uint8_t *chars, uint32_t cap, uint32_t *sync_errors);
+/* experiments/ultracom/Src/main.c:130-168: code, magnitude, frequency[j + 1] per frame */
+void ref_fsk_codes(const float *mag, size_t nframes, uint32_t half, float fs, uint32_t n, uint32_t sof_bin, uint32_t eof_bin,
+                   uint32_t hex0_bin, uint32_t hex_step, uint32_t tolerance, float mag_threshold, uint8_t *code, float *magnitude,
+                   float *frequency);
+/* parser(), :175-236, over one stream's codes */
+uint32_t ref_fsk_parse(const uint8_t *code, uint32_t nframes, uint32_t tq_n, uint8_t *chars, uint32_t cap, uint32_t *nsof,
+                       uint32_t *neof);
 void ref_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, uint32_t n, float fs, float f0,
                        float f1, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp, double noise_sigma,
                        int32_t *pcm, uint32_t *offsets, uint8_t *messages);

@@ -106,3 +106,40 @@ def make_iq_stream(nframes, carrier=18000.0, bw=3000.0, snr_db=10.0, amp=2.0e4, 
     x = np.where(bits[:, None] == 1, waves[0][None, :], waves[1][None, :]) * amp
     x = x + np.random.default_rng(seed_noise).standard_normal((nframes, n)) * sigma
     return (np.rint(x).astype(np.int64) * 256).astype(np.int32), bits
+
+
+# ---- inputs of the two earlier detectors --------------------------------------------------------------
+def make_onoff_stream(bits_bytes, idle=4, amp=3.0e4, snr_db=20.0, seed=21, fs=FS, n=N, f_lo=17000.0, f_hi=19000.0):
+    """experiments/chirp framing (Inc/main.h:95-98): a byte = 3 HIGH frames (sync), then 8 bits x 2 frames each
+    (HIGH frame pair = 1, silent pair = 0), one frame of slack; HIGH = a linear chirp across the counted band."""
+    t = np.arange(n) / fs
+    T = n / fs
+    chirp = np.sin(2.0 * np.pi * (f_lo * t + 0.5 * (f_hi - f_lo) / T * t * t))
+    levels = [0] * idle
+    for byte in bits_bytes:
+        levels += [1, 1, 1]
+        for b in range(7, -1, -1):
+            levels += [1, 1] if (byte >> b) & 1 else [0, 0]
+        levels += [0] * (idle + 1)
+    sigma = np.sqrt(0.5 * amp * amp / (10.0 ** (snr_db / 10.0)))
+    rng = np.random.default_rng(seed)
+    x = np.stack([chirp * amp * lv for lv in levels]) + rng.standard_normal((len(levels), n)) * sigma
+    return (np.rint(x).astype(np.int64) * 256).astype(np.int32), np.array(levels, np.int8)
+
+
+def make_fsk_stream(message, repeat=4, amp=3.0e4, snr_db=20.0, seed=22, n=N, sof=340, eof=344, hex0=348, step=4, gap=2):
+    """experiments/ultracom framing: start tone, two hex-digit tones per byte (MSB nibble first), end tone; every
+    tone lasts `repeat` frames (parser() wants a code three frames in a row at TQ_N = 2), `gap` silent frames
+    between tones so repeated digits are seen as new codes."""
+    bins = [sof]
+    for byte in message:
+        bins += [hex0 + step * (byte >> 4), hex0 + step * (byte & 15)]
+    bins.append(eof)
+    t = np.arange(n)
+    frames, codes = [], []
+    for b in bins:
+        frames += [np.sin(2.0 * np.pi * b * t / n) * amp] * repeat + [np.zeros(n)] * gap
+        codes += [b] * repeat + [0] * gap
+    sigma = np.sqrt(0.5 * amp * amp / (10.0 ** (snr_db / 10.0)))
+    x = np.stack(frames) + np.random.default_rng(seed).standard_normal((len(frames), n)) * sigma
+    return (np.rint(x).astype(np.int64) * 256).astype(np.int32), np.array(codes)

@@ -726,6 +726,106 @@ int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t 
     return USC_OK;
 }
 
+void usc_onoff_default_config(usc_onoff_config* c) {
+    if (!c) return;
+    c->f1_hz = 17000.0f; c->f2_hz = 18000.0f; c->magnitude_threshold = 3000.0f;
+    c->high_frac = 0.1f; c->low_frac = 0.05f;
+    c->frame_start = 3; c->frame_bit = 2; c->sync_threshold = 2; c->sampling_offset = 1;
+}
+
+void usc_fsk_default_config(usc_fsk_config* c) {
+    if (!c) return;
+    c->sof_bin = 340; c->eof_bin = 344; c->hex0_bin = 348; c->hex_step = 4; c->tolerance = 0; c->tq_n = 2;
+    c->magnitude_threshold = 5000.0f;
+}
+
+static int band_common(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, band_params* p) {
+    if (!h || !pcm || pcm_format > USC_PCM_I32 || h->cfg.n != 2048 || !h->d_tw_pass || !h->d_tw_split) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;
+    memset(p, 0, sizeof(*p));
+    p->pcm = pcm; p->nframes = nframes;
+    p->hann = (const float2*) h->d_hann; p->tw_pass = h->d_tw_pass; p->tw_split = h->d_tw_split;
+    p->inv_sqrt_n = 1.0f / sqrtf(2048.0f);
+    p->fs = h->cfg.fs;
+    p->band_lo = 1; p->band_hi = 0;                       /* empty band */
+    return USC_OK;
+}
+
+int usc_band_magnitudes(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, float* mag) {
+    band_params p;
+    int rc = band_common(h, pcm, pcm_format, nframes, &p);
+    if (rc) return rc;
+    if (!mag) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    p.mag = mag;
+    LAUNCHED(h, launch_band2048(p, pcm_format, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+int usc_onoff_detect(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                     const usc_onoff_config* cfg, uint16_t* strength, int8_t* level, uint8_t* chars, uint32_t cap,
+                     uint32_t* nchars, uint32_t* sync_errors) {
+    band_params p;
+    const size_t F = (size_t) nstreams * nframes;
+    int rc = band_common(h, pcm, pcm_format, F, &p);
+    if (rc) return rc;
+    if (!cfg || cfg->frame_bit == 0) return USC_ERR_ARGUMENT;
+    if (!F) return USC_OK;
+    /* chirp/Src/main.c:372-387: first bins at or above F1 and F1 + 2 (F2 - F1) on the float frequency axis */
+    const float freq1 = cfg->f1_hz, freq2 = (float) ((double) cfg->f1_hz + 2.0 * ((double) cfg->f2_hz - (double) cfg->f1_hz));
+    uint32_t b1 = 0, b2 = 0;
+    for (uint32_t i = 0; i < 1024; ++i) {
+        const float f = (float) i * h->cfg.fs / 2048.0f;
+        if (b1 == 0 && f >= freq1) b1 = i;
+        if (b2 == 0 && f >= freq2) b2 = i;
+    }
+    if (b1 == 0 || b2 < b1 || b2 >= 512) return USC_ERR_ARGUMENT;
+    p.band_lo = b1; p.band_hi = b2;
+    p.onoff_threshold = cfg->magnitude_threshold;
+    p.thr_high = (uint16_t) ((float) (b2 - b1 + 1) * cfg->high_frac);
+    p.thr_low = (uint16_t) ((float) (b2 - b1 + 1) * cfg->low_frac);
+    const bool want_decode = chars || nchars || sync_errors;
+    int8_t* lv = level;
+    if (want_decode && !lv) {
+        if ((rc = reserve_work(h, F))) return rc;
+        lv = (int8_t*) h->d_work;
+    }
+    p.strength = strength; p.level = lv;
+    LAUNCHED(h, launch_band2048(p, pcm_format, h->num_sms, h->stream));
+    if (want_decode)
+        LAUNCHED(h, launch_onoff_decode(lv, nstreams, nframes, cfg->frame_start, cfg->frame_bit, cfg->sync_threshold,
+                                        cfg->sampling_offset, chars, cap, nchars, sync_errors, h->stream));
+    return USC_OK;
+}
+
+int usc_fsk_detect(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                   const usc_fsk_config* cfg, uint8_t* code, float* magnitude, float* frequency, uint8_t* chars,
+                   uint32_t cap, uint32_t* nchars, uint32_t* nsof, uint32_t* neof) {
+    band_params p;
+    const size_t F = (size_t) nstreams * nframes;
+    int rc = band_common(h, pcm, pcm_format, F, &p);
+    if (rc) return rc;
+    if (!cfg || cfg->tq_n == 0) return USC_ERR_ARGUMENT;
+    const uint32_t lo = cfg->sof_bin < cfg->eof_bin ? cfg->sof_bin : cfg->eof_bin;
+    const uint32_t hi_hex = cfg->hex0_bin + 15u * cfg->hex_step;
+    uint32_t hi = cfg->sof_bin > cfg->eof_bin ? cfg->sof_bin : cfg->eof_bin;
+    if (hi_hex > hi) hi = hi_hex;
+    if ((cfg->hex0_bin < lo ? cfg->hex0_bin : lo) < cfg->tolerance || hi + cfg->tolerance >= 512) return USC_ERR_ARGUMENT;
+    if (!F) return USC_OK;
+    p.sof_bin = cfg->sof_bin; p.eof_bin = cfg->eof_bin; p.hex0_bin = cfg->hex0_bin; p.hex_step = cfg->hex_step;
+    p.tolerance = cfg->tolerance; p.fsk_threshold = cfg->magnitude_threshold;
+    const bool want_parse = chars || nchars || nsof || neof;
+    uint8_t* cd = code;
+    if (!cd) {
+        if ((rc = reserve_work(h, F))) return rc;
+        cd = (uint8_t*) h->d_work;
+    }
+    p.code = cd; p.code_mag = magnitude; p.code_freq = frequency;
+    LAUNCHED(h, launch_band2048(p, pcm_format, h->num_sms, h->stream));
+    if (want_parse) LAUNCHED(h, launch_fsk_parse(cd, nstreams, nframes, cfg->tq_n, chars, cap, nchars, nsof, neof, h->stream));
+    return USC_OK;
+}
+
 int usc_spectrum_analyzer(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nframes, float ac_coupling_hz,
                           float* mag, float* db, float* peak, uint32_t* peak_idx) {
     /* fft() of experiments/basic/Src/main.c:107-142: window, RFFT, magnitude/sqrt(N), AC coupling, dB, arg-max */

@@ -64,6 +64,20 @@ __global__ void k_fft_generic(fft_plan_dev plan, const float* in, float* out, ui
 // ------------------------------------------------------------------------------------------------
 // K1: fused receiver demodulator, N = 2048 (one warp per frame)
 // ------------------------------------------------------------------------------------------------
+// legacy detectors (k_legacy.cu): window + RFFT + magnitude/sqrt(N) over bins [0, 512), then band count and tone lookup
+struct band_params {
+    const void* pcm; size_t nframes;
+    const float2* hann; const float2* tw_pass; const float2* tw_split;
+    float inv_sqrt_n, fs;
+    float* mag;                                             // optional: nframes x 512 magnitudes
+    // on/off chirp detector
+    uint32_t band_lo, band_hi; float onoff_threshold; uint32_t thr_high, thr_low;
+    uint16_t* strength; int8_t* level;
+    // FSK tone lookup
+    uint32_t sof_bin, eof_bin, hex0_bin, hex_step, tolerance; float fsk_threshold;
+    uint8_t* code; float* code_mag; float* code_freq;
+};
+
 struct demod_params {
     const void* pcm;            // nframes x 2048 samples (or fifo base when gather != 0)
     size_t nframes;

@@ -64,6 +64,12 @@ cudaError_t launch_iq_fused(const void* pcm, uint32_t pcm_format, uint32_t nstre
                             float* mag_down, uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st);
 cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml, const uint32_t* il, uint32_t left0,
                            float* mag, uint32_t* idx, size_t count, cudaStream_t st);
+cudaError_t launch_band2048(const band_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
+cudaError_t launch_onoff_decode(const int8_t* level, uint32_t nstreams, uint32_t nframes, uint32_t frame_start, uint32_t frame_bit,
+                                uint32_t sync_threshold, uint32_t sampling_offset, uint8_t* chars, uint32_t cap, uint32_t* nchars,
+                                uint32_t* sync_errors, cudaStream_t st);
+cudaError_t launch_fsk_parse(const uint8_t* code, uint32_t nstreams, uint32_t nframes, uint32_t tq_n, uint8_t* chars, uint32_t cap,
+                             uint32_t* nchars, uint32_t* nsof, uint32_t* neof, cudaStream_t st);
 cudaError_t launch_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
                                  uint32_t n, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, const int32_t* table,
                                  int32_t gain, int32_t* pcm, uint32_t* offsets, uint8_t* messages, cudaStream_t st);

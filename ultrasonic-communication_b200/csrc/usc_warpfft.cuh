@@ -253,6 +253,30 @@ __device__ __forceinline__ void peak_tail(const float (&pw)[NB], int lane, uint3
     }
 }
 
+// squared magnitudes of the real-FFT bins k = lane + 32 d1, d1 < NB, of both halves (no peak search)
+template <int NB>
+__device__ __forceinline__ void mag2_window_pair(const float2 (&zr)[32], const float2 (&zi)[32], const float2 (&ws)[NB],
+                                                 int lane, float (&pa)[NB], float (&pb)[NB]) {
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const float2 sr = lane == 0 ? zr[(32 - d1) & 31] : zr[31 - d1];
+        const float2 si = lane == 0 ? zi[(32 - d1) & 31] : zi[31 - d1];
+        const float2 zcr = make_float2(__shfl_sync(0xffffffffu, sr.x, src), __shfl_sync(0xffffffffu, sr.y, src));
+        const float2 zci = make_float2(__shfl_sync(0xffffffffu, si.x, src), __shfl_sync(0xffffffffu, si.y, src));
+        float2 xr, xi;
+        rfft_split2(zr[d1], zi[d1], zcr, zci, ws[d1].x, ws[d1].y, xr, xi);
+        if (d1 == 0) {                                 // packed bin 0 = (X[0], X[N/2]) on lane 0
+            const float2 dr = __fadd2_rn(zr[0], zi[0]), di = __fadd2_rn(zr[0], neg2(zi[0]));
+            xr = lane == 0 ? dr : xr;
+            xi = lane == 0 ? di : xi;
+        }
+        const float2 p = __ffma2_rn(xr, xr, __fmul2_rn(xi, xi));
+        pa[d1] = p.x;
+        pb[d1] = p.y;
+    }
+}
+
 template <int NB>
 __device__ __forceinline__ void peak_window_pair(const float2 (&zr)[32], const float2 (&zi)[32], const float2 (&ws)[NB],
                                                  int lane, uint32_t bw2, float& bestA, uint32_t& idxA, float& bestB,

@@ -37,6 +37,17 @@ rx_result_dtype = np.dtype([("state", "u4"), ("sync_position", "u4"), ("lock_fra
 
 scan_entry_dtype = np.dtype([("mag_max_right", "f4"), ("mag_max_left", "f4"), ("max_idx_right", "u4"), ("max_idx_left", "u4")])
 
+class OnOffConfig(C.Structure):
+    _fields_ = [("f1_hz", C.c_float), ("f2_hz", C.c_float), ("magnitude_threshold", C.c_float), ("high_frac", C.c_float),
+                ("low_frac", C.c_float), ("frame_start", C.c_uint32), ("frame_bit", C.c_uint32), ("sync_threshold", C.c_uint32),
+                ("sampling_offset", C.c_uint32)]
+
+
+class FskConfig(C.Structure):
+    _fields_ = [("sof_bin", C.c_uint32), ("eof_bin", C.c_uint32), ("hex0_bin", C.c_uint32), ("hex_step", C.c_uint32),
+                ("tolerance", C.c_uint32), ("tq_n", C.c_uint32), ("magnitude_threshold", C.c_float)]
+
+
 # every symbol include/usc.h declares (tests/test_abi.py checks the .so exports each one)
 SYMBOLS = [
     "usc_default_config", "usc_create", "usc_destroy", "usc_set_stream", "usc_sync", "usc_error_string",
@@ -45,7 +56,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -297,6 +308,27 @@ class Handle:
 
     def scan4(self, pcm2n, batch, out):
         _ck(load().usc_scan4(self._h, _ptr(pcm2n), C.c_uint32(batch), _ptr(out)))
+
+    def band_magnitudes(self, pcm, pcm_format, nframes, mag):
+        _ck(load().usc_band_magnitudes(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes), _ptr(mag)))
+
+    def onoff_detect(self, pcm, pcm_format, nstreams, nframes, cfg=None, strength=None, level=None, chars=None, cap=0,
+                     nchars=None, sync_errors=None):
+        if cfg is None:
+            cfg = OnOffConfig()
+            load().usc_onoff_default_config(C.byref(cfg))
+        _ck(load().usc_onoff_detect(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                    C.byref(cfg), _ptr(strength), _ptr(level), _ptr(chars), C.c_uint32(cap), _ptr(nchars),
+                                    _ptr(sync_errors)))
+
+    def fsk_detect(self, pcm, pcm_format, nstreams, nframes, cfg=None, code=None, magnitude=None, frequency=None, chars=None,
+                   cap=0, nchars=None, nsof=None, neof=None):
+        if cfg is None:
+            cfg = FskConfig()
+            load().usc_fsk_default_config(C.byref(cfg))
+        _ck(load().usc_fsk_detect(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                  C.byref(cfg), _ptr(code), _ptr(magnitude), _ptr(frequency), _ptr(chars), C.c_uint32(cap),
+                                  _ptr(nchars), _ptr(nsof), _ptr(neof)))
 
     def spectrum_analyzer(self, pcm, pcm_format, nframes, ac_coupling_hz, mag=None, db=None, peak=None, peak_idx=None):
         _ck(load().usc_spectrum_analyzer(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nframes),
