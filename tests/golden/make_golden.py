@@ -9,6 +9,8 @@ needs /root/reference).  Outputs (all under tests/golden/):
                        imported by path): chirps, chirp_orth, time_shift, add_delay, and the
                        ChirpSynchronization.ipynb cell 5-11 products with the printed peak frequencies.
   fir_taps.npz         the 27 FIR taps literal at experiments/iq_modulation/Src/iq_modem.c:18.
+  wire_excerpt.json    verbatim head / tail lines of one capture's .raw / .flt / .fft files (the PC agent's
+                       CSV wire formats, agent/README.md:5-11) with the row indices they came from.
 """
 import glob
 import os
@@ -102,7 +104,24 @@ def fir_taps():
     print("fir taps:", taps.size)
 
 
+def wire_excerpt():
+    import json
+    base = sorted(glob.glob(os.path.join(REF, "agent", "chirp_experiment", "*.raw")))[0][:-4]
+    out = {"capture": os.path.basename(base)}
+    for ext in ("raw", "flt", "fft"):
+        lines = open(base + "." + ext).read().splitlines()
+        rows = [1, 2, 3, 700, 1023 if ext == "fft" else 2047]            # 1-based file line = data row + 1 (header is line 0)
+        out[ext] = {"header": lines[0], "nlines": len(lines), "rows": {str(r): lines[r] for r in rows}}
+    with open(os.path.join(HERE, "wire_excerpt.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wire_excerpt.json:", out["capture"])
+
+
 if __name__ == "__main__":
+    if "--wire-only" in sys.argv:
+        wire_excerpt()
+        sys.exit(0)
+    wire_excerpt()
     device_triples()
     refsim_vectors()
     fir_taps()

@@ -44,3 +44,32 @@ def test_reference_style_caller_links_and_matches_oracle(tmp_path):
     z[0::2] = frame
     peak, bin_ = R.arm_max_f32(R.arm_cmplx_mag_f32(R.Cfft(N)(z)))
     assert np.float32(float.fromhex(lines["cfft"][0])) == peak and int(lines["cfft"][1]) == bin_
+
+
+def test_analyser_host_reproduces_a_device_capture(device_triples, tmp_path):
+    """analyser_host (plain C over the C-ABI + the CSV wire formats): a captured .raw in, the .fft / .flt
+    files and the firmware's UART dump out; the .fft magnitudes match the Cortex-M4's own .fft (<= 1e-4),
+    the .flt matches the device's .flt text to the printed precision."""
+    import subprocess
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ultrasonic-communication_b200")
+    exe = os.path.join(pkg, "host", "analyser_host")
+    assert os.path.exists(exe), "run python __graft_entry__.py first"
+    i = [k for k, ok in enumerate(device_triples["consistent"]) if ok][0]
+    name = str(device_triples["names"][i])
+    fs = 1000.0 * float(name.split("(kHz)")[0].split("_")[-1])
+    raw = device_triples["raw"][i].astype(np.int64)
+    rawf = tmp_path / "cap.raw"
+    rawf.write_text("Index,Amplitude\n" + "".join("%d,%d\n" % (k, v) for k, v in enumerate(raw)))
+    out = tmp_path / "out"
+    r = subprocess.run([exe, str(rawf), str(fs), str(out), "M2A"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    fft = np.loadtxt(str(out) + ".fft", delimiter=",", skiprows=1)
+    flt = np.loadtxt(str(out) + ".flt", delimiter=",", skiprows=1)[:, 1]
+    dev = device_triples["fft_mag"][i]
+    sel = device_triples["fft_freq"][i] >= 1000.0
+    big = sel & (dev >= 0.01 * dev[sel].max())
+    assert (np.abs(fft[:, 1][big] - dev[big]) / dev[big]).max() < 1e-4
+    assert np.all(fft[:, 1][~sel] == 1.0)                                   # AC coupling
+    assert np.abs(flt - device_triples["flt"][i]).max() <= 1e-6 * max(1.0, np.abs(flt).max())
+    lines = r.stdout.splitlines()
+    assert lines[1] == "MEMS mic: M2A" and lines[3] == "Frequency(Hz),Magnitude,Magnitude(dB)" and lines[-1] == "EOFLT"

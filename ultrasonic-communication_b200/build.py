@@ -70,6 +70,12 @@ def build(force=False, verbose=False):
     if force or _stale(shim_lib, [shim_src, LIB] + headers):
         _run(["gcc"] + CC_FLAGS + ["-shared", shim_src, "-o", shim_lib, "-L", HERE, "-lusc", "-Wl,-rpath," + HERE,
                                   "-Wl,-rpath,$ORIGIN"], os.path.join(OBJ, "shim.log"))
+    # the reference's CSV wire formats: plain host C, no CUDA (include/usc_wire.h)
+    wire_src = os.path.join(HERE, "host", "usc_wire.c")
+    wire_lib = os.path.join(HERE, "libusc_wire.so")
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    if force or _stale(wire_lib, [wire_src, os.path.join(inc, "usc_wire.h"), os.path.join(inc, "usc.h")]):
+        _run(["gcc"] + CC_FLAGS + ["-Wextra", "-shared", "-I", inc, wire_src, "-o", wire_lib], os.path.join(OBJ, "wire.log"))
     # the plain-C host driver links against the C-ABI only (no CUDA headers): proves the boundary
     host_src = os.path.join(HERE, "host", "receiver_host.c")
     host_bin = os.path.join(HERE, "host", "receiver_host")
@@ -77,6 +83,11 @@ def build(force=False, verbose=False):
         _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-I", os.path.join(os.path.dirname(HERE), "include"), host_src,
               "-o", host_bin, "-L", HERE, "-lusc", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."],
              os.path.join(OBJ, "host.log"))
+    ana_src = os.path.join(HERE, "host", "analyser_host.c")
+    ana_bin = os.path.join(HERE, "host", "analyser_host")
+    if force or _stale(ana_bin, [ana_src, LIB, wire_lib, os.path.join(inc, "usc.h"), os.path.join(inc, "usc_wire.h")]):
+        _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-I", inc, ana_src, "-o", ana_bin, "-L", HERE, "-lusc", "-lusc_wire",
+              "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."], os.path.join(OBJ, "host_analyser.log"))
     return LIB
 
 
