@@ -95,7 +95,8 @@ int usc_get_table(const usc_handle *h, const char *what, float *dst, size_t cap)
 uint64_t usc_launch_count(const usc_handle *h);
 
 /* device memory helpers so a plain-C host needs no CUDA headers */
-int usc_malloc(void **dptr, size_t bytes);
+int usc_malloc(void **dptr, size_t bytes);                    /* on the CURRENT device */
+int usc_malloc_on(usc_handle *h, void **dptr, size_t bytes);  /* on the handle's device (processes holding several GPUs) */
 int usc_free(void *dptr);
 int usc_malloc_host(void **hptr, size_t bytes); /* pinned */
 int usc_free_host(void *hptr);

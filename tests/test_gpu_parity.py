@@ -404,3 +404,21 @@ def test_scan4_freq_domain_experiment_bit_exact():
             assert np.float32(g["mag_max_right"]).view(np.uint32) == np.float32(want[i][0]).view(np.uint32)
             assert np.float32(g["mag_max_left"]).view(np.uint32) == np.float32(want[i][2]).view(np.uint32)
     hf.close()
+
+
+def test_two_devices_in_one_process():
+    """Handles on different GPUs of one process: per-device kernel configuration and device switching inside
+    the library (skipped on a one-GPU box; the bench's multi-GPU mode is one process per GPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    pcm, _ = synth.make_frames(64)
+    want = R.RefReceiver().demod_frames(pcm, nthreads=4)
+    hs = [usc.Handle(device=d) for d in (0, 1)]
+    outs = [h.demod_frames_host(pcm) for h in hs]
+    outs += [h.demod_frames_host(pcm) for h in reversed(hs)]
+    for got in outs:
+        for g, w in zip(got[:4], want):
+            assert np.array_equal(g.view(np.uint32), w.view(np.uint32))
+    for h in hs:
+        h.close()

@@ -210,7 +210,8 @@ cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nfr
     compress_params p{pcm, nframes, window, H, tw_pass, tw_split, out_frames, max_val, max_idx};
     size_t ctas = ((nframes + 1) / 2 + kCWarps - 1) / kCWarps;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     if (!configured) {
         cudaError_t e;
         if ((e = cudaFuncSetAttribute(k_compress2048<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemTotal))) return e;
@@ -240,7 +241,8 @@ __global__ void k_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zer
 
 cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zero_upper, cudaStream_t st) {
     int grid = batch < 148u * 16u ? (int) batch : 148 * 16;
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     if (!configured && n * sizeof(float) > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_pipeline_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;

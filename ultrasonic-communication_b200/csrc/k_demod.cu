@@ -320,20 +320,21 @@ static cudaError_t launch_demod_nb(const demod_params& p, uint32_t pcm_format, i
     constexpr int W = USC_DUAL_WARPS;
     size_t ctas = (p.nframes + W - 1) / W;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;            // persistent: one CTA per SM
-    static bool configured[2] = {false, false};
+    static per_device<bool> configured_pd[2];
+    bool* configured[2] = {&configured_pd[0].get(), &configured_pd[1].get()};
     const int smem = dual_smem<W>::total;
     if (pcm_format == 1u) {
-        if (!configured[1]) {
+        if (!*configured[1]) {
             cudaError_t e = cudaFuncSetAttribute(k_demod2048<int32_t, NB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            configured[1] = true;
+            *configured[1] = true;
         }
         k_demod2048<int32_t, NB, W><<<(int) ctas, W * 32, smem, st>>>(p);
     } else {
-        if (!configured[0]) {
+        if (!*configured[0]) {
             cudaError_t e = cudaFuncSetAttribute(k_demod2048<float, NB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            configured[0] = true;
+            *configured[0] = true;
         }
         k_demod2048<float, NB, W><<<(int) ctas, W * 32, smem, st>>>(p);
     }
@@ -344,19 +345,20 @@ template <int NB>
 static cudaError_t launch_pair_nb(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
     size_t ctas = ((p.nframes + 1) / 2 + kDualWarps - 1) / kDualWarps;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
-    static bool configured[2] = {false, false};
+    static per_device<bool> configured_pd[2];
+    bool* configured[2] = {&configured_pd[0].get(), &configured_pd[1].get()};
     if (pcm_format == 1u) {
-        if (!configured[1]) {
+        if (!*configured[1]) {
             cudaError_t e = cudaFuncSetAttribute(k_demod2048_pair<int32_t, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal);
             if (e != cudaSuccess) return e;
-            configured[1] = true;
+            *configured[1] = true;
         }
         k_demod2048_pair<int32_t, NB><<<(int) ctas, kDualWarps * 32, kPairSmemTotal, st>>>(p);
     } else {
-        if (!configured[0]) {
+        if (!*configured[0]) {
             cudaError_t e = cudaFuncSetAttribute(k_demod2048_pair<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal);
             if (e != cudaSuccess) return e;
-            configured[0] = true;
+            *configured[0] = true;
         }
         k_demod2048_pair<float, NB><<<(int) ctas, kDualWarps * 32, kPairSmemTotal, st>>>(p);
     }

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(kIqWarps * 32, 1) k_iq_backend(const float2* _
 cudaError_t launch_iq_backend(const float* R, size_t nframes, const float* chirp, const float* hann, const float2* tw_pass,
                               uint32_t window, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
                               uint8_t* bit, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_iq_backend, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqSmem);
         if (e != cudaSuccess) return e;
@@ -431,7 +432,8 @@ cudaError_t launch_iq_fused(const void* pcm, uint32_t pcm_format, uint32_t nstre
                             const float* car_cos, const float* car_sin, const float* taps, uint32_t ntaps, const float* chirp,
                             const float* hann, const float2* tw_pass, uint32_t window, float* mag_up, uint32_t* idx_up,
                             float* mag_down, uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_iq_fused<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqfSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_iq_fused<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqfSmem);

@@ -236,7 +236,8 @@ __global__ void k_fsk_parse(const uint8_t* __restrict__ code, uint32_t nstreams,
 cudaError_t launch_band2048(const band_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {
     size_t ctas = ((p.nframes + 1) / 2 + kBandWarps - 1) / kBandWarps;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_band2048_pair<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band2048_pair<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandSmem);

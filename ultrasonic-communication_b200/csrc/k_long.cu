@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
 
 template <typename PCM, int R0>
 static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     const int smem = long_smem<R0>::total;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_demod_long<PCM, R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -361,7 +362,8 @@ static cudaError_t launch_long32_t(const long_params& p, const float2* tw_l0, in
     // The loop inside the kernel strides by the number of clusters launched, so launch exactly as many as
     // can be resident at once (fewer than SMs / cluster size: clusters do not straddle GPCs) — a cluster
     // left for a second wave would run its whole share after everyone else has finished.
-    static int max_clusters = 0;
+    static per_device<int> max_clusters_pd;
+    int& max_clusters = max_clusters_pd.get();
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = kL32Cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;

@@ -378,7 +378,8 @@ static rx_params make_params(const rx_launch& a) {
 }
 
 static cudaError_t rx_prepare() {
-    static bool done = false;
+    static per_device<bool> done_pd;
+    bool& done = done_pd.get();
     if (done) return cudaSuccess;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_receiver_run<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kSyWarps * 32, 2) k_dsp2048c(demod_params p) {
 }
 
 cudaError_t launch_dsp2048c(const demod_params& p, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_dsp2048c, cudaFuncAttributeMaxDynamicSharedMemorySize, kSySmem);
         if (e != cudaSuccess) return e;

@@ -52,6 +52,12 @@ struct usc_handle {
 };
 
 static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? USC_OK : USC_ERR_CUDA_BASE - (int) e; }
+/* every entry point makes the handle's device current (a process may hold handles on several GPUs) */
+#define USC_ENTER(h)                                                                            \
+    do {                                                                                        \
+        int cur__ = -1;                                                                         \
+        if ((h) && cudaGetDevice(&cur__) == cudaSuccess && cur__ != (h)->device) cudaSetDevice((h)->device); \
+    } while (0)
 #define CK(expr)                                   \
     do {                                           \
         cudaError_t e__ = (expr);                  \
@@ -256,6 +262,7 @@ void usc_destroy(usc_handle* h) {
 }
 
 int usc_set_stream(usc_handle* h, void* cuda_stream) {
+    USC_ENTER(h);
     if (!h) return USC_ERR_ARGUMENT;
     h->stream = (cudaStream_t) cuda_stream;
     return USC_OK;
@@ -302,6 +309,12 @@ int usc_malloc(void** dptr, size_t bytes) {
     CK(cudaMalloc(dptr, bytes));
     return USC_OK;
 }
+int usc_malloc_on(usc_handle* h, void** dptr, size_t bytes) {
+    USC_ENTER(h);
+    if (!h) return USC_ERR_ARGUMENT;
+    return usc_malloc(dptr, bytes);
+}
+
 int usc_free(void* dptr) {
     CK(cudaFree(dptr));
     return USC_OK;
@@ -316,29 +329,36 @@ int usc_free_host(void* hptr) {
     return USC_OK;
 }
 int usc_memcpy_h2d(usc_handle* h, void* dst, const void* src, size_t bytes) {
+    USC_ENTER(h);
     if (!h) return USC_ERR_ARGUMENT;
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
     return USC_OK;
 }
 int usc_memcpy_d2h(usc_handle* h, void* dst, const void* src, size_t bytes) {
+    USC_ENTER(h);
     if (!h) return USC_ERR_ARGUMENT;
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     return USC_OK;
 }
 int usc_memset(usc_handle* h, void* dst, int value, size_t bytes) {
+    USC_ENTER(h);
     if (!h) return USC_ERR_ARGUMENT;
     CK(cudaMemsetAsync(dst, value, bytes, h->stream));
     return USC_OK;
 }
 
 /* ---- batched CMSIS-shaped operators ---- */
-#define LAUNCHED(h, expr)        \
-    do {                         \
-        CK(expr);                \
-        (h)->launches++;         \
+/* launches go to the handle's device even when the caller has made another one current in between */
+#define LAUNCHED(h, expr)                                          \
+    do {                                                           \
+        int cur__ = -1;                                            \
+        if (cudaGetDevice(&cur__) == cudaSuccess && cur__ != (h)->device) CK(cudaSetDevice((h)->device)); \
+        CK(expr);                                                  \
+        (h)->launches++;                                           \
     } while (0)
 
 int usc_i32_to_f32(usc_handle* h, const int32_t* src, float* dst, size_t count) {
+    USC_ENTER(h);
     if (!h || !src || !dst) return USC_ERR_ARGUMENT;
     if (!count) return USC_OK;
     LAUNCHED(h, launch_i32_to_f32(src, dst, count, h->stream));
@@ -346,6 +366,7 @@ int usc_i32_to_f32(usc_handle* h, const int32_t* src, float* dst, size_t count) 
 }
 int usc_arm_mult_f32_batch(usc_handle* h, const float* a, size_t sa, const float* b, size_t sb, float* dst,
                            size_t sd, uint32_t block_size, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !a || !b || !dst) return USC_ERR_ARGUMENT;
     if (!block_size || !batch) return USC_OK;
     LAUNCHED(h, launch_mult(a, sa, b, sb, dst, sd, block_size, batch, h->stream));
@@ -353,6 +374,7 @@ int usc_arm_mult_f32_batch(usc_handle* h, const float* a, size_t sa, const float
 }
 int usc_arm_scale_f32_batch(usc_handle* h, const float* src, float scale, float* dst, uint32_t block_size,
                             uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !src || !dst) return USC_ERR_ARGUMENT;
     if (!block_size || !batch) return USC_OK;
     LAUNCHED(h, launch_scale(src, scale, dst, (size_t) block_size * batch, h->stream));
@@ -360,6 +382,7 @@ int usc_arm_scale_f32_batch(usc_handle* h, const float* src, float scale, float*
 }
 int usc_arm_cmplx_mult_cmplx_f32_batch(usc_handle* h, const float* a, size_t sa, const float* b, size_t sb,
                                        float* dst, size_t sd, uint32_t num_samples, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !a || !b || !dst) return USC_ERR_ARGUMENT;
     if (!num_samples || !batch) return USC_OK;
     LAUNCHED(h, launch_cmul(a, sa, b, sb, dst, sd, num_samples, batch, h->stream));
@@ -367,6 +390,7 @@ int usc_arm_cmplx_mult_cmplx_f32_batch(usc_handle* h, const float* a, size_t sa,
 }
 int usc_arm_cmplx_mult_real_f32_batch(usc_handle* h, const float* cplx, size_t sc, const float* real, size_t sr,
                                       float* dst, size_t sd, uint32_t num_samples, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !cplx || !real || !dst) return USC_ERR_ARGUMENT;
     if (!num_samples || !batch) return USC_OK;
     LAUNCHED(h, launch_cmul_real(cplx, sc, real, sr, dst, sd, num_samples, batch, h->stream));
@@ -374,6 +398,7 @@ int usc_arm_cmplx_mult_real_f32_batch(usc_handle* h, const float* cplx, size_t s
 }
 int usc_arm_cmplx_mag_f32_batch(usc_handle* h, const float* src, size_t ss, float* dst, size_t sd,
                                 uint32_t num_samples, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !src || !dst) return USC_ERR_ARGUMENT;
     if (!num_samples || !batch) return USC_OK;
     LAUNCHED(h, launch_cmag(src, ss, dst, sd, num_samples, batch, h->stream));
@@ -381,6 +406,7 @@ int usc_arm_cmplx_mag_f32_batch(usc_handle* h, const float* src, size_t ss, floa
 }
 int usc_arm_max_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t block_size, float* result,
                           uint32_t* index, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !src || !result || !block_size) return USC_ERR_ARGUMENT;
     if (!batch) return USC_OK;
     LAUNCHED(h, launch_max(src, ss, block_size, result, index, batch, h->stream));
@@ -388,6 +414,7 @@ int usc_arm_max_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t b
 }
 int usc_arm_mean_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t block_size, float* result,
                            uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !src || !result || !block_size) return USC_ERR_ARGUMENT;
     if (!batch) return USC_OK;
     LAUNCHED(h, launch_mean(src, ss, block_size, result, batch, h->stream));
@@ -395,6 +422,7 @@ int usc_arm_mean_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t 
 }
 int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in, float* out, uint8_t ifft_flag,
                                 uint32_t batch) {
+    USC_ENTER(h);
     /* supported lengths: CMSIS's 32..4096 (arm_math.h:2242-2244 returns ARM_MATH_ARGUMENT_ERROR
      * otherwise) extended to 8192 while one transform fits shared memory */
     if (!h || !in || !out || !pow2(fft_len) || fft_len < 32 || fft_len > 65536) return USC_ERR_ARGUMENT;
@@ -413,6 +441,7 @@ int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in
     return USC_OK;
 }
 int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t ifft_flag, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !data || !pow2(fft_len) || fft_len < 16 || fft_len > 32768) return USC_ERR_ARGUMENT;
     if (ifft_flag && fft_len > 8192) return USC_ERR_ARGUMENT;
     if (!batch) return USC_OK;
@@ -430,6 +459,7 @@ int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t
 }
 int usc_arm_fir_f32_batch(usc_handle* h, const float* coeffs_host, uint32_t num_taps, float* state,
                           const float* src, float* dst, uint32_t block_size, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !coeffs_host || !state || !src || !dst || num_taps < 1 || num_taps > 256 || !block_size ||
         block_size > 8192)
         return USC_ERR_ARGUMENT;
@@ -488,6 +518,7 @@ static int demod_generic(usc_handle* h, const void* pcm, uint32_t pcm_format, si
 
 int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, float* mag_up,
                      uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
+    USC_ENTER(h);
     if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
     if (h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;     /* frames are fetched by 16-byte-aligned bulk copies */
@@ -532,6 +563,7 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
 }
 
 int usc_host_workspace(usc_handle* h, size_t chunk_frames) {
+    USC_ENTER(h);
     if (!h || !chunk_frames || h->cfg.n != 2048) return USC_ERR_ARGUMENT;
     if (h->lane_frames == chunk_frames) return USC_OK;
     for (int i = 0; i < 3; ++i) {
@@ -555,6 +587,7 @@ int usc_host_workspace(usc_handle* h, size_t chunk_frames) {
 
 int usc_demod_frames_host(usc_handle* h, const void* pcm_host, uint32_t pcm_format, size_t nframes,
                           float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
+    USC_ENTER(h);
     if (!h || !pcm_host || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
     if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
@@ -590,6 +623,7 @@ int usc_demod_frames_host(usc_handle* h, const void* pcm_host, uint32_t pcm_form
 
 int usc_dsp(usc_handle* h, const float* fifo, size_t fifo_stride, const uint32_t* sync_position,
             const float* mag_mean, int updown, usc_history* hist, uint32_t batch) {
+    USC_ENTER(h);
     if (!h || !fifo || !sync_position || !mag_mean || !hist) return USC_ERR_ARGUMENT;
     if (h->cfg.n != 2048) return USC_ERR_ARGUMENT;
     if (h->cfg.chirp_variant == USC_CHIRP_S) {
@@ -635,6 +669,7 @@ static int fill_rx(usc_handle* h, rx_launch* a, const void* pcm, uint32_t pcm_fo
 
 int usc_receiver_run(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                      size_t stream_stride, uint8_t* uart, uint32_t uart_cap, usc_rx_result* results) {
+    USC_ENTER(h);
     rx_launch a;
     int rc = fill_rx(h, &a, pcm, pcm_format, nstreams, nframes, stream_stride);
     if (rc) return rc;
@@ -647,6 +682,7 @@ int usc_receiver_run(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32
 
 int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                     size_t stream_stride, uint32_t sync_add, float* mag, uint32_t* idx) {
+    USC_ENTER(h);
     rx_launch a;
     int rc = fill_rx(h, &a, pcm, pcm_format, nstreams, nframes, stream_stride);
     if (rc) return rc;
@@ -658,6 +694,7 @@ int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_
 }
 
 int usc_scan4(usc_handle* h, const float* pcm2n, uint32_t batch, usc_scan_entry* out) {
+    USC_ENTER(h);
     /* experiments/chirp_compression_freq_domain/Src/main.c:113-160, 245-251 on `batch` 2n-sample buffers */
     if (!h || !pcm2n || !out || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     const uint32_t n = h->cfg.n, bw8 = h->bandwidth * 8;
@@ -701,6 +738,7 @@ static int ensure_symbol_table(usc_handle* h, double amp) {
 int usc_synth_streams(usc_handle* h, uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes,
                       size_t stream_stride, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp,
                       double noise_sigma, int32_t* pcm, uint32_t* offsets, uint8_t* messages) {
+    USC_ENTER(h);
     if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
     const uint32_t n = h->cfg.n;
     if (((uintptr_t) pcm & 7u) != 0 || (stream_stride & 1u) || stream_stride < (size_t) nframes * n) return USC_ERR_ARGUMENT;
@@ -715,6 +753,7 @@ int usc_synth_streams(usc_handle* h, uint64_t seed, uint64_t first_stream, uint3
 
 int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp, double noise_sigma,
                      int32_t* pcm, uint8_t* bits) {
+    USC_ENTER(h);
     if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;
     if (!nframes) return USC_OK;
@@ -752,6 +791,7 @@ static int band_common(usc_handle* h, const void* pcm, uint32_t pcm_format, size
 }
 
 int usc_band_magnitudes(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, float* mag) {
+    USC_ENTER(h);
     band_params p;
     int rc = band_common(h, pcm, pcm_format, nframes, &p);
     if (rc) return rc;
@@ -765,6 +805,7 @@ int usc_band_magnitudes(usc_handle* h, const void* pcm, uint32_t pcm_format, siz
 int usc_onoff_detect(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                      const usc_onoff_config* cfg, uint16_t* strength, int8_t* level, uint8_t* chars, uint32_t cap,
                      uint32_t* nchars, uint32_t* sync_errors) {
+    USC_ENTER(h);
     band_params p;
     const size_t F = (size_t) nstreams * nframes;
     int rc = band_common(h, pcm, pcm_format, F, &p);
@@ -801,6 +842,7 @@ int usc_onoff_detect(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32
 int usc_fsk_detect(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                    const usc_fsk_config* cfg, uint8_t* code, float* magnitude, float* frequency, uint8_t* chars,
                    uint32_t cap, uint32_t* nchars, uint32_t* nsof, uint32_t* neof) {
+    USC_ENTER(h);
     band_params p;
     const size_t F = (size_t) nstreams * nframes;
     int rc = band_common(h, pcm, pcm_format, F, &p);
@@ -828,6 +870,7 @@ int usc_fsk_detect(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t
 
 int usc_spectrum_analyzer(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nframes, float ac_coupling_hz,
                           float* mag, float* db, float* peak, uint32_t* peak_idx) {
+    USC_ENTER(h);
     /* fft() of experiments/basic/Src/main.c:107-142: window, RFFT, magnitude/sqrt(N), AC coupling, dB, arg-max */
     if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
     const uint32_t n = h->cfg.n;
@@ -855,6 +898,7 @@ int usc_spectrum_analyzer(usc_handle* h, const void* pcm, uint32_t pcm_format, u
 
 int usc_iq_init(usc_handle* h, float carrier_hz, float bw_hz, const float* fir_coeffs_host, uint32_t num_taps,
                 uint32_t window_bins) {
+    USC_ENTER(h);
     if (!h || !fir_coeffs_host || num_taps < 1 || num_taps > 64) return USC_ERR_ARGUMENT;
     const uint32_t n = h->cfg.n, half = n / 2;
     if (n < 64 || n > 4096 || window_bins < 1 || window_bins > half / 2) return USC_ERR_ARGUMENT;
@@ -890,6 +934,7 @@ int usc_iq_init(usc_handle* h, float carrier_hz, float bw_hz, const float* fir_c
 int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                  size_t stream_stride, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
                  uint8_t* bit) {
+    USC_ENTER(h);
     if (!h || !pcm || pcm_format > USC_PCM_I32 || !h->d_iq_taps) return USC_ERR_ARGUMENT;
     const uint32_t n = h->cfg.n, half = n / 2, W = h->iq_window;
     if (stream_stride < (size_t) nframes * n) return USC_ERR_ARGUMENT;
@@ -936,6 +981,7 @@ int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t n
 }
 
 int usc_pipeline(usc_handle* h, const float* frames, float* mags, int updown, uint32_t batch) {
+    USC_ENTER(h);
     /* operator-by-operator form of receiver/Src/main.c:163-180 (full spectrum wanted, so nothing
      * to prune): mult, mult, rfft, mag into the lower half, zeros above (hazard H1 defined). */
     if (!h || !frames || !mags) return USC_ERR_ARGUMENT;
@@ -952,6 +998,7 @@ int usc_pipeline(usc_handle* h, const float* frames, float* mags, int updown, ui
 
 int usc_compress_chirp(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t nframes, int use_up,
                        float* out_frames, float* max_val, uint32_t* max_idx) {
+    USC_ENTER(h);
     if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
     if (h->cfg.n != 2048 || h->cfg.chirp_variant != USC_CHIRP_T || !h->d_H_up) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 7u) != 0 || ((uintptr_t) out_frames & 7u) != 0) return USC_ERR_ARGUMENT;

@@ -4,6 +4,18 @@
 #include "usc_kernels.cuh"
 
 namespace usc {
+
+// One-time per-kernel launch configuration (opt-in shared memory size, cluster occupancy) is a property of
+// the (kernel, device) pair: a process that opens handles on several GPUs must configure each of them.
+template <typename T> struct per_device {
+    T v[64] = {};
+    T& get() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+        return v[d];
+    }
+};
+
 cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cudaStream_t st);
 cudaError_t launch_spectrum_tail(const float* spec, uint32_t n, float inv_sqrt_n, uint32_t ac_bins, float* mag, float* db,
                                  float* peak, uint32_t* peak_idx, uint32_t batch, cudaStream_t st);

@@ -51,7 +51,7 @@ class FskConfig(C.Structure):
 # every symbol include/usc.h declares (tests/test_abi.py checks the .so exports each one)
 SYMBOLS = [
     "usc_default_config", "usc_create", "usc_destroy", "usc_set_stream", "usc_sync", "usc_error_string",
-    "usc_get_geometry", "usc_get_table", "usc_launch_count", "usc_malloc", "usc_free", "usc_malloc_host",
+    "usc_get_geometry", "usc_get_table", "usc_launch_count", "usc_malloc", "usc_malloc_on", "usc_free", "usc_malloc_host",
     "usc_free_host", "usc_memcpy_h2d", "usc_memcpy_d2h", "usc_memset", "usc_i32_to_f32",
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
@@ -112,7 +112,7 @@ class DeviceBuffer:
         self.h = handle
         self.nbytes = int(nbytes)
         p = C.c_void_p()
-        _ck(load().usc_malloc(C.byref(p), C.c_size_t(max(self.nbytes, 1))))
+        _ck(load().usc_malloc_on(handle._h, C.byref(p), C.c_size_t(max(self.nbytes, 1))))
         self.ptr = p.value
 
     @classmethod
