@@ -193,6 +193,20 @@ typedef struct usc_rx_result {
  * H1/H3/H4/H5 are defined as in DESIGN.md §3.4. */
 int usc_receiver_run(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                      size_t stream_stride, uint8_t *uart, uint32_t uart_cap, usc_rx_result *results);
+/* Everything the state machine carries from one frame to the next (state, turn, counters, sync_position,
+ * the partial byte, mag_stat[12], the history magnitudes).  Opaque to the caller; all-zero = a receiver
+ * that has just started.  160 bytes per stream, in device memory. */
+typedef struct usc_rx_state { uint32_t opaque[40]; } usc_rx_state;
+/* K7 on a stream that arrives in pieces: the same loop as usc_receiver_run, resumed.  `state` (nstreams
+ * records, device memory, zeroed before the first chunk) is read at entry and written back at exit.
+ * Each stream's buffer holds `carry_frames` = min(2, frames already processed) frames of history (the
+ * receiver's FIFO spans three frames, main.c:659-668) followed by the `nframes` new frames; stream s starts
+ * at pcm + s*stream_stride.  uart receives the bytes produced by THIS chunk (results[s].nbytes of them),
+ * lock_frame and frames_seen count from the start of the stream.  Any split into chunks gives the same
+ * bytes and the same final state as one call over the whole stream. */
+int usc_receiver_run_chunk(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                           size_t stream_stride, uint32_t carry_frames, usc_rx_state *state, uint8_t *uart,
+                           uint32_t uart_cap, usc_rx_result *results);
 /* K4.  The sliding-correlation search grid alone (main.c:447-451) for every frame of every stream:
  * 4 x dsp(UP) at N/2 + (t&1)*N/8 + i*N/4 on the FIFO of frame t, after synchronous addition of
  * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */

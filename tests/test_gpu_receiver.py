@@ -120,3 +120,44 @@ def test_receiver_argument_errors(h):
         h.receiver_run(d, usc.PCM_I32, 1, 2, 2 * N, None, 0, None)   # nothing to write
     with pytest.raises(usc.UscError):
         h.sync_search(d, usc.PCM_I32, 1, 2, 2 * N, 0, r, r)          # sync_add >= 1
+
+
+@pytest.mark.parametrize("splits", [(70,), (1, 69), (2, 3, 65), (35, 35), (10, 20, 5, 35), tuple([7] * 10)])
+def test_receiver_run_in_chunks_equals_one_call(splits):
+    """usc_receiver_run_chunk: any split of the stream into chunks (each carrying two frames of history)
+    gives the bytes, lock frame and final state of one call over the whole stream — and of the oracle."""
+    F = 70
+    msgs = [b"Hi", b"ok", b"zz"]
+    streams = np.stack([synth.make_stream(m, snr_db=snr, start_offset=off, nframes=F, seed=70 + i)
+                        for i, (m, snr, off) in enumerate(zip(msgs, (20.0, 12.0, 3.0), (0, 777, 1999)))])
+    S = len(msgs)
+    h = usc.Handle()
+    whole, res = h.receiver_run_host(streams, uart_cap=32)
+    d_state = h.empty(160 * S)
+    h_memset = usc.load().usc_memset
+    assert h_memset(h._h, __import__("ctypes").c_void_p(d_state.ptr), 0, __import__("ctypes").c_size_t(160 * S)) == 0
+    out = [b""] * S
+    t0 = 0
+    last = None
+    for n in splits:
+        carry = min(2, t0)
+        chunk = np.ascontiguousarray(streams[:, t0 - carry:t0 + n])          # [S, carry + n, N]
+        d = h.buffer(chunk)
+        d_u, d_r = h.empty(S * 32), h.empty(S * usc.rx_result_dtype.itemsize)
+        h.receiver_run_chunk(d, usc.PCM_I32, S, n, (carry + n) * N, carry, d_state, d_u, 32, d_r)
+        h.sync()
+        r = d_r.to_numpy(usc.rx_result_dtype)
+        u = d_u.to_numpy(np.uint8).reshape(S, 32)
+        for s in range(S):
+            out[s] += bytes(u[s, :min(int(r["nbytes"][s]), 32)])
+        t0 += n
+        last = r
+    assert t0 == F
+    rx = R.RefReceiver()
+    for s in range(S):
+        assert out[s] == whole[s], (s, out[s], whole[s])
+        want, st = R.receiver_run(rx, streams[s], cap=32)
+        assert out[s] == want[:32]
+        for k in ("state", "sync_position", "lock_frame", "lock_position", "frames_seen", "turn", "sync_cnt"):
+            assert last[k][s] == res[k][s], (k, s)
+    h.close()

@@ -35,12 +35,14 @@ struct rx_params {
     uint8_t* uart; uint32_t uart_cap; rx_result_rec* results;
     // sync search
     uint32_t sync_add; float* ss_mag; uint32_t* ss_idx;
+    // chunked operation of K7: `carry` frames of history precede the nframes new ones; state is loaded / stored
+    uint32_t carry; rx_state_rec* rx_state;
 };
 
 template <typename PCM>
-__device__ __forceinline__ float2 load_pair(const PCM* __restrict__ stream, int64_t nsamples, int64_t g) {
+__device__ __forceinline__ float2 load_pair(const PCM* __restrict__ stream, int64_t nsamples, int64_t g, int64_t gmin = 0) {
     using V2 = typename vec2<PCM>::type;
-    if (g >= 0 && g + 1 < nsamples) {                  // g is even (window starts are multiples of N/8)
+    if (g >= gmin && g + 1 < nsamples) {                  // g is even (window starts are multiples of N/8)
         const V2 raw = *reinterpret_cast<const V2*>(stream + g);
         return make_float2(pcm_to_float(raw.x), pcm_to_float(raw.y));
     }
@@ -56,10 +58,11 @@ template <typename PCM, bool MULTI>
 __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t nsamples, int64_t gA, int64_t gB,
                                          const float2* chirpA, const float2* chirpB, const rx_tables& tb,
                                          uint32_t sync_add, float2* tile, const float2 (&ws)[kRxNB], int lane,
-                                         uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB) {
+                                         uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB,
+                                         int64_t gmin = 0) {
     float2 re[32], im[32];
     if (!MULTI) {
-        if (gA >= 0 && gB >= 0 && gA + 2048 <= nsamples && gB + 2048 <= nsamples) {    // both windows inside the stream
+        if (gA >= gmin && gB >= gmin && gA + 2048 <= nsamples && gB + 2048 <= nsamples) {    // both windows inside the stream
             using V2 = typename vec2<PCM>::type;
             const V2* pa = reinterpret_cast<const V2*>(stream + gA) + lane;
             const V2* pb = reinterpret_cast<const V2*>(stream + gB) + lane;
@@ -73,7 +76,7 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
                 const int m = lane + 32 * b;
-                const float2 xa = load_pair<PCM>(stream, nsamples, gA + 2 * m), xb = load_pair<PCM>(stream, nsamples, gB + 2 * m);
+                const float2 xa = load_pair<PCM>(stream, nsamples, gA + 2 * m, gmin), xb = load_pair<PCM>(stream, nsamples, gB + 2 * m, gmin);
                 re[b] = make_float2(xa.x, xb.x);
                 im[b] = make_float2(xa.y, xb.y);
             }
@@ -159,21 +162,29 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
 
     const uint32_t nwarps = gridDim.x * kRxWarps;
     for (uint32_t s = blockIdx.x * kRxWarps + warp; s < p.nstreams; s += nwarps) {
-        const PCM* stream = static_cast<const PCM*>(p.pcm) + (size_t) s * p.stream_stride;
-        const int64_t nsamples = (int64_t) p.nframes * N;
+        // sample 0 of `stream` is the first NEW frame; a resumed chunk has `carry` frames of history before it
+        const PCM* stream = static_cast<const PCM*>(p.pcm) + (size_t) s * p.stream_stride + (size_t) p.carry * N;
+        const int64_t nsamples = (int64_t) p.nframes * N, gmin = -(int64_t) p.carry * N;
         uint8_t* uart = p.uart ? p.uart + (size_t) s * p.uart_cap : nullptr;
         // state (main.c:311-339), identical in every lane
         uint32_t state = 0, turn = 0, sync_cnt = 0, pos = N / 2, max_idx = 0, msg = 0, msg_cnt = 0, nout = 0;
         int32_t lock_frame = -1;
-        uint32_t lock_pos = 0;
+        uint32_t lock_pos = 0, frames_before = 0;
         float mag_mean = 0.0f;
+        const rx_state_rec* saved = p.rx_state && p.rx_state[s].magic == kRxStateMagic ? p.rx_state + s : nullptr;
+        if (saved) {
+            state = saved->state; turn = saved->turn; sync_cnt = saved->sync_cnt; pos = saved->pos; max_idx = saved->max_idx;
+            msg = saved->msg; msg_cnt = saved->msg_cnt; lock_frame = saved->lock_frame; lock_pos = saved->lock_pos;
+            frames_before = saved->frames_seen; mag_mean = saved->mag_mean;
+        }
         // mag_stat[12] | history mag_max[8] | history mag_mean[4] live in shared memory (the packed core
         // needs the registers); every lane reads them (broadcast), lane 0 writes
         float* mag_stat = reinterpret_cast<float*>(s_rx + 4096 + kRxWarps * 1024) + warp * 32;
         float* hmag = mag_stat + 12;
         float* hmean = mag_stat + 20;
         __syncwarp();
-        if (lane < 12) mag_stat[lane] = 1E37f;
+        if (saved) { if (lane < 24) mag_stat[lane] = saved->stat[lane]; }
+        else if (lane < 12) mag_stat[lane] = 1E37f;
         else if (lane < 24) mag_stat[lane] = 0.0f;
         __syncwarp();
 
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
                 float ma, mb;
                 uint32_t ka, kb;
                 dsp_pair<PCM, false>(stream, nsamples, fifo0 + (a_ok ? qa : (int64_t) pos), fifo0 + (b_ok ? qb : (int64_t) pos), ca, cb, tb,
-                              1, tile, ws, lane, bw2, ma, ka, mb, kb);
+                              1, tile, ws, lane, bw2, ma, ka, mb, kb, gmin);
                 if (searching) {
                     const int sa = (int) (4 * pass + turn), sb = sa + 2;  // history[i*2 + turn]
                     __syncwarp();
@@ -304,15 +315,26 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
                 state = 0;
             }
             if (prev != 2 && state == 2 && lock_frame < 0) {
-                lock_frame = (int32_t) t;
+                lock_frame = (int32_t) (frames_before + t);
                 lock_pos = pos;
             }
         }
         if (lane == 0 && p.results) {
             rx_result_rec r;
             r.state = state; r.sync_position = pos; r.lock_frame = lock_frame; r.lock_position = lock_pos;
-            r.nbytes = nout; r.frames_seen = p.nframes; r.turn = turn; r.sync_cnt = sync_cnt;
+            r.nbytes = nout; r.frames_seen = frames_before + p.nframes; r.turn = turn; r.sync_cnt = sync_cnt;
             p.results[s] = r;
+        }
+        if (p.rx_state) {
+            __syncwarp();
+            rx_state_rec* o = p.rx_state + s;
+            if (lane < 24) o->stat[lane] = mag_stat[lane];
+            if (lane == 0) {
+                o->magic = kRxStateMagic; o->state = state; o->turn = turn; o->sync_cnt = sync_cnt; o->pos = pos; o->max_idx = max_idx;
+                o->msg = msg; o->msg_cnt = msg_cnt; o->lock_frame = lock_frame; o->lock_pos = lock_pos;
+                o->frames_seen = frames_before + p.nframes; o->mag_mean = mag_mean;
+            }
+            __syncwarp();
         }
     }
 }
@@ -374,6 +396,7 @@ static rx_params make_params(const rx_launch& a) {
     p.bandwidth2 = a.bandwidth2; p.snr_threshold = a.snr_threshold;
     p.uart = a.uart; p.uart_cap = a.uart_cap; p.results = a.results;
     p.sync_add = a.sync_add < 1 ? 1 : a.sync_add; p.ss_mag = a.ss_mag; p.ss_idx = a.ss_idx;
+    p.carry = a.carry; p.rx_state = a.rx_state;
     return p;
 }
 

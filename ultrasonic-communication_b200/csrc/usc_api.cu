@@ -680,6 +680,25 @@ int usc_receiver_run(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32
     return USC_OK;
 }
 
+static_assert(sizeof(usc_rx_state) == sizeof(rx_state_rec), "usc_rx_state layout");
+
+int usc_receiver_run_chunk(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                           size_t stream_stride, uint32_t carry_frames, usc_rx_state* state, uint8_t* uart,
+                           uint32_t uart_cap, usc_rx_result* results) {
+    USC_ENTER(h);
+    rx_launch a;
+    if (carry_frames > 2) return USC_ERR_ARGUMENT;
+    if (stream_stride < ((size_t) nframes + carry_frames) * 2048) return USC_ERR_ARGUMENT;
+    int rc = fill_rx(h, &a, pcm, pcm_format, nstreams, nframes, stream_stride);
+    if (rc) return rc;
+    if (!state) return USC_ERR_ARGUMENT;
+    if (!nstreams || !nframes) return USC_OK;
+    a.uart = uart; a.uart_cap = uart_cap; a.results = (rx_result_rec*) results;
+    a.carry = carry_frames; a.rx_state = (rx_state_rec*) state;
+    LAUNCHED(h, launch_receiver_run(a, h->num_sms, h->stream));
+    return USC_OK;
+}
+
 int usc_sync_search(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                     size_t stream_stride, uint32_t sync_add, float* mag, uint32_t* idx) {
     USC_ENTER(h);

@@ -22,12 +22,24 @@ struct rx_result_rec {   // == usc_rx_result (include/usc.h)
     uint32_t lock_position, nbytes, frames_seen, turn, sync_cnt;
 };
 
+constexpr uint32_t kRxStateMagic = 0x55534337u;      // "USC7"
+struct rx_state_rec {    // == usc_rx_state (include/usc.h): everything the state machine carries between frames, 160 bytes
+    uint32_t magic, state, turn, sync_cnt, pos, max_idx, msg, msg_cnt;
+    int32_t lock_frame;
+    uint32_t lock_pos, frames_seen;
+    float mag_mean;
+    float stat[24];      // mag_stat[12] | history mag_max[8] | history mag_mean[4]
+    uint32_t reserved[4];
+};
+static_assert(sizeof(rx_state_rec) == 160, "usc_rx_state layout");
+
 struct rx_launch {       // arguments of K4 / K7
     const void* pcm; uint32_t pcm_format; uint32_t nstreams; uint32_t nframes; size_t stream_stride;
     const float2* up; const float2* down; const float2* hann; const float2* tw_pass; const float2* tw_split;
     uint32_t bandwidth2; float snr_threshold;
     uint8_t* uart; uint32_t uart_cap; rx_result_rec* results;
     uint32_t sync_add; float* ss_mag; uint32_t* ss_idx;
+    uint32_t carry; rx_state_rec* rx_state;              // chunked K7 (usc_receiver_run_chunk)
 };
 
 // ------------------------------------------------------------------------------------------------

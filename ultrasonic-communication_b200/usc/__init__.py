@@ -56,7 +56,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -278,6 +278,11 @@ class Handle:
     def receiver_run(self, pcm, pcm_format, nstreams, nframes, stream_stride, uart, uart_cap, results):
         _ck(load().usc_receiver_run(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
                                     C.c_size_t(stream_stride), _ptr(uart), C.c_uint32(uart_cap), _ptr(results)))
+
+    def receiver_run_chunk(self, pcm, pcm_format, nstreams, nframes, stream_stride, carry_frames, state, uart, uart_cap, results):
+        _ck(load().usc_receiver_run_chunk(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                          C.c_size_t(stream_stride), C.c_uint32(carry_frames), _ptr(state), _ptr(uart),
+                                          C.c_uint32(uart_cap), _ptr(results)))
 
     def sync_search(self, pcm, pcm_format, nstreams, nframes, stream_stride, sync_add, mag, idx):
         _ck(load().usc_sync_search(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
