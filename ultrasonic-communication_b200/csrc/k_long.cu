@@ -20,6 +20,10 @@
 
 namespace usc {
 
+#ifndef USC_LONG_UNROLL
+#define USC_LONG_UNROLL 4
+#endif
+constexpr int kLongUnroll = USC_LONG_UNROLL;            // level-0 rounds whose loads are issued together
 constexpr int kLongNB = 5;                            // c < 160 covers bandwidth2 / R0 <= 160
 constexpr int kLongKeep = 32 * kLongNB;               // kept outputs per side of each sub-spectrum
 
@@ -52,6 +56,8 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
     for (size_t f = blockIdx.x; f < p.nframes; f += gridDim.x) {
         const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * p.n);
         // ---- level 0: radix-R0 over b, twiddle, park sub-sequence d ----
+        // (unrolled so the global loads of several rounds are in flight together: the phase is latency-bound)
+#pragma unroll kLongUnroll
         for (uint32_t a = tid; a < 1024u; a += T) {
             float2 re[R0], im[R0];
 #pragma unroll
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_rank();
-    constexpr uint32_t nc = 32768u;
+    constexpr uint32_t nc = 32768u; (void) nc;
     for (int i = tid; i < 1024; i += kL32Threads) s_tw[i] = p.tw_pass[i];
     float2* s_l0 = reinterpret_cast<float2*>(s_raw + L::l0);
     for (int d = 1; d < 32; ++d) s_l0[d * kL32Threads + tid] = tw_l0[d * 1024 + rank * kL32Threads + tid];
