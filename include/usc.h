@@ -243,6 +243,14 @@ int usc_synth_frames(usc_handle *h, uint64_t seed, uint64_t first_frame, size_t 
 int usc_synth_streams(usc_handle *h, uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes,
                       size_t stream_stride, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp,
                       double noise_sigma, int32_t *pcm, uint32_t *offsets, uint8_t *messages);
+/* Renders a 16-bit track recorded at one rate at another, band-limited, by the exact ratio up/down
+ * (fs_out = fs_in * up / down; the transmitter's 44.1 kHz WAV at the receiver's 78.125 kHz is 3125/1764;
+ * include/usc_tx.h builds that track).  32-tap Hann-windowed-sinc polyphase FIR, integer phase arithmetic,
+ * one FMA per tap in ascending order: the oracle's twin gives the same words.  out[j] = round(y_j) * 256
+ * (int32 words in the DFSDM layout, ready for every PCM_I32 entry point), n_out <= ceil(n_in * up / down).
+ * in / out are device pointers; up <= 8192. */
+int usc_resample_i16_to_pcm(usc_handle *h, const int16_t *in, size_t n_in, uint32_t up, uint32_t down, int32_t *out,
+                            size_t n_out);
 /* ---- the reference's two earlier detectors, n = 2048 only ------------------------
  * Both share the analyser's front half: (float) pcm x Hann -> RFFT -> magnitude * 1/sqrt(N)
  * (experiments/chirp/Src/main.c:200-216, experiments/ultracom/Src/main.c:115-128), computed for bins

@@ -503,6 +503,16 @@ def fsk_parse(code, tq_n=2, cap=64):
     return bytes(chars[:min(n, cap)]), n, sof.value, eof.value
 
 
+def resample_i16_to_pcm(x, up, down, n_out=None):
+    x = np.ascontiguousarray(x, dtype=np.int16)
+    if n_out is None:
+        n_out = (x.size * up + down - 1) // down
+    out = np.empty(n_out, np.int32)
+    lib().ref_resample_i16_to_pcm(x.ctypes.data_as(C.c_void_p), C.c_size_t(x.size), C.c_uint32(up), C.c_uint32(down),
+                                  out.ctypes.data_as(i32p), C.c_size_t(n_out))
+    return out
+
+
 def synth_streams(seed, first_stream, nstreams, nframes, lead_in, msg_bytes, guard, amp, noise_sigma, n=2048, fs=78125.0,
                   f0=16000.0, f1=19000.0):
     """CPU twin of usc_synth_streams -> (pcm [nstreams, nframes, n] int32, offsets, messages [nstreams, msg_bytes])."""

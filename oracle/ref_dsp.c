@@ -1023,6 +1023,31 @@ uint32_t ref_fsk_parse(const uint8_t *code, uint32_t nframes, uint32_t tq_n, uin
     return out;
 }
 
+void ref_resample_i16_to_pcm(const int16_t *in, size_t n_in, uint32_t up, uint32_t down, int32_t *out, size_t n_out) {
+    const uint32_t K = 32;
+    float *taps = (float *) malloc(sizeof(float) * (size_t) up * K);
+    for (uint32_t p = 0; p < up; ++p)
+        for (uint32_t i = 0; i < K; ++i) {
+            double x = ((double) i - (double) (K / 2) + 1.0) - (double) p / (double) up;
+            double sc = x == 0.0 ? 1.0 : sin(M_PI * x) / (M_PI * x);
+            double w = 0.5 + 0.5 * cos(2.0 * M_PI * x / (double) K);
+            taps[(size_t) p * K + i] = (float) (sc * w);
+        }
+    for (size_t j = 0; j < n_out; ++j) {
+        unsigned long long pos = (unsigned long long) j * down;
+        long long k0 = (long long) (pos / up);
+        const float *h = taps + (size_t) (pos % up) * K;
+        float acc = 0.0f;
+        for (uint32_t i = 0; i < K; ++i) {
+            long long k = k0 - (long long) (K / 2) + 1 + i;
+            float x = (k >= 0 && (size_t) k < n_in) ? (float) in[k] : 0.0f;
+            acc = FMA(x, h[i], acc);
+        }
+        out[j] = (int32_t) lrintf(acc) * 256;
+    }
+    free(taps);
+}
+
 static void synth_tables(uint32_t n, float fs, float f0, float f1, double amp, int32_t *tab) {
     const double T = (double) n / (double) fs, k = ((double) f1 - (double) f0) / T;
     for (int down = 0; down < 2; ++down)

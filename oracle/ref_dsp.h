@@ -223,6 +223,8 @@ void ref_fsk_codes(const float *mag, size_t nframes, uint32_t half, float fs, ui
 /* parser(), :175-236, over one stream's codes */
 uint32_t ref_fsk_parse(const uint8_t *code, uint32_t nframes, uint32_t tq_n, uint8_t *chars, uint32_t cap, uint32_t *nsof,
                        uint32_t *neof);
+/* twin of usc_resample_i16_to_pcm: 32-tap Hann-windowed-sinc polyphase FIR at the exact ratio up/down */
+void ref_resample_i16_to_pcm(const int16_t *in, size_t n_in, uint32_t up, uint32_t down, int32_t *out, size_t n_out);
 void ref_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, uint32_t n, float fs, float f0,
                        float f1, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, double amp, double noise_sigma,
                        int32_t *pcm, uint32_t *offsets, uint8_t *messages);

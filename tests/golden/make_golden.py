@@ -9,6 +9,9 @@ needs /root/reference).  Outputs (all under tests/golden/):
                        imported by path): chirps, chirp_orth, time_shift, add_delay, and the
                        ChirpSynchronization.ipynb cell 5-11 products with the printed peak frequencies.
   fir_taps.npz         the 27 FIR taps literal at experiments/iq_modulation/Src/iq_modem.c:18.
+  tx_vectors.npz       the transmitter of generator/ChirpGenerator.ipynb cells 1-3 run through the reference's own
+                       simulation/signal.py: H, L symbols at 44.1 kHz and the whole int16 tone of the message "Hi"
+                       (G + 7H + L + bits + 12G, astype(int16) as Signal.play() writes it to the WAV file).
   wire_excerpt.json    verbatim head / tail lines of one capture's .raw / .flt / .fft files (the PC agent's
                        CSV wire formats, agent/README.md:5-11) with the row indices they came from.
 """
@@ -104,6 +107,22 @@ def fir_taps():
     print("fir taps:", taps.size)
 
 
+def tx_vectors():
+    sig = np_oracle.load_reference_simulation("signal")
+    s = sig.Signal(f0=16000, f1=19000, fs=44100, T=0.0262, A=20000)          # ChirpGenerator.ipynb cell 1
+    H, L, G = s.chirp_orth(), s.chirp_orth(updown="down"), s.silence()
+    tone = G
+    data = []
+    for a in [ord(c) for c in "Hi"]:                                         # ascii(), cell 1
+        for i in range(8):
+            data.append(H if (a & (0b10000000 >> i)) > 0 else L)
+    for t in [H] * 7 + [L] + data + [G] * 12:                                # cell 3
+        tone = np.append(tone, t)
+    np.savez_compressed(os.path.join(HERE, "tx_vectors.npz"), H=H, L=L, tone_i16=np.real(tone).astype(np.int16),
+                        fs=np.array([44100.0]), T=np.array([0.0262]))
+    print("tx vectors:", H.size, tone.size)
+
+
 def wire_excerpt():
     import json
     base = sorted(glob.glob(os.path.join(REF, "agent", "chirp_experiment", "*.raw")))[0][:-4]
@@ -121,6 +140,10 @@ if __name__ == "__main__":
     if "--wire-only" in sys.argv:
         wire_excerpt()
         sys.exit(0)
+    if "--tx-only" in sys.argv:
+        tx_vectors()
+        sys.exit(0)
+    tx_vectors()
     wire_excerpt()
     device_triples()
     refsim_vectors()

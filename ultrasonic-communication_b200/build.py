@@ -74,8 +74,11 @@ def build(force=False, verbose=False):
     wire_src = os.path.join(HERE, "host", "usc_wire.c")
     wire_lib = os.path.join(HERE, "libusc_wire.so")
     inc = os.path.join(os.path.dirname(HERE), "include")
-    if force or _stale(wire_lib, [wire_src, os.path.join(inc, "usc_wire.h"), os.path.join(inc, "usc.h")]):
-        _run(["gcc"] + CC_FLAGS + ["-Wextra", "-shared", "-I", inc, wire_src, "-o", wire_lib], os.path.join(OBJ, "wire.log"))
+    tx_src = os.path.join(HERE, "host", "usc_tx.c")                 # transmitter symbols, framing, WAV I/O (include/usc_tx.h)
+    if force or _stale(wire_lib, [wire_src, tx_src, os.path.join(inc, "usc_wire.h"), os.path.join(inc, "usc_tx.h"),
+                                  os.path.join(inc, "usc.h")]):
+        _run(["gcc"] + CC_FLAGS + ["-Wextra", "-shared", "-I", inc, wire_src, tx_src, "-o", wire_lib, "-lm"],
+             os.path.join(OBJ, "wire.log"))
     # the plain-C host driver links against the C-ABI only (no CUDA headers): proves the boundary
     host_src = os.path.join(HERE, "host", "receiver_host.c")
     host_bin = os.path.join(HERE, "host", "receiver_host")

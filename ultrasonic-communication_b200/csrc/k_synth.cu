@@ -113,6 +113,36 @@ __global__ void k_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t n
     }
 }
 
+// Band-limited rate conversion by the exact ratio up/down (the transmitter's 44.1 kHz track at the receiver's
+// 78.125 kHz: 3125/1764): output j sits at input position j*down/up = k0 + p/up, all in integers, and is the
+// ktaps-tap polyphase FIR  y = sum_i x[k0 - ktaps/2 + 1 + i] * h[p][i]  (taps ascending, one FMA each; samples
+// outside the track are zero).  Result rounded to nearest and stored as a x256 DFSDM-style word.
+__global__ void k_resample_i16(const int16_t* __restrict__ in, size_t n_in, uint32_t up, uint32_t down, uint32_t ktaps,
+                               const float* __restrict__ taps, int32_t* __restrict__ out, size_t n_out) {
+    for (size_t j = (size_t) blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (size_t) gridDim.x * blockDim.x) {
+        const unsigned long long pos = (unsigned long long) j * down;
+        const long long k0 = (long long) (pos / up);
+        const uint32_t ph = (uint32_t) (pos % up);
+        const float* h = taps + (size_t) ph * ktaps;
+        const long long first = k0 - (long long) (ktaps / 2) + 1;
+        float acc = 0.0f;
+        for (uint32_t i = 0; i < ktaps; ++i) {
+            const long long k = first + i;
+            const float x = (k >= 0 && (size_t) k < n_in) ? (float) in[k] : 0.0f;
+            acc = __fmaf_rn(x, h[i], acc);
+        }
+        out[j] = __float2int_rn(acc) * 256;
+    }
+}
+
+cudaError_t launch_resample_i16(const int16_t* in, size_t n_in, uint32_t up, uint32_t down, uint32_t ktaps, const float* taps,
+                                int32_t* out, size_t n_out, cudaStream_t st) {
+    size_t b = (n_out + 255) / 256;
+    if (b > 148u * 32u) b = 148u * 32u;
+    k_resample_i16<<<(int) (b ? b : 1), 256, 0, st>>>(in, n_in, up, down, ktaps, taps, out, n_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
                                  uint32_t n, uint32_t lead_in, uint32_t msg_bytes, uint32_t guard, const int32_t* table,
                                  int32_t gain, int32_t* pcm, uint32_t* offsets, uint8_t* messages, cudaStream_t st) {

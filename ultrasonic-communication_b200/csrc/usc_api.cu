@@ -28,6 +28,7 @@ struct usc_handle {
     uint32_t bandwidth, bandwidth2, idx_left_zero;
     std::vector<float> hann, up, down, H_up, H_down;
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
+    float* d_rs_taps = nullptr; uint32_t rs_up = 0;       // resampler polyphase table (usc_resample_i16_to_pcm)
     float2 *d_tw_pass, *d_tw_split, *d_tw_l0;      // d_tw_l0: W_32768^(a d), [d][a], 65536-point frames only
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
     // I/Q path (usc_iq_init): carrier tables, baseband chirp and its conjugate, half-length Hann, FIR taps
@@ -249,7 +250,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
 void usc_destroy(usc_handle* h) {
     if (!h) return;
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
-    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
+    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_rs_taps); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
     cudaFree(h->d_sym_table);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
@@ -781,6 +782,27 @@ int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t 
     if (rc) return rc;
     LAUNCHED(h, launch_synth_frames(seed, first_frame, nframes, n, h->d_sym_table, usc_host_noise_gain(noise_sigma), pcm, bits,
                                     h->stream));
+    return USC_OK;
+}
+
+int usc_resample_i16_to_pcm(usc_handle* h, const int16_t* in, size_t n_in, uint32_t up, uint32_t down, int32_t* out,
+                            size_t n_out) {
+    USC_ENTER(h);
+    if (!h || !in || !out || !up || !down || up > 8192u) return USC_ERR_ARGUMENT;
+    if (n_out > ((unsigned long long) n_in * up + down - 1) / down) return USC_ERR_ARGUMENT;
+    if (!n_out) return USC_OK;
+    const uint32_t ktaps = 32;
+    if (!h->d_rs_taps || h->rs_up != up) {
+        std::vector<float> taps((size_t) up * ktaps);
+        usc_host_resample_taps(up, ktaps, taps.data());
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_rs_taps);
+        h->d_rs_taps = nullptr;
+        int rc = upload(taps.data(), taps.size() * sizeof(float), (void**) &h->d_rs_taps);
+        if (rc) return rc;
+        h->rs_up = up;
+    }
+    LAUNCHED(h, launch_resample_i16(in, n_in, up, down, ktaps, h->d_rs_taps, out, n_out, h->stream));
     return USC_OK;
 }
 

@@ -125,3 +125,13 @@ int32_t usc_host_noise_gain(double sigma) {
     const double unit = sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0);
     return (int32_t) llround(sigma / unit * 65536.0);
 }
+
+void usc_host_resample_taps(uint32_t up, uint32_t ktaps, float *taps) {
+    for (uint32_t p = 0; p < up; ++p)
+        for (uint32_t i = 0; i < ktaps; ++i) {
+            const double x = ((double) i - (double) (ktaps / 2) + 1.0) - (double) p / (double) up;
+            const double s = x == 0.0 ? 1.0 : sin(M_PI * x) / (M_PI * x);
+            const double w = 0.5 + 0.5 * cos(2.0 * M_PI * x / (double) ktaps);
+            taps[(size_t) p * ktaps + i] = (float) (s * w);
+        }
+}

@@ -33,6 +33,10 @@ int32_t usc_host_noise_gain(double sigma);
 /* (F1 - F0) * NN / fs truncated to uint32 (receiver/Src/main.c:372). */
 uint32_t usc_host_bandwidth(uint32_t n, float fs, float f0, float f1);
 
+/* Polyphase table of the band-limited resampler (usc_resample_i16_to_pcm): `up` phases x `ktaps` taps,
+ * h[p][i] = sinc(x) * (0.5 + 0.5 cos(2 pi x / ktaps)), x = (i - ktaps/2 + 1) - p/up, in double, rounded to float. */
+void usc_host_resample_taps(uint32_t up, uint32_t ktaps, float *taps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,7 +56,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -313,6 +313,10 @@ class Handle:
 
     def scan4(self, pcm2n, batch, out):
         _ck(load().usc_scan4(self._h, _ptr(pcm2n), C.c_uint32(batch), _ptr(out)))
+
+    def resample_i16_to_pcm(self, src, n_in, up, down, dst, n_out):
+        _ck(load().usc_resample_i16_to_pcm(self._h, _ptr(src), C.c_size_t(n_in), C.c_uint32(up), C.c_uint32(down), _ptr(dst),
+                                           C.c_size_t(n_out)))
 
     def band_magnitudes(self, pcm, pcm_format, nframes, mag):
         _ck(load().usc_band_magnitudes(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes), _ptr(mag)))
