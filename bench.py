@@ -369,7 +369,7 @@ def main():
                          "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "kernel": "k_demod2048<int,5,8>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL * NFRAMES,
-                         "note": "bound by the L1/shared-memory data path (80 %) and the fp32 pipe (65 %), DESIGN.md 4.1; frac is vs HBM"},
+                         "note": "bound by the L1/shared-memory data path (76 %) and the fp32 pipe (62 %), DESIGN.md 4.1; frac is vs HBM"},
             "e2e": {"value": NFRAMES * world * args.e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": NFRAMES * N * 4, "d2h_bytes_per_step": NFRAMES * 17,
                     "steps": args.e2e_steps, "results_match_device_path": e2e_ok},

@@ -52,3 +52,10 @@ if which == "long32":
         hh.demod_frames(x, usc.PCM_I32, nf, o[0], o[1], o[2], o[3], b)
     torch.cuda.synchronize()
     print("done long32", reps)
+if which == "legacy":
+    h = usc.Handle()
+    lv = torch.empty(F, dtype=torch.int8, device=dev); s16 = torch.empty(F, dtype=torch.int16, device=dev)
+    for _ in range(reps):
+        h.onoff_detect(pcm, usc.PCM_I32, 4096, 38, None, s16, lv)
+    torch.cuda.synchronize()
+    print("done legacy", reps)
