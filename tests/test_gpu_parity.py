@@ -422,3 +422,62 @@ def test_two_devices_in_one_process():
             assert np.array_equal(g.view(np.uint32), w.view(np.uint32))
     for h in hs:
         h.close()
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 64, 517])
+def test_warp_fft_operators_bit_exact(B, monkeypatch):
+    """The receiver's own lengths (rfft 2048, cfft 1024) run on the packed register core (k_fft_warp.cu): odd and
+    even batches, out of place and in place, forward and inverse, on a handle configured for another frame
+    length (tables built on first use) — equal to the oracle and to the generic shared-memory kernel."""
+    rng = np.random.default_rng(B)
+    hh = usc.Handle(usc.default_config(n=4096))
+    x = (rng.standard_normal((B, 2048)) * 3e4).astype(np.float32)
+    x[0, :] = 0.0
+    r, c = R.Rfft(2048), R.Cfft(1024)
+    d, o = hh.buffer(x), hh.empty(x.nbytes)
+    hh.arm_rfft_fast_f32(2048, d, o, 0, B)
+    fwd = o.to_numpy(np.float32).reshape(B, 2048)
+    want = np.stack([r(x[i]) for i in range(B)])
+    assert np.array_equal(fwd.view(np.uint32), want.view(np.uint32))
+    hh.arm_rfft_fast_f32(2048, o, o, 1, B)                  # inverse in place
+    wantb = np.stack([r(want[i], inverse=True) for i in range(B)])
+    assert np.array_equal(o.to_numpy(np.float32).reshape(B, 2048).view(np.uint32), wantb.view(np.uint32))
+    for inv in (False, True):
+        dc = hh.buffer(x)
+        hh.arm_cfft_f32(1024, dc, inv, B)
+        wantc = np.stack([c(x[i], inverse=inv) for i in range(B)])
+        assert np.array_equal(dc.to_numpy(np.float32).reshape(B, 2048).view(np.uint32), wantc.view(np.uint32))
+    # the generic kernel gives the same bits (USC_FFT_GENERIC routes around the warp-level operators)
+    monkeypatch.setenv("USC_FFT_GENERIC", "1")
+    hh.arm_rfft_fast_f32(2048, d, o, 0, B)
+    assert np.array_equal(o.to_numpy(np.float32).reshape(B, 2048).view(np.uint32), want.view(np.uint32))
+    hh.close()
+
+
+def test_streaming_operators_row_form_bit_exact(h):
+    """mult / cmplx_mult_cmplx / cmplx_mag on aligned rows of the receiver's length take the float4 row kernels:
+    broadcast tables (stride 0), in place, out of place — same bits as the oracle's scalar loops."""
+    rng = np.random.default_rng(77)
+    B, L = 9, 2048
+    a = (rng.standard_normal((B, L)) * 1e3).astype(np.float32)
+    w = rng.standard_normal(L).astype(np.float32)
+    b = rng.standard_normal((B, L)).astype(np.float32)
+    da, dw, db, do = h.buffer(a), h.buffer(w), h.buffer(b), h.empty(a.nbytes)
+    h.arm_mult_f32(da, L, dw, 0, do, L, L, B)
+    assert np.array_equal(do.to_numpy(np.float32).reshape(B, L), a * w[None, :])
+    h.arm_mult_f32(da, L, db, L, do, L, L, B)
+    assert np.array_equal(do.to_numpy(np.float32).reshape(B, L), a * b)
+    h.arm_cmplx_mult_cmplx_f32(da, L, dw, 0, do, L, L // 2, B)
+    want = np.stack([R.arm_cmplx_mult_cmplx_f32(a[i], w) for i in range(B)])
+    assert np.array_equal(do.to_numpy(np.float32).reshape(B, L).view(np.uint32), want.view(np.uint32))
+    dm = h.empty(4 * B * (L // 2))
+    h.arm_cmplx_mag_f32(da, L, dm, L // 2, L // 2, B)
+    wantm = np.stack([R.arm_cmplx_mag_f32(a[i]) for i in range(B)])
+    assert np.array_equal(dm.to_numpy(np.float32).reshape(B, L // 2).view(np.uint32), wantm.view(np.uint32))
+    d2 = h.buffer(a)
+    h.arm_mult_f32(d2, L, dw, 0, d2, L, L, B)                                  # in place
+    assert np.array_equal(d2.to_numpy(np.float32).reshape(B, L), a * w[None, :])
+    d3 = h.buffer(a)
+    h.arm_cmplx_mult_cmplx_f32(d3, L, db, L, d3, L, L // 2, B)                  # in place
+    want = np.stack([R.arm_cmplx_mult_cmplx_f32(a[i], b[i]) for i in range(B)])
+    assert np.array_equal(d3.to_numpy(np.float32).reshape(B, L).view(np.uint32), want.view(np.uint32))

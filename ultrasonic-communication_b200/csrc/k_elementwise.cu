@@ -40,6 +40,50 @@ __global__ void k_mult(const float* a, size_t sa, const float* b, size_t sb, flo
     }
 }
 
+// Row-wise float4 forms of the three streaming operators of the receiver chain (mult, cmplx_mult_cmplx, cmplx_mag)
+// for the common case — rows of at least 256 floats, everything 16-byte aligned: one CTA walks a row, so there is
+// no per-element division and every access is a 16-byte vector.  Same rounded operations as the scalar kernels.
+__device__ __forceinline__ bool is16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__global__ void __launch_bounds__(256) k_mult_rows(const float* __restrict__ a, size_t sa, const float* __restrict__ b, size_t sb,
+                                                   float* __restrict__ dst, size_t sd, uint32_t len4, uint32_t batch) {
+    for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
+        const float4* pa = reinterpret_cast<const float4*>(a + (size_t) v * sa);
+        const float4* pb = reinterpret_cast<const float4*>(b + (size_t) v * sb);
+        float4* pd = reinterpret_cast<float4*>(dst + (size_t) v * sd);
+        for (uint32_t e = threadIdx.x; e < len4; e += blockDim.x) {
+            const float4 x = pa[e], y = pb[e];
+            pd[e] = make_float4(__fmul_rn(x.x, y.x), __fmul_rn(x.y, y.y), __fmul_rn(x.z, y.z), __fmul_rn(x.w, y.w));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_cmul_rows(const float* __restrict__ a, size_t sa, const float* __restrict__ b, size_t sb,
+                                                   float* __restrict__ dst, size_t sd, uint32_t len4, uint32_t batch) {
+    for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
+        const float4* pa = reinterpret_cast<const float4*>(a + (size_t) v * sa);
+        const float4* pb = reinterpret_cast<const float4*>(b + (size_t) v * sb);
+        float4* pd = reinterpret_cast<float4*>(dst + (size_t) v * sd);
+        for (uint32_t e = threadIdx.x; e < len4; e += blockDim.x) {          // two complex products per float4
+            const float4 x = pa[e], y = pb[e];
+            float4 r;
+            cmul(x.x, x.y, y.x, y.y, r.x, r.y);
+            cmul(x.z, x.w, y.z, y.w, r.z, r.w);
+            pd[e] = r;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_cmag_rows(const float* __restrict__ src, size_t ss, float* __restrict__ dst, size_t sd,
+                                                   uint32_t out4, uint32_t batch) {
+    for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
+        const float4* ps = reinterpret_cast<const float4*>(src + (size_t) v * ss);
+        float4* pd = reinterpret_cast<float4*>(dst + (size_t) v * sd);
+        for (uint32_t e = threadIdx.x; e < out4; e += blockDim.x) {           // four magnitudes from eight floats
+            const float4 x = ps[2 * e], y = ps[2 * e + 1];
+            pd[e] = make_float4(cmag(x.x, x.y), cmag(x.z, x.w), cmag(y.x, y.y), cmag(y.z, y.w));
+        }
+    }
+}
+
 // arm_scale_f32 — arm_math.h:2508
 __global__ void k_scale(const float* src, float scale, float* dst, size_t total) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x)
@@ -252,7 +296,10 @@ cudaError_t launch_i32_to_f32(const int32_t* src, float* dst, size_t count, cuda
 }
 cudaError_t launch_mult(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
                         uint32_t len, uint32_t batch, cudaStream_t st) {
-    k_mult<<<blocks_for((size_t) len * batch, 256), 256, 0, st>>>(a, sa, b, sb, dst, sd, len, batch);
+    const bool rows = len >= 256 && (len & 3u) == 0 && !((sa | sb | sd) & 3u) && ((uintptr_t) a & 15u) == 0 &&
+                      ((uintptr_t) b & 15u) == 0 && ((uintptr_t) dst & 15u) == 0 && (a != dst || sa == sd);
+    if (rows) k_mult_rows<<<batch < 148u * 16u ? batch : 148u * 16u, 256, 0, st>>>(a, sa, b, sb, dst, sd, len / 4, batch);
+    else k_mult<<<blocks_for((size_t) len * batch, 256), 256, 0, st>>>(a, sa, b, sb, dst, sd, len, batch);
     return cudaGetLastError();
 }
 cudaError_t launch_scale(const float* src, float scale, float* dst, size_t total, cudaStream_t st) {
@@ -261,7 +308,10 @@ cudaError_t launch_scale(const float* src, float scale, float* dst, size_t total
 }
 cudaError_t launch_cmul(const float* a, size_t sa, const float* b, size_t sb, float* dst, size_t sd,
                         uint32_t ncplx, uint32_t batch, cudaStream_t st) {
-    k_cmul<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(a, sa, b, sb, dst, sd, ncplx, batch);
+    const bool rows = ncplx >= 128 && (ncplx & 1u) == 0 && !((sa | sb | sd) & 3u) && ((uintptr_t) a & 15u) == 0 &&
+                      ((uintptr_t) b & 15u) == 0 && ((uintptr_t) dst & 15u) == 0 && (a != dst || sa == sd) && (b != dst || sb == sd);
+    if (rows) k_cmul_rows<<<batch < 148u * 16u ? batch : 148u * 16u, 256, 0, st>>>(a, sa, b, sb, dst, sd, ncplx / 2, batch);
+    else k_cmul<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(a, sa, b, sb, dst, sd, ncplx, batch);
     return cudaGetLastError();
 }
 cudaError_t launch_cmul_real(const float* c, size_t sc, const float* r, size_t sr, float* dst, size_t sd,
@@ -271,7 +321,11 @@ cudaError_t launch_cmul_real(const float* c, size_t sc, const float* r, size_t s
 }
 cudaError_t launch_cmag(const float* src, size_t ss, float* dst, size_t sd, uint32_t ncplx, uint32_t batch,
                         cudaStream_t st) {
-    k_cmag<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(src, ss, dst, sd, ncplx, batch);
+    // out of place only for the row form: in place (dst == src) the magnitudes of a row overwrite inputs other threads still need
+    const bool rows = ncplx >= 256 && (ncplx & 3u) == 0 && !((ss | sd) & 3u) && ((uintptr_t) src & 15u) == 0 &&
+                      ((uintptr_t) dst & 15u) == 0 && (dst + (size_t) batch * sd <= src || src + (size_t) batch * ss <= dst);
+    if (rows) k_cmag_rows<<<batch < 148u * 16u ? batch : 148u * 16u, 256, 0, st>>>(src, ss, dst, sd, ncplx / 4, batch);
+    else k_cmag<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(src, ss, dst, sd, ncplx, batch);
     return cudaGetLastError();
 }
 cudaError_t launch_max(const float* src, size_t ss, uint32_t len, float* result, uint32_t* index,

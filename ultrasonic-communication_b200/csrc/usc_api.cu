@@ -28,6 +28,7 @@ struct usc_handle {
     uint32_t bandwidth, bandwidth2, idx_left_zero;
     std::vector<float> hann, up, down, H_up, H_down;
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
+    float2 *d_op_pass = nullptr, *d_op_split = nullptr;    // tables of the warp-level FFT operators when cfg.n != 2048
     float* d_rs_taps = nullptr; uint32_t rs_up = 0;       // resampler polyphase table (usc_resample_i16_to_pcm)
     float2 *d_tw_pass, *d_tw_split, *d_tw_l0;      // d_tw_l0: W_32768^(a d), [d][a], 65536-point frames only
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
@@ -250,7 +251,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
 void usc_destroy(usc_handle* h) {
     if (!h) return;
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
-    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_rs_taps); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
+    cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_rs_taps); cudaFree(h->d_op_pass); cudaFree(h->d_op_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
     cudaFree(h->d_sym_table);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
@@ -421,9 +422,41 @@ int usc_arm_mean_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t 
     LAUNCHED(h, launch_mean(src, ss, block_size, result, batch, h->stream));
     return USC_OK;
 }
+/* Tables of the warp-level FFT operators (k_fft_warp.cu): W_1024^(a d) as [d][a] and the 2048-point split
+ * twiddles.  A handle configured for n = 2048 already owns them; other handles build them on first use. */
+static int ensure_op_tables(usc_handle* h, const float2** pass, const float2** split) {
+    if (h->d_tw_pass && h->d_tw_split) { *pass = h->d_tw_pass; *split = h->d_tw_split; return USC_OK; }
+    if (!h->d_op_pass) {
+        float2* master = nullptr;
+        int rc = get_twiddles(h, 2048, &master);
+        if (rc) return rc;
+        const std::vector<float>& tw = h->tw_host[2048];
+        std::vector<float> pass_h(2 * 1024), split_h(2 * 1024);
+        for (uint32_t d = 0; d < 32; ++d)
+            for (uint32_t a = 0; a < 32; ++a) {
+                const uint32_t j = a * d * 2;                       /* W_1024^(ad) = W_2048^(2ad) */
+                pass_h[2 * (d * 32 + a)] = tw[2 * j];
+                pass_h[2 * (d * 32 + a) + 1] = tw[2 * j + 1];
+            }
+        for (uint32_t k = 0; k < 1024; ++k) { split_h[2 * k] = tw[2 * k]; split_h[2 * k + 1] = -tw[2 * k + 1]; }
+        if ((rc = upload(pass_h.data(), pass_h.size() * 4, (void**) &h->d_op_pass))) return rc;
+        if ((rc = upload(split_h.data(), split_h.size() * 4, (void**) &h->d_op_split))) return rc;
+    }
+    *pass = h->d_op_pass; *split = h->d_op_split;
+    return USC_OK;
+}
+
 int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in, float* out, uint8_t ifft_flag,
                                 uint32_t batch) {
     USC_ENTER(h);
+    if (h && in && out && fft_len == 2048 && batch && (((uintptr_t) in | (uintptr_t) out) & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+        /* the receiver's own length: two transforms per warp on the packed register core, one pass over HBM */
+        const float2 *pass, *split;
+        int rc = ensure_op_tables(h, &pass, &split);
+        if (rc) return rc;
+        LAUNCHED(h, launch_fft_warp(ifft_flag ? FFT_C2R : FFT_R2C, in, out, batch, pass, split, h->num_sms, h->stream));
+        return USC_OK;
+    }
     /* supported lengths: CMSIS's 32..4096 (arm_math.h:2242-2244 returns ARM_MATH_ARGUMENT_ERROR
      * otherwise) extended to 8192 while one transform fits shared memory */
     if (!h || !in || !out || !pow2(fft_len) || fft_len < 32 || fft_len > 65536) return USC_ERR_ARGUMENT;
@@ -443,6 +476,13 @@ int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in
 }
 int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t ifft_flag, uint32_t batch) {
     USC_ENTER(h);
+    if (h && data && fft_len == 1024 && batch && ((uintptr_t) data & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+        const float2 *pass, *split;
+        int rc = ensure_op_tables(h, &pass, &split);
+        if (rc) return rc;
+        LAUNCHED(h, launch_fft_warp(ifft_flag ? FFT_C2C_INV : FFT_C2C_FWD, data, data, batch, pass, split, h->num_sms, h->stream));
+        return USC_OK;
+    }
     if (!h || !data || !pow2(fft_len) || fft_len < 16 || fft_len > 32768) return USC_ERR_ARGUMENT;
     if (ifft_flag && fft_len > 8192) return USC_ERR_ARGUMENT;
     if (!batch) return USC_OK;
