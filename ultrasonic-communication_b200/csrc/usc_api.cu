@@ -446,6 +446,19 @@ static int ensure_op_tables(usc_handle* h, const float2** pass, const float2** s
     return USC_OK;
 }
 
+/* forward transform in place on an aligned scratch buffer: the warp-level operator where it exists, else the generic kernel */
+static int fft_forward_inplace(usc_handle* h, int mode, uint32_t n_complex, const fft_plan_dev& plan, float* buf, uint32_t batch) {
+    if (n_complex == 1024 && ((uintptr_t) buf & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+        const float2 *pass, *split;
+        int rc = ensure_op_tables(h, &pass, &split);
+        if (rc) return rc;
+        LAUNCHED(h, launch_fft_warp(mode, buf, buf, batch, pass, split, h->num_sms, h->stream));
+        return USC_OK;
+    }
+    LAUNCHED(h, launch_fft_generic(mode, plan, buf, buf, batch, h->stream));
+    return USC_OK;
+}
+
 int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in, float* out, uint8_t ifft_flag,
                                 uint32_t batch) {
     USC_ENTER(h);
@@ -771,7 +784,7 @@ int usc_scan4(usc_handle* h, const float* pcm2n, uint32_t batch, usc_scan_entry*
         const float* src = pcm2n + (size_t) (n / 4) * i;                               /* main.c:246-249 */
         LAUNCHED(h, launch_mult(src, 2 * (size_t) n, h->d_down, 0, w, n, n, batch, h->stream));   /* mult_ref_chirp (down-chirp) */
         LAUNCHED(h, launch_mult(w, n, h->d_hann, 0, w, n, n, batch, h->stream));
-        LAUNCHED(h, launch_fft_generic(FFT_R2C, plan, w, w, batch, h->stream));
+        if ((rc = fft_forward_inplace(h, FFT_R2C, n / 2, plan, w, batch))) return rc;
         LAUNCHED(h, launch_pipeline_tail(w, n, batch, 0, h->stream));                  /* in-place magnitudes, upper half kept */
         LAUNCHED(h, launch_max(w, n, bw8, mr, ir, batch, h->stream));
         LAUNCHED(h, launch_max(w + (n - bw8), n, bw8, ml, il, batch, h->stream));
@@ -969,7 +982,7 @@ int usc_spectrum_analyzer(usc_handle* h, const void* pcm, uint32_t pcm_format, u
     }
     fft_plan_dev plan;
     if ((rc = make_plan(h, n / 2, n, &plan))) return rc;
-    LAUNCHED(h, launch_fft_generic(FFT_R2C, plan, x, x, nframes, h->stream));
+    if ((rc = fft_forward_inplace(h, FFT_R2C, n / 2, plan, x, nframes))) return rc;
     /* fft_frequency[i] = i*fs/N < FFT_AC_COUPLING_HZ (main.c:127,250): count of leading bins forced to 1.0 */
     uint32_t ac_bins = 0;
     while (ac_bins < n / 2 && (float) ac_bins * h->cfg.fs / (float) n < ac_coupling_hz) ++ac_bins;
@@ -1051,7 +1064,7 @@ int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t n
     for (int hyp = 0; hyp < 2; ++hyp) {
         LAUNCHED(h, launch_cmul(R, n, refs[hyp], 0, P, n, half, (uint32_t) F, h->stream));
         LAUNCHED(h, launch_cmul_real(P, n, h->d_iq_hann, 0, P, n, half, (uint32_t) F, h->stream));
-        LAUNCHED(h, launch_fft_generic(FFT_C2C_FWD, plan, P, P, (uint32_t) F, h->stream));
+        if ((rc = fft_forward_inplace(h, FFT_C2C_FWD, half, plan, P, (uint32_t) F))) return rc;
         LAUNCHED(h, launch_cmag(P, n, M, half, half, (uint32_t) F, h->stream));
         LAUNCHED(h, launch_max(M, half, W, mr, ir, (uint32_t) F, h->stream));
         LAUNCHED(h, launch_max(M + (half - W), half, W, ml, il, (uint32_t) F, h->stream));
