@@ -447,6 +447,13 @@ def test_warp_fft_operators_bit_exact(B, monkeypatch):
         hh.arm_cfft_f32(1024, dc, inv, B)
         wantc = np.stack([c(x[i], inverse=inv) for i in range(B)])
         assert np.array_equal(dc.to_numpy(np.float32).reshape(B, 2048).view(np.uint32), wantc.view(np.uint32))
+    y = (rng.standard_normal((B, 4096)) * 3e4).astype(np.float32)           # arm_cfft_sR_f32_len2048
+    c2 = R.Cfft(2048)
+    for inv in (False, True):
+        dc = hh.buffer(y)
+        hh.arm_cfft_f32(2048, dc, inv, B)
+        wantc = np.stack([c2(y[i], inverse=inv) for i in range(B)])
+        assert np.array_equal(dc.to_numpy(np.float32).reshape(B, 4096).view(np.uint32), wantc.view(np.uint32))
     # the generic kernel gives the same bits (USC_FFT_GENERIC routes around the warp-level operators)
     monkeypatch.setenv("USC_FFT_GENERIC", "1")
     hh.arm_rfft_fast_f32(2048, d, o, 0, B)

@@ -25,6 +25,7 @@ rep("arm_cmplx_mult_cmplx_f32", timeit(lambda: h.arm_cmplx_mult_cmplx_f32(x, N, 
 rep("arm_rfft_fast_f32 2048", timeit(lambda: h.arm_rfft_fast_f32(N, x, y, 0, B)), 2 * G)
 rep("arm_rfft_fast_f32 2048 inv", timeit(lambda: h.arm_rfft_fast_f32(N, y, x, 1, B)), 2 * G)
 rep("arm_cfft_f32 1024", timeit(lambda: h.arm_cfft_f32(1024, x, 0, B)), 2 * G)
+rep("arm_cfft_f32 2048", timeit(lambda: h.arm_cfft_f32(2048, x, 0, B // 2)), 2 * G)
 rep("arm_cmplx_mag_f32", timeit(lambda: h.arm_cmplx_mag_f32(y, N, m, N // 2, N // 2, B)), G + G // 2)
 rep("arm_max_f32 (1024)", timeit(lambda: h.arm_max_f32(m, N // 2, N // 2, v, ix, B)), G // 2)
 rep("arm_max_f32 (156 of 1024)", timeit(lambda: h.arm_max_f32(m, N // 2, 156, v, ix, B)), B * 156 * 4)

@@ -150,6 +150,93 @@ __global__ void __launch_bounds__(kFwWarps * 32, 1) k_fft_warp(const float* __re
     }
 }
 
+// arm_cfft_f32 at 2048 points (arm_cfft_sR_f32_len2048, the length of experiments/synchronization): canonical plan
+// [2, 32, 32] — one radix-2 stage (z[a] +- z[a + 1024], odd half x W_2048^a) feeds two 1024-point transforms that
+// produce the even and the odd bins; the two ride in the f32x2 halves, so a warp carries ONE transform per pass.
+template <bool INVERSE>
+__global__ void __launch_bounds__(kFwWarps * 32, 1) k_cfft2048_warp(const float* __restrict__ in, float* __restrict__ out, size_t batch,
+                                                                    const float2* __restrict__ tw_pass,
+                                                                    const float2* __restrict__ tw_master /* W_2048^a, a < 1024 */) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(s_raw);
+    float2* s_tw0 = reinterpret_cast<float2*>(s_raw + 8192);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = s_raw + kFwTabs + warp * kFwWarpBytes;
+    float2* stage = reinterpret_cast<float2*>(wbase);                 // 2048 float2
+    float2* tile = reinterpret_cast<float2*>(wbase + 16384);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + kFwBar) + warp;
+    const size_t nwarps = (size_t) gridDim.x * kFwWarps;
+    size_t q = (size_t) blockIdx.x * kFwWarps + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (q < batch) {
+            mbar_expect_tx(bar, 16384u);
+            bulk_g2s(stage, in + q * 4096, 16384u, bar);
+        }
+    }
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        s_tw[i] = tw_pass[i];
+        s_tw0[i] = tw_master[i];
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    for (; q < batch; q += nwarps) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        float2 re[32], im[32];                                        // (.x, .y) = (even-bin transform, odd-bin transform)
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int a = lane + 32 * b;
+            float2 lo = stage[a], hi = stage[a + 1024];
+            if (INVERSE) { lo = make_float2(lo.y, lo.x); hi = make_float2(hi.y, hi.x); }
+            const float er = __fadd_rn(lo.x, hi.x), ei = __fadd_rn(lo.y, hi.y);     // radix-2, d = 0
+            const float dr = __fsub_rn(lo.x, hi.x), di = __fsub_rn(lo.y, hi.y);     // d = 1, then x W_2048^a
+            const float2 w = s_tw0[a];
+            float orr, oii;
+            cmul(dr, di, w.x, w.y, orr, oii);
+            re[b] = make_float2(er, orr);
+            im[b] = make_float2(ei, oii);
+        }
+        __syncwarp();
+        if (lane == 0 && q + nwarps < batch) {
+            mbar_expect_tx(bar, 16384u);
+            bulk_g2s(stage, in + (q + nwarps) * 4096, 16384u, bar);
+        }
+        fft1024_pair(re, im, tile, s_tw, lane);
+        float4* o = reinterpret_cast<float4*>(out + q * 4096);
+#pragma unroll
+        for (int d1 = 0; d1 < 32; ++d1) {
+            const int c = lane + 32 * d1;                             // X[2c] and X[2c + 1]
+            if (INVERSE) {
+                const float sc = 1.0f / 2048.0f;
+                const float2 a0 = __fmul2_rn(im[d1], bc2(sc)), a1 = __fmul2_rn(re[d1], bc2(sc));   // swap back, scale
+                o[c] = make_float4(a0.x, a1.x, a0.y, a1.y);
+            } else {
+                o[c] = make_float4(re[d1].x, im[d1].x, re[d1].y, im[d1].y);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_cfft2048_warp(bool inverse, float* data, size_t batch, const float2* tw_pass, const float2* tw_master,
+                                 int num_sms, cudaStream_t st) {
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_cfft2048_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cfft2048_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    size_t ctas = (batch + kFwWarps - 1) / kFwWarps;
+    if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
+    if (inverse) k_cfft2048_warp<true><<<(int) ctas, kFwWarps * 32, kFwSmem, st>>>(data, data, batch, tw_pass, tw_master);
+    else k_cfft2048_warp<false><<<(int) ctas, kFwWarps * 32, kFwSmem, st>>>(data, data, batch, tw_pass, tw_master);
+    return cudaGetLastError();
+}
+
 template <int MODE>
 static cudaError_t launch_mode(const float* in, float* out, size_t batch, const float2* tw_pass, const float2* tw_split,
                                int num_sms, cudaStream_t st) {

@@ -489,6 +489,16 @@ int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in
 }
 int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t ifft_flag, uint32_t batch) {
     USC_ENTER(h);
+    if (h && data && fft_len == 2048 && batch && ((uintptr_t) data & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+        /* arm_cfft_sR_f32_len2048 (experiments/synchronization): [2, 32, 32] on the register core, one transform per warp pass */
+        const float2 *pass, *split;
+        float2* master = nullptr;
+        int rc = ensure_op_tables(h, &pass, &split);
+        if (!rc) rc = get_twiddles(h, 2048, &master);
+        if (rc) return rc;
+        LAUNCHED(h, launch_cfft2048_warp(ifft_flag != 0, data, batch, pass, master, h->num_sms, h->stream));
+        return USC_OK;
+    }
     if (h && data && fft_len == 1024 && batch && ((uintptr_t) data & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
         const float2 *pass, *split;
         int rc = ensure_op_tables(h, &pass, &split);

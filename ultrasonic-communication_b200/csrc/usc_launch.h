@@ -84,6 +84,8 @@ cudaError_t launch_fsk_parse(const uint8_t* code, uint32_t nstreams, uint32_t nf
                              uint32_t* nchars, uint32_t* nsof, uint32_t* neof, cudaStream_t st);
 cudaError_t launch_resample_i16(const int16_t* in, size_t n_in, uint32_t up, uint32_t down, uint32_t ktaps, const float* taps,
                                 int32_t* out, size_t n_out, cudaStream_t st);
+cudaError_t launch_cfft2048_warp(bool inverse, float* data, size_t batch, const float2* tw_pass, const float2* tw_master,
+                                 int num_sms, cudaStream_t st);
 cudaError_t launch_fft_warp(int mode, const float* in, float* out, size_t batch, const float2* tw_pass, const float2* tw_split,
                             int num_sms, cudaStream_t st);
 cudaError_t launch_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
