@@ -36,4 +36,17 @@ hq = usc.Handle(); hq.iq_init(18000.0, 3000.0, taps, 32)           # K5: whole I
 pq = np.stack([synth.make_iq_stream(5, seed_bits=s)[0] for s in range(3)])
 dq = hq.buffer(pq); oq = [hq.empty(4 * 15) for _ in range(4)]; bq = hq.empty(15)
 hq.iq_demod(dq, usc.PCM_I32, 3, 5, 5 * N, oq[0], oq[1], oq[2], oq[3], bq); hq.sync()
+xr = h.buffer(np.random.default_rng(1).standard_normal((5, 2048)).astype(np.float32)); yr = h.empty(5 * 2048 * 4)
+h.arm_rfft_fast_f32(2048, xr, yr, 0, 5); h.arm_rfft_fast_f32(2048, yr, yr, 1, 5)            # warp-level FFT operators
+h.arm_cfft_f32(1024, xr, 0, 5); h.arm_cfft_f32(1024, xr, 1, 5); h.arm_cfft_f32(2048, xr, 0, 2); h.arm_cfft_f32(2048, xr, 1, 2); h.sync()
+ps, _ = synth.make_onoff_stream(b"A"); dps = h.buffer(ps); F1 = ps.shape[0]
+lv, cd, ch, nc = h.empty(F1), h.empty(F1), h.empty(8), h.empty(4)
+h.onoff_detect(dps, usc.PCM_I32, 1, F1, None, None, lv, ch, 8, nc); h.fsk_detect(dps, usc.PCM_I32, 1, F1, None, cd, None, None, ch, 8, nc); h.sync()   # legacy detectors
+tr = h.buffer(np.random.default_rng(2).integers(-2000, 2000, 5000).astype(np.int16)); to = h.empty(4 * 8858)
+h.resample_i16_to_pcm(tr, 5000, 3125, 1764, to, 8858); h.sync()                             # resampler
+stt = h.empty(160 * 3); usc.load().usc_memset(h._h, __import__("ctypes").c_void_p(stt.ptr), 0, __import__("ctypes").c_size_t(480))
+st3 = np.repeat(st, 3, 0); u3, r3 = h.empty(3 * 32), h.empty(3 * 32)
+h.receiver_run_chunk(h.buffer(st3[:, :30]), usc.PCM_I32, 3, 30, 30 * N, 0, stt, u3, 32, r3)
+h.receiver_run_chunk(h.buffer(np.ascontiguousarray(st3[:, 28:70])), usc.PCM_I32, 3, 40, 42 * N, 2, stt, u3, 32, r3); h.sync()   # K7 in chunks
+sp = h.empty(4 * 4 * 50 * N); h.synth_streams(1, 0, 4, 50, 50 * N, 5, 2, 3, 2.0e4, 2000.0, sp); h.sync()   # stream generator
 print("sanitize workload done")
