@@ -675,7 +675,7 @@ void ref_receiver_step(const ref_receiver *rx, ref_rx_state *st, float thr, cons
     case REF_IDLE:
         st->sync_cnt = 0;
         ref_arm_mean_f32(&st->mag_stat[4], 8, &st->mag_mean);              /* main.c:431 */
-        /* fall through (main.c:434) */
+        __attribute__((fallthrough));                                      /* as the firmware does, main.c:434 */
     case REF_SYNCHRONIZING:
         for (uint32_t i = 0; i < 4; ++i) {                                  /* main.c:447-451 */
             st->sync_position = n / 2 + st->turn * offset + shift * i;
