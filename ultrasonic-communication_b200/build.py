@@ -15,7 +15,7 @@ OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libusc.so")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Wno-deprecated-gpu-targets",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v",
               "--expt-relaxed-constexpr"]
 CC_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-Wall"]

@@ -38,7 +38,6 @@ constexpr int kWarpsPerCta = 4;
 // the front end is one LDS away.  The L1/shared data path (128 B per clock per SM) carries, per
 // frame, PCM 8 KB + table 16 KB + Hann 8 KB + exchange 2 x 16 KB + twiddles 8 KB = 72 KB.
 constexpr int kDualWarps = 8;                         // warps per CTA of the pair kernel below
-constexpr int kTile4 = 32 * 32;
 
 // Shared memory of the dual kernel with W warps: twiddles 8 KB | (up,down) table 16 KB | Hann 8 KB |
 // per warp: XOR-swizzled 32x32 float2 tile 8 KB + PCM stage 8 KB | mbarriers.
