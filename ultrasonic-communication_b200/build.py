@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
                 if verbose:
                     print(out)
     if jobs or force or _stale(LIB, objs):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static", "-lm"],
+        _run([NVCC, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static", "-lm"],
              os.path.join(OBJ, "link.log"))
     # CMSIS exact-name host-pointer shim (tests / drop-in demonstration), plain C over the C-ABI
     shim_src = os.path.join(CSRC, "usc_cmsis_shim.c")
