@@ -71,3 +71,49 @@ def test_receiver_state_machine_follows_the_threshold(thr):
         want, st = R.receiver_run(rx, streams[s], snr_threshold=thr, cap=32)
         assert out[s] == want and res["lock_frame"][s] == st.lock_frame and res["sync_position"][s] == st.sync_position, s
     h.close()
+
+
+@pytest.mark.parametrize("fs,f1,f2", [(100000.0, 17000.0, 18000.0), (78125.0, 16000.0, 17500.0), (100000.0, 15000.0, 19000.0)])
+@pytest.mark.parametrize("F", [1, 2, 63])
+def test_compression_follows_the_configuration(fs, f1, f2, F):
+    """K2 under other sampling rates / bands, odd and even batches, int32 and float PCM: peak value, lag and the
+    compressed frames bit for bit (experiments/chirp_compression_time_domain chain)."""
+    hc = usc.Handle(usc.default_config(fs=fs, f0=f1, f1=f2, chirp_variant=usc.CHIRP_T, window=usc.HANN_SYMMETRIC))
+    c = R.RefCompressor(fs=fs, f1=f1, f2=f2)
+    assert np.array_equal(hc.table("H_down").view(np.uint32), c.table("H_down").view(np.uint32))
+    rng = np.random.default_rng(int(fs + f1) % 1000 + F)
+    p = hc.table("up")
+    pcm = np.stack([np.rint(np.roll(p, int(rng.integers(0, N))) * 15000 + rng.standard_normal(N) * 9000) for _ in range(F)])
+    pcm = (pcm.astype(np.int64) * 256).astype(np.int32)
+    d_out, d_v, d_i = hc.empty(4 * F * N), hc.empty(4 * F), hc.empty(4 * F)
+    for fmt, data in ((usc.PCM_I32, pcm), (usc.PCM_F32, pcm.astype(np.float32))):
+        d = hc.buffer(data)
+        hc.compress_chirp(d, fmt, F, False, d_out, d_v, d_i)
+        hc.sync()
+        wv, wi = c.compress_frames(pcm, use_up=False, nthreads=2)
+        assert np.array_equal(d_i.to_numpy(np.uint32), wi)
+        assert np.array_equal(d_v.to_numpy(np.float32).view(np.uint32), wv.view(np.uint32))
+        want = np.stack([c.compress(pcm[i].astype(np.float32), False) for i in range(F)])
+        assert np.array_equal(d_out.to_numpy(np.float32).reshape(F, N).view(np.uint32), want.view(np.uint32))
+    hc.close()
+
+
+def test_iq_path_takes_float_pcm_too(fir_taps):
+    taps = fir_taps.astype(np.float32)[::-1].copy()
+    h = usc.Handle()
+    h.iq_init(18000.0, 3000.0, taps, 32)
+    pcm = np.stack([synth.make_iq_stream(9, snr_db=5.0, seed_bits=s, seed_noise=100 + s)[0] for s in range(2)])
+    outs = []
+    for fmt, data in ((usc.PCM_I32, pcm), (usc.PCM_F32, pcm.astype(np.float32))):
+        d = h.buffer(data)
+        o = [h.empty(4 * 18) for _ in range(4)]
+        b = h.empty(18)
+        h.iq_demod(d, fmt, 2, 9, 9 * N, o[0], o[1], o[2], o[3], b)
+        h.sync()
+        outs.append([x.to_numpy(np.uint32) for x in o] + [b.to_numpy(np.uint8)])
+    for a, b2 in zip(*outs):
+        assert np.array_equal(a, b2)
+    q = R.RefIq(taps)
+    want = q.demod(pcm[1])
+    assert np.array_equal(outs[0][0][9:], want[0].view(np.uint32)) and np.array_equal(outs[0][1][9:], want[1])
+    h.close()
