@@ -322,7 +322,17 @@ def main():
     torch.cuda.synchronize()
     accuracy = float((bit == bits).float().mean().item())
 
-    # end-to-end through the host-buffer C-ABI call: pinned host PCM -> H2D -> K1 -> D2H results
+    # end-to-end through the host-buffer C-ABI call: pinned host PCM -> H2D -> K1 -> D2H results.
+    # The host buffers are first touched from CPUs next to this rank's GPU (NVML's ideal affinity), so that with
+    # several ranks each PCIe link is fed from its own NUMA node; the previous affinity comes back afterwards.
+    old_affinity, numa_note = os.sched_getaffinity(0), "unchanged"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa_note = "host buffers touched from %d CPUs local to GPU %d" % (len(os.sched_getaffinity(0)), local_rank)
+    except Exception as exc:                             # cpuset of the container may exclude them
+        numa_note = "NVML affinity not applied (%s)" % type(exc).__name__
     host_pcm = torch.empty((NFRAMES, N), dtype=torch.int32).pin_memory()
     host_pcm.copy_(pcm)
     h_mu = torch.empty(NFRAMES, dtype=torch.float32).pin_memory()
@@ -343,6 +353,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_ok = bool(torch.equal(h_bit, bit.cpu()) and torch.equal(h_iu, idx_up.cpu()))
+    os.sched_setaffinity(0, old_affinity)
 
     times = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -372,7 +383,7 @@ def main():
                          "note": "bound by the L1/shared-memory data path (76 %) and the fp32 pipe (62 %), DESIGN.md 4.1; frac is vs HBM"},
             "e2e": {"value": NFRAMES * world * args.e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": NFRAMES * N * 4, "d2h_bytes_per_step": NFRAMES * 17,
-                    "steps": args.e2e_steps, "results_match_device_path": e2e_ok},
+                    "steps": args.e2e_steps, "results_match_device_path": e2e_ok, "host_numa": numa_note},
             "roofline_single_hypothesis": {
                 "bound": "hbm", "achieved": (N * 4 + 8) * NFRAMES / (ms_single * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": (N * 4 + 8) * NFRAMES / (ms_single * 1e-3) / 1e9 / peak,
