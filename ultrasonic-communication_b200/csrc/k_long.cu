@@ -1,6 +1,6 @@
-// k_long.cu — K6: the receiver chain fused for long frames, N = 2048*R0 with R0 = 4 or 8 (8192- and
-// 16384-point frames of BASELINE config 5).  Same reference path as K1 (cast, de-chirp, Hann, RFFT,
-// magnitude, arg-max over [0, bandwidth2), both hypotheses; receiver/Src/main.c:163-215), one HBM pass.
+// k_long.cu — K6: the receiver chain fused for long frames, N = 2048*R0 with R0 = 2, 4 or 8 (4096 points — the
+// longest CMSIS supports — and the 8192- and 16384-point frames of BASELINE config 5).  Same reference path as
+// K1 (cast, de-chirp, Hann, RFFT, magnitude, arg-max over [0, bandwidth2), both hypotheses; receiver/Src/main.c:163-215), one HBM pass.
 //
 // The N/2-point complex FFT has the canonical plan [R0, 32, 32]: one radix-R0 level over a
 // (m = a + 1024 b), then R0 independent 1024-point transforms whose outputs interleave
@@ -163,7 +163,7 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int per_sm = R0 == 4 ? 2 : 1;
+    const int per_sm = R0 == 2 ? 4 : (R0 == 4 ? 2 : 1);
     size_t ctas = p.nframes < (size_t) num_sms * per_sm ? p.nframes : (size_t) num_sms * per_sm;
     k_demod_long<PCM, R0><<<(int) ctas, R0 * 32, smem, st>>>(p);
     return cudaGetLastError();
@@ -410,6 +410,7 @@ cudaError_t launch_demod_long(const void* pcm, uint32_t pcm_format, size_t nfram
                               int num_sms, cudaStream_t st) {
     long_params p{pcm, nframes, n, reinterpret_cast<const float4*>(chirp_ud), hann, tw_master, tw_pass, bandwidth2,
                   mag_up, idx_up, mag_down, idx_down, bit};
+    if (n == 4096) return pcm_format == 1u ? launch_long_t<int32_t, 2>(p, num_sms, st) : launch_long_t<float, 2>(p, num_sms, st);
     if (n == 8192) return pcm_format == 1u ? launch_long_t<int32_t, 4>(p, num_sms, st) : launch_long_t<float, 4>(p, num_sms, st);
     if (n == 16384) return pcm_format == 1u ? launch_long_t<int32_t, 8>(p, num_sms, st) : launch_long_t<float, 8>(p, num_sms, st);
     return cudaErrorInvalidValue;

@@ -587,7 +587,7 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     if (h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;     /* frames are fetched by 16-byte-aligned bulk copies */
     if (!nframes) return USC_OK;
-    if ((h->cfg.n == 8192 || h->cfg.n == 16384) && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u)) {
+    if ((h->cfg.n == 4096 || h->cfg.n == 8192 || h->cfg.n == 16384) && !getenv("USC_LONG_UNFUSED") && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u)) {
         /* long frames: one CTA per frame, level 0 from global memory, packed 1024-point cores (k_long.cu) */
         float2* master = nullptr;
         int rc = get_twiddles(h, h->cfg.n, &master);
