@@ -20,6 +20,7 @@ namespace usc {
 constexpr int kRxWarps = 8;
 constexpr int kRxNB = 5;
 constexpr int kRxSmem = 4 * 8192 + kRxWarps * 8192 + kRxWarps * 128;   // tables | per-warp 8 KB tile | per-warp state
+constexpr int kRxSmemMulti = kRxSmem + kRxWarps * 1792 * 8;            // + per-warp sum of the window union (synchronous addition)
 
 struct rx_tables {
     const float2* up;       // shared-memory copies
@@ -47,6 +48,21 @@ __device__ __forceinline__ float2 load_pair(const PCM* __restrict__ stream, int6
         return make_float2(pcm_to_float(raw.x), pcm_to_float(raw.y));
     }
     return make_float2(0.0f, 0.0f);                    // before the stream starts the FIFO holds zeros
+}
+
+// second half of dsp(): de-chirp, Hann, FFT, right-window peaks, on samples already in (re, im) = (x[2m], x[2m+1])
+__device__ __forceinline__ void dsp_pair_tail(float2 (&re)[32], float2 (&im)[32], const float2* chirpA, const float2* chirpB,
+                                              const rx_tables& tb, float2* tile, const float2 (&ws)[kRxNB], int lane,
+                                              uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB) {
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+        const int m = lane + 32 * b;
+        const float2 ca = chirpA[m], cb = chirpB[m], w = tb.hann[m];
+        re[b] = make_float2(__fmul_rn(__fmul_rn(re[b].x, ca.x), w.x), __fmul_rn(__fmul_rn(re[b].y, cb.x), w.x));
+        im[b] = make_float2(__fmul_rn(__fmul_rn(im[b].x, ca.y), w.y), __fmul_rn(__fmul_rn(im[b].y, cb.y), w.y));
+    }
+    fft1024_pair(re, im, tile, tb.tw, lane);
+    peak_window_pair<kRxNB>(re, im, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 
 // TWO dsp() calls at once (halves .x / .y of the packed core): windows starting at stream samples gA
@@ -124,15 +140,7 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
             }
         }
     }
-#pragma unroll
-    for (int b = 0; b < 32; ++b) {
-        const int m = lane + 32 * b;
-        const float2 ca = chirpA[m], cb = chirpB[m], w = tb.hann[m];
-        re[b] = make_float2(__fmul_rn(__fmul_rn(re[b].x, ca.x), w.x), __fmul_rn(__fmul_rn(re[b].y, cb.x), w.x));
-        im[b] = make_float2(__fmul_rn(__fmul_rn(im[b].x, ca.y), w.y), __fmul_rn(__fmul_rn(im[b].y, cb.y), w.y));
-    }
-    fft1024_pair(re, im, tile, tb.tw, lane);
-    peak_window_pair<kRxNB>(re, im, ws, lane, bw2, magA, idxA, magB, idxB);
+    dsp_pair_tail(re, im, chirpA, chirpB, tb, tile, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 
 __device__ __forceinline__ void load_tables(const rx_params& p, float2* s_up, float2* s_down, float2* s_hann, float2* s_tw) {
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
     __syncthreads();
     const rx_tables tb{s_up, s_down, s_hann, s_tw};
     float2* tile = s_rx + 4096 + warp * 1024;
+    float2* sum = s_rx + 4096 + kRxWarps * 1024 + kRxWarps * 16 + warp * 1792;     // MULTI only: 14 KB per warp behind the common layout
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const size_t total = (size_t) p.nstreams * p.nframes;
     const size_t nwarps = (size_t) gridDim.x * kRxWarps;
@@ -375,11 +384,64 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
                 }
             }
         }
+        if (MULTI) {
+            // Synchronous addition: the four search windows overlap (hop N/4), so the K-frame sum is formed ONCE over
+            // their union (1.75 N samples, oldest FIFO first as the per-window form does) and parked in shared memory.
+            using V2 = typename vec2<PCM>::type;
+            const int64_t base = fifo0 + N / 2 + (t & 1u) * offset;
+            const int64_t oldest = base - (int64_t) (p.sync_add - 1) * N;
+            const bool inside = oldest >= 0 && base + 3584 <= nsamples;
+            __syncwarp();
+            if (inside) {                                                  // two batches of 28 pairs per lane: 28 loads in flight
+#pragma unroll 1
+                for (uint32_t u0 = 0; u0 < 1792u; u0 += 896u) {
+                    float2 acc[28];
+                    const V2* src0 = reinterpret_cast<const V2*>(stream + oldest) + u0 + lane;
+#pragma unroll
+                    for (int q = 0; q < 28; ++q) {
+                        const V2 r = src0[32 * q];
+                        acc[q] = make_float2(pcm_to_float(r.x), pcm_to_float(r.y));
+                    }
+                    for (uint32_t j = p.sync_add - 1; j-- > 0;) {
+                        const V2* srcj = reinterpret_cast<const V2*>(stream + base - (int64_t) j * N) + u0 + lane;
+                        V2 r[28];
+#pragma unroll
+                        for (int q = 0; q < 28; ++q) r[q] = srcj[32 * q];
+#pragma unroll
+                        for (int q = 0; q < 28; ++q) acc[q] = __fadd2_rn(acc[q], make_float2(pcm_to_float(r[q].x), pcm_to_float(r[q].y)));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 28; ++q) sum[u0 + lane + 32 * q] = acc[q];
+                }
+            } else {
+                for (uint32_t u = lane; u < 1792u; u += 32u) {             // stream edges: checked loads
+                    float2 acc = load_pair<PCM>(stream, nsamples, oldest + 2 * u);
+                    for (uint32_t j = p.sync_add - 1; j-- > 0;) {
+                        const float2 r = load_pair<PCM>(stream, nsamples, base - (int64_t) j * N + 2 * u);
+                        acc = make_float2(__fadd_rn(acc.x, r.x), __fadd_rn(acc.y, r.y));
+                    }
+                    sum[u] = acc;
+                }
+            }
+            __syncwarp();
+        }
         for (uint32_t i = 0; i < 4; i += 2) {
             const uint32_t pa = N / 2 + (t & 1u) * offset + shift * i, pb = pa + shift;
             float ma, mb;
             uint32_t ka, kb;
-            dsp_pair<PCM, MULTI>(stream, nsamples, fifo0 + pa, fifo0 + pb, tb.up, tb.up, tb, p.sync_add, tile, ws, lane, p.bandwidth2,
+            if (MULTI) {
+                float2 re[32], im[32];
+                const float2* sa = sum + (shift / 2) * i;
+                const float2* sb = sa + shift / 2;
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    const float2 xa = sa[lane + 32 * b], xb = sb[lane + 32 * b];
+                    re[b] = make_float2(xa.x, xb.x);
+                    im[b] = make_float2(xa.y, xb.y);
+                }
+                dsp_pair_tail(re, im, tb.up, tb.up, tb, tile, ws, lane, p.bandwidth2, ma, ka, mb, kb);
+            } else
+            dsp_pair<PCM, false>(stream, nsamples, fifo0 + pa, fifo0 + pb, tb.up, tb.up, tb, 1, tile, ws, lane, p.bandwidth2,
                           ma, ka, mb, kb);
             if (lane == 0) {
                 p.ss_mag[w * 4 + i] = ma; p.ss_idx[w * 4 + i] = ka;
@@ -409,8 +471,8 @@ static cudaError_t rx_prepare() {
     if ((e = cudaFuncSetAttribute(k_receiver_run<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_sync_search<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
     done = true;
     return cudaSuccess;
 }
@@ -436,10 +498,10 @@ cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const bool multi = p.sync_add > 1;
     if (a.pcm_format == 1u) {
-        if (multi) k_sync_search<int32_t, true><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+        if (multi) k_sync_search<int32_t, true><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
         else k_sync_search<int32_t, false><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
     } else {
-        if (multi) k_sync_search<float, true><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+        if (multi) k_sync_search<float, true><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
         else k_sync_search<float, false><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
     }
     return cudaGetLastError();
