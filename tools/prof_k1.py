@@ -59,3 +59,13 @@ if which == "legacy":
         h.onoff_detect(pcm, usc.PCM_I32, 4096, 38, None, s16, lv)
     torch.cuda.synchronize()
     print("done legacy", reps)
+if which in ("long8192", "long16384"):
+    n = int(which[4:])
+    hh = usc.Handle(usc.default_config(n=n))
+    nf = (1 << 28) // n
+    x = torch.empty((nf, n), dtype=torch.int32, device=dev)
+    hh.synth_frames(2, 0, nf, 2.0e4, 1.0e5, x)
+    for _ in range(reps):
+        hh.demod_frames(x, usc.PCM_I32, nf, o[0], o[1], o[2], o[3], b)
+    torch.cuda.synchronize()
+    print("done", which, reps)
