@@ -381,6 +381,12 @@ def main():
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "kernel": "k_demod2048<int,5,8>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL * NFRAMES,
                          "note": "bound by the L1/shared-memory data path (76 %) and the fp32 pipe (62 %), DESIGN.md 4.1; frac is vs HBM"},
+            # secondary roofline: algorithmic fp32 work of two real-FFT chains per symbol, 2.5 N log2 N + 8 N flops
+            # each, against the fp32 FMA peak of the measured SM clock (148 SMs x 128 lanes x 2 flops)
+            "roofline_fp32": {"bound": "fp32", "achieved": 2 * (2.5 * N * 11 + 8 * N) * NFRAMES / (ms_per_step * 1e-3) / 1e12,
+                              "peak": 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965) * 1e6 / 1e12, "unit": "TFLOP/s",
+                              "frac": 2 * (2.5 * N * 11 + 8 * N) * NFRAMES / (ms_per_step * 1e-3) / (148 * 128 * 2 * (clocks.get("sm_mhz") or 1965) * 1e6),
+                              "note": "nominal flop count of the textbook radix-2 chain; the kernel executes fewer (pruned last pass, trivial twiddles)"},
             "e2e": {"value": NFRAMES * world * args.e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": NFRAMES * N * 4, "d2h_bytes_per_step": NFRAMES * 17,
                     "steps": args.e2e_steps, "results_match_device_path": e2e_ok, "host_numa": numa_note},
