@@ -1,12 +1,14 @@
-// k_iq.cu — K5 front end of the I/Q baseband path (experiments/iq_modulation/Src/iq_modem.c:52-66):
-// carrier mix (arm_mult_f32 x2), 27-tap FIR on I and Q (arm_fir_f32, state carried from the previous
-// frame of the same stream), decimation by 2 and interleave to R = I + jQ (BASELINE config 3), fused
-// so the PCM crosses HBM once.  One CTA per (stream, frame); the mixed samples (with the numTaps-1
-// history samples from the previous frame) are staged in shared memory.  The rest of the chain
-// (x conj/plain baseband chirp, Hann, 1024-pt complex FFT, magnitude, windowed arg-max) runs on the
-// batched operators; k_iq_pick applies the left/right choice rule of the receiver (main.c:191-197).
+// k_iq.cu — K5: the I/Q baseband path (experiments/iq_modulation/Src/iq_modem.c:34-75, Src/main.c:117-134, with the
+// semantics of simulation/IQ_modulation.ipynb cells 16-31 and BASELINE config 3's decimation by 2).
+//   k_iq_fused        the whole path in one kernel (the product path for ntaps <= 32, window <= 32 bins): carrier mix,
+//                     FIR on I and Q with the state carried from the previous frame, /2, R = I + jQ, de-chirp both ways,
+//                     Hann, 1024-point complex FFT, windowed arg-max around DC, decision
+//   k_iq_frontend[_rb], k_iq_backend, k_iq_pick
+//                     the same chain in pieces (front end -> R in HBM -> fused back end, or -> batched operators):
+//                     fallback for longer filters / wider windows and the form USC_IQ_UNFUSED=1 selects for A/B runs
 #include "usc_kernels.cuh"
 #include "usc_launch.h"
+#include "usc_warpfft.cuh"
 
 namespace usc {
 
@@ -170,16 +172,11 @@ cudaError_t launch_iq_pick(const float* mr, const uint32_t* ir, const float* ml,
     return cudaGetLastError();
 }
 
-}  // namespace usc
-
 // ---- fused back end of the I/Q path ------------------------------------------------------------------
 // One warp per frame; the halves of the packed core carry the two hypotheses: .x = R x conj(chirp)
 // (up), .y = R x chirp (down).  Hann, the 1024-point complex FFT ([32,32] plan), magnitudes and the two
 // windowed arg-max searches around DC follow.  With window_bins <= 32 only outputs k = d0 (element 0)
 // and k = 992 + d0 (element 31) of the last pass are needed, so 30 of its 32 outputs are pruned.
-#include "usc_warpfft.cuh"
-
-namespace usc {
 
 constexpr int kIqWarps = 8;
 constexpr int kIqSmem = 8192 + 8192 + 4096 + kIqWarps * 8192;     // twiddles | chirp | Hann | per-warp tile
@@ -261,15 +258,12 @@ cudaError_t launch_iq_backend(const float* R, size_t nframes, const float* chirp
     return cudaGetLastError();
 }
 
-}  // namespace usc
-
 // ---- whole I/Q path in one kernel ---------------------------------------------------------------------
 // One warp per frame, persistent CTAs of 8 warps.  Stage: PCM (+ ntaps-1 samples of history) is cast,
 // mixed with the carrier and parked as (I, Q) pairs.  FIR: each lane owns four consecutive decimated
 // outputs per pass (eight passes); both rails ride one FFMA2 with the tap broadcast, taps ascending as in
 // arm_fir_f32.  The baseband frame R goes through the warp's region once (blocked -> strided), then the
 // back end above runs unchanged.  R never touches HBM.
-namespace usc {
 
 constexpr int kIqfWarps = 8;
 #ifndef USC_IQF_ROWS
