@@ -26,7 +26,7 @@ b = torch.empty(S * F, dtype=torch.uint8, device=dev)
 ms = timeit(lambda: h.iq_demod(pcm, usc.PCM_I32, S, F, F * N, o[0], o[2], o[1], o[3], b))
 print("K5 I/Q: %d frames %.2f ms  %.1f Mframes/s  %.0f GB/s (%.1f%% of 6552)" % (S * F, ms, S * F / ms / 1e3, S * F * 8216 / ms / 1e6, S * F * 8216 / ms / 1e6 / 65.52))
 h.close()
-for n in (4096, 8192, 16384, 65536):
+for n in (4096, 8192, 16384, 32768, 65536):
     hh = usc.Handle(usc.default_config(n=n)); hh.set_stream(st.cuda_stream)
     nf = (1 << 28) // n                       # 1 GiB of PCM
     x = torch.empty((nf, n), dtype=torch.int32, device=dev)

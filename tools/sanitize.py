@@ -27,7 +27,7 @@ hs = usc.Handle(usc.default_config(chirp_variant=usc.CHIRP_S))
 hs.dsp(f, 3 * N, pos, mean, usc.DOWN, hh, 1); hs.sync()            # K3
 x = h.buffer(np.random.default_rng(0).standard_normal((2, 65536)).astype(np.float32)); y = h.empty(2 * 65536 * 4)
 h.arm_rfft_fast_f32(65536, x, y, 0, 2); h.arm_rfft_fast_f32(4096, x, y, 0, 2); h.arm_rfft_fast_f32(4096, y, y, 1, 2); h.sync()
-for n, nf in ((4096, 5), (8192, 3), (16384, 2), (65536, 40)):                # K6: fused long frames, cluster kernel at 65536
+for n, nf in ((4096, 5), (8192, 3), (16384, 2), (32768, 70), (65536, 40)):                # K6: fused long frames, cluster kernel at 65536
     hl = usc.Handle(usc.default_config(n=n))
     pl, _ = synth.make_frames(nf, n=n, seed_noise=n)
     hl.demod_frames_host(pl); hl.close()

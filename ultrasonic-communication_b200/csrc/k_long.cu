@@ -169,30 +169,25 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
     return cudaGetLastError();
 }
 
-// ---- N = 65536: a cluster of CTAs owns a frame ---------------------------------------------------
-// Plan [32, 32, 32] over the 32768-point complex sequence.  Sub-sequences no longer fit one SM
-// (32 x 16 KB), so the cluster's distributed shared memory holds them: four CTAs of eight warps, eight
-// sub-sequences each (USC_L32_CLUSTER=8 builds the 8 x 4 split with two CTAs per SM; measured 8 % slower).
-// With T threads per CTA:
-//   level 0   CTA r, thread t takes a = T r + t: gathers z[a + 1024 b], b < 32, from global memory,
-//             de-chirp x Hann for both hypotheses, radix-32 butterfly, x W^(a d) (frame-invariant, kept
+// ---- N = 32768 / 65536: a thread-block cluster owns a frame -------------------------------------------
+// Plan [R0, 32, 32] with R0 = 16 or 32.  The R0 sub-sequences (16 KB each) no longer fit one SM, so the cluster's
+// distributed shared memory holds them: CL CTAs of eight warps, eight sub-sequences each (CL = R0 / 8).
+//   level 0   CTA r, thread t takes a = (1024 / CL) r + 256 i + t: gathers z[a + 1024 b], b < R0, from global
+//             memory, de-chirp x Hann for both hypotheses, radix-R0 butterfly, x W^(a d) (frame-invariant, kept
 //             in shared memory), and stores element d into the owner CTA's copy of sub-sequence d —
 //             16-byte remote stores over DSMEM
 //   core      after a cluster barrier, each warp runs the packed 32x32 core on one local sub-sequence
-//   split     after a second barrier each CTA takes the bins k = 32 c + d of its own d; the partner
-//             Z[nc - k] sits in sub-sequence (32 - d) mod 32, usually another CTA's: remote loads
+//   split     after a second barrier each CTA takes the bins k = R0 c + d of its own d; the partner
+//             Z[nc - k] sits in sub-sequence (R0 - d) mod R0, usually another CTA's: remote loads
 //   result    the partial arg-max results meet in CTA 0 (remote stores), third barrier, one thread
 //             writes the frame's outputs
-#ifndef USC_L32_CLUSTER
-#define USC_L32_CLUSTER 4
-#endif
-constexpr int kL32Cluster = USC_L32_CLUSTER, kL32Warps = 32 / kL32Cluster, kL32Threads = 32 * kL32Warps;
-constexpr int kL32PerSm = kL32Cluster == 8 ? 2 : 1;     // two co-resident CTAs of different clusters overlap their phases
-constexpr int kL32Shift = kL32Cluster == 8 ? 2 : 3;     // sub-sequence d lives in CTA d >> shift, slot d & (warps - 1)
-struct l32_smem {
-    // pass twiddles | 8 sub-sequences | result slots | this CTA's level-0 twiddles W^(a d), [d][thread] (frame-invariant)
-    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + kL32Warps * region, l0 = red + 256,
-                         total = l0 + 32 * kL32Threads * 8;
+// (An 8 x 4-warp split of the 65536-point case with two CTAs per SM was measured 8 % slower than 4 x 8.)
+constexpr int kClWarps = 8, kClThreads = 256;
+template <int R0> struct cl_smem {
+    static constexpr int CL = R0 / kClWarps, NR = 1024 / CL / kClThreads;          // cluster size, level-0 rounds per thread
+    // pass twiddles | 8 sub-sequences | result slots | this CTA's level-0 twiddles W^(a d), [d][round][thread]
+    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + kClWarps * region, l0 = red + 256,
+                         total = l0 + R0 * NR * kClThreads * 8;
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -218,46 +213,51 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <typename PCM>
-__global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_params p, const float2* __restrict__ tw_l0) {
-    using L = l32_smem;
+template <typename PCM, int R0>
+__global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
+    using L = cl_smem<R0>;
+    constexpr int CL = L::CL, NR = L::NR;
+    constexpr uint32_t nc = 1024u * R0, n = 2048u * R0;
     using V2 = typename vec2<PCM>::type;
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_rank();
-    constexpr uint32_t nc = 32768u; (void) nc;
-    for (int i = tid; i < 1024; i += kL32Threads) s_tw[i] = p.tw_pass[i];
+    for (int i = tid; i < 1024; i += kClThreads) s_tw[i] = p.tw_pass[i];
     float2* s_l0 = reinterpret_cast<float2*>(s_raw + L::l0);
-    for (int d = 1; d < 32; ++d) s_l0[d * kL32Threads + tid] = tw_l0[d * 1024 + rank * kL32Threads + tid];
+    for (int d = 1; d < R0; ++d)
+        for (int i = 0; i < NR; ++i)
+            s_l0[(d * NR + i) * kClThreads + tid] = tw_l0[d * 1024 + rank * (1024 / CL) + i * kClThreads + tid];
     __syncthreads();
     const uint32_t bw2 = p.bandwidth2;
     float2 w_split[kLongNB];                             // split twiddles of this thread's bins, frame-invariant too
 #pragma unroll
     for (int j = 0; j < kLongNB; ++j) {
-        const uint32_t k = 32u * ((tid >> kL32Shift) + 32u * j) + rank * kL32Warps + (tid & (kL32Warps - 1u));
+        const uint32_t k = (uint32_t) R0 * ((tid >> 3) + 32u * j) + rank * kClWarps + (tid & 7u);
         w_split[j] = p.tw_master[k];
     }
     // peer addresses of the sub-sequence area and of CTA 0's result slots
-    uint32_t peer_sub[kL32Cluster];
+    uint32_t peer_sub[CL];
 #pragma unroll
-    for (int r = 0; r < kL32Cluster; ++r) peer_sub[r] = map_to_rank(s_raw + L::sub, r);
+    for (int r = 0; r < CL; ++r) peer_sub[r] = map_to_rank(s_raw + L::sub, r);
     const uint32_t red0 = map_to_rank(s_raw + L::red, 0);
     cluster_sync_all();                                  // every CTA of the cluster is resident before remote traffic
 
     for (size_t f = cluster_id_x(); f < p.nframes; f += cluster_count_x()) {
-        const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * 65536u);
-        if (f + cluster_count_x() < p.nframes) {         // next frame of this cluster towards L2 (each CTA a quarter)
-            const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + cluster_count_x()) * 65536u);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kL32Threads + tid) * 256));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kL32Threads + tid) * 256 + 128));
+        const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * n);
+        if (f + cluster_count_x() < p.nframes) {         // next frame of this cluster towards L2 (each CTA its share)
+            const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + cluster_count_x()) * n);
+            constexpr uint32_t per_thread = n * 4u / (CL * kClThreads);                      // 256 bytes
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kClThreads + tid) * per_thread));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kClThreads + tid) * per_thread + 128));
         }
         // ---- level 0 ----
-        {
-            const uint32_t a = rank * kL32Threads + tid;
-            float2 re[32], im[32];
+#pragma unroll 1
+        for (int i = 0; i < NR; ++i) {
+            const uint32_t a = rank * (1024u / CL) + i * kClThreads + tid;
+            float2 re[R0], im[R0];
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
+            for (int b = 0; b < R0; ++b) {
                 const uint32_t m = a + 1024u * b;
                 const V2 raw = src[m];
                 const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
@@ -267,15 +267,15 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
                 re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));      // scalar: see usc_arith.cuh
                 im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
             }
-            fft_base2<32>(re, im);
+            fft_base2<R0>(re, im);
 #pragma unroll
-            for (int d = 0; d < 32; ++d) {
+            for (int d = 0; d < R0; ++d) {
                 float2 xr = re[d], xi = im[d];
                 if (d != 0) {
-                    const float2 w = s_l0[d * kL32Threads + tid];                    // W_32768^(a d)
+                    const float2 w = s_l0[(d * NR + i) * kClThreads + tid];            // W_nc^(a d)
                     cmul2(re[d], im[d], w.x, w.y, xr, xi);
                 }
-                const uint32_t base = peer_sub[d >> kL32Shift] + (uint32_t) (d & (kL32Warps - 1)) * L::region;
+                const uint32_t base = peer_sub[d >> 3] + (uint32_t) (d & 7) * L::region;
                 st_cluster_f4(base + a * 16u, make_float4(xr.x, xr.y, xi.x, xi.y));       // one 16-byte remote store per element
             }
         }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
         // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread
 #pragma unroll
         for (int j = 0; j < kLongNB; ++j) {
-            const uint32_t c = (tid >> kL32Shift) + 32u * j, dl = tid & (kL32Warps - 1u), d = rank * kL32Warps + dl, k = 32u * c + d;
+            const uint32_t c = (tid >> 3) + 32u * j, dl = tid & 7u, d = rank * kClWarps + dl, k = (uint32_t) R0 * c + d;
             if (k >= bw2) continue;
             const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + 8192)[c];
             float2 xr, xi;
@@ -315,9 +315,9 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
                 xr = __fadd2_rn(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w));
                 xi = __fadd2_rn(make_float2(zk.x, zk.y), neg2(make_float2(zk.z, zk.w)));
             } else {
-                // nc - k = 32 (1024 - c) for d = 0 (c >= 1), else 32 (1023 - c) + (32 - d)
-                const uint32_t d2 = (32u - d) & 31u, c2 = d == 0 ? 1024u - c : 1023u - c;
-                const uint32_t addr = peer_sub[d2 >> kL32Shift] + (d2 & (kL32Warps - 1u)) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+                // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d)
+                const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? 1024u - c : 1023u - c;
+                const uint32_t addr = peer_sub[d2 >> 3] + (d2 & 7u) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
                 const float4 zc = ld_cluster_f4(addr);
                 const float2 w = w_split[j];
                 rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
         }
         __syncthreads();
         if (tid == 0) {
-            for (int w2 = 1; w2 < kL32Warps; ++w2) {
+            for (int w2 = 1; w2 < kClWarps; ++w2) {
                 argmax_combine(bu, iu, red[32 + w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 1]);
                 argmax_combine(bd, id, red[32 + w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 3]);
             }
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
             const float4* r4 = reinterpret_cast<const float4*>(s_raw + L::red);
             float4 v = r4[0];
             bu = v.x; iu = __float_as_uint(v.y); bd = v.z; id = __float_as_uint(v.w);
-            for (int r = 1; r < kL32Cluster; ++r) {
+            for (int r = 1; r < CL; ++r) {
                 v = r4[r];
                 argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
                 argmax_combine(bd, id, v.z, __float_as_uint(v.w));
@@ -363,45 +363,48 @@ __global__ void __launch_bounds__(kL32Threads, kL32PerSm) k_demod_long32(long_pa
     cluster_sync_all();                                  // no CTA leaves while a peer may still address its memory
 }
 
-template <typename PCM>
-static cudaError_t launch_long32_t(const long_params& p, const float2* tw_l0, int num_sms, cudaStream_t st) {
+template <typename PCM, int R0>
+static cudaError_t launch_cluster_t(const long_params& p, const float2* tw_l0, int num_sms, cudaStream_t st) {
     // The loop inside the kernel strides by the number of clusters launched, so launch exactly as many as
     // can be resident at once (fewer than SMs / cluster size: clusters do not straddle GPCs) — a cluster
     // left for a second wave would run its whole share after everyone else has finished.
+    using L = cl_smem<R0>;
     static per_device<int> max_clusters_pd;
     int& max_clusters = max_clusters_pd.get();
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = kL32Cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = L::CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kL32Threads);
-    cfg.dynamicSmemBytes = l32_smem::total;
+    cfg.blockDim = dim3(kClThreads);
+    cfg.dynamicSmemBytes = L::total;
     cfg.stream = st;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(k_demod_long32<PCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, l32_smem::total);
+        cudaError_t e = cudaFuncSetAttribute(k_demod_cluster<PCM, R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
         if (e != cudaSuccess) return e;
-        cfg.gridDim = dim3((unsigned) (num_sms * kL32PerSm / kL32Cluster * kL32Cluster));
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, k_demod_long32<PCM>, &cfg);
+        cfg.gridDim = dim3((unsigned) (num_sms / L::CL * L::CL));
+        int nmax = 0;
+        e = cudaOccupancyMaxActiveClusters(&nmax, k_demod_cluster<PCM, R0>, &cfg);
         if (e != cudaSuccess) return e;
-        if (n < 1) return cudaErrorLaunchOutOfResources;
-        max_clusters = n;
+        if (nmax < 1) return cudaErrorLaunchOutOfResources;
+        max_clusters = nmax;
     }
     size_t clusters = (size_t) max_clusters;
     if (clusters > p.nframes) clusters = p.nframes;
-    cfg.gridDim = dim3((unsigned) (clusters * kL32Cluster));
-    return cudaLaunchKernelEx(&cfg, k_demod_long32<PCM>, p, tw_l0);
+    cfg.gridDim = dim3((unsigned) (clusters * L::CL));
+    return cudaLaunchKernelEx(&cfg, k_demod_cluster<PCM, R0>, p, tw_l0);
 }
 
-cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* chirp_ud, const float2* hann,
-                                const float2* tw_master, const float2* tw_pass, const float2* tw_l0, uint32_t bandwidth2,
-                                float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit,
-                                int num_sms, cudaStream_t st) {
-    long_params p{pcm, nframes, 65536u, reinterpret_cast<const float4*>(chirp_ud), hann, tw_master, tw_pass, bandwidth2,
+cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, uint32_t n, const float2* chirp_ud,
+                                const float2* hann, const float2* tw_master, const float2* tw_pass, const float2* tw_l0,
+                                uint32_t bandwidth2, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                                uint8_t* bit, int num_sms, cudaStream_t st) {
+    long_params p{pcm, nframes, n, reinterpret_cast<const float4*>(chirp_ud), hann, tw_master, tw_pass, bandwidth2,
                   mag_up, idx_up, mag_down, idx_down, bit};
-    return pcm_format == 1u ? launch_long32_t<int32_t>(p, tw_l0, num_sms, st) : launch_long32_t<float>(p, tw_l0, num_sms, st);
+    if (n == 65536u) return pcm_format == 1u ? launch_cluster_t<int32_t, 32>(p, tw_l0, num_sms, st) : launch_cluster_t<float, 32>(p, tw_l0, num_sms, st);
+    if (n == 32768u) return pcm_format == 1u ? launch_cluster_t<int32_t, 16>(p, tw_l0, num_sms, st) : launch_cluster_t<float, 16>(p, tw_l0, num_sms, st);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_demod_long(const void* pcm, uint32_t pcm_format, size_t nframes, uint32_t n, const float2* chirp_ud,

@@ -30,7 +30,7 @@ struct usc_handle {
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
     float2 *d_op_pass = nullptr, *d_op_split = nullptr;    // tables of the warp-level FFT operators when cfg.n != 2048
     float* d_rs_taps = nullptr; uint32_t rs_up = 0;       // resampler polyphase table (usc_resample_i16_to_pcm)
-    float2 *d_tw_pass, *d_tw_split, *d_tw_l0;      // d_tw_l0: W_32768^(a d), [d][a], 65536-point frames only
+    float2 *d_tw_pass, *d_tw_split, *d_tw_l0;      // d_tw_l0: W_{n/2}^(a d), [d][a], 32768- and 65536-point frames only
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
     // I/Q path (usc_iq_init): carrier tables, baseband chirp and its conjugate, half-length Hann, FIR taps
     std::vector<float> iq_cos, iq_sin, iq_chirp, iq_hann;
@@ -207,10 +207,11 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
                 pass[2 * (d * 32 + a) + 1] = tw[2 * j + 1];
             }
         if ((rc = upload(pass.data(), pass.size() * 4, (void**) &h->d_tw_pass))) { usc_destroy(h); return rc; }
-        if (n == 65536) {
-            // level-0 twiddles of the [32, 32, 32] plan: W_32768^(a d) = W_n^(2 a d), laid out [d][a] for coalescing
-            std::vector<float> l0(2 * 32 * 1024);
-            for (uint32_t d = 0; d < 32; ++d)
+        if (n == 65536 || n == 32768) {
+            // level-0 twiddles of the [R0, 32, 32] plan (R0 = n / 2048): W_{n/2}^(a d) = W_n^(2 a d), laid out [d][a] for coalescing
+            const uint32_t r0 = n / 2048;
+            std::vector<float> l0(2 * (size_t) r0 * 1024);
+            for (uint32_t d = 0; d < r0; ++d)
                 for (uint32_t a = 0; a < 1024; ++a) {
                     const uint32_t j = 2 * a * d;
                     l0[2 * (d * 1024 + a)] = tw[2 * j];
@@ -597,12 +598,13 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
                                       h->num_sms, h->stream));
         return USC_OK;
     }
-    if (h->cfg.n == 65536 && h->d_tw_l0 && h->bandwidth2 > 0 && h->bandwidth2 <= 5120u && !getenv("USC_LONG_UNFUSED")) {
-        /* 65536-point frames: a four-CTA cluster per frame, sub-sequences in distributed shared memory (k_long.cu) */
+    if ((h->cfg.n == 65536 || h->cfg.n == 32768) && h->d_tw_l0 && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u) &&
+        !getenv("USC_LONG_UNFUSED")) {
+        /* 32768 / 65536-point frames: a cluster of two / four CTAs per frame, sub-sequences in distributed shared memory (k_long.cu) */
         float2* master = nullptr;
         int rc = get_twiddles(h, h->cfg.n, &master);
         if (rc) return rc;
-        LAUNCHED(h, launch_demod_long32(pcm, pcm_format, nframes, (const float2*) h->d_ud, (const float2*) h->d_hann, master,
+        LAUNCHED(h, launch_demod_long32(pcm, pcm_format, nframes, h->cfg.n, (const float2*) h->d_ud, (const float2*) h->d_hann, master,
                                         h->d_tw_pass, h->d_tw_l0, h->bandwidth2, mag_up, idx_up, mag_down, idx_down, bit,
                                         h->num_sms, h->stream));
         return USC_OK;

@@ -50,10 +50,10 @@ cudaError_t fft_generic_prepare();   // opt in to large dynamic shared memory (o
 cudaError_t launch_demod2048(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
 cudaError_t launch_demod2048_single(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st);
 cudaError_t launch_dsp2048(const demod_params& p, int num_sms, cudaStream_t st);
-cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* chirp_ud, const float2* hann,
-                                const float2* tw_master, const float2* tw_pass, const float2* tw_l0, uint32_t bandwidth2,
-                                float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit,
-                                int num_sms, cudaStream_t st);
+cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, uint32_t n, const float2* chirp_ud,
+                                const float2* hann, const float2* tw_master, const float2* tw_pass, const float2* tw_l0,
+                                uint32_t bandwidth2, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                                uint8_t* bit, int num_sms, cudaStream_t st);
 cudaError_t launch_demod_long(const void* pcm, uint32_t pcm_format, size_t nframes, uint32_t n, const float2* chirp_ud,
                               const float2* hann, const float2* tw_master, const float2* tw_pass, uint32_t bandwidth2,
                               float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit,
