@@ -217,7 +217,7 @@ template <typename PCM, int R0>
 __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
     using L = cl_smem<R0>;
     constexpr int CL = L::CL, NR = L::NR;
-    constexpr uint32_t nc = 1024u * R0, n = 2048u * R0;
+    constexpr uint32_t n = 2048u * R0;                  // real samples per frame; the complex length is nc = n / 2
     using V2 = typename vec2<PCM>::type;
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
