@@ -181,13 +181,13 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
 //             Z[nc - k] sits in sub-sequence (R0 - d) mod R0, usually another CTA's: remote loads
 //   result    the partial arg-max results meet in CTA 0 (remote stores), third barrier, one thread
 //             writes the frame's outputs
-// (An 8 x 4-warp split of the 65536-point case with two CTAs per SM was measured 8 % slower than 4 x 8.)
-constexpr int kClWarps = 8, kClThreads = 256;
-template <int R0> struct cl_smem {
-    static constexpr int CL = R0 / kClWarps, NR = 1024 / CL / kClThreads;          // cluster size, level-0 rounds per thread
+// W = warps (sub-sequences) per CTA is a template parameter: the 4-warp forms with two CTAs per SM were measured
+// slower (65536 points as 8 x 4: 8 %; 16384 points as a 2 x 4 cluster against the plain 8-warp CTA above: 9 %).
+template <int R0, int W> struct cl_smem {                                         // W warps (= sub-sequences) per CTA
+    static constexpr int T = 32 * W, CL = R0 / W, NR = 1024 / CL / T, SH = W == 8 ? 3 : 2;   // threads, cluster size, level-0 rounds per thread
     // pass twiddles | 8 sub-sequences | result slots | this CTA's level-0 twiddles W^(a d), [d][round][thread]
-    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + kClWarps * region, l0 = red + 256,
-                         total = l0 + R0 * NR * kClThreads * 8;
+    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + W * region, l0 = red + 256,
+                         total = l0 + R0 * NR * T * 8;
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -213,27 +213,27 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <typename PCM, int R0>
-__global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
-    using L = cl_smem<R0>;
-    constexpr int CL = L::CL, NR = L::NR;
+template <typename PCM, int R0, int W>
+__global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
+    using L = cl_smem<R0, W>;
+    constexpr int CL = L::CL, NR = L::NR, T = L::T, SH = L::SH;
     constexpr uint32_t n = 2048u * R0;                  // real samples per frame; the complex length is nc = n / 2
     using V2 = typename vec2<PCM>::type;
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_rank();
-    for (int i = tid; i < 1024; i += kClThreads) s_tw[i] = p.tw_pass[i];
+    for (int i = tid; i < 1024; i += T) s_tw[i] = p.tw_pass[i];
     float2* s_l0 = reinterpret_cast<float2*>(s_raw + L::l0);
     for (int d = 1; d < R0; ++d)
         for (int i = 0; i < NR; ++i)
-            s_l0[(d * NR + i) * kClThreads + tid] = tw_l0[d * 1024 + rank * (1024 / CL) + i * kClThreads + tid];
+            s_l0[(d * NR + i) * T + tid] = tw_l0[d * 1024 + rank * (1024 / CL) + i * T + tid];
     __syncthreads();
     const uint32_t bw2 = p.bandwidth2;
     float2 w_split[kLongNB];                             // split twiddles of this thread's bins, frame-invariant too
 #pragma unroll
     for (int j = 0; j < kLongNB; ++j) {
-        const uint32_t k = (uint32_t) R0 * ((tid >> 3) + 32u * j) + rank * kClWarps + (tid & 7u);
+        const uint32_t k = (uint32_t) R0 * ((tid >> SH) + 32u * j) + rank * W + (tid & (W - 1u));
         w_split[j] = p.tw_master[k];
     }
     // peer addresses of the sub-sequence area and of CTA 0's result slots
@@ -247,14 +247,14 @@ __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, 
         const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * n);
         if (f + cluster_count_x() < p.nframes) {         // next frame of this cluster towards L2 (each CTA its share)
             const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + cluster_count_x()) * n);
-            constexpr uint32_t per_thread = n * 4u / (CL * kClThreads);                      // 256 bytes
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kClThreads + tid) * per_thread));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * kClThreads + tid) * per_thread + 128));
+            constexpr uint32_t per_thread = n * 4u / (CL * T);                               // 256 bytes
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * T + tid) * per_thread));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * T + tid) * per_thread + 128));
         }
         // ---- level 0 ----
 #pragma unroll 1
         for (int i = 0; i < NR; ++i) {
-            const uint32_t a = rank * (1024u / CL) + i * kClThreads + tid;
+            const uint32_t a = rank * (1024u / CL) + i * T + tid;
             float2 re[R0], im[R0];
 #pragma unroll
             for (int b = 0; b < R0; ++b) {
@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, 
             for (int d = 0; d < R0; ++d) {
                 float2 xr = re[d], xi = im[d];
                 if (d != 0) {
-                    const float2 w = s_l0[(d * NR + i) * kClThreads + tid];            // W_nc^(a d)
+                    const float2 w = s_l0[(d * NR + i) * T + tid];                     // W_nc^(a d)
                     cmul2(re[d], im[d], w.x, w.y, xr, xi);
                 }
-                const uint32_t base = peer_sub[d >> 3] + (uint32_t) (d & 7) * L::region;
+                const uint32_t base = peer_sub[d >> SH] + (uint32_t) (d & (W - 1)) * L::region;
                 st_cluster_f4(base + a * 16u, make_float4(xr.x, xr.y, xi.x, xi.y));       // one 16-byte remote store per element
             }
         }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, 
         // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread
 #pragma unroll
         for (int j = 0; j < kLongNB; ++j) {
-            const uint32_t c = (tid >> 3) + 32u * j, dl = tid & 7u, d = rank * kClWarps + dl, k = (uint32_t) R0 * c + d;
+            const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl, k = (uint32_t) R0 * c + d;
             if (k >= bw2) continue;
             const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + 8192)[c];
             float2 xr, xi;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, 
             } else {
                 // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d)
                 const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? 1024u - c : 1023u - c;
-                const uint32_t addr = peer_sub[d2 >> 3] + (d2 & 7u) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+                const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
                 const float4 zc = ld_cluster_f4(addr);
                 const float2 w = w_split[j];
                 rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, 
         }
         __syncthreads();
         if (tid == 0) {
-            for (int w2 = 1; w2 < kClWarps; ++w2) {
+            for (int w2 = 1; w2 < W; ++w2) {
                 argmax_combine(bu, iu, red[32 + w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 1]);
                 argmax_combine(bd, id, red[32 + w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 3]);
             }
@@ -363,29 +363,29 @@ __global__ void __launch_bounds__(kClThreads, 1) k_demod_cluster(long_params p, 
     cluster_sync_all();                                  // no CTA leaves while a peer may still address its memory
 }
 
-template <typename PCM, int R0>
+template <typename PCM, int R0, int W>
 static cudaError_t launch_cluster_t(const long_params& p, const float2* tw_l0, int num_sms, cudaStream_t st) {
     // The loop inside the kernel strides by the number of clusters launched, so launch exactly as many as
     // can be resident at once (fewer than SMs / cluster size: clusters do not straddle GPCs) — a cluster
     // left for a second wave would run its whole share after everyone else has finished.
-    using L = cl_smem<R0>;
+    using L = cl_smem<R0, W>;
     static per_device<int> max_clusters_pd;
     int& max_clusters = max_clusters_pd.get();
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = L::CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kClThreads);
+    cfg.blockDim = dim3(L::T);
     cfg.dynamicSmemBytes = L::total;
     cfg.stream = st;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(k_demod_cluster<PCM, R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+        cudaError_t e = cudaFuncSetAttribute(k_demod_cluster<PCM, R0, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
         if (e != cudaSuccess) return e;
-        cfg.gridDim = dim3((unsigned) (num_sms / L::CL * L::CL));
+        cfg.gridDim = dim3((unsigned) (num_sms * (W == 8 ? 1 : 2) / L::CL * L::CL));
         int nmax = 0;
-        e = cudaOccupancyMaxActiveClusters(&nmax, k_demod_cluster<PCM, R0>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&nmax, k_demod_cluster<PCM, R0, W>, &cfg);
         if (e != cudaSuccess) return e;
         if (nmax < 1) return cudaErrorLaunchOutOfResources;
         max_clusters = nmax;
@@ -393,7 +393,7 @@ static cudaError_t launch_cluster_t(const long_params& p, const float2* tw_l0, i
     size_t clusters = (size_t) max_clusters;
     if (clusters > p.nframes) clusters = p.nframes;
     cfg.gridDim = dim3((unsigned) (clusters * L::CL));
-    return cudaLaunchKernelEx(&cfg, k_demod_cluster<PCM, R0>, p, tw_l0);
+    return cudaLaunchKernelEx(&cfg, k_demod_cluster<PCM, R0, W>, p, tw_l0);
 }
 
 cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nframes, uint32_t n, const float2* chirp_ud,
@@ -402,8 +402,8 @@ cudaError_t launch_demod_long32(const void* pcm, uint32_t pcm_format, size_t nfr
                                 uint8_t* bit, int num_sms, cudaStream_t st) {
     long_params p{pcm, nframes, n, reinterpret_cast<const float4*>(chirp_ud), hann, tw_master, tw_pass, bandwidth2,
                   mag_up, idx_up, mag_down, idx_down, bit};
-    if (n == 65536u) return pcm_format == 1u ? launch_cluster_t<int32_t, 32>(p, tw_l0, num_sms, st) : launch_cluster_t<float, 32>(p, tw_l0, num_sms, st);
-    if (n == 32768u) return pcm_format == 1u ? launch_cluster_t<int32_t, 16>(p, tw_l0, num_sms, st) : launch_cluster_t<float, 16>(p, tw_l0, num_sms, st);
+    if (n == 65536u) return pcm_format == 1u ? launch_cluster_t<int32_t, 32, 8>(p, tw_l0, num_sms, st) : launch_cluster_t<float, 32, 8>(p, tw_l0, num_sms, st);
+    if (n == 32768u) return pcm_format == 1u ? launch_cluster_t<int32_t, 16, 8>(p, tw_l0, num_sms, st) : launch_cluster_t<float, 16, 8>(p, tw_l0, num_sms, st);
     return cudaErrorInvalidValue;
 }
 
