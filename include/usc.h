@@ -123,7 +123,9 @@ int usc_arm_cmplx_mult_cmplx_f32_batch(usc_handle *h, const float *a, size_t str
 int usc_arm_cmplx_mult_real_f32_batch(usc_handle *h, const float *cplx, size_t stride_c, const float *real,
                                       size_t stride_r, float *dst, size_t stride_dst, uint32_t num_samples,
                                       uint32_t batch);
-/* arm_cmplx_mag_f32, arm_math.h:6312-6315 */
+/* arm_cmplx_mag_f32, arm_math.h:6312-6315.  src and dst may be disjoint, or the reference's in-place form
+ * (receiver/Src/main.c:178 `arm_cmplx_mag_f32(signal, signal, NN)`): dst == src with stride_dst == stride_src >=
+ * 2*num_samples (any strides when batch == 1).  Any other overlap returns USC_ERR_ARGUMENT. */
 int usc_arm_cmplx_mag_f32_batch(usc_handle *h, const float *src, size_t stride_src, float *dst,
                                 size_t stride_dst, uint32_t num_samples, uint32_t batch);
 /* arm_max_f32, arm_math.h:6537-6541: first occurrence of the maximum */
@@ -156,14 +158,24 @@ int usc_arm_fir_f32_batch(usc_handle *h, const float *coeffs_host, uint32_t num_
  * dsp(.., DOWN) alone — at half the cost per frame. */
 int usc_demod_frames(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, float *mag_up,
                      uint32_t *idx_up, float *mag_down, uint32_t *idx_down, uint8_t *bit);
-/* The same chain on HOST buffers (the call a firmware-style host makes once per capture): frames are
- * cut into chunks that flow through three stream lanes (H2D copy, K1, D2H of the results) so the
- * copies overlap the kernel.  Blocking: results are in the host arrays on return.  pcm_host should
- * be pinned (usc_malloc_host) for the copies to overlap.  usc_host_workspace() sizes the device
- * staging explicitly (frames per chunk); it is called with 4096 on first use otherwise. */
+/* ---- the same stages on HOST buffers (the call a firmware-style host makes once per capture) -------
+ * The input is cut into chunks that flow through three stream lanes (H2D copy, kernel, D2H of the results), so
+ * the copies overlap the kernels.  Blocking: results are in the host arrays on return.  pcm_host should be
+ * pinned (usc_malloc_host) for the copies to overlap.  usc_host_workspace() sets the chunk size in units of
+ * 8 KB of PCM (one 2048-sample frame) and allocates the device staging; 4096 is used otherwise.  The
+ * staging grows on demand, never on a steady-state call.
+ *   usc_demod_frames_host   K1 / K6: every frame length with a fused kernel (2048 ... 65536); chunks of frames
+ *   usc_iq_demod_host       K5 (fused kernel configurations): chunks of whole streams (the FIR state runs along
+ *                           a stream); stream s starts at pcm_host + s*stream_stride samples
+ *   usc_receiver_run_host   K7: a chunk is a slice of time of ALL streams (one warp serves a stream), resumed
+ *                           through the carried per-stream state of usc_receiver_run_chunk; the two frames of
+ *                           FIFO history are re-sent with each chunk.  uart / results are host arrays. */
 int usc_host_workspace(usc_handle *h, size_t chunk_frames);
 int usc_demod_frames_host(usc_handle *h, const void *pcm_host, uint32_t pcm_format, size_t nframes,
                           float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down, uint8_t *bit);
+int usc_iq_demod_host(usc_handle *h, const void *pcm_host, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                      size_t stream_stride, float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
+                      uint8_t *bit);
 /* pipeline() of receiver/Src/main.c:163-180 on `batch` frames, one hypothesis: frames (n floats
  * each, stride n) -> n floats each: magnitudes of the n/2 packed bins, zeros above (hazard H1). */
 int usc_pipeline(usc_handle *h, const float *frames, float *mags, int updown, uint32_t batch);
@@ -207,6 +219,8 @@ typedef struct usc_rx_state { uint32_t opaque[40]; } usc_rx_state;
 int usc_receiver_run_chunk(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
                            size_t stream_stride, uint32_t carry_frames, usc_rx_state *state, uint8_t *uart,
                            uint32_t uart_cap, usc_rx_result *results);
+int usc_receiver_run_host(usc_handle *h, const void *pcm_host, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                          size_t stream_stride, uint8_t *uart, uint32_t uart_cap, usc_rx_result *results);
 /* K4.  The sliding-correlation search grid alone (main.c:447-451) for every frame of every stream:
  * 4 x dsp(UP) at N/2 + (t&1)*N/8 + i*N/4 on the FIFO of frame t, after synchronous addition of
  * `sync_add` (>= 1) frame-aligned FIFOs (misc/Formula.ipynb cell 9).  mag/idx: nstreams*nframes*4. */

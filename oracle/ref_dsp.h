@@ -155,6 +155,11 @@ void ref_demod_frames_i32(const ref_receiver *rx, const int32_t *pcm, size_t nfr
 void ref_demod_frames_f32(const ref_receiver *rx, const float *pcm, size_t nframes,
                           float *mag_up, uint32_t *idx_up, float *mag_down, uint32_t *idx_down,
                           int nthreads);
+/* Tuned form of the two functions above (ref_fast.c: SIMD across frames, iterative plan, per-thread scratch;
+ * bit-identical results).  n must be 2048.  Returns 0, or -1 for an unsupported receiver.  The CPU arm of bench.py. */
+int ref_fast_demod_frames(const ref_receiver *rx, const void *pcm, int is_float, size_t nframes, float *mag_up,
+                          uint32_t *idx_up, float *mag_down, uint32_t *idx_down, int nthreads);
+int ref_fast_simd_width(void);          /* 16 (AVX-512), 8 (AVX2 + FMA) or 0 (plain form) */
 
 /* ---- complex-FFT variant (experiments/synchronization/Src/main.c:135-213, chirp.c:16-57) ---- */
 typedef struct {

@@ -488,3 +488,38 @@ def test_streaming_operators_row_form_bit_exact(h):
     h.arm_cmplx_mult_cmplx_f32(d3, L, db, L, d3, L, L // 2, B)                  # in place
     want = np.stack([R.arm_cmplx_mult_cmplx_f32(a[i], b[i]) for i in range(B)])
     assert np.array_equal(d3.to_numpy(np.float32).reshape(B, L).view(np.uint32), want.view(np.uint32))
+
+
+def test_cmplx_mag_in_place_is_the_reference_call_form(h):
+    """receiver/Src/main.c:178 calls arm_cmplx_mag_f32(signal, signal, NN): dst == src.  Magnitude e lands on an
+    input of magnitude e/2, so the batched operator must order reads before writes (cross-thread race)."""
+    rng = np.random.default_rng(31)
+    for B, L in ((1, 2048), (37, 2048), (5, 300), (3, 65536)):
+        a = rng.standard_normal((B, L)).astype(np.float32)
+        want = np.stack([R.arm_cmplx_mag_f32(a[i]) for i in range(B)])
+        d = h.buffer(a)
+        h.arm_cmplx_mag_f32(d, L, d, L, L // 2, B)
+        got = d.to_numpy(np.float32).reshape(B, L)
+        assert np.array_equal(got[:, :L // 2].view(np.uint32), want.view(np.uint32)), (B, L)
+        assert np.array_equal(got[:, L // 2:], a[:, L // 2:])          # the upper half of each row is not touched
+    # an overlap that is not the in-place form has no defined result: refused
+    a = rng.standard_normal((4, 512)).astype(np.float32)
+    d = h.buffer(a)
+    with pytest.raises(usc.UscError) as ei:
+        h.arm_cmplx_mag_f32(d, 512, d, 256, 256, 4)
+    assert ei.value.code == usc.USC_ERR_ARGUMENT
+
+
+def test_pipeline_on_the_longest_frame():
+    """usc_pipeline on a 65536-point handle (the tail kernel asked for n*4 bytes of shared memory)."""
+    n = 65536
+    hh = usc.Handle(usc.default_config(n=n))
+    rx = R.RefReceiver(n=n)
+    rng = np.random.default_rng(32)
+    x = (rng.standard_normal((2, n)) * 1e4).astype(np.float32)
+    d, o = hh.buffer(x), hh.empty(x.nbytes)
+    hh.pipeline(d, o, usc.UP, 2)
+    got = o.to_numpy(np.float32).reshape(2, n)
+    want = np.stack([rx.pipeline(x[i], up=True) for i in range(2)])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    hh.close()

@@ -223,32 +223,28 @@ cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nfr
     return cudaGetLastError();
 }
 
-// tail of pipeline(): packed spectrum (n floats) -> n/2 magnitudes + n/2 zeros, in place, one CTA
-// per vector staged through shared memory (receiver/Src/main.c:178 with hazard H1 defined).
+// tail of pipeline(): packed spectrum (n floats) -> n/2 magnitudes + n/2 zeros, in place, one CTA per vector
+// (receiver/Src/main.c:178 with hazard H1 defined).  Ascending chunks, read -> barrier -> write: magnitude i lands
+// on a float whose own consumer (magnitude i/2) has already been computed, so no staging buffer that grows with n.
 __global__ void k_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zero_upper) {
-    extern __shared__ float s_vec[];
     for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
         float* p = data + (size_t) v * n;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_vec[i] = p[i];
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            if (i < n / 2) p[i] = cmag(s_vec[2 * i], s_vec[2 * i + 1]);
-            else if (zero_upper) p[i] = 0.0f;          // otherwise the packed-spectrum floats stay (in-place semantics)
+        for (uint32_t base = 0; base < n / 2; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            float m = 0.0f;
+            if (i < n / 2) m = cmag(p[2 * i], p[2 * i + 1]);
+            __syncthreads();
+            if (i < n / 2) p[i] = m;
+            __syncthreads();
         }
-        __syncthreads();
+        if (zero_upper)                                     // otherwise the packed-spectrum floats stay (in-place semantics)
+            for (uint32_t i = n / 2 + threadIdx.x; i < n; i += blockDim.x) p[i] = 0.0f;
     }
 }
 
 cudaError_t launch_pipeline_tail(float* data, uint32_t n, uint32_t batch, int zero_upper, cudaStream_t st) {
     int grid = batch < 148u * 16u ? (int) batch : 148 * 16;
-    static per_device<bool> configured_pd;
-    bool& configured = configured_pd.get();
-    if (!configured && n * sizeof(float) > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_pipeline_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    k_pipeline_tail<<<grid, 256, n * sizeof(float), st>>>(data, n, batch, zero_upper);
+    k_pipeline_tail<<<grid, 256, 0, st>>>(data, n, batch, zero_upper);
     return cudaGetLastError();
 }
 

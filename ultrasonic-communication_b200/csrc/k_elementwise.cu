@@ -129,6 +129,24 @@ __global__ void k_cmag(const float* src, size_t ss, float* dst, size_t sd, uint3
     }
 }
 
+// In-place form (dst == src, the way the reference always calls it: receiver/Src/main.c:178
+// `arm_cmplx_mag_f32(signal, signal, NN)`): magnitude e overwrites a float that is the input of magnitude e/2.
+// One CTA owns a row and walks it in ascending chunks of blockDim.x magnitudes; every chunk is read into registers,
+// then a barrier, then written — a chunk's outputs land only on inputs of chunks already consumed (or its own).
+__global__ void k_cmag_inplace(float* data, size_t stride, uint32_t ncplx, uint32_t batch) {
+    for (uint32_t v = blockIdx.x; v < batch; v += gridDim.x) {
+        float* p = data + (size_t) v * stride;
+        for (uint32_t base = 0; base < ncplx; base += blockDim.x) {
+            const uint32_t e = base + threadIdx.x;
+            float m = 0.0f;
+            if (e < ncplx) m = cmag(p[2 * e], p[2 * e + 1]);
+            __syncthreads();
+            if (e < ncplx) p[e] = m;
+            __syncthreads();
+        }
+    }
+}
+
 // arm_max_f32 — arm_math.h:6537-6541.  One warp per vector; first occurrence of the maximum.
 __global__ void k_max(const float* src, size_t ss, uint32_t len, float* result, uint32_t* index, uint32_t batch) {
     const int lane = threadIdx.x & 31;
@@ -321,9 +339,15 @@ cudaError_t launch_cmul_real(const float* c, size_t sc, const float* r, size_t s
 }
 cudaError_t launch_cmag(const float* src, size_t ss, float* dst, size_t sd, uint32_t ncplx, uint32_t batch,
                         cudaStream_t st) {
-    // out of place only for the row form: in place (dst == src) the magnitudes of a row overwrite inputs other threads still need
+    const bool disjoint = dst + ((size_t) (batch - 1) * sd + ncplx) <= src || src + ((size_t) (batch - 1) * ss + 2 * (size_t) ncplx) <= dst;
+    if (!disjoint) {
+        // The one aliased form with defined results is CMSIS's in-place call: same base, same row pitch, rows apart.
+        if (dst != src || (batch > 1 && (ss != sd || ss < 2 * (size_t) ncplx))) return cudaErrorInvalidValue;
+        k_cmag_inplace<<<batch < 148u * 16u ? batch : 148u * 16u, 256, 0, st>>>(dst, ss, ncplx, batch);
+        return cudaGetLastError();
+    }
     const bool rows = ncplx >= 256 && (ncplx & 3u) == 0 && !((ss | sd) & 3u) && ((uintptr_t) src & 15u) == 0 &&
-                      ((uintptr_t) dst & 15u) == 0 && (dst + (size_t) batch * sd <= src || src + (size_t) batch * ss <= dst);
+                      ((uintptr_t) dst & 15u) == 0;
     if (rows) k_cmag_rows<<<batch < 148u * 16u ? batch : 148u * 16u, 256, 0, st>>>(src, ss, dst, sd, ncplx / 4, batch);
     else k_cmag<<<blocks_for((size_t) ncplx * batch, 256), 256, 0, st>>>(src, ss, dst, sd, ncplx, batch);
     return cudaGetLastError();

@@ -43,23 +43,37 @@ struct usc_handle {
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
     std::map<uint32_t, std::vector<float>> tw_host;
     uint64_t launches;
-    // host-buffer path (usc_demod_frames_host): kLanes chunk pipelines, each with its own stream
-    static const int kLanes = 3;
-    size_t lane_frames;                                // frames per chunk
+    // A/B and debugging switches, read ONCE in usc_create (USC_FFT_GENERIC, USC_LONG_UNFUSED, USC_IQ_UNFUSED):
+    // the hot path never looks at the process environment
+    bool dbg_fft_generic = false, dbg_long_unfused = false, dbg_iq_unfused = false;
+    // host-buffer paths (usc_*_host): three chunk pipelines ("lanes"), each with its own stream, a device input
+    // arena and a device result arena; sized by usc_host_workspace or on first use, grown on demand
+    size_t lane_frames;                                // preferred chunk, in units of 8 KB (one 2048-sample frame)
+    size_t lane_in_bytes, lane_out_bytes;
     cudaStream_t lane_stream[3];
-    void* lane_in[3];
-    float *lane_mu[3], *lane_md[3];
-    uint32_t *lane_iu[3], *lane_id[3];
-    uint8_t* lane_bit[3];
+    cudaEvent_t lane_done[3];                          // kernel of the lane's current chunk has finished (K7 ordering)
+    void *lane_in[3], *lane_out[3];
+    // K7 host path: per-stream carried state on the device, per-chunk pinned staging of uart bytes / results
+    usc_rx_state* rxh_state; size_t rxh_state_n;
+    uint8_t* rxh_stage; size_t rxh_stage_bytes;        // pinned host memory
 };
 
 static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? USC_OK : USC_ERR_CUDA_BASE - (int) e; }
-/* every entry point makes the handle's device current (a process may hold handles on several GPUs) */
-#define USC_ENTER(h)                                                                            \
-    do {                                                                                        \
-        int cur__ = -1;                                                                         \
-        if ((h) && cudaGetDevice(&cur__) == cudaSuccess && cur__ != (h)->device) cudaSetDevice((h)->device); \
-    } while (0)
+/* Every entry point makes the handle's device current for the duration of the call and puts the caller's
+   device back on every return path (a process may hold handles on several GPUs, or run torch on another one). */
+struct device_guard {
+    int prev = -1;
+    bool switched = false;
+    explicit device_guard(int want) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess;
+    }
+    ~device_guard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    device_guard(const device_guard&) = delete;
+    device_guard& operator=(const device_guard&) = delete;
+};
+#define USC_ENTER(h) device_guard guard__((h) ? (h)->device : -1)
 #define CK(expr)                                   \
     do {                                           \
         cudaError_t e__ = (expr);                  \
@@ -143,9 +157,14 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));                    // no device -> error: there is no CPU fallback
     if (device < 0 || device >= ndev) return USC_ERR_ARGUMENT;
-    CK(cudaSetDevice(device));
+    device_guard guard__(device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));      // before the handle exists: nothing to release on failure
     usc_handle* h = new (std::nothrow) usc_handle();
     if (!h) return USC_ERR_NOMEM;
+    h->dbg_fft_generic = getenv("USC_FFT_GENERIC") != nullptr;
+    h->dbg_long_unfused = getenv("USC_LONG_UNFUSED") != nullptr;
+    h->dbg_iq_unfused = getenv("USC_IQ_UNFUSED") != nullptr;
     h->cfg = *cfg;
     h->device = device;
     h->stream = 0;
@@ -160,9 +179,9 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->d_iq_cos = h->d_iq_sin = h->d_iq_chirp = h->d_iq_conj = h->d_iq_hann = h->d_iq_taps = nullptr;
     h->iq_ntaps = h->iq_window = 0;
     h->lane_frames = 0;
-    for (int i = 0; i < 3; ++i) { h->lane_stream[i] = nullptr; h->lane_in[i] = nullptr; h->lane_mu[i] = h->lane_md[i] = nullptr; h->lane_iu[i] = h->lane_id[i] = nullptr; h->lane_bit[i] = nullptr; }
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    h->lane_in_bytes = h->lane_out_bytes = 0;
+    for (int i = 0; i < 3; ++i) { h->lane_stream[i] = nullptr; h->lane_done[i] = nullptr; h->lane_in[i] = h->lane_out[i] = nullptr; }
+    h->rxh_state = nullptr; h->rxh_state_n = 0; h->rxh_stage = nullptr; h->rxh_stage_bytes = 0;
     h->num_sms = prop.multiProcessorCount;
     const uint32_t n = cfg->n;
     h->bandwidth = usc_host_bandwidth(n, cfg->fs, cfg->f0, cfg->f1);        /* main.c:372 */
@@ -251,16 +270,19 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
 
 void usc_destroy(usc_handle* h) {
     if (!h) return;
+    device_guard guard__(h->device);
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
     cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_rs_taps); cudaFree(h->d_op_pass); cudaFree(h->d_op_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
     cudaFree(h->d_sym_table);
     for (auto& kv : h->tw_cache) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) {
-        cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
-        cudaFree(h->lane_id[i]); cudaFree(h->lane_bit[i]);
+        cudaFree(h->lane_in[i]); cudaFree(h->lane_out[i]);
+        if (h->lane_done[i]) cudaEventDestroy(h->lane_done[i]);
         if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
     }
+    cudaFree(h->rxh_state);
+    if (h->rxh_stage) cudaFreeHost(h->rxh_stage);
     delete h;
 }
 
@@ -272,6 +294,7 @@ int usc_set_stream(usc_handle* h, void* cuda_stream) {
 }
 
 int usc_sync(usc_handle* h) {
+    USC_ENTER(h);
     if (!h) return USC_ERR_ARGUMENT;
     CK(cudaStreamSynchronize(h->stream));
     return USC_OK;
@@ -351,13 +374,11 @@ int usc_memset(usc_handle* h, void* dst, int value, size_t bytes) {
 }
 
 /* ---- batched CMSIS-shaped operators ---- */
-/* launches go to the handle's device even when the caller has made another one current in between */
-#define LAUNCHED(h, expr)                                          \
-    do {                                                           \
-        int cur__ = -1;                                            \
-        if (cudaGetDevice(&cur__) == cudaSuccess && cur__ != (h)->device) CK(cudaSetDevice((h)->device)); \
-        CK(expr);                                                  \
-        (h)->launches++;                                           \
+/* launches run under the entry point's device_guard, so the handle's device is current here */
+#define LAUNCHED(h, expr)     \
+    do {                      \
+        CK(expr);             \
+        (h)->launches++;      \
     } while (0)
 
 int usc_i32_to_f32(usc_handle* h, const int32_t* src, float* dst, size_t count) {
@@ -404,7 +425,9 @@ int usc_arm_cmplx_mag_f32_batch(usc_handle* h, const float* src, size_t ss, floa
     USC_ENTER(h);
     if (!h || !src || !dst) return USC_ERR_ARGUMENT;
     if (!num_samples || !batch) return USC_OK;
-    LAUNCHED(h, launch_cmag(src, ss, dst, sd, num_samples, batch, h->stream));
+    const cudaError_t e = launch_cmag(src, ss, dst, sd, num_samples, batch, h->stream);
+    if (e == cudaErrorInvalidValue) return USC_ERR_ARGUMENT;      /* overlapping src/dst other than the in-place form */
+    LAUNCHED(h, e);
     return USC_OK;
 }
 int usc_arm_max_f32_batch(usc_handle* h, const float* src, size_t ss, uint32_t block_size, float* result,
@@ -449,7 +472,7 @@ static int ensure_op_tables(usc_handle* h, const float2** pass, const float2** s
 
 /* forward transform in place on an aligned scratch buffer: the warp-level operator where it exists, else the generic kernel */
 static int fft_forward_inplace(usc_handle* h, int mode, uint32_t n_complex, const fft_plan_dev& plan, float* buf, uint32_t batch) {
-    if (n_complex == 1024 && ((uintptr_t) buf & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+    if (n_complex == 1024 && ((uintptr_t) buf & 15u) == 0 && !h->dbg_fft_generic) {
         const float2 *pass, *split;
         int rc = ensure_op_tables(h, &pass, &split);
         if (rc) return rc;
@@ -463,7 +486,7 @@ static int fft_forward_inplace(usc_handle* h, int mode, uint32_t n_complex, cons
 int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in, float* out, uint8_t ifft_flag,
                                 uint32_t batch) {
     USC_ENTER(h);
-    if (h && in && out && fft_len == 2048 && batch && (((uintptr_t) in | (uintptr_t) out) & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+    if (h && in && out && fft_len == 2048 && batch && (((uintptr_t) in | (uintptr_t) out) & 15u) == 0 && !h->dbg_fft_generic) {
         /* the receiver's own length: two transforms per warp on the packed register core, one pass over HBM */
         const float2 *pass, *split;
         int rc = ensure_op_tables(h, &pass, &split);
@@ -490,7 +513,7 @@ int usc_arm_rfft_fast_f32_batch(usc_handle* h, uint32_t fft_len, const float* in
 }
 int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t ifft_flag, uint32_t batch) {
     USC_ENTER(h);
-    if (h && data && fft_len == 2048 && batch && ((uintptr_t) data & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+    if (h && data && fft_len == 2048 && batch && ((uintptr_t) data & 15u) == 0 && !h->dbg_fft_generic) {
         /* arm_cfft_sR_f32_len2048 (experiments/synchronization): [2, 32, 32] on the register core, one transform per warp pass */
         const float2 *pass, *split;
         float2* master = nullptr;
@@ -500,7 +523,7 @@ int usc_arm_cfft_f32_batch(usc_handle* h, uint32_t fft_len, float* data, uint8_t
         LAUNCHED(h, launch_cfft2048_warp(ifft_flag != 0, data, batch, pass, master, h->num_sms, h->stream));
         return USC_OK;
     }
-    if (h && data && fft_len == 1024 && batch && ((uintptr_t) data & 15u) == 0 && !getenv("USC_FFT_GENERIC")) {
+    if (h && data && fft_len == 1024 && batch && ((uintptr_t) data & 15u) == 0 && !h->dbg_fft_generic) {
         const float2 *pass, *split;
         int rc = ensure_op_tables(h, &pass, &split);
         if (rc) return rc;
@@ -588,7 +611,7 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     if (h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
     if (((uintptr_t) pcm & 15u) != 0) return USC_ERR_ARGUMENT;     /* frames are fetched by 16-byte-aligned bulk copies */
     if (!nframes) return USC_OK;
-    if ((h->cfg.n == 4096 || h->cfg.n == 8192 || h->cfg.n == 16384) && !getenv("USC_LONG_UNFUSED") && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u)) {
+    if ((h->cfg.n == 4096 || h->cfg.n == 8192 || h->cfg.n == 16384) && !h->dbg_long_unfused && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u)) {
         /* long frames: one CTA per frame, level 0 from global memory, packed 1024-point cores (k_long.cu) */
         float2* master = nullptr;
         int rc = get_twiddles(h, h->cfg.n, &master);
@@ -599,7 +622,7 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
         return USC_OK;
     }
     if ((h->cfg.n == 65536 || h->cfg.n == 32768) && h->d_tw_l0 && h->bandwidth2 > 0 && h->bandwidth2 <= 160u * (h->cfg.n / 2048u) &&
-        !getenv("USC_LONG_UNFUSED")) {
+        !h->dbg_long_unfused) {
         /* 32768 / 65536-point frames: a cluster of two / four CTAs per frame, sub-sequences in distributed shared memory (k_long.cu) */
         float2* master = nullptr;
         int rc = get_twiddles(h, h->cfg.n, &master);
@@ -628,62 +651,205 @@ int usc_demod_frames(usc_handle* h, const void* pcm, uint32_t pcm_format, size_t
     return USC_OK;
 }
 
-int usc_host_workspace(usc_handle* h, size_t chunk_frames) {
-    USC_ENTER(h);
-    if (!h || !chunk_frames || h->cfg.n != 2048) return USC_ERR_ARGUMENT;
-    if (h->lane_frames == chunk_frames) return USC_OK;
-    for (int i = 0; i < 3; ++i) {
-        cudaFree(h->lane_in[i]); cudaFree(h->lane_mu[i]); cudaFree(h->lane_md[i]); cudaFree(h->lane_iu[i]);
-        cudaFree(h->lane_id[i]); cudaFree(h->lane_bit[i]);
-        h->lane_in[i] = nullptr; h->lane_mu[i] = h->lane_md[i] = nullptr; h->lane_iu[i] = h->lane_id[i] = nullptr; h->lane_bit[i] = nullptr;
-    }
-    h->lane_frames = 0;
+/* ---- host-buffer entry points: chunks flow through three lanes (H2D copy, kernel, D2H of the results) ---- */
+static int ensure_lanes(usc_handle* h, size_t in_bytes, size_t out_bytes) {
     for (int i = 0; i < 3; ++i) {
         if (!h->lane_stream[i]) CK(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
-        CK(cudaMalloc(&h->lane_in[i], chunk_frames * 2048 * 4));
-        CK(cudaMalloc((void**) &h->lane_mu[i], chunk_frames * 4));
-        CK(cudaMalloc((void**) &h->lane_md[i], chunk_frames * 4));
-        CK(cudaMalloc((void**) &h->lane_iu[i], chunk_frames * 4));
-        CK(cudaMalloc((void**) &h->lane_id[i], chunk_frames * 4));
-        CK(cudaMalloc((void**) &h->lane_bit[i], chunk_frames));
+        if (!h->lane_done[i]) CK(cudaEventCreateWithFlags(&h->lane_done[i], cudaEventDisableTiming));
     }
-    h->lane_frames = chunk_frames;
+    if (in_bytes > h->lane_in_bytes) {
+        for (int i = 0; i < 3; ++i) { CK(cudaStreamSynchronize(h->lane_stream[i])); cudaFree(h->lane_in[i]); h->lane_in[i] = nullptr; }
+        h->lane_in_bytes = 0;
+        for (int i = 0; i < 3; ++i) CK(cudaMalloc(&h->lane_in[i], in_bytes));
+        h->lane_in_bytes = in_bytes;
+    }
+    if (out_bytes > h->lane_out_bytes) {
+        for (int i = 0; i < 3; ++i) { CK(cudaStreamSynchronize(h->lane_stream[i])); cudaFree(h->lane_out[i]); h->lane_out[i] = nullptr; }
+        h->lane_out_bytes = 0;
+        for (int i = 0; i < 3; ++i) CK(cudaMalloc(&h->lane_out[i], out_bytes));
+        h->lane_out_bytes = out_bytes;
+    }
     return USC_OK;
+}
+/* the five per-frame result vectors of a chunk of `cap` frames inside a lane's result arena (256-byte aligned) */
+struct frame_results {
+    float *mu, *md; uint32_t *iu, *id; uint8_t* bit;
+    static size_t bytes(size_t cap) { return 4 * ((cap * 4 + 255) & ~(size_t) 255) + ((cap + 255) & ~(size_t) 255); }
+    frame_results(void* arena, size_t cap) {
+        const size_t v = (cap * 4 + 255) & ~(size_t) 255;
+        char* p = (char*) arena;
+        mu = (float*) p; md = (float*) (p + v); iu = (uint32_t*) (p + 2 * v); id = (uint32_t*) (p + 3 * v); bit = (uint8_t*) (p + 4 * v);
+    }
+};
+/* runs `body` with the handle's stream swapped for a lane stream (the device-pointer entry points launch on h->stream) */
+struct stream_swap {
+    usc_handle* h; cudaStream_t saved;
+    stream_swap(usc_handle* h_, cudaStream_t st) : h(h_), saved(h_->stream) { h->stream = st; }
+    ~stream_swap() { h->stream = saved; }
+};
+static int sync_lanes(usc_handle* h) {
+    for (int l = 0; l < 3; ++l) CK(cudaStreamSynchronize(h->lane_stream[l]));
+    return USC_OK;
+}
+static int copy_frame_results(const frame_results& r, size_t f0, size_t nf, float* mag_up, uint32_t* idx_up, float* mag_down,
+                              uint32_t* idx_down, uint8_t* bit, cudaStream_t st) {
+    if (mag_up) CK(cudaMemcpyAsync(mag_up + f0, r.mu, nf * 4, cudaMemcpyDeviceToHost, st));
+    if (idx_up) CK(cudaMemcpyAsync(idx_up + f0, r.iu, nf * 4, cudaMemcpyDeviceToHost, st));
+    if (mag_down) CK(cudaMemcpyAsync(mag_down + f0, r.md, nf * 4, cudaMemcpyDeviceToHost, st));
+    if (idx_down) CK(cudaMemcpyAsync(idx_down + f0, r.id, nf * 4, cudaMemcpyDeviceToHost, st));
+    if (bit) CK(cudaMemcpyAsync(bit + f0, r.bit, nf, cudaMemcpyDeviceToHost, st));
+    return USC_OK;
+}
+
+int usc_host_workspace(usc_handle* h, size_t chunk_frames) {
+    USC_ENTER(h);
+    if (!h || !chunk_frames) return USC_ERR_ARGUMENT;
+    h->lane_frames = chunk_frames;
+    return ensure_lanes(h, chunk_frames * 8192, frame_results::bytes(chunk_frames));
 }
 
 int usc_demod_frames_host(usc_handle* h, const void* pcm_host, uint32_t pcm_format, size_t nframes,
                           float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down, uint8_t* bit) {
     USC_ENTER(h);
     if (!h || !pcm_host || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
-    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S) return USC_ERR_ARGUMENT;
-    if (h->bandwidth2 == 0 || h->bandwidth2 > 512) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n;
+    if (h->cfg.chirp_variant == USC_CHIRP_S || h->bandwidth2 == 0) return USC_ERR_ARGUMENT;
+    /* frame lengths with a fused kernel only: the operator chain of the other lengths shares one scratch arena */
+    const bool fused = (n == 2048 && h->bandwidth2 <= 512) ||
+                       (n >= 4096 && n <= 65536 && h->bandwidth2 <= 160u * (n / 2048u) && !h->dbg_long_unfused && (n <= 16384 || h->d_tw_l0));
+    if (!fused) return USC_ERR_ARGUMENT;
     if (!nframes) return USC_OK;
-    if (!h->lane_frames) {
-        int rc = usc_host_workspace(h, 4096);
-        if (rc) return rc;
-    }
-    const size_t cf = h->lane_frames;
+    if (!h->lane_frames) h->lane_frames = 4096;
+    size_t cf = h->lane_frames * 2048 / n;                       /* frames of n samples per chunk */
+    if (!cf) cf = 1;
+    int rc = ensure_lanes(h, cf * n * 4, frame_results::bytes(cf));
+    if (rc) return rc;
     const char* src = (const char*) pcm_host;
     size_t chunk = 0;
     for (size_t f0 = 0; f0 < nframes; f0 += cf, ++chunk) {
         const int l = (int) (chunk % 3);
         const size_t nf = nframes - f0 < cf ? nframes - f0 : cf;
         cudaStream_t st = h->lane_stream[l];
-        CK(cudaMemcpyAsync(h->lane_in[l], src + f0 * 2048 * 4, nf * 2048 * 4, cudaMemcpyHostToDevice, st));
-        demod_params p;
-        fill_common(h, &p);
-        p.pcm = h->lane_in[l];
-        p.nframes = nf;
-        p.mag_up = h->lane_mu[l]; p.idx_up = h->lane_iu[l]; p.mag_down = h->lane_md[l]; p.idx_down = h->lane_id[l];
-        p.bit = h->lane_bit[l];
-        LAUNCHED(h, launch_demod2048(p, pcm_format, h->num_sms, st));
-        if (mag_up) CK(cudaMemcpyAsync(mag_up + f0, h->lane_mu[l], nf * 4, cudaMemcpyDeviceToHost, st));
-        if (idx_up) CK(cudaMemcpyAsync(idx_up + f0, h->lane_iu[l], nf * 4, cudaMemcpyDeviceToHost, st));
-        if (mag_down) CK(cudaMemcpyAsync(mag_down + f0, h->lane_md[l], nf * 4, cudaMemcpyDeviceToHost, st));
-        if (idx_down) CK(cudaMemcpyAsync(idx_down + f0, h->lane_id[l], nf * 4, cudaMemcpyDeviceToHost, st));
-        if (bit) CK(cudaMemcpyAsync(bit + f0, h->lane_bit[l], nf, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->lane_in[l], src + f0 * n * 4, nf * n * 4, cudaMemcpyHostToDevice, st));
+        frame_results r(h->lane_out[l], cf);
+        {
+            stream_swap sw(h, st);
+            rc = usc_demod_frames(h, h->lane_in[l], pcm_format, nf, r.mu, r.iu, r.md, r.id, r.bit);
+        }
+        if (rc) return rc;
+        if ((rc = copy_frame_results(r, f0, nf, mag_up, idx_up, mag_down, idx_down, bit, st))) return rc;
     }
-    for (int l = 0; l < 3; ++l) CK(cudaStreamSynchronize(h->lane_stream[l]));
+    return sync_lanes(h);
+}
+
+int usc_iq_demod_host(usc_handle* h, const void* pcm_host, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                      size_t stream_stride, float* mag_up, uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
+                      uint8_t* bit) {
+    USC_ENTER(h);
+    if (!h || !pcm_host || pcm_format > USC_PCM_I32 || !h->d_iq_taps) return USC_ERR_ARGUMENT;
+    const uint32_t n = h->cfg.n;
+    if (n != 2048 || h->iq_window > 32 || h->iq_ntaps > 32 || !h->d_tw_pass || h->dbg_iq_unfused) return USC_ERR_ARGUMENT;   /* fused kernel only */
+    if (stream_stride < (size_t) nframes * n) return USC_ERR_ARGUMENT;
+    if (!nstreams || !nframes) return USC_OK;
+    if (!h->lane_frames) h->lane_frames = 4096;
+    /* the FIR state runs along a stream, so chunks are whole streams */
+    size_t cs = h->lane_frames / nframes;
+    if (!cs) cs = 1;
+    const size_t row = (size_t) nframes * n * 4;                 /* bytes of one stream on the device (packed) */
+    int rc = ensure_lanes(h, cs * row, frame_results::bytes(cs * nframes));
+    if (rc) return rc;
+    const char* src = (const char*) pcm_host;
+    size_t chunk = 0;
+    for (size_t s0 = 0; s0 < nstreams; s0 += cs, ++chunk) {
+        const int l = (int) (chunk % 3);
+        const size_t ns = nstreams - s0 < cs ? nstreams - s0 : cs;
+        cudaStream_t st = h->lane_stream[l];
+        CK(cudaMemcpy2DAsync(h->lane_in[l], row, src + s0 * stream_stride * 4, stream_stride * 4, row, ns, cudaMemcpyHostToDevice, st));
+        frame_results r(h->lane_out[l], cs * nframes);
+        {
+            stream_swap sw(h, st);
+            rc = usc_iq_demod(h, h->lane_in[l], pcm_format, (uint32_t) ns, nframes, (size_t) nframes * n, r.mu, r.iu, r.md, r.id, r.bit);
+        }
+        if (rc) return rc;
+        if ((rc = copy_frame_results(r, s0 * nframes, ns * nframes, mag_up, idx_up, mag_down, idx_down, bit, st))) return rc;
+    }
+    return sync_lanes(h);
+}
+
+int usc_receiver_run_host(usc_handle* h, const void* pcm_host, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                          size_t stream_stride, uint8_t* uart, uint32_t uart_cap, usc_rx_result* results) {
+    USC_ENTER(h);
+    if (!h || !pcm_host || pcm_format > USC_PCM_I32 || (!uart && !results)) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S || h->bandwidth2 == 0 || h->bandwidth2 > 160) return USC_ERR_ARGUMENT;
+    if ((stream_stride & 1u) != 0 || stream_stride < (size_t) nframes * 2048) return USC_ERR_ARGUMENT;
+    if (uart && !uart_cap) return USC_ERR_ARGUMENT;
+    if (!nstreams || !nframes) return USC_OK;
+    if (!h->lane_frames) h->lane_frames = 4096;
+    /* The state machine runs along a stream and one warp serves a stream, so a chunk holds ALL streams and a slice of
+     * time: cf new frames per stream behind the two frames of FIFO history the receiver keeps (main.c:659-668),
+     * resumed through the carried per-stream state exactly as usc_receiver_run_chunk documents. */
+    size_t cf = h->lane_frames / nstreams;
+    if (cf < 6) cf = 6;
+    if (cf > nframes) cf = nframes;
+    const size_t nchunks = (nframes + cf - 1) / cf;
+    const uint32_t cap = uart ? uart_cap : 0;
+    const size_t dev_stride = (cf + 2) * 2048;                    /* samples per stream in a lane buffer */
+    const size_t uart_bytes = ((size_t) nstreams * cap + 255) & ~(size_t) 255;
+    const size_t out_bytes = uart_bytes + (size_t) nstreams * sizeof(usc_rx_result);
+    int rc = ensure_lanes(h, (size_t) nstreams * dev_stride * 4, out_bytes);
+    if (rc) return rc;
+    if (h->rxh_state_n < nstreams) {
+        if ((rc = sync_lanes(h))) return rc;
+        cudaFree(h->rxh_state); h->rxh_state = nullptr; h->rxh_state_n = 0;
+        CK(cudaMalloc((void**) &h->rxh_state, (size_t) nstreams * sizeof(usc_rx_state)));
+        h->rxh_state_n = nstreams;
+    }
+    if (h->rxh_stage_bytes < nchunks * out_bytes) {
+        if (h->rxh_stage) cudaFreeHost(h->rxh_stage);
+        h->rxh_stage = nullptr; h->rxh_stage_bytes = 0;
+        CK(cudaMallocHost((void**) &h->rxh_stage, nchunks * out_bytes));
+        h->rxh_stage_bytes = nchunks * out_bytes;
+    }
+    CK(cudaMemsetAsync(h->rxh_state, 0, (size_t) nstreams * sizeof(usc_rx_state), h->lane_stream[0]));
+    CK(cudaEventRecord(h->lane_done[2], h->lane_stream[0]));      /* "previous kernel" of the first chunk */
+    const char* src = (const char*) pcm_host;
+    const int esz = 4;
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int l = (int) (c % 3), lprev = (int) ((c + 2) % 3);
+        const size_t f0 = c * cf, nf = nframes - f0 < cf ? nframes - f0 : cf;
+        const uint32_t carry = f0 >= 2 ? 2u : (uint32_t) f0;
+        cudaStream_t st = h->lane_stream[l];
+        CK(cudaMemcpy2DAsync(h->lane_in[l], dev_stride * esz, src + (f0 - carry) * 2048 * esz, stream_stride * esz,
+                             (nf + carry) * 2048 * esz, nstreams, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamWaitEvent(st, h->lane_done[lprev], 0));      /* the carried state of chunk c-1 must be written */
+        uint8_t* d_uart = cap ? (uint8_t*) h->lane_out[l] : nullptr;
+        usc_rx_result* d_res = (usc_rx_result*) ((char*) h->lane_out[l] + uart_bytes);
+        {
+            stream_swap sw(h, st);
+            rc = usc_receiver_run_chunk(h, h->lane_in[l], pcm_format, nstreams, (uint32_t) nf, dev_stride, carry, h->rxh_state, d_uart,
+                                        cap, d_res);
+        }
+        if (rc) return rc;
+        CK(cudaEventRecord(h->lane_done[l], st));
+        CK(cudaMemcpyAsync(h->rxh_stage + c * out_bytes, h->lane_out[l], out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if ((rc = sync_lanes(h))) return rc;
+    /* stitch the chunks on the host: bytes are appended per stream in chunk order; the last chunk's record is the result */
+    std::vector<uint32_t> filled(nstreams, 0);
+    for (size_t c = 0; c < nchunks; ++c) {
+        const uint8_t* cu = h->rxh_stage + c * out_bytes;
+        const usc_rx_result* cr = (const usc_rx_result*) (cu + uart_bytes);
+        for (uint32_t s = 0; s < nstreams; ++s) {
+            const uint32_t nb = cr[s].nbytes;
+            if (uart) {
+                const uint32_t have = nb < cap ? nb : cap;
+                for (uint32_t i = 0; i < have && filled[s] + i < cap; ++i) uart[(size_t) s * cap + filled[s] + i] = cu[(size_t) s * cap + i];
+            }
+            filled[s] += nb;
+        }
+        if (results && c + 1 == nchunks)
+            for (uint32_t s = 0; s < nstreams; ++s) { results[s] = cr[s]; results[s].nbytes = filled[s]; }
+    }
     return USC_OK;
 }
 
@@ -1047,7 +1213,7 @@ int usc_iq_demod(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t n
     const size_t F = (size_t) nstreams * nframes;
     if (!F) return USC_OK;
     if (F > 0xffffffffu) return USC_ERR_ARGUMENT;
-    if (n == 2048 && W <= 32 && h->iq_ntaps <= 32 && h->d_tw_pass && !getenv("USC_IQ_UNFUSED")) {
+    if (n == 2048 && W <= 32 && h->iq_ntaps <= 32 && h->d_tw_pass && !h->dbg_iq_unfused) {
         /* whole path in one kernel: mix, FIR, de-chirp both ways, Hann, FFT, windowed peaks (k_iq.cu) */
         LAUNCHED(h, launch_iq_fused(pcm, pcm_format, nstreams, nframes, stream_stride, h->d_iq_cos, h->d_iq_sin, h->d_iq_taps,
                                     h->iq_ntaps, h->d_iq_chirp, h->d_iq_hann, h->d_tw_pass, W, mag_up, idx_up, mag_down,

@@ -56,7 +56,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_iq_demod_host", "usc_receiver_run_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -259,19 +259,33 @@ class Handle:
         _ck(load().usc_demod_frames(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes), _ptr(mag_up),
                                     _ptr(idx_up), _ptr(mag_down), _ptr(idx_down), _ptr(bit)))
 
+    @staticmethod
+    def _hp(x):
+        """raw HOST address of an int / numpy array / (pinned) torch tensor"""
+        if x is None:
+            return C.c_void_p(0)
+        if isinstance(x, int):
+            return C.c_void_p(x)
+        if isinstance(x, np.ndarray):
+            return C.c_void_p(x.ctypes.data)
+        return C.c_void_p(x.data_ptr())
+
+    def iq_demod_hostbuf(self, pcm_host, pcm_format, nstreams, nframes, stream_stride, mag_up, idx_up, mag_down, idx_down, bit):
+        hp = self._hp
+        _ck(load().usc_iq_demod_host(self._h, hp(pcm_host), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                     C.c_size_t(stream_stride), hp(mag_up), hp(idx_up), hp(mag_down), hp(idx_down), hp(bit)))
+
+    def receiver_run_hostbuf(self, pcm_host, pcm_format, nstreams, nframes, stream_stride, uart, uart_cap, results):
+        hp = self._hp
+        _ck(load().usc_receiver_run_host(self._h, hp(pcm_host), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                         C.c_size_t(stream_stride), hp(uart), C.c_uint32(uart_cap), hp(results)))
+
     def host_workspace(self, chunk_frames):
         _ck(load().usc_host_workspace(self._h, C.c_size_t(chunk_frames)))
 
     def demod_frames_hostbuf(self, pcm_host_ptr, pcm_format, nframes, mag_up, idx_up, mag_down, idx_down, bit):
         """usc_demod_frames_host on raw HOST addresses (ints / numpy arrays / pinned torch tensors)."""
-        def hp(x):
-            if x is None:
-                return C.c_void_p(0)
-            if isinstance(x, int):
-                return C.c_void_p(x)
-            if isinstance(x, np.ndarray):
-                return C.c_void_p(x.ctypes.data)
-            return C.c_void_p(x.data_ptr())
+        hp = self._hp
         _ck(load().usc_demod_frames_host(self._h, hp(pcm_host_ptr), C.c_uint32(pcm_format), C.c_size_t(nframes),
                                          hp(mag_up), hp(idx_up), hp(mag_down), hp(idx_down), hp(bit)))
 
