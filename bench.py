@@ -13,11 +13,16 @@ A "step" is one pass of the hot path over that batch (one launch of the fused ke
             PCM -> chunked H2D -> K1 -> D2H of the per-frame results, all inside the timed region
   roofline  algorithmic bytes (8208 B/symbol: 8192 in + 16 out) / average launch duration vs the
             measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle port (oracle/ref_dsp.c, OpenMP over frames) on this box's host cores
-                on a bounded sample of the same workload
+  cpu_baseline  the CPU port of the same chain on this box's host cores on a bounded sample of the workload: the tuned
+                form (oracle/ref_fast.c: one frame per SIMD lane, iterative plan, per-thread scratch, bit-identical to
+                the plain restatement oracle/ref_dsp.c, whose rate is reported beside it)
+  configs   one measured entry per further BASELINE.json config, same launch: "3" I/Q path (K5, 16384 streams),
+            "4" synchroniser + receiver state machine (K7, and K4 with K = 1/2/4 added frames) on this rank's shard of
+            262144/8 streams x 10 s, "5" 8192/16384/65536-point frames (K6) — each with value, ms, roofline, a sampled
+            oracle check and an e2e figure through the host-buffer C-ABI call
 
 `--impl reference` times the CPU implementation alone (the reference's C chain cannot be built for
-the host: CMSIS-DSP is vendored only as an ARM archive; the oracle port stands in).
+the host: CMSIS-DSP is vendored only as an ARM archive; the tuned oracle port stands in).
 Multi-GPU: one process per GPU (torchrun), streams sharded, no data-path collective, weak scaling.
 """
 import argparse
@@ -120,28 +125,43 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_hash():
+    """sha1 over the sources of the bench kernel: profiles/k1_traffic.json records it at capture time."""
+    import hashlib
+    hsh = hashlib.sha1()
+    for f in ("k_demod.cu", "usc_warpfft.cuh", "usc_arith.cuh"):
+        with open(os.path.join(ROOT, "ultrasonic-communication_b200", "csrc", f), "rb") as fh:
+            hsh.update(fh.read())
+    return hsh.hexdigest()[:16]
+
+
 def profiled_traffic():
-    """dram bytes per launch of K1 from the committed ncu --set full capture, if any."""
+    """dram bytes per launch of K1 from the committed ncu --set full capture (ncu cannot run inside the bench);
+    None when the kernel's sources changed since that capture (tools/update_traffic.py refreshes it)."""
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p))
+            t = json.load(open(p))
+            if t.get("kernel_source_sha1") == kernel_source_hash():
+                return t
+            return {"dram_bytes_per_launch": None, "stale": "kernel sources changed since the ncu capture"}
         except Exception:
             pass
     return None
 
 
-def cpu_port(nframes_sample, threads, budget_s=12.0, seed=7):
-    """The CPU oracle port (test infrastructure) timed as the reported baseline."""
+def cpu_port(nframes_sample, threads, budget_s=10.0, fast=True):
+    """The CPU port (test infrastructure) timed as the reported baseline: passes over a bounded sample of the same
+    dataset until the budget is spent.  fast: the tuned form (ref_fast.c); else the plain restatement (ref_dsp.c)."""
     from oracle import pyref
     rx = pyref.RefReceiver()
     pcm, _ = pyref.synth_frames(SEED, 0, nframes_sample, AMP, NOISE_SIGMA)      # the same dataset, first frames
-    rx.demod_frames(pcm[:256], nthreads=threads)                # warm the threads
-    # about 12 s of CPU work in total: passes over the sample until the budget is spent
+    run = rx.demod_frames_fast if fast else rx.demod_frames
+    run(pcm[:512], nthreads=threads)                # warm the threads
     t_start = time.perf_counter()
     passes = 0
     while True:
-        rx.demod_frames(pcm, nthreads=threads)
+        run(pcm, nthreads=threads)
         passes += 1
         elapsed = time.perf_counter() - t_start
         if elapsed >= budget_s or passes >= 4096:
@@ -179,6 +199,12 @@ def cpu_numpy(nframes_sample, threads, budget_s=4.0):
     return nframes_sample * passes / dt, dt, passes
 
 
+def cpu_simd_note():
+    from oracle import pyref
+    w = pyref.lib().ref_fast_simd_width()
+    return {16: "AVX-512, 16 frames per vector", 8: "AVX2, 8 frames per vector"}.get(w, "scalar")
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU implementation alone, all host threads, bounded sample per step."""
     if rank != 0:
@@ -189,10 +215,10 @@ def run_reference(args, rank):
     rx = pyref.RefReceiver()
     pcm, _ = pyref.synth_frames(SEED, 0, sample, AMP, NOISE_SIGMA)
     for _ in range(max(args.warmup, 1)):
-        rx.demod_frames(pcm[:4096], nthreads=threads)
+        rx.demod_frames_fast(pcm[:4096], nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        rx.demod_frames(pcm, nthreads=threads)
+        rx.demod_frames_fast(pcm, nthreads=threads)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     line = {
@@ -200,14 +226,216 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": sample, "n": N, "hypotheses": 2,
-                   "note": "CPU oracle port of the receiver chain (reference C chain not buildable on host: "
+                   "note": "tuned CPU port of the receiver chain (reference C chain not buildable on host: "
                            "CMSIS-DSP vendored only as an ARM-Thumb archive); bounded sample of the workload per step"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d frames x %d steps, OpenMP over frames" % (sample, args.steps)},
+                         "sample": "%d frames x %d steps, OpenMP over blocks of frames, %s" % (sample, args.steps, cpu_simd_note())},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ---- the further BASELINE.json configs (3, 4, 5): measured in the same launch, reported under "configs" ----------------
+def _dev_ms(torch, stream, fn, reps, warm):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _wall_s(torch, barrier, fn, reps):
+    fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    barrier()
+    return (time.perf_counter() - t0) / reps
+
+
+IQ_CARRIER, IQ_BW = 18000.0, 3000.0
+C3_STREAMS, C3_E2E_STREAMS = 16384, 2048
+C4_STREAMS_TOTAL, C4_FRAMES, C4_MSG, C4_LEAD, C4_GUARD, C4_SIGMA = 262144, 381, 12, 40, 12, 2000.0
+C4_E2E_STREAMS = 384                     # 384 x 381 frames = 1.2 GB: fits the pinned arena of config 2's e2e leg
+C5_LENGTHS = ((8192, -15.0), (16384, -15.0), (65536, -20.0))
+
+
+def config3(torch, usc, pyref, dev, stream, rank, barrier, arena):
+    """BASELINE config 3: the I/Q baseband path (K5) over 16384 streams x 38 frames per GPU.  Input: the I/Q transmitter's
+    symbols (usc_synth_iq_frames: A cos(2 pi (fc - fb(t)) t), simulation/IQ_modulation.ipynb cell 4) + noise, SNR 0 dB."""
+    taps = np.load(os.path.join(ROOT, "tests", "golden", "fir_taps.npz"))["taps"].astype(np.float32)[::-1].copy()
+    h = usc.Handle(device=dev.index)
+    h.set_stream(stream.cuda_stream)
+    h.iq_init(IQ_CARRIER, IQ_BW, taps, 32)
+    S, F = C3_STREAMS, FRAMES_PER_STREAM
+    nfr = S * F
+    sigma = AMP / np.sqrt(2.0)                               # a cosine of amplitude A has power A^2/2: SNR 0 dB
+    pcm = torch.empty((nfr, N), dtype=torch.int32, device=dev)
+    bits = torch.empty(nfr, dtype=torch.uint8, device=dev)
+    first = rank * nfr
+    h.synth_iq_frames(SEED + 3, first, nfr, IQ_CARRIER, IQ_BW, -1, 0.0, AMP, sigma, pcm, bits)
+    o = [torch.empty(nfr, dtype=torch.float32, device=dev) for _ in range(2)] + \
+        [torch.empty(nfr, dtype=torch.int32, device=dev) for _ in range(2)]
+    b = torch.empty(nfr, dtype=torch.uint8, device=dev)
+    ms = _dev_ms(torch, stream, lambda: h.iq_demod(pcm, usc.PCM_I32, S, F, F * N, o[0], o[2], o[1], o[3], b), reps=5, warm=2)
+    acc = float((b == bits).float().mean().item())
+    # sampled oracle check: two streams of this rank's shard regenerated on the CPU
+    q = pyref.RefIq(taps)
+    ok = True
+    for sidx in (0, S - 1):
+        p1, _ = pyref.synth_iq_frames(SEED + 3, first + sidx * F, F, IQ_CARRIER, IQ_BW, -1, 0.0, AMP, sigma)
+        want = q.demod(p1)
+        sl = slice(sidx * F, (sidx + 1) * F)
+        ok &= bool(np.array_equal(o[0][sl].cpu().numpy().view(np.uint32), want[0].view(np.uint32)) and
+                   np.array_equal(o[2][sl].cpu().numpy().astype(np.uint32), want[1]) and
+                   np.array_equal(o[1][sl].cpu().numpy().view(np.uint32), want[2].view(np.uint32)))
+    # e2e through usc_iq_demod_host on a bounded sample of the shard
+    Se = C3_E2E_STREAMS
+    ne = Se * F
+    hp = arena[:ne * N].view(ne, N)
+    hp.copy_(pcm[:ne])
+    ho = [torch.empty(ne, dtype=torch.float32).pin_memory() for _ in range(2)] + \
+         [torch.empty(ne, dtype=torch.int32).pin_memory() for _ in range(2)]
+    hb = torch.empty(ne, dtype=torch.uint8).pin_memory()
+    e2e_s = _wall_s(torch, barrier, lambda: h.iq_demod_hostbuf(hp, usc.PCM_I32, Se, F, F * N, ho[0], ho[2], ho[1], ho[3], hb), 2)
+    e2e_ok = bool(torch.equal(hb, b[:ne].cpu()) and torch.equal(ho[2], o[2][:ne].cpu()))
+    h.close()
+    return {"times": {"c3_ms": ms, "c3_e2e_s": e2e_s}, "ok": ok and e2e_ok,
+            "info": {"frames": nfr, "e2e_frames": ne, "accuracy": acc}}
+
+
+def config4(torch, usc, pyref, dev, stream, rank, world, barrier, arena):
+    """BASELINE config 4: 262144 streams x 10 s sharded over 8 GPUs -> 32768 streams x 381 frames per GPU (102 GB), one wave.
+    K7 = the receiver's whole main loop (sliding-correlation search, lock, decode); K4 = the search grid alone with
+    synchronous addition of K = 1, 2, 4 frames."""
+    h = usc.Handle(device=dev.index)
+    h.set_stream(stream.cuda_stream)
+    S, F, MB = C4_STREAMS_TOTAL // 8, C4_FRAMES, C4_MSG
+    first = rank * S
+    pcm = torch.empty((S, F * N), dtype=torch.int32, device=dev)
+    msgs = torch.empty((S, MB), dtype=torch.uint8, device=dev)
+    h.synth_streams(SEED + 4, first, S, F, F * N, C4_LEAD, MB, C4_GUARD, AMP, C4_SIGMA, pcm, None, msgs)
+    uart = torch.zeros((S, 64), dtype=torch.uint8, device=dev)
+    res = torch.zeros((S, 8), dtype=torch.int32, device=dev)
+    times = {"c4_k7_ms": _dev_ms(torch, stream, lambda: h.receiver_run(pcm, usc.PCM_I32, S, F, F * N, uart, 64, res), reps=2, warm=1)}
+    u, m, r = uart.cpu().numpy(), msgs.cpu().numpy(), res.cpu().numpy()
+    decoded = int(sum(bytes(u[s, :MB + 1]) == bytes(m[s]) + b"\n" for s in range(S)))
+    rx = pyref.RefReceiver()
+    ok = True
+    for sidx in (0, S - 1):                                  # oracle on regenerated streams: bytes and lock frame
+        p1, _, _ = pyref.synth_streams(SEED + 4, first + sidx, 1, F, C4_LEAD, MB, C4_GUARD, AMP, C4_SIGMA)
+        want, stt = pyref.receiver_run(rx, p1[0], cap=64)
+        ok &= bool(bytes(u[sidx, :min(int(r[sidx, 4]), 64)]) == want[:64] and int(r[sidx, 2]) == stt.lock_frame)
+    mag = torch.empty((S, F, 4), dtype=torch.float32, device=dev)
+    idx = torch.empty((S, F, 4), dtype=torch.int32, device=dev)
+    p1, _, _ = pyref.synth_streams(SEED + 4, first + 1, 1, F, C4_LEAD, MB, C4_GUARD, AMP, C4_SIGMA)
+    for K in (1, 2, 4):
+        times["c4_k4_K%d_ms" % K] = _dev_ms(torch, stream, lambda: h.sync_search(pcm, usc.PCM_I32, S, F, F * N, K, mag, idx), reps=2, warm=1)
+        wm, wi = pyref.sync_search(rx, p1[0], K)
+        ok &= bool(np.array_equal(idx[1].cpu().numpy().astype(np.uint32), wi) and
+                   np.array_equal(mag[1].cpu().numpy().view(np.uint32), wm.view(np.uint32)))
+    del mag, idx
+    # e2e through usc_receiver_run_host on a bounded sample of the shard
+    Se = C4_E2E_STREAMS
+    hp = arena[:Se * F * N].view(Se, F * N)
+    hp.copy_(pcm[:Se])
+    hu = torch.zeros((Se, 64), dtype=torch.uint8).pin_memory()
+    hr = torch.zeros((Se, 8), dtype=torch.int32).pin_memory()
+    h.host_workspace(32 * Se)                                # 32 frames of every stream per chunk
+    times["c4_e2e_s"] = _wall_s(torch, barrier, lambda: h.receiver_run_hostbuf(hp, usc.PCM_I32, Se, F, F * N, hu, 64, hr), 1)
+    e2e_ok = bool(np.array_equal(hu.numpy(), u[:Se]) and np.array_equal(hr.numpy(), r[:Se]))
+    h.close()
+    del pcm
+    torch.cuda.empty_cache()
+    return {"times": times, "ok": ok and e2e_ok, "info": {"streams": S, "frames_per_stream": F, "decoded": decoded, "e2e_streams": Se}}
+
+
+def config5(torch, usc, pyref, dev, stream, rank, barrier, arena):
+    """BASELINE config 5: 8192 / 16384 / 65536-point chirp frames at low SNR, total samples per GPU = config 2's."""
+    times, info, ok = {}, {}, True
+    for n, snr in C5_LENGTHS:
+        h = usc.Handle(usc.default_config(n=n, sweep_T=n / FS), device=dev.index)   # the chirp fills the frame, as the generator's symbols do
+        h.set_stream(stream.cuda_stream)
+        nf = (NFRAMES * N) // n
+        sigma = AMP * 10.0 ** (-snr / 20.0)
+        x = torch.empty((nf, n), dtype=torch.int32, device=dev)
+        bits = torch.empty(nf, dtype=torch.uint8, device=dev)
+        first = rank * nf
+        h.synth_frames(SEED + 5, first, nf, AMP, sigma, x, bits)
+        o = [torch.empty(nf, dtype=torch.float32, device=dev) for _ in range(2)] + \
+            [torch.empty(nf, dtype=torch.int32, device=dev) for _ in range(2)]
+        b = torch.empty(nf, dtype=torch.uint8, device=dev)
+        times["c5_%d_ms" % n] = _dev_ms(torch, stream, lambda: h.demod_frames(x, usc.PCM_I32, nf, o[0], o[2], o[1], o[3], b), reps=5, warm=2)
+        p1, _ = pyref.synth_frames(SEED + 5, first + nf - 1, 1, AMP, sigma, n=n)
+        want = pyref.RefReceiver(n=n, sweep_T=n / FS).demod_frames(p1, nthreads=1)
+        ok &= bool(o[0][nf - 1].item() == want[0][0] and o[2][nf - 1].item() == want[1][0] and
+                   o[1][nf - 1].item() == want[2][0] and o[3][nf - 1].item() == want[3][0])
+        hp = arena[:nf * n].view(nf, n)
+        hp.copy_(x)
+        ho = [torch.empty(nf, dtype=torch.float32).pin_memory() for _ in range(2)] + \
+             [torch.empty(nf, dtype=torch.int32).pin_memory() for _ in range(2)]
+        hb = torch.empty(nf, dtype=torch.uint8).pin_memory()
+        times["c5_%d_e2e_s" % n] = _wall_s(torch, barrier, lambda: h.demod_frames_hostbuf(hp, usc.PCM_I32, nf, ho[0], ho[2], ho[1], ho[3], hb), 2)
+        ok &= bool(torch.equal(hb, b.cpu()) and torch.equal(ho[2], o[2].cpu()))
+        info[str(n)] = {"frames": nf, "snr_db": snr, "accuracy": float((b == bits).float().mean().item())}
+        h.close()
+        del x
+    return {"times": times, "ok": ok, "info": info}
+
+
+def configs_report(t, ok, infos, world, peak):
+    """the "configs" object of the JSON line from the rank-maximal timings"""
+    def roof(bytes_per_gpu, ms):
+        a = bytes_per_gpu / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "algorithmic_bytes": bytes_per_gpu}
+    out = {}
+    i3 = infos["3"]
+    out["3"] = {
+        "workload": "I/Q baseband path: carrier mix + 2 x 27-tap FIR + decimate by 2 + 1024-pt complex FFT, both hypotheses, %d streams x %d frames per GPU"
+                    % (C3_STREAMS, FRAMES_PER_STREAM),
+        "kernel": "k_iq_fused<int>", "value": i3["frames"] * world / (t["c3_ms"] * 1e-3), "unit": UNIT, "ms": t["c3_ms"],
+        "roofline": roof(i3["frames"] * (N * 4 + 24), t["c3_ms"]),
+        "e2e": {"value": i3["e2e_frames"] * world / t["c3_e2e_s"], "unit": UNIT, "call": "usc_iq_demod_host",
+                "h2d_bytes_per_step": i3["e2e_frames"] * N * 4, "d2h_bytes_per_step": i3["e2e_frames"] * 17,
+                "sample": "%d streams of the shard" % C3_E2E_STREAMS},
+        "input": "usc_synth_iq_frames: A cos(2 pi (fc - fb(t)) t) + noise, SNR 0 dB (simulation/IQ_modulation.ipynb cell 4)",
+        "symbol_accuracy_vs_tx_bits": i3["accuracy"], "oracle_check": ok["3"]}
+    i4 = infos["4"]
+    fr4 = i4["streams"] * i4["frames_per_stream"]
+    c4 = {
+        "workload": "time-frame synchronisation + receiver state machine: %d streams x 10 s sharded over 8 GPUs -> %d streams x %d frames (%.0f GB) per GPU, one wave"
+                    % (C4_STREAMS_TOTAL, i4["streams"], i4["frames_per_stream"], fr4 * N * 4 / 1e9),
+        "kernel": "k_receiver_run<int>", "value": fr4 * world / (t["c4_k7_ms"] * 1e-3), "unit": UNIT, "ms": t["c4_k7_ms"],
+        "roofline": roof(fr4 * N * 4 + i4["streams"] * 96, t["c4_k7_ms"]),
+        "messages_decoded_rank0": i4["decoded"], "streams_per_gpu": i4["streams"],
+        "sync_search": {}, "oracle_check": ok["4"],
+        "e2e": {"value": i4["e2e_streams"] * i4["frames_per_stream"] * world / t["c4_e2e_s"], "unit": UNIT,
+                "call": "usc_receiver_run_host", "h2d_bytes_per_step": i4["e2e_streams"] * i4["frames_per_stream"] * N * 4,
+                "d2h_bytes_per_step": i4["e2e_streams"] * 96, "sample": "%d streams of the shard" % C4_E2E_STREAMS}}
+    for K in (1, 2, 4):
+        ms = t["c4_k4_K%d_ms" % K]
+        c4["sync_search"]["K%d" % K] = {"kernel": "k_sync_search", "frames_added": K, "value": fr4 * world / (ms * 1e-3), "unit": "frames/s",
+                                        "ms": ms, "roofline": roof(fr4 * (N * 4 + 32), ms)}
+    out["4"] = c4
+    c5 = {"workload": "long chirp frames at low SNR, %d samples per GPU per pass" % (NFRAMES * N), "by_n": {}, "oracle_check": ok["5"]}
+    for n, _ in C5_LENGTHS:
+        i5 = infos["5"][str(n)]
+        ms = t["c5_%d_ms" % n]
+        c5["by_n"][str(n)] = {
+            "kernel": "k_demod_long" if n <= 16384 else "k_demod_cluster", "frames": i5["frames"], "snr_db": i5["snr_db"],
+            "value": i5["frames"] * world / (ms * 1e-3), "unit": UNIT, "msamples_per_s": i5["frames"] * world * n / (ms * 1e-3) / 1e6,
+            "ms": ms, "roofline": roof(i5["frames"] * (4 * n + 16), ms), "symbol_accuracy_vs_tx_bits": i5["accuracy"],
+            "e2e": {"value": i5["frames"] * world / t["c5_%d_e2e_s" % n], "unit": UNIT, "call": "usc_demod_frames_host",
+                    "h2d_bytes_per_step": i5["frames"] * n * 4, "d2h_bytes_per_step": i5["frames"] * 17}}
+    out["5"] = c5
+    return out
 
 
 def main():
@@ -218,6 +446,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3/4/5 measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -353,12 +582,37 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_ok = bool(torch.equal(h_bit, bit.cpu()) and torch.equal(h_iu, idx_up.cpu()))
-    os.sched_setaffinity(0, old_affinity)
 
-    times = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    # the further BASELINE configs (3, 4, 5), measured on this rank's shard in the same launch
+    cfg_times, cfg_ok, cfg_infos = {}, {}, {}
+    if not args.no_configs:
+        from oracle import pyref                              # sampled oracle checks only (the checker, never the timed path)
+        arena = host_pcm.view(-1)
+        for key, fn in (("3", lambda: config3(torch, usc, pyref, dev, stream, rank, barrier, arena)),
+                        ("5", lambda: config5(torch, usc, pyref, dev, stream, rank, barrier, arena)),
+                        ("4", lambda: config4(torch, usc, pyref, dev, stream, rank, world, barrier, arena))):
+            r = fn()
+            cfg_times.update(r["times"])
+            cfg_ok[key], cfg_infos[key] = r["ok"], r["info"]
+    os.sched_setaffinity(0, old_affinity)
+    del host_pcm
+
+    keys = sorted(cfg_times)
+    times = torch.tensor([ms_total, e2e_s, ms_single] + [cfg_times[k] for k in keys], dtype=torch.float64, device=dev)
+    oks = torch.tensor([int(e2e_ok)] + [int(cfg_ok[k]) for k in sorted(cfg_ok)], dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)          # timing only; no data-path collective
-    ms_total, e2e_s = float(times[0].item()), float(times[1].item())
+        dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+    ms_total, e2e_s, ms_single = (float(v) for v in times[:3].tolist())
+    cfg_times = dict(zip(keys, (float(v) for v in times[3:].tolist())))
+    e2e_ok = bool(oks[0].item())
+    cfg_ok = dict(zip(sorted(cfg_ok), (bool(v) for v in oks[1:].tolist())))
+    # the ranks are done with each other: the CPU legs below run on rank 0 alone with no rank spinning in a barrier
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
@@ -405,18 +659,22 @@ def main():
         }
         if not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
-            v, dt, passes = cpu_port(32768, threads)
+            v, dt, passes = cpu_port(32768, threads, budget_s=10.0, fast=True)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d passes over 32768 frames of the same workload, OpenMP over frames, %.1f s of wall time"
-                                              % (passes, dt)}
+                                    "sample": "%d passes over 32768 frames of the same workload, OpenMP over blocks of frames, %s, %.1f s of wall time"
+                                              % (passes, cpu_simd_note(), dt),
+                                    "form": "oracle/ref_fast.c: one frame per SIMD lane, iterative plan, per-thread scratch; bit-identical to oracle/ref_dsp.c"}
+            pv, pdt, ppasses = cpu_port(8192, threads, budget_s=4.0, fast=False)
+            line["cpu_baseline"]["plain_restatement"] = {
+                "value": pv, "unit": UNIT, "cores": threads,
+                "sample": "%d passes over 8192 frames, oracle/ref_dsp.c (the readable scalar restatement), %.1f s" % (ppasses, pdt)}
             nv, ndt, npasses = cpu_numpy(8192, threads)
             line["cpu_baseline"]["numpy_chain"] = {
                 "value": nv, "unit": UNIT, "cores": threads,
                 "sample": "%d passes over 8192 frames, scipy.fft.rfft(workers=%d) composition of the same chain, %.1f s" % (npasses, threads, ndt)}
+        if cfg_times:
+            line["configs"] = configs_report(cfg_times, cfg_ok, cfg_infos, world, peak)
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -246,6 +246,14 @@ int usc_scan4(usc_handle *h, const float *pcm2n, uint32_t batch, usc_scan_entry 
  * the oracle regenerates any frame bit for bit on the CPU.  bits (nframes, may be NULL): 1 = up. */
 int usc_synth_frames(usc_handle *h, uint64_t seed, uint64_t first_frame, size_t nframes, double amp,
                      double noise_sigma, int32_t *pcm, uint8_t *bits);
+/* The same generator fed with the I/Q transmitter's symbols (generator/ChirpGeneratorIQmodulation.ipynb cells 2-9,
+ * simulation/IQ_modulation.ipynb cell 4): symbol = amp * cos(2 pi (carrier + sideband * fb(t)) t + phase), fb the
+ * baseband chirp -bw/2 .. +bw/2 over one frame (up) or the reverse (down), t = linspace(0, n/fs, n).  sideband +1 and
+ * phase -pi/2 is the generator notebook's chirp_iq(); sideband -1 and phase 0 is the simulation's chirp_x_carrier(),
+ * the sense usc_iq_demod decides as bit 1 = up.  Input of BASELINE config 3.  Same noise, layout and CPU twin. */
+int usc_synth_iq_frames(usc_handle *h, uint64_t seed, uint64_t first_frame, size_t nframes, double carrier_hz,
+                        double bw_hz, int sideband, double phase_rad, double amp, double noise_sigma, int32_t *pcm,
+                        uint8_t *bits);
 /* Whole synthetic receiver streams in the transmitter's frame format (generator/ChirpGenerator.ipynb
  * cell 2): stream g (global index first_stream + s) repeats the pattern
  * lead_in x G (silence), 7 x H (up symbol), 1 x L (down symbol), 8*msg_bytes data symbols (MSB first,

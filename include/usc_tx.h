@@ -18,6 +18,10 @@ extern "C" {
 uint32_t usc_tx_symbol_len(double fs, double T);
 /* kind: 0 G, 1 H, 2 L.  out[i] = A (cos(arg) + sin(arg)), arg = 2 pi f(t) t - pi/2 on t = linspace(0, T, n). */
 int usc_tx_symbol(double fs, double f0, double f1, double T, double A, int kind, double *out, uint32_t cap);
+/* The I/Q transmitter's symbol, generator/ChirpGeneratorIQmodulation.ipynb cell 5 chirp_iq(): out[i] =
+ * A cos(2 pi (fc + fb) t + phase), fb = -bw/2 + k t/2 (kind 1, up) or +bw/2 - k t/2 (kind 2, down), k = bw/T,
+ * t = linspace(0, T, n); kind 0 = silence.  The notebook's tone (cell 9) is 100 x the up symbol as int16. */
+int usc_tx_symbol_iq(double fs, double bw, double fc, double T, double A, double phase, int kind, double *out, uint32_t cap);
 /* number of samples of the framed message: (1 + 7 + 1 + 8*msg_len + guard) symbols */
 size_t usc_tx_frame_len(double fs, double T, uint32_t msg_len, uint32_t guard);
 /* the whole tone as int16 (C truncation == numpy astype(int16)); guard = 12 in the notebook */

@@ -467,6 +467,16 @@ def synth_frames(seed, first_frame, nframes, amp, noise_sigma, n=2048, fs=78125.
     return pcm, bits
 
 
+def synth_iq_frames(seed, first_frame, nframes, carrier, bw, sideband, phase, amp, noise_sigma, n=2048, fs=78125.0):
+    """CPU twin of usc_synth_iq_frames -> (pcm [nframes, n] int32, bits)."""
+    pcm = np.empty((nframes, n), np.int32)
+    bits = np.empty(nframes, np.uint8)
+    lib().ref_synth_iq_frames(C.c_uint64(seed), C.c_uint64(first_frame), C.c_size_t(nframes), C.c_uint32(n), C.c_float(fs),
+                              C.c_double(carrier), C.c_double(bw), C.c_int(sideband), C.c_double(phase), C.c_double(amp),
+                              C.c_double(noise_sigma), pcm.ctypes.data_as(i32p), bits.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return pcm, bits
+
+
 def legacy_magnitudes(pcm, nthreads=4):
     """[nframes, n] int32 -> [nframes, n/2] magnitudes of the legacy detectors' shared front half."""
     pcm = np.ascontiguousarray(pcm, dtype=np.int32)

@@ -1059,6 +1059,19 @@ static void synth_tables(uint32_t n, float fs, float f0, float f1, double amp, i
         }
 }
 
+/* I/Q transmitter symbols: generator/ChirpGeneratorIQmodulation.ipynb cell 5 (sideband +1, phase -pi/2),
+ * simulation/IQ_modulation.ipynb cell 4 (sideband -1, phase 0) */
+static void synth_tables_iq(uint32_t n, float fs, double carrier, double bw, int sideband, double phase, double amp, int32_t *tab) {
+    const double T = (double) n / (double) fs, k = bw / T;
+    for (int down = 0; down < 2; ++down)
+        for (uint32_t i = 0; i < n; ++i) {
+            double t = T * (double) i / (double) (n - 1);
+            double fb = down ? bw / 2.0 - k * t / 2.0 : -bw / 2.0 + k * t / 2.0;
+            double arg = (2.0 * M_PI * (carrier + (sideband < 0 ? -fb : fb)) * t) + phase;
+            tab[(size_t) down * n + i] = (int32_t) llround(amp * cos(arg));
+        }
+}
+
 static uint32_t synth_msg_byte(uint32_t k0, uint32_t k1, uint64_t g, uint32_t m) {
     uint32_t r[4];
     philox(k0, k1, (uint32_t) g, (uint32_t) (g >> 32), 0x4D5347u, m >> 4, r);
@@ -1116,10 +1129,8 @@ void ref_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, 
     free(tab);
 }
 
-void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
-                      double amp, double noise_sigma, int32_t *pcm, uint8_t *bits) {
-    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
-    synth_tables(n, fs, f0, f1, amp, tab);
+static void synth_frames_from_table(const int32_t *tab, uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n,
+                                    double noise_sigma, int32_t *pcm, uint8_t *bits) {
     const int32_t gain = (int32_t) llround(noise_sigma / sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0) * 65536.0);
     const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
     for (size_t fl = 0; fl < nframes; ++fl) {
@@ -1137,5 +1148,20 @@ void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint3
             pcm[fl * n + 2 * blk + 1] = (t2[1] + (int32_t) (((int64_t) s1 * gain) / 65536)) * 256;
         }
     }
+}
+
+void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
+                      double amp, double noise_sigma, int32_t *pcm, uint8_t *bits) {
+    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
+    synth_tables(n, fs, f0, f1, amp, tab);
+    synth_frames_from_table(tab, seed, first_frame, nframes, n, noise_sigma, pcm, bits);
+    free(tab);
+}
+
+void ref_synth_iq_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, double carrier, double bw,
+                         int sideband, double phase, double amp, double noise_sigma, int32_t *pcm, uint8_t *bits) {
+    int32_t *tab = (int32_t *) malloc(sizeof(int32_t) * 2 * n);
+    synth_tables_iq(n, fs, carrier, bw, sideband, phase, amp, tab);
+    synth_frames_from_table(tab, seed, first_frame, nframes, n, noise_sigma, pcm, bits);
     free(tab);
 }

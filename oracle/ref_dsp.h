@@ -235,6 +235,10 @@ void ref_synth_streams(uint64_t seed, uint64_t first_stream, uint32_t nstreams, 
                        int32_t *pcm, uint32_t *offsets, uint8_t *messages);
 void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, float f0, float f1,
                       double amp, double noise_sigma, int32_t *pcm, uint8_t *bits);
+/* twin of usc_synth_iq_frames: the I/Q transmitter's symbols (generator/ChirpGeneratorIQmodulation.ipynb cell 5,
+ * simulation/IQ_modulation.ipynb cell 4) through the same generator */
+void ref_synth_iq_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, double carrier, double bw,
+                         int sideband, double phase, double amp, double noise_sigma, int32_t *pcm, uint8_t *bits);
 
 /* ---- receiver state machine (receiver/Src/main.c:417-580) ---- */
 enum { REF_IDLE = 0, REF_SYNCHRONIZING = 1, REF_SYNCHRONIZED = 2, REF_DATA_RECEIVING = 3 };   /* main.c:108-111 */

@@ -95,3 +95,44 @@ def test_reference_transmitter_track_decodes_at_the_receiver_rate(golden):
     nframes = pcm.size // 2048
     out, st = R.receiver_run(R.RefReceiver(), pcm[:nframes * 2048].reshape(nframes, 2048), cap=16)
     assert out == b"Hi\n" and st.lock_frame > 20
+
+
+def test_iq_transmitter_symbol_is_the_notebooks_chirp_iq(tx):
+    """generator/ChirpGeneratorIQmodulation.ipynb cells 2-5: chirp_iq() at fs 44100, T 0.0205, BW 3000, carrier 18000,
+    amplitude 20000, phase -pi/2 — restated with numpy exactly as the cell is written — and the notebook's own known
+    answer (cell 8 prints spectral peaks at 16830.2 and 19171.8 Hz for both symbols)."""
+    fs, Tq, BWq, FC, Aq = 44100.0, 0.0205, 3000.0, 18000.0, 20000.0
+    n = int(Tq * fs)
+    assert tx.usc_tx_symbol_len(C.c_double(fs), C.c_double(Tq)) == n == 904
+    t = np.linspace(0, Tq, n)
+    k = float(BWq) / float(Tq)
+    for kind, fb in ((1, -BWq / 2 + k * t / 2.0), (2, BWq / 2 - k * t / 2.0)):
+        want = np.cos((2.0 * np.pi * (FC + fb) * t) + (-np.pi / 2.0)) * Aq
+        s = np.zeros(n)
+        assert tx.usc_tx_symbol_iq(C.c_double(fs), C.c_double(BWq), C.c_double(FC), C.c_double(Tq), C.c_double(Aq),
+                                   C.c_double(-np.pi / 2.0), C.c_int(kind), s.ctypes.data_as(C.c_void_p), C.c_uint32(n)) == n
+        assert np.abs(s - want).max() <= 1e-9 * Aq
+        a = np.abs(np.fft.fftshift(np.fft.fft(s)))
+        freq = np.fft.fftshift(np.fft.fftfreq(n, 1 / fs))
+        pos = freq > 0
+        # the two spectral horns of a linear chirp: the notebook's peakutils output 16830.2 / 19171.8 Hz
+        lo = freq[pos][np.argmax(np.where(freq[pos] < FC, a[pos], 0))]
+        hi = freq[pos][np.argmax(np.where(freq[pos] > FC, a[pos], 0))]
+        assert abs(lo - 16830.19911504) < 1e-6 and abs(hi - 19171.7920354) < 1e-6
+    assert tx.usc_tx_symbol_iq(C.c_double(fs), C.c_double(BWq), C.c_double(FC), C.c_double(Tq), C.c_double(Aq), C.c_double(0.0),
+                               C.c_int(0), s.ctypes.data_as(C.c_void_p), C.c_uint32(n)) == n and not s.any()
+
+
+def test_iq_generator_twin_feeds_the_iq_demodulator(fir_taps):
+    """The I/Q transmitter through the counter-based generator (CPU twin of usc_synth_iq_frames) decodes through the
+    oracle's I/Q demodulator: in the simulation notebook's sense (carrier - fb) bit 1 = up."""
+    taps = fir_taps.astype(np.float32)[::-1].copy()
+    q = R.RefIq(taps)
+    pcm, bits = R.synth_iq_frames(11, 0, 24, 18000.0, 3000.0, -1, 0.0, 2.0e4, 6000.0)
+    assert np.all(pcm % 256 == 0) and 4 < bits.sum() < 20
+    mu, iu, md, idn = q.demod(pcm)
+    assert np.array_equal((~(md > mu)).astype(np.uint8), bits)
+    # the generator notebook's sense (carrier + fb) mirrors the sweep: the same demodulator then reads the complement
+    pcm2, bits2 = R.synth_iq_frames(11, 0, 24, 18000.0, 3000.0, +1, -np.pi / 2, 2.0e4, 6000.0)
+    mu, iu, md, idn = q.demod(pcm2)
+    assert np.array_equal(bits2, bits) and np.array_equal((md > mu).astype(np.uint8), bits2)

@@ -38,6 +38,7 @@ struct usc_handle {
     uint32_t iq_ntaps, iq_window;
     int32_t* d_sym_table;                             // synthetic generator: up/down symbol tables (2n int32)
     double sym_amp;
+    double sym_iq[4];                                 // carrier, bw, sideband, phase of the cached table; carrier 0 = chirp_orth symbols
     float* d_work;                                    // grow-on-demand scratch (large FFTs, generic demod)
     size_t work_bytes;
     std::map<uint32_t, float2*> tw_cache;             // master twiddle tables by length
@@ -176,6 +177,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->work_bytes = 0;
     h->d_sym_table = nullptr;
     h->sym_amp = 0.0;
+    h->sym_iq[0] = h->sym_iq[1] = h->sym_iq[2] = h->sym_iq[3] = 0.0;
     h->d_iq_cos = h->d_iq_sin = h->d_iq_chirp = h->d_iq_conj = h->d_iq_hann = h->d_iq_taps = nullptr;
     h->iq_ntaps = h->iq_window = 0;
     h->lane_frames = 0;
@@ -971,17 +973,21 @@ int usc_scan4(usc_handle* h, const float* pcm2n, uint32_t batch, usc_scan_entry*
     return USC_OK;
 }
 
-static int ensure_symbol_table(usc_handle* h, double amp) {
+/* the generator's symbol tables (2n int32: up, down), cached per handle: chirp_orth symbols (carrier == 0) or the I/Q transmitter's */
+static int ensure_symbol_table(usc_handle* h, double amp, double carrier = 0.0, double bw = 0.0, int sideband = 0, double phase = 0.0) {
     const uint32_t n = h->cfg.n;
-    if (!h->d_sym_table || h->sym_amp != amp) {
+    const double key[4] = {carrier, bw, (double) sideband, phase};
+    if (!h->d_sym_table || h->sym_amp != amp || memcmp(key, h->sym_iq, sizeof key) != 0) {
         std::vector<int32_t> tab(2 * (size_t) n);
-        usc_host_symbol_tables(n, h->cfg.fs, h->cfg.f0, h->cfg.f1, amp, tab.data());
+        if (carrier == 0.0) usc_host_symbol_tables(n, h->cfg.fs, h->cfg.f0, h->cfg.f1, amp, tab.data());
+        else usc_host_iq_symbol_tables(n, h->cfg.fs, carrier, bw, sideband, phase, amp, tab.data());
         CK(cudaStreamSynchronize(h->stream));
         cudaFree(h->d_sym_table);
         h->d_sym_table = nullptr;
         int rc = upload(tab.data(), tab.size() * sizeof(int32_t), (void**) &h->d_sym_table);
         if (rc) return rc;
         h->sym_amp = amp;
+        memcpy(h->sym_iq, key, sizeof key);
     }
     return USC_OK;
 }
@@ -1012,6 +1018,20 @@ int usc_synth_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t 
     int rc = ensure_symbol_table(h, amp);
     if (rc) return rc;
     LAUNCHED(h, launch_synth_frames(seed, first_frame, nframes, n, h->d_sym_table, usc_host_noise_gain(noise_sigma), pcm, bits,
+                                    h->stream));
+    return USC_OK;
+}
+
+int usc_synth_iq_frames(usc_handle* h, uint64_t seed, uint64_t first_frame, size_t nframes, double carrier_hz, double bw_hz,
+                        int sideband, double phase_rad, double amp, double noise_sigma, int32_t* pcm, uint8_t* bits) {
+    USC_ENTER(h);
+    if (!h || !pcm || !(amp >= 0.0) || !(noise_sigma >= 0.0) || amp + 8.0 * noise_sigma > 8.0e6) return USC_ERR_ARGUMENT;
+    if (!(carrier_hz > 0.0) || !(bw_hz >= 0.0) || (sideband != 1 && sideband != -1)) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 7u) != 0) return USC_ERR_ARGUMENT;
+    if (!nframes) return USC_OK;
+    int rc = ensure_symbol_table(h, amp, carrier_hz, bw_hz, sideband, phase_rad);
+    if (rc) return rc;
+    LAUNCHED(h, launch_synth_frames(seed, first_frame, nframes, h->cfg.n, h->d_sym_table, usc_host_noise_gain(noise_sigma), pcm, bits,
                                     h->stream));
     return USC_OK;
 }

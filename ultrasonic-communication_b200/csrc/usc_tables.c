@@ -120,6 +120,18 @@ void usc_host_symbol_tables(uint32_t n, float fs, float f0, float f1, double amp
         }
 }
 
+void usc_host_iq_symbol_tables(uint32_t n, float fs, double carrier, double bw, int sideband, double phase, double amp,
+                               int32_t *out) {
+    const double T = (double) n / (double) fs, k = bw / T, sgn = sideband < 0 ? -1.0 : 1.0;
+    for (int down = 0; down < 2; ++down)
+        for (uint32_t i = 0; i < n; ++i) {
+            const double t = T * (double) i / (double) (n - 1);
+            const double fb = down ? bw / 2.0 - k * t / 2.0 : -bw / 2.0 + k * t / 2.0;
+            const double arg = (2.0 * M_PI * (carrier + sgn * fb) * t) + phase;
+            out[(size_t) down * n + i] = (int32_t) llround(amp * cos(arg));
+        }
+}
+
 int32_t usc_host_noise_gain(double sigma) {
     /* sum of four independent 16-bit uniforms: variance 4 * (65536^2 - 1) / 12 */
     const double unit = sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0);

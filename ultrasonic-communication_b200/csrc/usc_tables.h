@@ -28,6 +28,11 @@ uint32_t usc_host_radices(uint32_t n, uint32_t *rad);
  * chirp_orth law of simulation/signal.py:45-53 (t = linspace(0, T, n), T = n/fs, phase -pi/2), evaluated
  * in double.  out: 2n int32 — the up symbol then the down symbol. */
 void usc_host_symbol_tables(uint32_t n, float fs, float f0, float f1, double amp, int32_t *out);
+/* I/Q transmitter symbols (generator/ChirpGeneratorIQmodulation.ipynb cell 5, simulation/IQ_modulation.ipynb cell 4):
+ * out[down*n + i] = round(amp * cos(2 pi (fc + sideband * fb(t_i)) t_i + phase)), fb = -bw/2 + k t/2 (up) or
+ * +bw/2 - k t/2 (down), k = bw/T, t = linspace(0, T, n), T = n/fs */
+void usc_host_iq_symbol_tables(uint32_t n, float fs, double carrier, double bw, int sideband, double phase, double amp,
+                               int32_t *out);
 /* noise gain of the integer generator for a target standard deviation (PCM units before the x256) */
 int32_t usc_host_noise_gain(double sigma);
 /* (F1 - F0) * NN / fs truncated to uint32 (receiver/Src/main.c:372). */

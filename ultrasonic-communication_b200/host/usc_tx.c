@@ -25,6 +25,24 @@ int usc_tx_symbol(double fs, double f0, double f1, double T, double A, int kind,
     return (int) n;
 }
 
+int usc_tx_symbol_iq(double fs, double bw, double fc, double T, double A, double phase, int kind, double *out, uint32_t cap) {
+    const uint32_t n = usc_tx_symbol_len(fs, T);
+    if (!out || n < 2 || cap < n || kind < 0 || kind > 2) return -1;
+    if (kind == 0) {
+        memset(out, 0, sizeof(double) * n);
+        return (int) n;
+    }
+    const double f0 = -bw / 2.0, f1 = bw / 2.0;                        /* cell 3 */
+    const double step = T / (double) (n - 1), k = (f1 - f0) / T;       /* numpy.linspace(0, T, n) */
+    for (uint32_t i = 0; i < n; ++i) {
+        const double t = i == n - 1 ? T : (double) i * step;
+        const double fb = kind == 1 ? f0 + k * t / 2.0 : f1 - k * t / 2.0;
+        const double arg = (2.0 * M_PI * (fc + fb) * t) + phase;
+        out[i] = cos(arg) * A;                                          /* chirp_iq(), cell 5 */
+    }
+    return (int) n;
+}
+
 size_t usc_tx_frame_len(double fs, double T, uint32_t msg_len, uint32_t guard) {
     return (size_t) usc_tx_symbol_len(fs, T) * (1u + 7u + 1u + 8u * (size_t) msg_len + guard);
 }

@@ -56,7 +56,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_iq_demod_host", "usc_receiver_run_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_iq_demod_host", "usc_receiver_run_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_iq_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
 ]
 
 _lib = None
@@ -313,6 +313,11 @@ class Handle:
         res = d_r.to_numpy(rx_result_dtype)
         u = d_u.to_numpy(np.uint8).reshape(S, uart_cap)
         return [bytes(u[s, :min(int(res["nbytes"][s]), uart_cap)]) for s in range(S)], res
+
+    def synth_iq_frames(self, seed, first_frame, nframes, carrier, bw, sideband, phase, amp, noise_sigma, pcm, bits=None):
+        _ck(load().usc_synth_iq_frames(self._h, C.c_uint64(seed), C.c_uint64(first_frame), C.c_size_t(nframes), C.c_double(carrier),
+                                       C.c_double(bw), C.c_int(sideband), C.c_double(phase), C.c_double(amp), C.c_double(noise_sigma),
+                                       _ptr(pcm), _ptr(bits)))
 
     def synth_streams(self, seed, first_stream, nstreams, nframes, stream_stride, lead_in, msg_bytes, guard, amp, noise_sigma,
                       pcm, offsets=None, messages=None):
