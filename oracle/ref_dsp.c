@@ -49,14 +49,40 @@ float32_t ref_arm_cos_f32(float32_t x) {
 
 /* arm_sin_cos_f32 — arm_math.h:4634-4637 (degrees in).  Call sites: receiver/Src/chirp.c:36,
  * experiments/synchronization/Src/chirp.c:37, experiments/iq_modulation/Src/iq_modem.c:43.
- * UNPINNED (no capture holds a chirp table).  Defined as the correctly rounded value of
- * sin/cos(theta_deg * pi/180) evaluated in double: the device's table interpolation differs by
- * <= ~1e-6, far below the 1e-4 budget and below the 1e-4 rad phase error already carried by the
- * float32 theta itself (ulp(186000 deg) = 0.0156 deg). */
+ * CMSIS-DSP V1.4.5's published algorithm: |theta|/360 -> fractional turns -> 512-entry sine table read at the
+ * sine and the quarter-turn-shifted cosine index, cubic (Hermite) interpolation using the other function's table
+ * values as derivatives (Dn = 2 pi/512), sine negated for negative theta.
+ * PINNED to the reference's own binary: the operation sequence below was checked, instruction by instruction,
+ * against the machine code of arm_sin_cos_f32 in receiver/Drivers/CMSIS/Lib/libarm_cortexM4lf_math.a (31 separate
+ * VMUL/VADD/VSUB, no fused multiply-add; literals 0x3B360B61, 512.0f, 0x3C490FDB), and sinTable_f32 as stored in
+ * that archive equals g_sin_table bit for bit (tools/cmsis_archive_probe.py, tests/golden/cmsis_archive.npz). */
 void ref_arm_sin_cos_f32(float32_t theta_deg, float32_t *pSinVal, float32_t *pCosVal) {
-    double rad = (double) theta_deg * (M_PI / 180.0);
-    *pSinVal = (float) sin(rad);
-    *pCosVal = (float) cos(rad);
+    sin_table_init();
+    float in = theta_deg * 0.00277777777778f;
+    if (in < 0.0f) in = -in;
+    in = in - (float) (int32_t) in;
+    float findex = (float) FAST_MATH_TABLE_SIZE * in;
+    uint16_t indexS = ((uint16_t) findex) & 0x1ff;
+    uint16_t indexC = (uint16_t) ((indexS + (FAST_MATH_TABLE_SIZE / 4)) & 0x1ff);
+    float fract = findex - (float) indexS;
+    const float Dn = 0.0122718463030f;
+    /* cosine: values from the cosine index, derivatives = -sine */
+    float f1 = g_sin_table[indexC], f2 = g_sin_table[indexC + 1];
+    float d1 = -g_sin_table[indexS], d2 = -g_sin_table[indexS + 1];
+    float Df = f2 - f1;
+    float temp = Dn * (d1 + d2) - 2 * Df;
+    temp = fract * temp + (3 * Df - (d2 + 2 * d1) * Dn);
+    temp = fract * temp + d1 * Dn;
+    *pCosVal = fract * temp + f1;
+    /* sine: values from the sine index, derivatives = cosine */
+    f1 = g_sin_table[indexS]; f2 = g_sin_table[indexS + 1];
+    d1 = g_sin_table[indexC]; d2 = g_sin_table[indexC + 1];
+    Df = f2 - f1;
+    temp = Dn * (d1 + d2) - 2 * Df;
+    temp = fract * temp + (3 * Df - (d2 + 2 * d1) * Dn);
+    temp = fract * temp + d1 * Dn;
+    *pSinVal = fract * temp + f1;
+    if (theta_deg < 0.0f) *pSinVal = -*pSinVal;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -36,10 +36,31 @@ float usc_host_arm_cos_f32(float x) {
     return (1.0f - frac) * s_sine[idx] + frac * s_sine[idx + 1];
 }
 
+/* CMSIS-DSP V1.4.5 arm_sin_cos_f32 (arm_math.h:4634-4637), degrees in: turns of |theta|, the 512-entry table read at
+ * the sine position and a quarter turn later, cubic interpolation whose end-point slopes are the other function's
+ * table values times 2 pi/512; the sine takes theta's sign.  Plain float operations in this order (the vendored
+ * archive's code has no fused multiply-add). */
+static float hermite512(float y0, float y1, float s0, float s1, float frac) {
+    const float step = 0.0122718463030f;
+    const float rise = y1 - y0;
+    float acc = step * (s0 + s1) - 2 * rise;
+    acc = frac * acc + (3 * rise - (s1 + 2 * s0) * step);
+    acc = frac * acc + s0 * step;
+    return frac * acc + y0;
+}
+
 void usc_host_arm_sin_cos_f32(float theta_deg, float *s, float *c) {
-    double rad = (double) theta_deg * (M_PI / 180.0);
-    *s = (float) sin(rad);
-    *c = (float) cos(rad);
+    sine_table_init();
+    float turns = theta_deg * 0.00277777777778f;
+    if (turns < 0.0f) turns = -turns;
+    turns = turns - (float) (int32_t) turns;
+    const float pos = (float) SINE_TABLE_SIZE * turns;
+    const uint16_t is = ((uint16_t) pos) & 0x1ff;
+    const uint16_t ic = (uint16_t) ((is + SINE_TABLE_SIZE / 4) & 0x1ff);
+    const float frac = pos - (float) is;
+    *c = hermite512(s_sine[ic], s_sine[ic + 1], -s_sine[is], -s_sine[is + 1], frac);
+    const float sv = hermite512(s_sine[is], s_sine[is + 1], s_sine[ic], s_sine[ic + 1], frac);
+    *s = theta_deg < 0.0f ? -sv : sv;
 }
 
 void usc_host_hann(float *w, uint32_t n, uint32_t kind) {
