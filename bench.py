@@ -342,6 +342,15 @@ def config4(torch, usc, pyref, dev, stream, rank, world, barrier, arena):
         ok &= bool(np.array_equal(idx[1].cpu().numpy().astype(np.uint32), wi) and
                    np.array_equal(mag[1].cpu().numpy().view(np.uint32), wm.view(np.uint32)))
     del mag, idx
+    # K8: the overlap-save synchroniser (every lag, each sample read once) on the same shard
+    omv = torch.empty(S * (F - 1), dtype=torch.float32, device=dev)
+    omi = torch.empty(S * (F - 1), dtype=torch.int32, device=dev)
+    times["c4_os_ms"] = _dev_ms(torch, stream, lambda: h.correlate_os(pcm, usc.PCM_I32, S, F, F * N, False, None, omv, omi), reps=2, warm=1)
+    tmpl = pyref.arm_mult_f32(h.table("down"), h.table("hann"))
+    _, wv, wi = pyref.correlate_os(tmpl, p1[0].reshape(F, N))
+    sl = slice(1 * (F - 1), 2 * (F - 1))
+    ok &= bool(np.array_equal(omi[sl].cpu().numpy().astype(np.uint32), wi) and np.array_equal(omv[sl].cpu().numpy().view(np.uint32), wv.view(np.uint32)))
+    del omv, omi
     # e2e through usc_receiver_run_host on a bounded sample of the shard
     Se = C4_E2E_STREAMS
     hp = arena[:Se * F * N].view(Se, F * N)
@@ -423,6 +432,10 @@ def configs_report(t, ok, infos, world, peak):
         ms = t["c4_k4_K%d_ms" % K]
         c4["sync_search"]["K%d" % K] = {"kernel": "k_sync_search", "frames_added": K, "value": fr4 * world / (ms * 1e-3), "unit": "frames/s",
                                         "ms": ms, "roofline": roof(fr4 * (N * 4 + 32), ms)}
+    ms = t["c4_os_ms"]
+    c4["overlap_save"] = {"kernel": "k_correlate_os<int>", "call": "usc_correlate_os", "what": "linear matched filter at every lag (2n windows, hop n, 4096-point real transforms), peak per block",
+                          "value": i4["streams"] * (i4["frames_per_stream"] - 1) * world / (ms * 1e-3), "unit": "blocks/s", "ms": ms,
+                          "roofline": roof(fr4 * N * 4 + i4["streams"] * (i4["frames_per_stream"] - 1) * 8, ms)}
     out["4"] = c4
     c5 = {"workload": "long chirp frames at low SNR, %d samples per GPU per pass" % (NFRAMES * N), "by_n": {}, "oracle_check": ok["5"]}
     for n, _ in C5_LENGTHS:

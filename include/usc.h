@@ -337,6 +337,18 @@ int usc_iq_demod(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t n
  * may be NULL when only the peaks are wanted. */
 int usc_compress_chirp(usc_handle *h, const void *pcm, uint32_t pcm_format, size_t nframes, int use_up,
                        float *out_frames, float *max_val, uint32_t *max_idx);
+/* K8.  Overlap-save frame synchroniser (BASELINE.json north_star; no counterpart function in the reference, which
+ * probes four offsets per frame — usc_sync_search keeps that arithmetic).  compress_chirp()'s three steps
+ * (experiments/chirp_compression_time_domain/Src/chirp.c:78-83: RFFT, arm_cmplx_mult_cmplx_f32 by the spectrum of
+ * window x reference chirp, inverse RFFT) run on 2n-sample windows advancing by n samples, the template zero-padded to
+ * 2n, so that lags [n, 2n) of block b are the LINEAR filter output y[t] = sum_m g[m] x[t - m] at t = (b+1) n ... (b+2) n - 1:
+ * every lag of the stream, sample resolution, each PCM sample read from HBM once.  Per stream of nframes frames
+ * (stream_stride samples apart, 16-byte aligned) there are nframes-1 blocks; per block: out (n floats, may be NULL),
+ * max_val / max_idx = arm_max_f32 over the block's n lags (signed, first occurrence).  use_up selects the up chirp's
+ * spectrum as the filter (0 = the down chirp's, the reference's choice in compress_chirp).  n = 2048, real chirp
+ * variants (R, T, F). */
+int usc_correlate_os(usc_handle *h, const void *pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                     size_t stream_stride, int use_up, float *out, float *max_val, uint32_t *max_idx);
 
 #ifdef __cplusplus
 }

@@ -477,6 +477,22 @@ def synth_iq_frames(seed, first_frame, nframes, carrier, bw, sideband, phase, am
     return pcm, bits
 
 
+def correlate_os(tmpl, pcm):
+    """twin of usc_correlate_os for one stream: pcm [nframes, n] int32 or float32 -> (out [nframes-1, n], max, idx)"""
+    tmpl = f32(tmpl)
+    n = tmpl.size
+    pcm = np.ascontiguousarray(pcm)
+    nf = pcm.size // n
+    out = np.empty((nf - 1, n), np.float32)
+    mv, mi = np.empty(nf - 1, np.float32), np.empty(nf - 1, np.uint32)
+    pi = pcm.ctypes.data_as(i32p) if pcm.dtype == np.int32 else None
+    pf = _fp(pcm) if pcm.dtype == np.float32 else None
+    if pi is None and pf is None:
+        raise TypeError(pcm.dtype)
+    lib().ref_correlate_os(_fp(tmpl), C.c_uint32(n), pi, pf, C.c_uint32(nf), _fp(out), _fp(mv), _up(mi))
+    return out, mv, mi
+
+
 def legacy_magnitudes(pcm, nthreads=4):
     """[nframes, n] int32 -> [nframes, n/2] magnitudes of the legacy detectors' shared front half."""
     pcm = np.ascontiguousarray(pcm, dtype=np.int32)

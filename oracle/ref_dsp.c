@@ -868,6 +868,35 @@ void ref_compress_frames_i32(const ref_compressor *c, const int32_t *pcm, size_t
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* overlap-save frame synchroniser (twin of usc_correlate_os): compress_chirp's three steps        */
+/* (experiments/chirp_compression_time_domain/Src/chirp.c:78-83) on 2n-sample windows that advance  */
+/* by n, against G = rfft_2n(window * chirp zero-padded to 2n); lags [n, 2n) of each block are the  */
+/* linear filter output.  No input window (overlap-save filters the raw stream).                    */
+/* ------------------------------------------------------------------------------------------ */
+void ref_correlate_os(const float *tmpl /* n: window * chirp */, uint32_t n, const int32_t *pcm_i32, const float *pcm_f32,
+                      uint32_t nframes, float *out /* (nframes-1)*n or NULL */, float *max_val, uint32_t *max_idx) {
+    ref_rfft_fast_instance_f32 S;
+    if (nframes < 2 || ref_arm_rfft_fast_init_f32(&S, 2 * n) != REF_MATH_SUCCESS) return;
+    float *G = (float *) calloc(2 * n, sizeof(float)), *blk = (float *) malloc(sizeof(float) * 2 * n);
+    memcpy(G, tmpl, sizeof(float) * n);
+    ref_arm_rfft_fast_f32(&S, G, G, 0);
+    for (uint32_t b = 0; b + 1 < nframes; ++b) {
+        for (uint32_t i = 0; i < 2 * n; ++i)
+            blk[i] = pcm_i32 ? (float) pcm_i32[(size_t) b * n + i] : pcm_f32[(size_t) b * n + i];
+        ref_arm_rfft_fast_f32(&S, blk, blk, 0);
+        ref_arm_cmplx_mult_cmplx_f32(blk, G, blk, n);
+        ref_arm_rfft_fast_f32(&S, blk, blk, 1);
+        if (out) memcpy(out + (size_t) b * n, blk + n, sizeof(float) * n);
+        float v; uint32_t i;
+        ref_arm_max_f32(blk + n, n, &v, &i);
+        if (max_val) max_val[b] = v;
+        if (max_idx) max_idx[b] = i;
+    }
+    free(G); free(blk);
+    ref_arm_rfft_fast_free(&S);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* 4-offset scan — experiments/chirp_compression_freq_domain/Src/main.c:113-160, 245-251         */
 /* ------------------------------------------------------------------------------------------ */
 void ref_scan4(const ref_rfft_fast_instance_f32 *S, const float *hann, const float *chirp, uint32_t n, uint32_t bandwidth,

@@ -240,6 +240,11 @@ void ref_synth_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint3
 void ref_synth_iq_frames(uint64_t seed, uint64_t first_frame, size_t nframes, uint32_t n, float fs, double carrier, double bw,
                          int sideband, double phase, double amp, double noise_sigma, int32_t *pcm, uint8_t *bits);
 
+/* twin of usc_correlate_os: overlap-save linear filtering of one stream (nframes frames of n samples, int32 or float)
+ * with the n-sample template (window * chirp); per block b < nframes-1: the n valid lags, their arm_max_f32 */
+void ref_correlate_os(const float *tmpl, uint32_t n, const int32_t *pcm_i32, const float *pcm_f32, uint32_t nframes,
+                      float *out, float *max_val, uint32_t *max_idx);
+
 /* ---- receiver state machine (receiver/Src/main.c:417-580) ---- */
 enum { REF_IDLE = 0, REF_SYNCHRONIZING = 1, REF_SYNCHRONIZED = 2, REF_DATA_RECEIVING = 3 };   /* main.c:108-111 */
 

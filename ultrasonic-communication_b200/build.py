@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr"]
 CC_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-Wall"]
 
-CU = ["usc_api.cu", "k_demod.cu", "k_receiver.cu", "k_sync.cu", "k_iq.cu", "k_synth.cu", "k_long.cu", "k_legacy.cu", "k_compress.cu", "k_fft_generic.cu", "k_fft_warp.cu", "k_elementwise.cu"]
+CU = ["usc_api.cu", "k_demod.cu", "k_receiver.cu", "k_sync.cu", "k_iq.cu", "k_synth.cu", "k_long.cu", "k_legacy.cu", "k_compress.cu", "k_correlate.cu", "k_fft_generic.cu", "k_fft_warp.cu", "k_elementwise.cu"]
 C = ["usc_tables.c"]
 
 

@@ -1,0 +1,233 @@
+// k_correlate.cu — K8: overlap-save frame synchroniser (BASELINE north_star: "the frame synchronizer is an overlap-save
+// correlation kernel").
+//
+// compress_chirp() of experiments/chirp_compression_time_domain/Src/chirp.c:78-83 filters ONE n-sample frame with the
+// windowed reference chirp in the frequency domain (RFFT -> x H -> IRFFT): a circular result whose lags wrap.  The same
+// three CMSIS-shaped steps on 2n-sample windows that advance by n samples give the LINEAR filter output at every lag of
+// a stream (overlap-save): block b of a stream is samples [b n, b n + 2n); G = rfft_2n(template zero-padded to 2n);
+//   y_b = irfft_2n( rfft_2n(block) x G )          (arm_cmplx_mult_cmplx_f32 on the packed spectrum, quirk kept)
+// and y_b[l], l in [n, 2n), equals sum_m g[m] x[b n + l - m] with no wrap-around.  A stream of F frames has F - 1 blocks.
+//
+// Mapping: one warp walks consecutive blocks of one stream, so every PCM sample crosses HBM once: the upper half of
+// block b is the lower half of block b + 1 and stays in shared memory (two 8 KB halves used as a ring); only the n new
+// samples arrive per block, by a 1-D TMA bulk copy issued as soon as the old lower half is dead.
+// Per block: 4096-point real FFT = 2048-point complex FFT in the canonical plan [2, 32, 32] (even- and odd-bin
+// 1024-point transforms ride in the f32x2 halves of the packed register core) -> spectrum parked in natural order in
+// shared memory (the dead lower half + the idle exchange tile, 16 KB) -> split, x G, merge in place, one lane per
+// (k, 2048 - k) pair -> 2048-point inverse by forward-on-swapped-parts -> only the upper half of the outputs is live,
+// so half of the last pass is pruned -> signed first-occurrence arg-max over the n valid lags (arm_max_f32) and an
+// optional coalesced store of the n filtered samples.
+// Arithmetic: the canonical order of DESIGN.md §3 — bit-identical to the oracle's operator chain
+// (ref_correlate_os = ref_arm_rfft_fast_f32(4096) . ref_arm_cmplx_mult_cmplx_f32 . ref_arm_rfft_fast_f32(4096, inverse)).
+#include "usc_kernels.cuh"
+#include "usc_launch.h"
+#include "usc_warpfft.cuh"
+
+namespace usc {
+
+constexpr int kOsWarps = 8;
+constexpr int kOsTabs = 8192 + 8192 + 16384;           // pass twiddles | W_2048^a (radix-2 level) | W_4096^k split table
+constexpr int kOsWarpBytes = 3 * 8192;                 // half A | exchange tile | half B
+constexpr int kOsBar = kOsTabs + kOsWarps * kOsWarpBytes;
+constexpr int kOsSmem = kOsBar + kOsWarps * 8;
+
+struct os_params {
+    const void* pcm; uint32_t nstreams, nframes; size_t stream_stride;
+    const float2* G;                                   // packed spectrum of the zero-padded template, 2048 float2
+    const float2* tw_pass; const float2* tw0; const float2* tw_split;   // tw_split: (cos, sin)(2 pi k / 4096), k < 2048
+    uint32_t seg_blocks, nseg;                         // a work item = seg_blocks consecutive blocks of one stream
+    float* out; float* max_val; uint32_t* max_idx;
+};
+
+template <typename PCM>
+__global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(s_raw);
+    float2* s_tw0 = reinterpret_cast<float2*>(s_raw + 8192);
+    float2* s_ws = reinterpret_cast<float2*>(s_raw + 16384);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = s_raw + kOsTabs + warp * kOsWarpBytes;
+    float2* tile = reinterpret_cast<float2*>(wbase + 8192);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + kOsBar) + warp;
+    using V2 = typename vec2<PCM>::type;
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        if (i < 1024) {
+            s_tw[i] = p.tw_pass[i];
+            s_tw0[i] = p.tw0[i];
+        }
+        s_ws[i] = p.tw_split[i];
+    }
+    __syncthreads();
+
+    const uint32_t nblocks = p.nframes - 1;
+    const size_t nitems = (size_t) p.nstreams * p.nseg;
+    const size_t nwarps = (size_t) gridDim.x * kOsWarps;
+    const PCM* pcm = static_cast<const PCM*>(p.pcm);
+    uint32_t parity = 0;
+    for (size_t item = (size_t) blockIdx.x * kOsWarps + warp; item < nitems; item += nwarps) {
+        const uint32_t s = (uint32_t) (item / p.nseg), seg = (uint32_t) (item % p.nseg);
+        const uint32_t b0 = seg * p.seg_blocks;
+        const uint32_t b1 = min(b0 + p.seg_blocks, nblocks);
+        const PCM* stream = pcm + (size_t) s * p.stream_stride;
+        if (lane == 0) {                               // first block of the item: both halves
+            mbar_expect_tx(bar, 16384u);
+            bulk_g2s(wbase, stream + (size_t) b0 * 2048, 8192u, bar);
+            bulk_g2s(wbase + 16384, stream + (size_t) (b0 + 1) * 2048, 8192u, bar);
+        }
+        for (uint32_t b = b0; b < b1; ++b) {
+            const uint32_t odd = (b - b0) & 1u;        // which physical half holds the older n samples
+            const V2* lo_half = reinterpret_cast<const V2*>(wbase + (odd ? 16384 : 0));
+            const V2* hi_half = reinterpret_cast<const V2*>(wbase + (odd ? 0 : 16384));
+            float2* zs = reinterpret_cast<float2*>(wbase + (odd ? 8192 : 0));       // 2048 float2: dead lower half + tile
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            float2 re[32], im[32];                     // (.x, .y) = (even-bin transform, odd-bin transform)
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {             // radix-2 level of the [2,32,32] plan on z[m] = x[2m] + j x[2m+1]
+                const int a = lane + 32 * q;
+                const V2 l = lo_half[a], h = hi_half[a];
+                const float lx = pcm_to_float(l.x), ly = pcm_to_float(l.y), hx = pcm_to_float(h.x), hy = pcm_to_float(h.y);
+                const float er = __fadd_rn(lx, hx), ei = __fadd_rn(ly, hy);
+                const float dr = __fsub_rn(lx, hx), di = __fsub_rn(ly, hy);
+                const float2 w = s_tw0[a];
+                float orr, oii;
+                cmul(dr, di, w.x, w.y, orr, oii);
+                re[q] = make_float2(er, orr);
+                im[q] = make_float2(ei, oii);
+            }
+            __syncwarp();                              // the lower half has been consumed by every lane
+            fft1024_pair(re, im, tile, s_tw, lane);
+            // spectrum to shared memory in natural order: lane d0, element d1 holds Z[2c], Z[2c+1], c = d0 + 32 d1
+            {
+                float4* z4 = reinterpret_cast<float4*>(zs);
+#pragma unroll
+                for (int d1 = 0; d1 < 32; ++d1) z4[lane + 32 * d1] = make_float4(re[d1].x, im[d1].x, re[d1].y, im[d1].y);
+            }
+            __syncwarp();
+            // split -> x G -> merge, in place; this lane owns the pairs (k, 2048 - k), k = lane + 32 j
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const int k = lane + 32 * j, kc = (2048 - k) & 2047;
+                const float2 zk = zs[k], zc = zs[kc];
+                const float2 wk = s_ws[k], wc = s_ws[kc];
+                float xr, xi, cr_, ci_;
+                rfft_split(zk.x, zk.y, zc.x, zc.y, wk.x, wk.y, xr, xi);              // X[k]
+                rfft_split(zc.x, zc.y, zk.x, zk.y, wc.x, wc.y, cr_, ci_);            // X[2048 - k]
+                if (k == 0) {                                                         // packed (X[0], X[2048])
+                    xr = __fadd_rn(zk.x, zk.y);
+                    xi = __fsub_rn(zk.x, zk.y);
+                }
+                const float2 gk = __ldg(p.G + k), gc = __ldg(p.G + kc);
+                float yr, yi, ycr, yci;
+                cmul(xr, xi, gk.x, gk.y, yr, yi);                                     // arm_cmplx_mult_cmplx_f32 (quirk at k = 0)
+                cmul(cr_, ci_, gc.x, gc.y, ycr, yci);
+                float zr, zi, zcr, zci;
+                rfft_merge(yr, yi, ycr, yci, wk.x, wk.y, zr, zi);                     // 2 Z'[k]
+                rfft_merge(ycr, yci, yr, yi, wc.x, wc.y, zcr, zci);                   // 2 Z'[2048 - k]
+                if (k == 0) {
+                    zr = __fadd_rn(yr, yi);
+                    zi = __fsub_rn(yr, yi);
+                }
+                zs[k] = make_float2(zr, zi);
+                if (k != 0) zs[kc] = make_float2(zcr, zci);
+            }
+            if (lane == 0) {                           // bin 1024 pairs with itself
+                const float2 zk = zs[1024], wk = s_ws[1024];
+                float xr, xi, yr, yi, zr, zi;
+                rfft_split(zk.x, zk.y, zk.x, zk.y, wk.x, wk.y, xr, xi);
+                const float2 gk = __ldg(p.G + 1024);
+                cmul(xr, xi, gk.x, gk.y, yr, yi);
+                rfft_merge(yr, yi, yr, yi, wk.x, wk.y, zr, zi);
+                zs[1024] = make_float2(zr, zi);
+            }
+            __syncwarp();
+            // inverse = forward transform of the swapped parts (radix-2 level again)
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int a = lane + 32 * q;
+                const float2 l = zs[a], h = zs[a + 1024];
+                const float er = __fadd_rn(l.y, h.y), ei = __fadd_rn(l.x, h.x);
+                const float dr = __fsub_rn(l.y, h.y), di = __fsub_rn(l.x, h.x);
+                const float2 w = s_tw0[a];
+                float orr, oii;
+                cmul(dr, di, w.x, w.y, orr, oii);
+                re[q] = make_float2(er, orr);
+                im[q] = make_float2(ei, oii);
+            }
+            __syncwarp();                              // the parked spectrum is dead: its half can take the next n samples
+            if (lane == 0 && b + 1 < b1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of the parked spectrum before the bulk copy
+                mbar_expect_tx(bar, 8192u);
+                bulk_g2s(wbase + (odd ? 16384 : 0), stream + (size_t) (b + 2) * 2048, 8192u, bar);
+            }
+            fft1024_pair(re, im, tile, s_tw, lane);
+            // y[2m] = z[m].im / 4096, y[2m+1] = z[m].re / 4096; valid lags l = 2m (+1) in [2048, 4096): m = 2c (+1) with
+            // c = lane + 32 d1 >= 512, i.e. d1 >= 16 (the other outputs of the last pass are never computed)
+            const float sc = 1.0f / 4096.0f;
+            float best = -INFINITY;
+            uint32_t best_idx = 0xffffffffu;
+            float4* o4 = p.out ? reinterpret_cast<float4*>(p.out + ((size_t) s * nblocks + b) * 2048) : nullptr;
+#pragma unroll
+            for (int d1 = 16; d1 < 32; ++d1) {
+                const int c = lane + 32 * d1;
+                const float2 a0 = __fmul2_rn(im[d1], bc2(sc)), a1 = __fmul2_rn(re[d1], bc2(sc));
+                const float4 v = make_float4(a0.x, a1.x, a0.y, a1.y);                 // lags 4c-2048 .. 4c-2045
+                const uint32_t l0 = 4u * (uint32_t) c - 2048u;
+                if (v.x > best) { best = v.x; best_idx = l0; }
+                if (v.y > best) { best = v.y; best_idx = l0 + 1; }
+                if (v.z > best) { best = v.z; best_idx = l0 + 2; }
+                if (v.w > best) { best = v.w; best_idx = l0 + 3; }
+                if (o4) o4[c - 512] = v;
+            }
+            if (best_idx == 0xffffffffu) best_idx = 4u * (uint32_t) (lane + 512) - 2048u;   // all NaN / -inf: first own lag
+            warp_argmax(best, best_idx);
+            if (lane == 0) {
+                const size_t o = (size_t) s * nblocks + b;
+                if (p.max_val) p.max_val[o] = best;
+                if (p.max_idx) p.max_idx[o] = best_idx;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+cudaError_t launch_correlate_os(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                                const float2* G, const float2* tw_pass, const float2* tw0, const float2* tw_split, float* out,
+                                float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st) {
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_correlate_os<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_correlate_os<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    os_params p;
+    p.pcm = pcm; p.nstreams = nstreams; p.nframes = nframes; p.stream_stride = stream_stride;
+    p.G = G; p.tw_pass = tw_pass; p.tw0 = tw0; p.tw_split = tw_split;
+    p.out = out; p.max_val = max_val; p.max_idx = max_idx;
+    // segments: keep every sample's single HBM crossing (a segment re-reads one frame at its start) but split long
+    // streams when there are too few of them to fill the machine
+    const uint32_t nblocks = nframes - 1;
+    const size_t resident = (size_t) num_sms * kOsWarps;
+    uint32_t seg = nblocks;
+    if ((size_t) nstreams < 4 * resident) {
+        const size_t want = (4 * resident + nstreams - 1) / nstreams;                 // segments per stream
+        seg = (uint32_t) ((nblocks + want - 1) / want);
+        if (seg < 8) seg = nblocks < 8 ? nblocks : 8;
+    }
+    p.seg_blocks = seg;
+    p.nseg = (nblocks + seg - 1) / seg;
+    size_t ctas = ((size_t) nstreams * p.nseg + kOsWarps - 1) / kOsWarps;
+    if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
+    if (pcm_format == 1u) k_correlate_os<int32_t><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+    else k_correlate_os<float><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace usc

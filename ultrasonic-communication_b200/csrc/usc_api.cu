@@ -30,6 +30,7 @@ struct usc_handle {
     float *d_hann, *d_up, *d_down, *d_ud, *d_H_up, *d_H_down;
     float2 *d_op_pass = nullptr, *d_op_split = nullptr;    // tables of the warp-level FFT operators when cfg.n != 2048
     float* d_rs_taps = nullptr; uint32_t rs_up = 0;       // resampler polyphase table (usc_resample_i16_to_pcm)
+    float2 *d_G_up, *d_G_down, *d_tw_split4096;          // overlap-save synchroniser: template spectra (2n points), W_4096 split table
     float2 *d_tw_pass, *d_tw_split, *d_tw_l0;      // d_tw_l0: W_{n/2}^(a d), [d][a], 32768- and 65536-point frames only
     float* d_fir_coeffs;                              // 256 floats of scratch for usc_arm_fir_f32_batch
     // I/Q path (usc_iq_init): carrier tables, baseband chirp and its conjugate, half-length Hann, FIR taps
@@ -172,6 +173,7 @@ int usc_create(const usc_config* cfg, int device, usc_handle** out) {
     h->launches = 0;
     h->d_hann = h->d_up = h->d_down = h->d_ud = h->d_H_up = h->d_H_down = nullptr;
     h->d_tw_pass = h->d_tw_split = h->d_tw_l0 = nullptr;
+    h->d_G_up = h->d_G_down = h->d_tw_split4096 = nullptr;
     h->d_fir_coeffs = nullptr;
     h->d_work = nullptr;
     h->work_bytes = 0;
@@ -274,6 +276,7 @@ void usc_destroy(usc_handle* h) {
     if (!h) return;
     device_guard guard__(h->device);
     cudaFree(h->d_hann); cudaFree(h->d_up); cudaFree(h->d_down); cudaFree(h->d_ud); cudaFree(h->d_H_up); cudaFree(h->d_H_down);
+    cudaFree(h->d_G_up); cudaFree(h->d_G_down); cudaFree(h->d_tw_split4096);
     cudaFree(h->d_tw_pass); cudaFree(h->d_tw_split); cudaFree(h->d_tw_l0); cudaFree(h->d_rs_taps); cudaFree(h->d_op_pass); cudaFree(h->d_op_split); cudaFree(h->d_fir_coeffs); cudaFree(h->d_work);
     cudaFree(h->d_iq_cos); cudaFree(h->d_iq_sin); cudaFree(h->d_iq_chirp); cudaFree(h->d_iq_conj); cudaFree(h->d_iq_hann); cudaFree(h->d_iq_taps);
     cudaFree(h->d_sym_table);
@@ -1298,6 +1301,53 @@ int usc_compress_chirp(usc_handle* h, const void* pcm, uint32_t pcm_format, size
     LAUNCHED(h, launch_compress2048(pcm, pcm_format, nframes, (const float2*) h->d_hann,
                                     (const float2*) (use_up ? h->d_H_up : h->d_H_down), h->d_tw_pass,
                                     h->d_tw_split, out_frames, max_val, max_idx, h->num_sms, h->stream));
+    return USC_OK;
+}
+
+// tables of the overlap-save synchroniser, built on first use: G = rfft_4096(window * chirp, zero-padded) for both chirps
+// (the canonical FFT on the device, as init_ref_chirp's H), the W_4096 split table and the W_2048 radix-2 twiddles
+static int ensure_os_tables(usc_handle* h) {
+    if (h->d_G_up) return USC_OK;
+    const uint32_t n = h->cfg.n;
+    fft_plan_dev plan;
+    int rc = make_plan(h, n, 2 * n, &plan);
+    if (rc) return rc;
+    float2* tw2048 = nullptr;
+    if ((rc = get_twiddles(h, n, &tw2048))) return rc;
+    const std::vector<float>& tw = h->tw_host[2 * n];
+    std::vector<float> split(2 * (size_t) n);
+    for (uint32_t k = 0; k < n; ++k) {
+        split[2 * k] = tw[2 * k];
+        split[2 * k + 1] = -tw[2 * k + 1];
+    }
+    if ((rc = upload(split.data(), split.size() * 4, (void**) &h->d_tw_split4096))) return rc;
+    std::vector<float> gu(2 * (size_t) n, 0.0f), gd(2 * (size_t) n, 0.0f);
+    for (uint32_t i = 0; i < n; ++i) { gu[i] = h->up[i] * h->hann[i]; gd[i] = h->down[i] * h->hann[i]; }
+    float *du = nullptr, *dd = nullptr;
+    if ((rc = upload(gu.data(), gu.size() * 4, (void**) &du))) return rc;
+    if ((rc = upload(gd.data(), gd.size() * 4, (void**) &dd))) { cudaFree(du); return rc; }
+    cudaError_t e;
+    if ((e = launch_fft_generic(FFT_R2C, plan, du, du, 1, h->stream)) != cudaSuccess ||
+        (e = launch_fft_generic(FFT_R2C, plan, dd, dd, 1, h->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { cudaFree(du); cudaFree(dd); return cuda_rc(e); }
+    h->d_G_up = (float2*) du;
+    h->d_G_down = (float2*) dd;
+    return USC_OK;
+}
+
+int usc_correlate_os(usc_handle* h, const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,
+                     size_t stream_stride, int use_up, float* out, float* max_val, uint32_t* max_idx) {
+    USC_ENTER(h);
+    if (!h || !pcm || pcm_format > USC_PCM_I32) return USC_ERR_ARGUMENT;
+    if (h->cfg.n != 2048 || h->cfg.chirp_variant == USC_CHIRP_S || !h->d_tw_pass) return USC_ERR_ARGUMENT;
+    if (((uintptr_t) pcm & 15u) != 0 || (stream_stride & 3u) != 0 || ((uintptr_t) out & 15u) != 0) return USC_ERR_ARGUMENT;
+    if (nstreams && nframes >= 2 && stream_stride < (size_t) nframes * 2048) return USC_ERR_ARGUMENT;
+    if (!nstreams || nframes < 2) return USC_OK;
+    int rc = ensure_os_tables(h);
+    if (rc) return rc;
+    LAUNCHED(h, launch_correlate_os(pcm, pcm_format, nstreams, nframes, stream_stride, use_up ? h->d_G_up : h->d_G_down,
+                                    h->d_tw_pass, h->tw_cache[2048], h->d_tw_split4096, out, max_val, max_idx, h->num_sms,
+                                    h->stream));
     return USC_OK;
 }
 

@@ -62,6 +62,9 @@ cudaError_t launch_dsp2048c(const demod_params& p, int num_sms, cudaStream_t st)
 cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* window,
                                 const float2* H, const float2* tw_pass, const float2* tw_split, float* out_frames,
                                 float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st);
+cudaError_t launch_correlate_os(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                                const float2* G, const float2* tw_pass, const float2* tw0, const float2* tw_split, float* out,
+                                float* max_val, uint32_t* max_idx, int num_sms, cudaStream_t st);
 cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st);
 cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st);
 cudaError_t launch_iq_frontend(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes,

@@ -56,7 +56,7 @@ SYMBOLS = [
     "usc_arm_mult_f32_batch", "usc_arm_scale_f32_batch", "usc_arm_cmplx_mult_cmplx_f32_batch",
     "usc_arm_cmplx_mult_real_f32_batch", "usc_arm_cmplx_mag_f32_batch", "usc_arm_max_f32_batch",
     "usc_arm_mean_f32_batch", "usc_arm_rfft_fast_f32_batch", "usc_arm_cfft_f32_batch",
-    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_iq_demod_host", "usc_receiver_run_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_iq_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp",
+    "usc_arm_fir_f32_batch", "usc_demod_frames", "usc_host_workspace", "usc_demod_frames_host", "usc_iq_demod_host", "usc_receiver_run_host", "usc_receiver_run", "usc_receiver_run_chunk", "usc_sync_search", "usc_iq_init", "usc_iq_demod", "usc_spectrum_analyzer", "usc_synth_frames", "usc_synth_iq_frames", "usc_synth_streams", "usc_resample_i16_to_pcm", "usc_onoff_default_config", "usc_onoff_detect", "usc_fsk_default_config", "usc_fsk_detect", "usc_band_magnitudes", "usc_scan4", "usc_pipeline", "usc_dsp", "usc_compress_chirp", "usc_correlate_os",
 ]
 
 _lib = None
@@ -383,6 +383,10 @@ class Handle:
     def compress_chirp(self, pcm, pcm_format, nframes, use_up, out_frames=None, max_val=None, max_idx=None):
         _ck(load().usc_compress_chirp(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_size_t(nframes),
                                       C.c_int(1 if use_up else 0), _ptr(out_frames), _ptr(max_val), _ptr(max_idx)))
+
+    def correlate_os(self, pcm, pcm_format, nstreams, nframes, stream_stride, use_up, out=None, max_val=None, max_idx=None):
+        _ck(load().usc_correlate_os(self._h, _ptr(pcm), C.c_uint32(pcm_format), C.c_uint32(nstreams), C.c_uint32(nframes),
+                                    C.c_size_t(stream_stride), C.c_int(1 if use_up else 0), _ptr(out), _ptr(max_val), _ptr(max_idx)))
 
     # -- numpy convenience (host arrays in, host arrays out; used by tests) --------------------------
     def demod_frames_host(self, pcm):
