@@ -595,6 +595,16 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_ok = bool(torch.equal(h_bit, bit.cpu()) and torch.equal(h_iu, idx_up.cpu()))
+    # the ceiling of that path: bare pinned host -> device copies of the same buffer, all ranks at once
+    d_tmp = torch.empty_like(pcm)
+    d_tmp.copy_(host_pcm, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        d_tmp.copy_(host_pcm, non_blocking=True)
+    barrier()
+    bare_s = time.perf_counter() - t0
+    del d_tmp
 
     # the further BASELINE configs (3, 4, 5), measured on this rank's shard in the same launch
     cfg_times, cfg_ok, cfg_infos = {}, {}, {}
@@ -611,13 +621,13 @@ def main():
     del host_pcm
 
     keys = sorted(cfg_times)
-    times = torch.tensor([ms_total, e2e_s, ms_single] + [cfg_times[k] for k in keys], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_s, ms_single, bare_s] + [cfg_times[k] for k in keys], dtype=torch.float64, device=dev)
     oks = torch.tensor([int(e2e_ok)] + [int(cfg_ok[k]) for k in sorted(cfg_ok)], dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)          # timing only; no data-path collective
         dist.all_reduce(oks, op=dist.ReduceOp.MIN)
-    ms_total, e2e_s, ms_single = (float(v) for v in times[:3].tolist())
-    cfg_times = dict(zip(keys, (float(v) for v in times[3:].tolist())))
+    ms_total, e2e_s, ms_single, bare_s = (float(v) for v in times[:4].tolist())
+    cfg_times = dict(zip(keys, (float(v) for v in times[4:].tolist())))
     e2e_ok = bool(oks[0].item())
     cfg_ok = dict(zip(sorted(cfg_ok), (bool(v) for v in oks[1:].tolist())))
     # the ranks are done with each other: the CPU legs below run on rank 0 alone with no rank spinning in a barrier
@@ -656,7 +666,12 @@ def main():
                               "note": "nominal flop count of the textbook radix-2 chain; the kernel executes fewer (pruned last pass, trivial twiddles)"},
             "e2e": {"value": NFRAMES * world * args.e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": NFRAMES * N * 4, "d2h_bytes_per_step": NFRAMES * 17,
-                    "steps": args.e2e_steps, "results_match_device_path": e2e_ok, "host_numa": numa_note},
+                    "steps": args.e2e_steps, "results_match_device_path": e2e_ok, "host_numa": numa_note,
+                    "h2d_gbs_achieved": NFRAMES * world * args.e2e_steps * N * 4 / e2e_s / 1e9,
+                    "bare_pinned_h2d_gbs": NFRAMES * world * args.e2e_steps * N * 4 / bare_s / 1e9,
+                    "fraction_of_bare_copy": bare_s / e2e_s,
+                    "note": "bare_pinned_h2d_gbs = the same pinned buffers copied host -> device by all ranks at once with no "
+                            "kernel: the ceiling of the host-buffer path on this box"},
             "roofline_single_hypothesis": {
                 "bound": "hbm", "achieved": (N * 4 + 8) * NFRAMES / (ms_single * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": (N * 4 + 8) * NFRAMES / (ms_single * 1e-3) / 1e9 / peak,

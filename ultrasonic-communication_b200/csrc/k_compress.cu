@@ -166,16 +166,16 @@ __global__ void __launch_bounds__(kCWarps * 32, 1) k_compress2048(compress_param
             const V2 ra = xstage[m];
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 w = s_win[m];
-            // scalar multiplies: a packed mul.rn.f32x2 feeding the first butterfly's add would be contracted by ptxas
-            re[b] = make_float2(__fmul_rn(pcm_to_float(ra.x), w.x), __fmul_rn(pcm_to_float(rb.x), w.x));
-            im[b] = make_float2(__fmul_rn(pcm_to_float(ra.y), w.y), __fmul_rn(pcm_to_float(rb.y), w.y));
+            // packed window multiply; the first butterfly stage takes the products as FMAs by 1.0 (usc_arith.cuh)
+            re[b] = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(w.x));
+            im[b] = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(w.y));
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {
             mbar_expect_tx(bar, pair_bytes(q + nwarps));
             bulk_g2s(xstage, pcm + (q + nwarps) * 4096, pair_bytes(q + nwarps), bar);
         }
-        fft1024_pair(re, im, tile, s_tw, lane);
+        fft1024_pair<true>(re, im, tile, s_tw, lane);
         spectral_in_place(re, im, reinterpret_cast<float4*>(tile), s_H, s_ws, lane);
         fft1024_pair(re, im, tile, s_tw, lane);
         // swap back and scale by 1/N: a[2m] = z.im/N, a[2m+1] = z.re/N

@@ -43,7 +43,7 @@ constexpr int kDualWarps = 8;                         // warps per CTA of the pa
 // per warp: XOR-swizzled 32x32 float2 tile 8 KB + PCM stage 8 KB | mbarriers.
 template <int W> struct dual_smem {
     static constexpr int tw = 0, ud = 8192, hann = ud + 16384, warp = hann + 8192, warp_bytes = 8192 + 8192,
-                         bar = warp + W * warp_bytes, total = bar + W * 8;
+                         bar = warp + W * warp_bytes, ws = bar + 128, total = ws + 16 * 32 * 8;   // ws: split twiddles of the bins below bandwidth2
 };
 
 template <typename PCM, int NB, int W>
@@ -75,9 +75,8 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
         s_ud[i] = reinterpret_cast<const float4*>(p.chirp_ud)[i];
         s_hann[i] = p.hann[i];
     }
-    float2 ws[NB];
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
+    float2* s_ws = reinterpret_cast<float2*>(s_raw + L::ws);         // split twiddles: fetched when the epilogue needs them
+    for (int i = threadIdx.x; i < NB * 32; i += blockDim.x) s_ws[i] = p.tw_split[i];
     __syncthreads();
 
     uint32_t parity = 0;
@@ -92,19 +91,19 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
             float4 c = s_ud[m];                                       // (up[2m], down[2m], up[2m+1], down[2m+1])
             float2 w = s_hann[m];
-            // ((x*c)*w) for both hypotheses.  The window multiply stays SCALAR on purpose: ptxas 12.9 contracts
-            // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would fuse this product
-            // into the first butterfly's additions and break bit-parity; scalar mul.rn is never contracted.
+            // ((x*c)*w) for both hypotheses, packed.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
+            // with -fmad=false), which would fuse this product into the first butterfly's additions and break bit-parity:
+            // the first butterfly stage is therefore written as FMAs by 1.0 (fft_base2_prod), which cannot be contracted.
             const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
-            re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));
-            im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
+            re[b] = __fmul2_rn(tr, bc2(w.x));
+            im[b] = __fmul2_rn(ti, bc2(w.y));
         }
         __syncwarp();                                                 // every lane has consumed the stage
         if (lane == 0 && f + nwarps < p.nframes) {                    // refill it with this warp's next frame
             mbar_expect_tx(bar, 8192);
             bulk_g2s(xstage, pcm + (f + nwarps) * 2048, 8192, bar);
         }
-        fft_base2<32>(re, im);
+        fft_base2_prod<32>(re, im, s_tw[lane].x);                     // W^0 = 1.0f, read from the table: opaque to the compiler
 #pragma unroll
         for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both hypotheses
             const float2 w = s_tw[d * 32 + lane];
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
         fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
-        peak_window_pair<NB>(re, im, ws, lane, p.bandwidth2, mu, iu, md, id);
+        peak_window_pair_s<NB>(re, im, s_ws, lane, p.bandwidth2, mu, iu, md, id);
         if (lane == 0) {
             if (p.mag_up) p.mag_up[f] = mu;
             if (p.idx_up) p.idx_up[f] = iu;
@@ -203,18 +202,18 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 c = s_chirp[m], w = s_hann[m];
             // ((x*c)*w) on both frames at once: the per-lane table values broadcast to the two halves
-            // (window multiply scalar: see the note in k_demod2048 about ptxas contracting packed mul + add)
+            // (first butterfly stage as FMAs by 1.0: see the note in k_demod2048 about ptxas contracting packed mul + add)
             const float2 tr = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(c.x));
             const float2 ti = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(c.y));
-            re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));
-            im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
+            re[b] = __fmul2_rn(tr, bc2(w.x));
+            im[b] = __fmul2_rn(ti, bc2(w.y));
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {
             mbar_expect_tx(bar, pair_bytes(q + nwarps));
             bulk_g2s(xstage, pcm + (q + nwarps) * 4096, pair_bytes(q + nwarps), bar);
         }
-        fft_base2<32>(re, im);
+        fft_base2_prod<32>(re, im, s_tw[lane].x);
 #pragma unroll
         for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both halves
             const float2 w = s_tw[d * 32 + lane];

@@ -211,10 +211,10 @@ __global__ void __launch_bounds__(kIqWarps * 32, 1) k_iq_backend(const float2* _
             float ur, ui, dr, di;
             cmul(r.x, r.y, c.x, -c.y, ur, ui);           // arm_cmplx_mult_cmplx_f32(R, conj chirp)
             cmul(r.x, r.y, c.x, c.y, dr, di);            // arm_cmplx_mult_cmplx_f32(R, chirp)
-            re[b] = make_float2(__fmul_rn(ur, w), __fmul_rn(dr, w));     // arm_cmplx_mult_real_f32 (scalar: see usc_arith.cuh)
-            im[b] = make_float2(__fmul_rn(ui, w), __fmul_rn(di, w));
+            re[b] = __fmul2_rn(make_float2(ur, dr), bc2(w));              // arm_cmplx_mult_real_f32, packed (first stage: FMAs by 1.0)
+            im[b] = __fmul2_rn(make_float2(ui, di), bc2(w));
         }
-        fft1024_pair(re, im, tile, s_tw, lane);
+        fft1024_pair<true>(re, im, tile, s_tw, lane);
         // candidates of this lane: right window k = lane (element 0), left window k = 992 + lane (element 31)
         const float2 pr = __ffma2_rn(re[0], re[0], __fmul2_rn(im[0], im[0]));
         const float2 pl = __ffma2_rn(re[31], re[31], __fmul2_rn(im[31], im[31]));
@@ -391,11 +391,11 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
             const float t0 = __fmul_rn(r.y, c.y), t1 = __fmul_rn(r.y, c.x);
             const float2 pr2 = __ffma2_rn(bc2(r.x), bc2(c.x), make_float2(t0, -t0));      // (up.re, down.re)
             const float2 pi2 = __ffma2_rn(bc2(r.x), make_float2(-c.y, c.y), bc2(t1));     // (up.im, down.im)
-            re[b] = make_float2(__fmul_rn(pr2.x, w), __fmul_rn(pr2.y, w));                // scalar: see usc_arith.cuh
-            im[b] = make_float2(__fmul_rn(pi2.x, w), __fmul_rn(pi2.y, w));
+            re[b] = __fmul2_rn(pr2, bc2(w));                                              // packed (first stage: FMAs by 1.0)
+            im[b] = __fmul2_rn(pi2, bc2(w));
         }
         __syncwarp();
-        fft1024_pair(re, im, reinterpret_cast<float2*>(region), s_tw, lane);
+        fft1024_pair<true>(re, im, reinterpret_cast<float2*>(region), s_tw, lane);
         const float2 pr = __ffma2_rn(re[0], re[0], __fmul2_rn(im[0], im[0]));
         const float2 pl = __ffma2_rn(re[31], re[31], __fmul2_rn(im[31], im[31]));
         const bool in_r = (uint32_t) lane < W, in_l = 992u + lane >= 1024u - W;

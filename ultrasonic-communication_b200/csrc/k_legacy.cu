@@ -67,16 +67,16 @@ __global__ void __launch_bounds__(kBandWarps * 32, 1) k_band2048_pair(band_param
             const V2 ra = xstage[m];
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 w = s_hann[m];
-            // arm_mult_f32(fft_input, fft_window): scalar multiplies (they feed the first butterfly's adds, usc_arith.cuh)
-            re[b] = make_float2(__fmul_rn(pcm_to_float(ra.x), w.x), __fmul_rn(pcm_to_float(rb.x), w.x));
-            im[b] = make_float2(__fmul_rn(pcm_to_float(ra.y), w.y), __fmul_rn(pcm_to_float(rb.y), w.y));
+            // arm_mult_f32(fft_input, fft_window), packed; the first butterfly stage takes the products as FMAs by 1.0
+            re[b] = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(w.x));
+            im[b] = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(w.y));
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {
             mbar_expect_tx(bar, pair_bytes(q + nwarps));
             bulk_g2s(xstage, pcm + (q + nwarps) * 4096, pair_bytes(q + nwarps), bar);
         }
-        fft_base2<32>(re, im);
+        fft_base2_prod<32>(re, im, s_tw[lane].x);
 #pragma unroll
         for (int d = 1; d < 32; ++d) {
             const float2 w = s_tw[d * 32 + lane];

@@ -55,6 +55,15 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
 
     for (size_t f = blockIdx.x; f < p.nframes; f += gridDim.x) {
         const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * p.n);
+#ifndef USC_LONG_NO_PREFETCH
+        if (f + gridDim.x < p.nframes) {                 // this CTA's next frame towards L2 while the current one computes
+            const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + gridDim.x) * p.n);
+            constexpr uint32_t per_thread = 2048u * R0 * 4u / T;                             // 256 bytes
+#pragma unroll
+            for (uint32_t o = 0; o < per_thread; o += 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t) tid * per_thread + o));
+        }
+#endif
         // ---- level 0: radix-R0 over b, twiddle, park sub-sequence d ----
         // (unrolled so the global loads of several rounds are in flight together: the phase is latency-bound)
 #pragma unroll kLongUnroll
@@ -67,12 +76,12 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
                 const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
                 const float4 c = __ldg(p.chirp_ud + m);
                 const float2 w = __ldg(p.hann + m);
-                // window multiply scalar: ptxas contracts packed mul.rn + add.rn into FFMA2 (see k_demod.cu)
+                // packed window multiply; the first butterfly stage takes the products as FMAs by 1.0 (usc_arith.cuh)
                 const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
-                re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));
-                im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
+                re[b] = __fmul2_rn(tr, bc2(w.x));
+                im[b] = __fmul2_rn(ti, bc2(w.y));
             }
-            fft_base2<R0>(re, im);
+            fft_base2_prod<R0>(re, im, s_tw[lane].x);
 #pragma unroll
             for (int d = 0; d < R0; ++d) {
                 float2 xr = re[d], xi = im[d];
@@ -163,7 +172,13 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int per_sm = R0 == 2 ? 4 : (R0 == 4 ? 2 : 1);
+#ifndef USC_LONG_PER_SM2
+#define USC_LONG_PER_SM2 4
+#endif
+#ifndef USC_LONG_PER_SM4
+#define USC_LONG_PER_SM4 2
+#endif
+    const int per_sm = R0 == 2 ? USC_LONG_PER_SM2 : (R0 == 4 ? USC_LONG_PER_SM4 : 1);
     size_t ctas = p.nframes < (size_t) num_sms * per_sm ? p.nframes : (size_t) num_sms * per_sm;
     k_demod_long<PCM, R0><<<(int) ctas, R0 * 32, smem, st>>>(p);
     return cudaGetLastError();
@@ -264,10 +279,10 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
                 const float4 c = __ldg(p.chirp_ud + m);
                 const float2 w = __ldg(p.hann + m);
                 const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
-                re[b] = make_float2(__fmul_rn(tr.x, w.x), __fmul_rn(tr.y, w.x));      // scalar: see usc_arith.cuh
-                im[b] = make_float2(__fmul_rn(ti.x, w.y), __fmul_rn(ti.y, w.y));
+                re[b] = __fmul2_rn(tr, bc2(w.x));                                      // packed; first stage: FMAs by 1.0
+                im[b] = __fmul2_rn(ti, bc2(w.y));
             }
-            fft_base2<R0>(re, im);
+            fft_base2_prod<R0>(re, im, s_tw[lane].x);
 #pragma unroll
             for (int d = 0; d < R0; ++d) {
                 float2 xr = re[d], xi = im[d];

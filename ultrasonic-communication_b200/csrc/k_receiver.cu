@@ -58,10 +58,11 @@ __device__ __forceinline__ void dsp_pair_tail(float2 (&re)[32], float2 (&im)[32]
     for (int b = 0; b < 32; ++b) {
         const int m = lane + 32 * b;
         const float2 ca = chirpA[m], cb = chirpB[m], w = tb.hann[m];
-        re[b] = make_float2(__fmul_rn(__fmul_rn(re[b].x, ca.x), w.x), __fmul_rn(__fmul_rn(re[b].y, cb.x), w.x));
-        im[b] = make_float2(__fmul_rn(__fmul_rn(im[b].x, ca.y), w.y), __fmul_rn(__fmul_rn(im[b].y, cb.y), w.y));
+        // (x * c) * w on both halves, packed; the products meet FMAs by 1.0 in the first butterfly stage (usc_arith.cuh)
+        re[b] = __fmul2_rn(__fmul2_rn(re[b], make_float2(ca.x, cb.x)), bc2(w.x));
+        im[b] = __fmul2_rn(__fmul2_rn(im[b], make_float2(ca.y, cb.y)), bc2(w.y));
     }
-    fft1024_pair(re, im, tile, tb.tw, lane);
+    fft1024_pair<true>(re, im, tile, tb.tw, lane);
     peak_window_pair<kRxNB>(re, im, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 

@@ -132,6 +132,48 @@ __device__ __forceinline__ void bfly2_gen(float2& er, float2& ei, float2& or_, f
     er = sr; ei = si; or_ = dr; oi = di;
 }
 
+// First-stage butterfly whose inputs are PACKED PRODUCTS (the window multiplies of the fused front ends): written as
+// fused multiply-adds by `one` (= 1.0f read from a table, so the compiler cannot fold it): fma(O, 1, E) rounds E + O
+// once — the same bits as the addition — and a product can be neither the addend nor a multiplicand of a contracted
+// FMA, so ptxas's mul.f32x2 + add.f32x2 -> FFMA2 contraction (see CAVEAT above) has nothing to grab.
+__device__ __forceinline__ void bfly2_one_fma(float2& er, float2& ei, float2& or_, float2& oi, float one) {
+    const float2 p1 = bc2(one), m1 = bc2(-one);
+    float2 sr = __ffma2_rn(or_, p1, er), si = __ffma2_rn(oi, p1, ei);
+    float2 dr = __ffma2_rn(or_, m1, er), di = __ffma2_rn(oi, m1, ei);
+    er = sr; ei = si; or_ = dr; oi = di;
+}
+
+// fft_base2 for inputs that are packed products (see bfly2_one_fma); identical results
+template <int R>
+__device__ __forceinline__ void fft_base2_prod(float2 (&re)[R], float2 (&im)[R], float one) {
+    constexpr int BITS = ilog2(R);
+    float2 tr[R], ti[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        tr[i] = re[brev(i, BITS)];
+        ti[i] = im[brev(i, BITS)];
+    }
+#pragma unroll
+    for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * h) {
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+                const int a = blk + j, b = blk + j + h;
+                if (h == 1) bfly2_one_fma(tr[a], ti[a], tr[b], ti[b], one);
+                else if (j == 0) bfly2_one(tr[a], ti[a], tr[b], ti[b]);
+                else if (2 * j == h) bfly2_mj(tr[a], ti[a], tr[b], ti[b]);
+                else bfly2_gen(tr[a], ti[a], tr[b], ti[b], w32_re(j * (16 / h)), w32_im(j * (16 / h)));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        re[i] = tr[i];
+        im[i] = ti[i];
+    }
+}
+
 template <int R>
 __device__ __forceinline__ void fft_base2(float2 (&re)[R], float2 (&im)[R]) {
     constexpr int BITS = ilog2(R);

@@ -93,10 +93,14 @@ __device__ __forceinline__ void fft1024_warp2(float2 (&re)[32], float2 (&im)[32]
     fft_base2<32>(re, im);
 }
 
-// pass 1, inter-pass twiddle, two-round exchange (real parts, imaginary parts), pass 2 — on pairs
+// pass 1, inter-pass twiddle, two-round exchange (real parts, imaginary parts), pass 2 — on pairs.
+// PROD: the inputs are packed products (window multiplies): the first butterfly stage runs as FMAs by 1.0 (s_tw row 0
+// holds W^0 = 1.0f), see bfly2_one_fma in usc_arith.cuh; same bits.
+template <bool PROD = false>
 __device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32], float2* tile /* 32x32 float2, XOR-swizzled, 8 KB */,
                                              const float2* __restrict__ s_tw, int lane) {
-    fft_base2<32>(re, im);
+    if (PROD) fft_base2_prod<32>(re, im, s_tw[lane].x);
+    else fft_base2<32>(re, im);
 #pragma unroll
     for (int d = 1; d < 32; ++d) {
         const float2 w = s_tw[d * 32 + lane];
@@ -275,6 +279,36 @@ __device__ __forceinline__ void mag2_window_pair(const float2 (&zr)[32], const f
         pa[d1] = p.x;
         pb[d1] = p.y;
     }
+}
+
+// the same with the split twiddles fetched from shared memory when they are needed (ws_s[lane + 32 d1]) instead of
+// living in NB register pairs across the whole frame loop
+template <int NB>
+__device__ __forceinline__ void peak_window_pair_s(const float2 (&zr)[32], const float2 (&zi)[32], const float2* ws_s,
+                                                   int lane, uint32_t bw2, float& bestA, uint32_t& idxA, float& bestB,
+                                                   uint32_t& idxB) {
+    const int src = (32 - lane) & 31;
+    float pa[NB], pb[NB];
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const float2 sr = lane == 0 ? zr[(32 - d1) & 31] : zr[31 - d1];
+        const float2 si = lane == 0 ? zi[(32 - d1) & 31] : zi[31 - d1];
+        const float2 zcr = make_float2(__shfl_sync(0xffffffffu, sr.x, src), __shfl_sync(0xffffffffu, sr.y, src));
+        const float2 zci = make_float2(__shfl_sync(0xffffffffu, si.x, src), __shfl_sync(0xffffffffu, si.y, src));
+        const float2 w = ws_s[lane + 32 * d1];
+        float2 xr, xi;
+        rfft_split2(zr[d1], zi[d1], zcr, zci, w.x, w.y, xr, xi);
+        if (d1 == 0) {                                 // packed bin 0 = (X[0], X[N/2]) on lane 0
+            const float2 dr = __fadd2_rn(zr[0], zi[0]), di = __fadd2_rn(zr[0], neg2(zi[0]));
+            xr = lane == 0 ? dr : xr;
+            xi = lane == 0 ? di : xi;
+        }
+        const float2 p = __ffma2_rn(xr, xr, __fmul2_rn(xi, xi));
+        pa[d1] = p.x;
+        pb[d1] = p.y;
+    }
+    peak_tail<NB>(pa, lane, bw2, bestA, idxA);
+    peak_tail<NB>(pb, lane, bw2, bestB, idxB);
 }
 
 template <int NB>
