@@ -69,3 +69,11 @@ if which in ("long8192", "long16384"):
         hh.demod_frames(x, usc.PCM_I32, nf, o[0], o[1], o[2], o[3], b)
     torch.cuda.synchronize()
     print("done", which, reps)
+if which == "os":
+    h = usc.Handle()
+    S, Fr = 4096, 38
+    mv = torch.empty(S * (Fr - 1), dtype=torch.float32, device=dev); mi = torch.empty(S * (Fr - 1), dtype=torch.int32, device=dev)
+    for _ in range(reps):
+        h.correlate_os(pcm, usc.PCM_I32, S, Fr, Fr * 2048, False, None, mv, mi)
+    torch.cuda.synchronize()
+    print("done os", reps)

@@ -270,13 +270,36 @@ constexpr int kIqfWarps = 8;
 #define USC_IQF_ROWS 64
 #endif
 constexpr int kIqfRows = USC_IQF_ROWS;                                       // 32-sample rows loaded per lane before any is used
-constexpr uint32_t kIqfPairs = 1024 + kFirPairs + 4;                          // sample pairs per frame incl. history, zero tail
-constexpr uint32_t kIqfSlots = kIqfPairs + (kIqfPairs >> 2) + 1;              // pair p lives in float4 slot p + (p >> 2)
-constexpr int kIqfRegion = (int) kIqfSlots * 16;
 constexpr int kIqfTables = 8192 + 8192 + 4096 + 16384;                        // twiddles | chirp | Hann | (cos, sin)
-constexpr int kIqfSmem = kIqfTables + kIqfWarps * kIqfRegion;
+// NT = 0: the number of taps is a run-time value (<= 32): four outputs per lane and pass, tap pairs predicated.
+// NT > 0: the filter length is a compile-time constant (27 = the reference's, iq_modem.c:16-18): EIGHT outputs per
+// lane and pass — 21 instead of 2 x 19 shared-memory loads per eight outputs, exactly NT FMAs per output, no branches.
+// *dst = (x * c.x, x * c.y) with the packed product handed to the store as one 64-bit register: written through the
+// float2 intrinsics the compiler unpacks and repacks the pair (two MOVs per sample in the staging loop)
+__device__ __forceinline__ void st_mul2(float2* dst, float x, float2 c) {
+    asm volatile("{\n\t.reg .b64 a, b, r;\n\tmov.b64 a, {%1, %1};\n\tmov.b64 b, {%2, %3};\n\tmul.rn.f32x2 r, a, b;\n\t"
+                 "st.shared.b64 [%0], r;\n\t}" ::"r"(smem_u32(dst)), "f"(x), "f"(c.x), "f"(c.y) : "memory");
+}
 
-template <typename PCM>
+template <int NT> struct iqf_geom {
+    static_assert(NT == 0 || (NT & 1) == 1, "the specialised form pairs samples (2i, 2i+1) of the history-extended frame: odd filter lengths only");
+    static constexpr int OUT = NT ? 8 : kFirOut;                              // consecutive decimated outputs per lane and pass
+    static constexpr int SK = NT ? 3 : 2;                                     // pair p lives in float4 slot p + (p >> SK): conflict-free windows
+    static constexpr int NP = NT ? (NT + 1) / 2 : kFirTmax / 2;               // tap pairs
+    static constexpr int PS = NT ? (32 - (NT - 1)) / 2 : 0;                   // pairs of padding in front: PCM sample 0 lands on staged sample 32, so
+                                                                              // every 32-sample row a warp stores is one aligned, gap-free 256-byte run
+    static constexpr uint32_t pairs = 1024 + NP + OUT - 1 + 4 + PS;           // sample pairs per frame incl. history
+    static constexpr uint32_t slots = pairs + (pairs >> SK) + 1;
+    static constexpr int region = (int) slots * 16;
+    static constexpr int smem = kIqfTables + kIqfWarps * region;
+    // R (1024 decimated outputs, float2) is parked at the head of the region.  With OUT = 8 a lane stores 64 contiguous
+    // bytes per pass: float4 i goes to i ^ ((i >> 3) & 7), which spreads the lanes over all banks and leaves the strided
+    // reads of the back end (consecutive lanes, consecutive outputs) conflict-free as well.
+    __host__ __device__ static constexpr uint32_t r_f4(uint32_t i) { return NT ? i ^ ((i >> 3) & 7u) : i; }
+    __host__ __device__ static constexpr uint32_t r_index(uint32_t m) { return 2u * r_f4(m >> 1) + (m & 1u); }
+};
+
+template <typename PCM, int NT>
 __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __restrict__ pcm, uint32_t nstreams, uint32_t nframes,
                                                                 size_t stream_stride, const float* __restrict__ car_cos,
                                                                 const float* __restrict__ car_sin,
@@ -286,6 +309,10 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
                                                                 uint32_t* idx_up, float* mag_down, uint32_t* idx_down,
                                                                 uint8_t* bit) {
     constexpr uint32_t n = 2048;
+    using G = iqf_geom<NT>;
+    constexpr int OUT = G::OUT, SK = G::SK, NP = G::NP, PS = G::PS;
+    constexpr int kIqfRegion = G::region;
+    constexpr uint32_t ROWSTEP = 2u * (16u + (16u >> SK));                   // float2 per 32-sample row of the staged sequence
     extern __shared__ __align__(16) unsigned char s_f[];
     float2* s_tw = reinterpret_cast<float2*>(s_f);
     float2* s_c = reinterpret_cast<float2*>(s_f + 8192);
@@ -320,14 +347,14 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
         // Sample j = k + H of the staged sequence is PCM sample k: no bounds to test in the main part, and
         // sixteen independent loads are in flight per lane.
         {
-            const uint32_t jl = lane + H, pl = jl >> 1;
+            const uint32_t jl = lane + H + 2u * PS, pl = jl >> 1;
 #pragma unroll 1
             for (uint32_t r0 = 0; r0 < 64; r0 += kIqfRows) {
                 float x[kIqfRows];
 #pragma unroll
                 for (int u = 0; u < kIqfRows; ++u) x[u] = pcm_cast(cur[(r0 + u) * 32 + lane]);
-                // pair pl + 16 r sits in slot pl + (pl >> 2) + 20 r: a constant 40 float2 per row
-                float2* dst = smp + 2 * (pl + (pl >> 2)) + (jl & 1u) + 40u * r0;
+                // pair pl + 16 r sits in slot pl + (pl >> SK) + (16 + (16 >> SK)) r: a constant number of float2 per row
+                float2* dst = smp + 2 * (pl + (pl >> SK)) + (jl & 1u) + ROWSTEP * r0;
                 const float2* cs = s_cs + r0 * 32 + lane;
 #pragma unroll
                 for (int u0 = 0; u0 < kIqfRows; u0 += 8) {     // carrier values in batches so their loads overlap
@@ -335,13 +362,13 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
 #pragma unroll
                     for (int u = 0; u < 8; ++u) c[u] = cs[32 * (u0 + u)];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) dst[40 * (u0 + u)] = __fmul2_rn(bc2(x[u0 + u]), c[u]);
+                    for (int u = 0; u < 8; ++u) st_mul2(dst + ROWSTEP * (u0 + u), x[u0 + u], c[u]);
                 }
             }
             if ((uint32_t) lane < H) {                         // history: tail of the previous frame (zeros before frame 0)
-                const uint32_t k = n - H + lane, pp = (uint32_t) lane >> 1;
+                const uint32_t k = n - H + lane, pp = ((uint32_t) lane >> 1) + PS;
                 const float xh = fr > 0 ? pcm_cast(cur[(ptrdiff_t) lane - (ptrdiff_t) H]) : 0.0f;
-                smp[2 * (pp + (pp >> 2)) + (lane & 1)] = __fmul2_rn(bc2(xh), s_cs[k]);
+                smp[2 * (pp + (pp >> SK)) + (lane & 1)] = __fmul2_rn(bc2(xh), s_cs[k]);
             }
         }
         __syncwarp();
@@ -349,35 +376,45 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
         // Output m0 + j at tap pair ip reads sample pair m0 + j + ip: a window of four pairs slides one pair
         // per tap pair.  Per output the taps run in ascending order, one FMA each (arm_fir_f32).
 #pragma unroll 1
-        for (uint32_t pass = 0; pass < 8; ++pass) {
-            const uint32_t m0 = (pass * 32 + lane) * kFirOut;
-            float2 acc[kFirOut];
+        for (uint32_t pass = 0; pass < 32u / OUT; ++pass) {
+            const uint32_t m0 = (pass * 32 + lane) * OUT;
+            float2 acc[OUT];
 #pragma unroll
-            for (int j = 0; j < kFirOut; ++j) acc[j] = make_float2(0.0f, 0.0f);
-            float4 w[kFirTmax / 2 + kFirOut];
+            for (int j = 0; j < OUT; ++j) acc[j] = make_float2(0.0f, 0.0f);
+            float4 w[NP + OUT];
 #pragma unroll
-            for (int q = 0; q < kFirOut - 1; ++q) {
-                const uint32_t pp = m0 + q;
-                w[q] = reinterpret_cast<const float4*>(region)[pp + (pp >> 2)];
+            for (int q = 0; q < OUT - 1; ++q) {
+                const uint32_t pp = m0 + q + PS;
+                w[q] = reinterpret_cast<const float4*>(region)[pp + (pp >> SK)];
             }
 #pragma unroll
-            for (int ip = 0; ip < kFirTmax / 2; ++ip) {
-                // no early exit: predicated in place, so the accumulators keep their registers
-                const bool first = (uint32_t) (2 * ip) < ntaps, second = (uint32_t) (2 * ip + 1) < ntaps;
-                const uint32_t pp = m0 + ip + kFirOut - 1;
-                w[ip + kFirOut - 1] = reinterpret_cast<const float4*>(region)[pp + (pp >> 2)];
+            for (int ip = 0; ip < NP; ++ip) {
+                const uint32_t pp = m0 + ip + OUT - 1 + PS;
+                w[ip + OUT - 1] = reinterpret_cast<const float4*>(region)[pp + (pp >> SK)];
+                if (NT) {                                    // compile-time filter length: exactly NT FMAs per output
 #pragma unroll
-                for (int j = 0; j < kFirOut; ++j) {
-                    const float2 a0 = __ffma2_rn(make_float2(w[ip + j].x, w[ip + j].y), bc2(t[2 * ip]), acc[j]);
-                    acc[j] = first ? a0 : acc[j];
-                    const float2 a1 = __ffma2_rn(make_float2(w[ip + j].z, w[ip + j].w), bc2(t[2 * ip + 1]), acc[j]);
-                    acc[j] = second ? a1 : acc[j];
+                    for (int j = 0; j < OUT; ++j) acc[j] = __ffma2_rn(make_float2(w[ip + j].x, w[ip + j].y), bc2(t[2 * ip]), acc[j]);
+                    if (2 * ip + 1 < NT) {
+#pragma unroll
+                        for (int j = 0; j < OUT; ++j) acc[j] = __ffma2_rn(make_float2(w[ip + j].z, w[ip + j].w), bc2(t[2 * ip + 1]), acc[j]);
+                    }
+                } else {
+                    // no early exit: predicated in place, so the accumulators keep their registers
+                    const bool first = (uint32_t) (2 * ip) < ntaps, second = (uint32_t) (2 * ip + 1) < ntaps;
+#pragma unroll
+                    for (int j = 0; j < OUT; ++j) {
+                        const float2 a0 = __ffma2_rn(make_float2(w[ip + j].x, w[ip + j].y), bc2(t[2 * ip]), acc[j]);
+                        acc[j] = first ? a0 : acc[j];
+                        const float2 a1 = __ffma2_rn(make_float2(w[ip + j].z, w[ip + j].w), bc2(t[2 * ip + 1]), acc[j]);
+                        acc[j] = second ? a1 : acc[j];
+                    }
                 }
             }
             __syncwarp();                                    // this pass's samples overlap where R of pass 0 lands
-            float4* dst = reinterpret_cast<float4*>(region + (size_t) m0 * 8);
-            dst[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-            dst[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+            float4* dst = reinterpret_cast<float4*>(region);
+#pragma unroll
+            for (int j = 0; j < OUT; j += 2)
+                dst[G::r_f4((m0 >> 1) + (j >> 1))] = make_float4(acc[j].x, acc[j].y, acc[j + 1].x, acc[j + 1].y);
         }
         __syncwarp();
         // ---- back end: de-chirp both ways, Hann, FFT, windowed peaks ----
@@ -385,7 +422,7 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
             const int m = lane + 32 * b;
-            const float2 r = reinterpret_cast<const float2*>(region)[m], c = s_c[m];
+            const float2 r = reinterpret_cast<const float2*>(region)[G::r_index((uint32_t) m)], c = s_c[m];
             const float w = s_w[m];
             // cmul(R, conj c) and cmul(R, c) share their two rounded products; the FMAs ride one FFMA2 each
             const float t0 = __fmul_rn(r.y, c.y), t1 = __fmul_rn(r.y, c.x);
@@ -403,11 +440,15 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
         uint32_t out_i[2];
 #pragma unroll
         for (int hyp = 0; hyp < 2; ++hyp) {
-            float mr = in_r ? __fsqrt_rn(hyp ? pr.y : pr.x) : -INFINITY, ml = in_l ? __fsqrt_rn(hyp ? pl.y : pl.x) : -INFINITY;
-            uint32_t ir = in_r ? (uint32_t) lane : 0xffffffffu, il = in_l ? 992u + lane : 0xffffffffu;
-            warp_argmax(mr, ir);
-            warp_argmax(ml, il);
-            const bool left = ml > mr;
+            // arm_max_f32 over [0, W) and [1024 - W, 1024): magnitudes are >= 0, so their bit patterns order like the
+            // values and one redux.sync finds the maximum, a second one the first lane that holds it
+            const uint32_t br = in_r ? __float_as_uint(__fsqrt_rn(hyp ? pr.y : pr.x)) : 0u;
+            const uint32_t bl = in_l ? __float_as_uint(__fsqrt_rn(hyp ? pl.y : pl.x)) : 0u;
+            const uint32_t mrb = __reduce_max_sync(0xffffffffu, br), mlb = __reduce_max_sync(0xffffffffu, bl);
+            const uint32_t ir = __reduce_min_sync(0xffffffffu, in_r && br == mrb ? (uint32_t) lane : 0xffffffffu);
+            const uint32_t il = __reduce_min_sync(0xffffffffu, in_l && bl == mlb ? 992u + lane : 0xffffffffu);
+            const float mr = __uint_as_float(mrb), ml = __uint_as_float(mlb);
+            const bool left = ml > mr;                       // strict: right wins ties
             out_m[hyp] = left ? ml : mr;
             out_i[hyp] = left ? il : ir;
         }
@@ -422,28 +463,37 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
     }
 }
 
-cudaError_t launch_iq_fused(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
-                            const float* car_cos, const float* car_sin, const float* taps, uint32_t ntaps, const float* chirp,
-                            const float* hann, const float2* tw_pass, uint32_t window, float* mag_up, uint32_t* idx_up,
-                            float* mag_down, uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st) {
+template <typename PCM, int NT>
+static cudaError_t launch_iq_fused_t(const void* pcm, uint32_t nstreams, uint32_t nframes, size_t stream_stride, const float* car_cos,
+                                     const float* car_sin, const float* taps, uint32_t ntaps, const float* chirp, const float* hann,
+                                     const float2* tw_pass, uint32_t window, float* mag_up, uint32_t* idx_up, float* mag_down,
+                                     uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st) {
     static per_device<bool> configured_pd;
     bool& configured = configured_pd.get();
+    constexpr int smem = iqf_geom<NT>::smem;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_iq_fused<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqfSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_iq_fused<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIqfSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_iq_fused<PCM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const size_t total = (size_t) nstreams * nframes;
     size_t ctas = (total + kIqfWarps - 1) / kIqfWarps;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
-    if (pcm_format == 1u)
-        k_iq_fused<int32_t><<<(int) ctas, kIqfWarps * 32, kIqfSmem, st>>>((const int32_t*) pcm, nstreams, nframes, stream_stride,
-            car_cos, car_sin, taps, ntaps, (const float2*) chirp, hann, tw_pass, window, mag_up, idx_up, mag_down, idx_down, bit);
-    else
-        k_iq_fused<float><<<(int) ctas, kIqfWarps * 32, kIqfSmem, st>>>((const float*) pcm, nstreams, nframes, stream_stride,
-            car_cos, car_sin, taps, ntaps, (const float2*) chirp, hann, tw_pass, window, mag_up, idx_up, mag_down, idx_down, bit);
+    k_iq_fused<PCM, NT><<<(int) ctas, kIqfWarps * 32, smem, st>>>((const PCM*) pcm, nstreams, nframes, stream_stride, car_cos, car_sin,
+        taps, ntaps, (const float2*) chirp, hann, tw_pass, window, mag_up, idx_up, mag_down, idx_down, bit);
     return cudaGetLastError();
+}
+
+cudaError_t launch_iq_fused(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,
+                            const float* car_cos, const float* car_sin, const float* taps, uint32_t ntaps, const float* chirp,
+                            const float* hann, const float2* tw_pass, uint32_t window, float* mag_up, uint32_t* idx_up,
+                            float* mag_down, uint32_t* idx_down, uint8_t* bit, int num_sms, cudaStream_t st) {
+#define USC_IQF_ARGS pcm, nstreams, nframes, stream_stride, car_cos, car_sin, taps, ntaps, chirp, hann, tw_pass, window, mag_up, idx_up, \
+                     mag_down, idx_down, bit, num_sms, st
+    if (ntaps == 27u)                                        // the reference's filter (iq_modem.c:16-18): specialised form
+        return pcm_format == 1u ? launch_iq_fused_t<int32_t, 27>(USC_IQF_ARGS) : launch_iq_fused_t<float, 27>(USC_IQF_ARGS);
+    return pcm_format == 1u ? launch_iq_fused_t<int32_t, 0>(USC_IQF_ARGS) : launch_iq_fused_t<float, 0>(USC_IQF_ARGS);
+#undef USC_IQF_ARGS
 }
 
 }  // namespace usc
