@@ -264,7 +264,7 @@ IQ_CARRIER, IQ_BW = 18000.0, 3000.0
 C3_STREAMS, C3_E2E_STREAMS = 16384, 2048
 C4_STREAMS_TOTAL, C4_FRAMES, C4_MSG, C4_LEAD, C4_GUARD, C4_SIGMA = 262144, 381, 12, 40, 12, 2000.0
 C4_E2E_STREAMS = 384                     # 384 x 381 frames = 1.2 GB: fits the pinned arena of config 2's e2e leg
-C5_LENGTHS = ((8192, -15.0), (16384, -15.0), (65536, -20.0))
+C5_LENGTHS = ((8192, -10.0), (16384, -15.0), (65536, -20.0))   # SNRs at which the longer chirps still decode (accuracy is reported)
 
 
 def config3(torch, usc, pyref, dev, stream, rank, barrier, arena):

@@ -77,3 +77,13 @@ if which == "os":
         h.correlate_os(pcm, usc.PCM_I32, S, Fr, Fr * 2048, False, None, mv, mi)
     torch.cuda.synchronize()
     print("done os", reps)
+if which.startswith("long:"):
+    n = int(which.split(":")[1])
+    hh = usc.Handle(usc.default_config(n=n))
+    nf = (1 << 27) // n
+    x = torch.empty((nf, n), dtype=torch.int32, device=dev)
+    hh.synth_frames(2, 0, nf, 2.0e4, 1.0e5, x)
+    for _ in range(reps):
+        hh.demod_frames(x, usc.PCM_I32, nf, o[0], o[1], o[2], o[3], b)
+    torch.cuda.synchronize()
+    print("done", which, reps)
