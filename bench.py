@@ -702,6 +702,19 @@ def main():
                 "sample": "%d passes over 8192 frames, scipy.fft.rfft(workers=%d) composition of the same chain, %.1f s" % (npasses, threads, ndt)}
         if cfg_times:
             line["configs"] = configs_report(cfg_times, cfg_ok, cfg_infos, world, peak)
+        if world > 1 and torch.cuda.device_count() > 1:
+            # handles on two GPUs inside ONE process (per-device kernel configuration, device switching inside the
+            # library): the same frames through device 0 and device 1 must give the same bits
+            try:
+                chk = pcm[:4096].cpu().numpy()
+                res = []
+                for d in (0, 1, 0):
+                    hd = usc.Handle(device=d)
+                    res.append(hd.demod_frames_host(chk))
+                    hd.close()
+                line["two_devices_in_one_process"] = bool(all(np.array_equal(a, b) for r in res[1:] for a, b in zip(res[0], r)))
+            except Exception as exc:
+                line["two_devices_in_one_process"] = "error: %r" % (exc,)
         print(json.dumps(line))
 
 
