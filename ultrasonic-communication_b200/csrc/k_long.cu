@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
     for (int i = tid; i < 1024; i += T) s_tw[i] = p.tw_pass[i];
     __syncthreads();
     const uint32_t bw2 = p.bandwidth2;
+    float2 w_split[kLongNB];                           // split twiddles W_n^k of this thread's bins k = tid + T j: frame-invariant
+#pragma unroll
+    for (int j = 0; j < kLongNB; ++j) w_split[j] = p.tw_master[min((uint32_t) (tid + T * j), bw2 - 1u)];
 
     for (size_t f = blockIdx.x; f < p.nframes; f += gridDim.x) {
         const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * p.n);
@@ -122,7 +125,10 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
         };
         float bu = -INFINITY, bd = -INFINITY;
         uint32_t iu = 0xffffffffu, id = 0xffffffffu;
-        for (uint32_t k = tid; k < bw2; k += T) {
+#pragma unroll
+        for (int j = 0; j < kLongNB; ++j) {
+            const uint32_t k = tid + T * j;                                       // bw2 <= 160 R0 = kLongNB T
+            if (k >= bw2) break;
             const float4 zk = Y(k);
             float2 xr, xi;
             if (k == 0) {
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
                 xi = __fadd2_rn(make_float2(zk.x, zk.y), neg2(make_float2(zk.z, zk.w)));
             } else {
                 const float4 zc = Y(nc - k);
-                const float2 w = __ldg(p.tw_master + k);                          // W_n^k = (cos, -sin)
+                const float2 w = w_split[j];                                      // W_n^k = (cos, -sin)
                 rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
                             make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
             }
