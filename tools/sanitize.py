@@ -49,4 +49,17 @@ st3 = np.repeat(st, 3, 0); u3, r3 = h.empty(3 * 32), h.empty(3 * 32)
 h.receiver_run_chunk(h.buffer(st3[:, :30]), usc.PCM_I32, 3, 30, 30 * N, 0, stt, u3, 32, r3)
 h.receiver_run_chunk(h.buffer(np.ascontiguousarray(st3[:, 28:70])), usc.PCM_I32, 3, 40, 42 * N, 2, stt, u3, 32, r3); h.sync()   # K7 in chunks
 sp = h.empty(4 * 4 * 50 * N); h.synth_streams(1, 0, 4, 50, 50 * N, 5, 2, 3, 2.0e4, 2000.0, sp); h.sync()   # stream generator
+# K8 overlap-save synchroniser: several streams, segment splits, with and without the filtered stream
+po, _ = synth.make_frames(3 * 9); dpo = h.buffer(po.reshape(3, -1)); oo = h.empty(4 * 3 * 8 * N); mo, io = h.empty(4 * 24), h.empty(4 * 24)
+h.correlate_os(dpo, usc.PCM_I32, 3, 9, 9 * N, False, oo, mo, io); h.correlate_os(dpo, usc.PCM_I32, 3, 9, 9 * N, True, None, mo, io); h.sync()
+# K5 with a filter length other than the reference's 27 taps (run-time tap count form) and the I/Q generator
+hq2 = usc.Handle(); hq2.iq_init(18000.0, 3000.0, taps[:21].copy(), 32)
+hq2.iq_demod(dq, usc.PCM_I32, 3, 5, 5 * N, oq[0], oq[1], oq[2], oq[3], bq); hq2.sync()
+gi = h.empty(4 * 4 * N); h.synth_iq_frames(3, 0, 4, 18000.0, 3000.0, -1, 0.0, 2.0e4, 1.0e4, gi); h.sync()
+# host-buffer entry points (chunked through three stream lanes)
+import torch
+hp = torch.from_numpy(np.ascontiguousarray(pcm)).pin_memory()
+ho = [torch.empty(37, dtype=torch.float32).pin_memory() for _ in range(2)] + [torch.empty(37, dtype=torch.int32).pin_memory() for _ in range(2)]
+hb = torch.empty(37, dtype=torch.uint8).pin_memory()
+h.host_workspace(16); h.demod_frames_hostbuf(hp, usc.PCM_I32, 37, ho[0], ho[2], ho[1], ho[3], hb)
 print("sanitize workload done")
