@@ -22,10 +22,17 @@
 #include "usc_kernels.cuh"
 #include "usc_launch.h"
 #include "usc_warpfft.cuh"
+#include "usc_tmem.cuh"
 
 namespace usc {
 
 constexpr int kWarpsPerCta = 4;
+#ifndef USC_K1_TMEM
+#define USC_K1_TMEM 1                                   // tables in tensor memory (0: in shared memory, the round-1 form)
+#endif
+#ifndef USC_K1_TG
+#define USC_K1_TG 4                                     // front-end rows per TMEM load group (4 or 8)
+#endif
 // ---- dual-hypothesis kernel: both hypotheses ride in the halves of f32x2 registers ---------------
 // (.x = up-chirp, .y = down-chirp).  The PCM, the Hann table and the inter-pass twiddles are loaded
 // once for both; the two 32-point register FFTs issue as FADD2/FFMA2.
@@ -44,6 +51,10 @@ constexpr int kDualWarps = 8;                         // warps per CTA of the pa
 template <int W> struct dual_smem {
     static constexpr int tw = 0, ud = 8192, hann = ud + 16384, warp = hann + 8192, warp_bytes = 8192 + 8192,
                          bar = warp + W * warp_bytes, ws = bar + 128, total = ws + 16 * 32 * 8;   // ws: split twiddles of the bins below bandwidth2
+    static constexpr int tslot = bar + 64;              // TMEM base address written by tcgen05.alloc
+    // TMEM columns of lane a (one replica per lane quadrant): (up, down) chirp of m = a + 32 b at 4 b | Hann at 128 + 2 b |
+    // inter-pass twiddle W_1024^(a d) at 192 + 2 d
+    static constexpr int t_ud = 0, t_hann = 128, t_tw = 192, t_cols = 256;
 };
 
 template <typename PCM, int NB, int W>
@@ -70,20 +81,78 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             bulk_g2s(xstage, pcm + f * 2048, 8192, bar);
         }
     }
+#if USC_K1_TMEM
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw + L::tslot);
+    if (warp == 0) tmem_alloc<L::t_cols>(s_tslot);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp);
+    if (warp < 4) {                                                   // warp q fills lane quadrant q; warps q and q + 4 read it
+        for (int b = 0; b < 32; b += 2) {
+            const float4 c0 = reinterpret_cast<const float4*>(p.chirp_ud)[lane + 32 * b];
+            const float4 c1 = reinterpret_cast<const float4*>(p.chirp_ud)[lane + 32 * (b + 1)];
+            const uint32_t v[8] = {__float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c0.z), __float_as_uint(c0.w),
+                                   __float_as_uint(c1.x), __float_as_uint(c1.y), __float_as_uint(c1.z), __float_as_uint(c1.w)};
+            sttm8(tq + L::t_ud + 4 * b, v);
+        }
+        for (int b = 0; b < 32; b += 4) {
+            uint32_t v[8], t[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 w = p.hann[lane + 32 * (b + j)], z = p.tw_pass[(b + j) * 32 + lane];
+                v[2 * j] = __float_as_uint(w.x); v[2 * j + 1] = __float_as_uint(w.y);
+                t[2 * j] = __float_as_uint(z.x); t[2 * j + 1] = __float_as_uint(z.y);
+            }
+            sttm8(tq + L::t_hann + 2 * b, v);
+            sttm8(tq + L::t_tw + 2 * b, t);
+        }
+        sttm_wait();
+    }
+    const float one = p.tw_pass[lane].x;                              // W^0 = 1.0f, read from the table: opaque to the compiler
+#else
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
         s_tw[i] = p.tw_pass[i];
         s_ud[i] = reinterpret_cast<const float4*>(p.chirp_ud)[i];
         s_hann[i] = p.hann[i];
     }
+#endif
     float2* s_ws = reinterpret_cast<float2*>(s_raw + L::ws);         // split twiddles: fetched when the epilogue needs them
     for (int i = threadIdx.x; i < NB * 32; i += blockDim.x) s_ws[i] = p.tw_split[i];
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
 
     uint32_t parity = 0;
     for (; f < p.nframes; f += nwarps) {
         mbar_wait(bar, parity);
         parity ^= 1u;
         float2 re[32], im[32];                                        // (.x, .y) = (up, down)
+        // ((x*c)*w) for both hypotheses, packed.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
+        // with -fmad=false), which would fuse this product into the first butterfly's additions and break bit-parity:
+        // the first butterfly stage is therefore written as FMAs by 1.0 (fft_base2_prod), which cannot be contracted.
+#if USC_K1_TMEM
+#pragma unroll
+        for (int g = 0; g < 32 / USC_K1_TG; ++g) {                    // table values of USC_K1_TG rows per TMEM round trip
+#if USC_K1_TG == 8
+            uint32_t c[32], w[16];
+            ldtm32_16(tq + L::t_ud + 32 * g, c, tq + L::t_hann + 16 * g, w);
+#else
+            uint32_t c[16], w[8];
+            ldtm16_8(tq + L::t_ud + 16 * g, c, tq + L::t_hann + 8 * g, w);
+#endif
+#pragma unroll
+            for (int j = 0; j < USC_K1_TG; ++j) {
+                const int b = USC_K1_TG * g + j;
+                const V2 raw = xstage[lane + 32 * b];
+                const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
+                const float2 tr = __fmul2_rn(make_float2(__uint_as_float(c[4 * j]), __uint_as_float(c[4 * j + 1])), bc2(x0));
+                const float2 ti = __fmul2_rn(make_float2(__uint_as_float(c[4 * j + 2]), __uint_as_float(c[4 * j + 3])), bc2(x1));
+                re[b] = __fmul2_rn(tr, bc2(__uint_as_float(w[2 * j])));
+                im[b] = __fmul2_rn(ti, bc2(__uint_as_float(w[2 * j + 1])));
+            }
+        }
+#else
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
             const int m = lane + 32 * b;
@@ -91,18 +160,33 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
             float4 c = s_ud[m];                                       // (up[2m], down[2m], up[2m+1], down[2m+1])
             float2 w = s_hann[m];
-            // ((x*c)*w) for both hypotheses, packed.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
-            // with -fmad=false), which would fuse this product into the first butterfly's additions and break bit-parity:
-            // the first butterfly stage is therefore written as FMAs by 1.0 (fft_base2_prod), which cannot be contracted.
             const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
             re[b] = __fmul2_rn(tr, bc2(w.x));
             im[b] = __fmul2_rn(ti, bc2(w.y));
         }
+#endif
         __syncwarp();                                                 // every lane has consumed the stage
         if (lane == 0 && f + nwarps < p.nframes) {                    // refill it with this warp's next frame
             mbar_expect_tx(bar, 8192);
             bulk_g2s(xstage, pcm + (f + nwarps) * 2048, 8192, bar);
         }
+#if USC_K1_TMEM
+        fft_base2_prod<32>(re, im, one);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                                 // inter-pass twiddle, both hypotheses: 8 per TMEM round trip
+            uint32_t t[16];
+            ldtm16(tq + L::t_tw + 16 * g, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d = 8 * g + j;
+                if (d == 0) continue;
+                float2 tr, ti;
+                cmul2(re[d], im[d], __uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]), tr, ti);
+                re[d] = tr;
+                im[d] = ti;
+            }
+        }
+#else
         fft_base2_prod<32>(re, im, s_tw[lane].x);                     // W^0 = 1.0f, read from the table: opaque to the compiler
 #pragma unroll
         for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both hypotheses
@@ -112,6 +196,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             re[d] = tr;
             im[d] = ti;
         }
+#endif
         // exchange in two rounds (real parts, then imaginary parts): each 64-bit word is an (up, down)
         // register pair, so values land in place; XOR swizzle keeps both directions conflict-free
 #pragma unroll
@@ -138,6 +223,11 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
             if (p.bit) p.bit[f] = md > mu ? 0 : 1;     // receiver/Src/main.c:523: down only if strictly greater
         }
     }
+#if USC_K1_TMEM
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<L::t_cols>(*s_tslot);
+#endif
 }
 
 // ---- single-hypothesis kernel: TWO FRAMES ride in the halves of the f32x2 registers ----------------
