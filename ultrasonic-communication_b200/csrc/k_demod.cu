@@ -49,9 +49,13 @@ constexpr int kDualWarps = 8;                         // warps per CTA of the pa
 // Shared memory of the dual kernel with W warps: twiddles 8 KB | (up,down) table 16 KB | Hann 8 KB |
 // per warp: XOR-swizzled 32x32 float2 tile 8 KB + PCM stage 8 KB | mbarriers.
 template <int W> struct dual_smem {
+#if USC_K1_TMEM
+    static constexpr int tw = 0, ud = 0, hann = 0, warp = 0, warp_bytes = 8192 + 8192,     // the three tables live in TMEM
+#else
     static constexpr int tw = 0, ud = 8192, hann = ud + 16384, warp = hann + 8192, warp_bytes = 8192 + 8192,
+#endif
                          bar = warp + W * warp_bytes, ws = bar + 128, total = ws + 16 * 32 * 8;   // ws: split twiddles of the bins below bandwidth2
-    static constexpr int tslot = bar + 64;              // TMEM base address written by tcgen05.alloc
+    static constexpr int tslot = bar + 120;              // TMEM base address written by tcgen05.alloc
     // TMEM columns of lane a (one replica per lane quadrant): (up, down) chirp of m = a + 32 b at 4 b | Hann at 128 + 2 b |
     // inter-pass twiddle W_1024^(a d) at 192 + 2 d
     static constexpr int t_ud = 0, t_hann = 128, t_tw = 192, t_cols = 256;
@@ -89,23 +93,31 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
     tmem_fence_after_sync();
     const uint32_t tq = tmem_quadrant(*s_tslot, warp);
     if (warp < 4) {                                                   // warp q fills lane quadrant q; warps q and q + 4 read it
-        for (int b = 0; b < 32; b += 2) {
-            const float4 c0 = reinterpret_cast<const float4*>(p.chirp_ud)[lane + 32 * b];
-            const float4 c1 = reinterpret_cast<const float4*>(p.chirp_ud)[lane + 32 * (b + 1)];
-            const uint32_t v[8] = {__float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c0.z), __float_as_uint(c0.w),
-                                   __float_as_uint(c1.x), __float_as_uint(c1.y), __float_as_uint(c1.z), __float_as_uint(c1.w)};
-            sttm8(tq + L::t_ud + 4 * b, v);
-        }
-        for (int b = 0; b < 32; b += 4) {
-            uint32_t v[8], t[8];
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += 8) {                          // eight rows per round: 24 independent loads in flight
+            float4 c[8];
+            float2 w[8], z[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 w = p.hann[lane + 32 * (b + j)], z = p.tw_pass[(b + j) * 32 + lane];
-                v[2 * j] = __float_as_uint(w.x); v[2 * j + 1] = __float_as_uint(w.y);
-                t[2 * j] = __float_as_uint(z.x); t[2 * j + 1] = __float_as_uint(z.y);
+            for (int j = 0; j < 8; ++j) {
+                c[j] = reinterpret_cast<const float4*>(p.chirp_ud)[lane + 32 * (b0 + j)];
+                w[j] = p.hann[lane + 32 * (b0 + j)];
+                z[j] = p.tw_pass[(b0 + j) * 32 + lane];
             }
-            sttm8(tq + L::t_hann + 2 * b, v);
-            sttm8(tq + L::t_tw + 2 * b, t);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const uint32_t v[8] = {__float_as_uint(c[j].x), __float_as_uint(c[j].y), __float_as_uint(c[j].z), __float_as_uint(c[j].w),
+                                       __float_as_uint(c[j + 1].x), __float_as_uint(c[j + 1].y), __float_as_uint(c[j + 1].z), __float_as_uint(c[j + 1].w)};
+                sttm8(tq + L::t_ud + 4 * (b0 + j), v);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+                const uint32_t v[8] = {__float_as_uint(w[j].x), __float_as_uint(w[j].y), __float_as_uint(w[j + 1].x), __float_as_uint(w[j + 1].y),
+                                       __float_as_uint(w[j + 2].x), __float_as_uint(w[j + 2].y), __float_as_uint(w[j + 3].x), __float_as_uint(w[j + 3].y)};
+                const uint32_t t[8] = {__float_as_uint(z[j].x), __float_as_uint(z[j].y), __float_as_uint(z[j + 1].x), __float_as_uint(z[j + 1].y),
+                                       __float_as_uint(z[j + 2].x), __float_as_uint(z[j + 2].y), __float_as_uint(z[j + 3].x), __float_as_uint(z[j + 3].y)};
+                sttm8(tq + L::t_hann + 2 * (b0 + j), v);
+                sttm8(tq + L::t_tw + 2 * (b0 + j), t);
+            }
         }
         sttm_wait();
     }
@@ -237,17 +249,23 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
 // whose time per 8 KB frame is closest to the HBM roofline.  The 16 KB of PCM for a warp's next
 // frame pair arrive by one TMA bulk copy; to stay inside 227 KB of shared memory with 8 warps the
 // exchange goes through an 8 KB tile in two rounds (real parts, then imaginary parts).
+#ifndef USC_PAIR_TMEM
+#define USC_PAIR_TMEM 1                                 // tables in tensor memory, as in the dual kernel
+#endif
+#if USC_PAIR_TMEM
+constexpr int kPairSmemTabs = 0;
+#else
 constexpr int kPairSmemTabs = 3 * 8192;               // twiddles | chirp | Hann
+#endif
 constexpr int kPairWarpBytes = kTileFloat2 * 8 + 16384;   // padded 32x33 float2 tile + 2-frame PCM stage
 constexpr int kPairSmemBar = kPairSmemTabs + kDualWarps * kPairWarpBytes;
-constexpr int kPairSmemTotal = kPairSmemBar + kDualWarps * 8;
+constexpr int kPairSmemTotal = kPairSmemBar + kDualWarps * 8 + 8;
+// TMEM columns of lane a: (chirp pair, Hann pair) of m = a + 32 b at 4 b | inter-pass twiddle W_1024^(a d) at 128 + 2 d
+constexpr int kPairTcw = 0, kPairTtw = 128, kPairTcols = 256;
 
 template <typename PCM, int NB>
 __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_params p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    float2* s_tw = reinterpret_cast<float2*>(s_raw);
-    float2* s_chirp = reinterpret_cast<float2*>(s_raw + 8192);
-    float2* s_hann = reinterpret_cast<float2*>(s_raw + 16384);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = s_raw + kPairSmemTabs + warp * kPairWarpBytes;
     using V2 = typename vec2<PCM>::type;
@@ -269,15 +287,55 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
         }
     }
     const float2* chirp = p.updown ? p.chirp_up : p.chirp_down;
+#if USC_PAIR_TMEM
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw + kPairSmemBar + kDualWarps * 8);
+    if (warp == 0) tmem_alloc<kPairTcols>(s_tslot);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp);
+    if (warp < 4) {                                                   // warp q fills lane quadrant q; warps q and q + 4 read it
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += 8) {
+            float2 c[8], w[8], z[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = chirp[lane + 32 * (b0 + j)];
+                w[j] = p.hann[lane + 32 * (b0 + j)];
+                z[j] = p.tw_pass[(b0 + j) * 32 + lane];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const uint32_t v[8] = {__float_as_uint(c[j].x), __float_as_uint(c[j].y), __float_as_uint(w[j].x), __float_as_uint(w[j].y),
+                                       __float_as_uint(c[j + 1].x), __float_as_uint(c[j + 1].y), __float_as_uint(w[j + 1].x), __float_as_uint(w[j + 1].y)};
+                sttm8(tq + kPairTcw + 4 * (b0 + j), v);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+                const uint32_t t[8] = {__float_as_uint(z[j].x), __float_as_uint(z[j].y), __float_as_uint(z[j + 1].x), __float_as_uint(z[j + 1].y),
+                                       __float_as_uint(z[j + 2].x), __float_as_uint(z[j + 2].y), __float_as_uint(z[j + 3].x), __float_as_uint(z[j + 3].y)};
+                sttm8(tq + kPairTtw + 2 * (b0 + j), t);
+            }
+        }
+        sttm_wait();
+    }
+    const float one = p.tw_pass[lane].x;                              // W^0 = 1.0f, read from the table: opaque to the compiler
+#else
+    float2* s_tw = reinterpret_cast<float2*>(s_raw);
+    float2* s_chirp = reinterpret_cast<float2*>(s_raw + 8192);
+    float2* s_hann = reinterpret_cast<float2*>(s_raw + 16384);
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
         s_tw[i] = p.tw_pass[i];
         s_chirp[i] = chirp[i];
         s_hann[i] = p.hann[i];
     }
+#endif
     float2 ws[NB];
 #pragma unroll
     for (int d1 = 0; d1 < NB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
 
     uint32_t parity = 0;
     for (; q < npairs; q += nwarps) {
@@ -285,24 +343,59 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
         mbar_wait(bar, parity);
         parity ^= 1u;
         float2 re[32], im[32];                                        // (.x, .y) = (frame 2q, frame 2q+1)
+        // ((x*c)*w) on both frames at once: the per-lane table values broadcast to the two halves
+        // (first butterfly stage as FMAs by 1.0: see the note in k_demod2048 about ptxas contracting packed mul + add)
+#if USC_PAIR_TMEM
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {                                 // table values of four rows per TMEM round trip
+            uint32_t t[16];
+            ldtm16(tq + kPairTcw + 16 * g, t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 4 * g + j, m = lane + 32 * b;
+                const V2 ra = xstage[m];
+                const V2 rb = two ? xstage[1024 + m] : ra;
+                const float2 tr = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(__uint_as_float(t[4 * j])));
+                const float2 ti = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(__uint_as_float(t[4 * j + 1])));
+                re[b] = __fmul2_rn(tr, bc2(__uint_as_float(t[4 * j + 2])));
+                im[b] = __fmul2_rn(ti, bc2(__uint_as_float(t[4 * j + 3])));
+            }
+        }
+#else
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
             const int m = lane + 32 * b;
             const V2 ra = xstage[m];
             const V2 rb = two ? xstage[1024 + m] : ra;
             const float2 c = s_chirp[m], w = s_hann[m];
-            // ((x*c)*w) on both frames at once: the per-lane table values broadcast to the two halves
-            // (first butterfly stage as FMAs by 1.0: see the note in k_demod2048 about ptxas contracting packed mul + add)
             const float2 tr = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(c.x));
             const float2 ti = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(c.y));
             re[b] = __fmul2_rn(tr, bc2(w.x));
             im[b] = __fmul2_rn(ti, bc2(w.y));
         }
+#endif
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {
             mbar_expect_tx(bar, pair_bytes(q + nwarps));
             bulk_g2s(xstage, pcm + (q + nwarps) * 4096, pair_bytes(q + nwarps), bar);
         }
+#if USC_PAIR_TMEM
+        fft_base2_prod<32>(re, im, one);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                                 // inter-pass twiddle, both halves: 8 per TMEM round trip
+            uint32_t t[16];
+            ldtm16(tq + kPairTtw + 16 * g, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d = 8 * g + j;
+                if (d == 0) continue;
+                float2 tr, ti;
+                cmul2(re[d], im[d], __uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]), tr, ti);
+                re[d] = tr;
+                im[d] = ti;
+            }
+        }
+#else
         fft_base2_prod<32>(re, im, s_tw[lane].x);
 #pragma unroll
         for (int d = 1; d < 32; ++d) {                                // inter-pass twiddle, both halves
@@ -312,6 +405,7 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
             re[d] = tr;
             im[d] = ti;
         }
+#endif
         // exchange in two rounds through the 8 KB tile, one per component: each 64-bit word is a
         // (frame 2q, frame 2q+1) register pair, so values land in place with no repacking moves
 #pragma unroll
@@ -337,6 +431,11 @@ __global__ void __launch_bounds__(kDualWarps * 32, 1) k_demod2048_pair(demod_par
             if (idx) { idx[2 * q] = ia; if (two) idx[2 * q + 1] = ib; }
         }
     }
+#if USC_PAIR_TMEM
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kPairTcols>(*s_tslot);
+#endif
 }
 
 // dsp() for one hypothesis with a per-stream gather offset (receiver/Src/main.c:183-231).
