@@ -17,6 +17,7 @@
 #include "usc_kernels.cuh"
 #include "usc_launch.h"
 #include "usc_warpfft.cuh"
+#include "usc_tmem.cuh"
 
 namespace usc {
 
@@ -24,6 +25,21 @@ namespace usc {
 #define USC_LONG_UNROLL 4
 #endif
 constexpr int kLongUnroll = USC_LONG_UNROLL;            // level-0 rounds whose loads are issued together
+#ifndef USC_LONG_TMEM
+#define USC_LONG_TMEM 1                                 // frame-sized tables (chirp, Hann, level-0 twiddles) in tensor memory
+#endif
+// Tensor-memory layout of the frame-sized tables (R0 >= 4).  Thread tid handles a = tid + T i in level-0 round i and
+// always needs the same table entries: the (up, down) chirp and Hann values of m = a + 1024 b, b < R0, and the level-0
+// twiddles W^(a d), d = 1..R0-1 — 8 R0 - 2 words, padded to 8 R0 columns per round, 32 / R0 rounds: 256 columns of the
+// thread's own TMEM lane (warps 4..7 of the 8-warp form take columns 256..511).  The tables total 30 KB per 8 KB of
+// PCM; read through L2/L1 for every frame they were the kernel's largest stream.
+template <int R0> struct long_tmem {
+    static constexpr int per_round = 8 * R0, rounds = 32 / R0, c_ud = 0, c_hann = 4 * R0, c_tw = 6 * R0,
+                         cols = R0 == 8 ? 512 : 256;
+};
+template <int N> struct ldtm_n;
+template <> struct ldtm_n<32> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[32]) { ldtm32(ta, t); } };
+template <> struct ldtm_n<64> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[64]) { ldtm64(ta, t); } };
 constexpr int kLongNB = 5;                            // c < 160 covers bandwidth2 / R0 <= 160
 constexpr int kLongKeep = 32 * kLongNB;               // kept outputs per side of each sub-spectrum
 
@@ -37,7 +53,7 @@ struct long_params {
 
 template <int R0> struct long_smem {
     // per warp d: 16 KB region: sub-sequence d as (re pair[1024], im pair[1024]); later tile (8 KB) + kept outputs
-    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + R0 * region, total = red + R0 * 64;
+    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + R0 * region, tslot = red + R0 * 64, total = tslot + 16;
 };
 
 template <typename PCM, int R0>
@@ -50,7 +66,43 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
     constexpr int T = R0 * 32;
     const uint32_t nc = 1024u * R0;                    // complex length
     for (int i = tid; i < 1024; i += T) s_tw[i] = p.tw_pass[i];
+    constexpr bool kTmem = USC_LONG_TMEM && R0 >= 4;
+    using TM = long_tmem<R0 >= 4 ? R0 : 4>;
+    uint32_t tq = 0;
+    float one = 1.0f;
+    if (kTmem) {
+        uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw + L::tslot);
+        if (warp == 0) tmem_alloc<TM::cols>(s_tslot);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        tq = tmem_quadrant(*s_tslot, warp) + (warp >> 2) * 256u;
+#pragma unroll 1
+        for (int i = 0; i < TM::rounds; ++i) {            // this thread's table row, round by round
+            const uint32_t a = tid + T * i;
+            uint32_t v[TM::per_round];
+#pragma unroll
+            for (int b = 0; b < R0; ++b) {
+                const uint32_t m = a + 1024u * b;
+                const float4 c = __ldg(p.chirp_ud + m);
+                const float2 w = __ldg(p.hann + m);
+                v[TM::c_ud + 4 * b] = __float_as_uint(c.x); v[TM::c_ud + 4 * b + 1] = __float_as_uint(c.y);
+                v[TM::c_ud + 4 * b + 2] = __float_as_uint(c.z); v[TM::c_ud + 4 * b + 3] = __float_as_uint(c.w);
+                v[TM::c_hann + 2 * b] = __float_as_uint(w.x); v[TM::c_hann + 2 * b + 1] = __float_as_uint(w.y);
+                const float2 z = __ldg(p.tw_master + (size_t) a * b * 2u);      // W_nc^(a b); b = 0 gives (1, -0), kept as padding
+                v[TM::c_tw + 2 * b] = __float_as_uint(z.x); v[TM::c_tw + 2 * b + 1] = __float_as_uint(z.y);
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < TM::per_round; c0 += 8) {
+                const uint32_t v8[8] = {v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3], v[c0 + 4], v[c0 + 5], v[c0 + 6], v[c0 + 7]};
+                sttm8(tq + TM::per_round * i + c0, v8);
+            }
+        }
+        sttm_wait();
+        tmem_fence_before_sync();
+    }
     __syncthreads();
+    if (kTmem) { tmem_fence_after_sync(); one = s_tw[lane].x; }   // W^0 = 1.0f from the table: opaque to the compiler
     const uint32_t bw2 = p.bandwidth2;
     float2 w_split[kLongNB];                           // split twiddles W_n^k of this thread's bins k = tid + T j: frame-invariant
 #pragma unroll
@@ -68,6 +120,42 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
         }
 #endif
         // ---- level 0: radix-R0 over b, twiddle, park sub-sequence d ----
+        if (kTmem) {
+            // tables from this thread's TMEM row (one load per round); only the PCM comes from global memory, and the
+            // loads of kLongUnroll rounds are issued together
+#pragma unroll 1
+            for (int i0 = 0; i0 < TM::rounds; i0 += kLongUnroll) {
+                V2 raw[kLongUnroll][R0];
+#pragma unroll
+                for (int u = 0; u < kLongUnroll; ++u)
+#pragma unroll
+                    for (int b = 0; b < R0; ++b) raw[u][b] = src[tid + T * (i0 + u) + 1024u * b];
+#pragma unroll
+                for (int u = 0; u < kLongUnroll; ++u) {
+                    const uint32_t a = tid + T * (i0 + u);
+                    uint32_t t[TM::per_round];
+                    ldtm_n<TM::per_round>::ld(tq + TM::per_round * (i0 + u), t);
+                    float2 re[R0], im[R0];
+#pragma unroll
+                    for (int b = 0; b < R0; ++b) {
+                        const float x0 = pcm_to_float(raw[u][b].x), x1 = pcm_to_float(raw[u][b].y);
+                        const float2 tr = __fmul2_rn(make_float2(__uint_as_float(t[TM::c_ud + 4 * b]), __uint_as_float(t[TM::c_ud + 4 * b + 1])), bc2(x0));
+                        const float2 ti = __fmul2_rn(make_float2(__uint_as_float(t[TM::c_ud + 4 * b + 2]), __uint_as_float(t[TM::c_ud + 4 * b + 3])), bc2(x1));
+                        re[b] = __fmul2_rn(tr, bc2(__uint_as_float(t[TM::c_hann + 2 * b])));
+                        im[b] = __fmul2_rn(ti, bc2(__uint_as_float(t[TM::c_hann + 2 * b + 1])));
+                    }
+                    fft_base2_prod<R0>(re, im, one);
+#pragma unroll
+                    for (int d = 0; d < R0; ++d) {
+                        float2 xr = re[d], xi = im[d];
+                        if (d != 0) cmul2(re[d], im[d], __uint_as_float(t[TM::c_tw + 2 * d]), __uint_as_float(t[TM::c_tw + 2 * d + 1]), xr, xi);
+                        float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + d * L::region);
+                        reg[a] = xr;
+                        reg[1024 + a] = xi;
+                    }
+                }
+            }
+        } else {
         // (unrolled so the global loads of several rounds are in flight together: the phase is latency-bound)
 #pragma unroll kLongUnroll
         for (uint32_t a = tid; a < 1024u; a += T) {
@@ -96,6 +184,7 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
                 reg[a] = xr;
                 reg[1024 + a] = xi;
             }
+        }
         }
         __syncthreads();
         // ---- 1024-point packed core on sub-sequence `warp` ----
@@ -165,6 +254,11 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
             if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
         }
         __syncthreads();
+    }
+    if (kTmem) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc<TM::cols>(*reinterpret_cast<uint32_t*>(s_raw + L::tslot));
     }
 }
 

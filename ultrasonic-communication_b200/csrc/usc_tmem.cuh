@@ -55,6 +55,15 @@ __device__ __forceinline__ void ldtm32(uint32_t taddr, uint32_t (&a)[32]) {
                  "tcgen05.wait::ld.sync.aligned;"
                  : USC_R8(a, 0), USC_R8(a, 8), USC_R8(a, 16), USC_R8(a, 24) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void ldtm64(uint32_t taddr, uint32_t (&a)[64]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                 "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+                 "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : USC_R8(a, 0), USC_R8(a, 8), USC_R8(a, 16), USC_R8(a, 24), USC_R8(a, 32), USC_R8(a, 40), USC_R8(a, 48), USC_R8(a, 56)
+                 : "r"(taddr) : "memory");
+}
 // two loads in flight, one wait: 16 + 8 columns (four front-end rows: (up, down) chirp pairs of two samples + Hann pair)
 __device__ __forceinline__ void ldtm16_8(uint32_t ta, uint32_t (&a)[16], uint32_t tb, uint32_t (&b)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%24];\n\t"
