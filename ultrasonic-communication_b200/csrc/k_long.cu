@@ -25,6 +25,12 @@ namespace usc {
 #define USC_LONG_UNROLL 4
 #endif
 constexpr int kLongUnroll = USC_LONG_UNROLL;            // level-0 rounds whose loads are issued together
+#ifndef USC_LONG_OLD_TAIL
+#define USC_LONG_OLD_TAIL 0
+#endif
+#ifndef USC_LONG_STAGE
+#define USC_LONG_STAGE 1                                // PCM of the next frame staged in shared memory by TMA (0: gathered from global memory)
+#endif
 #ifndef USC_LONG_TMEM
 #define USC_LONG_TMEM 1                                 // frame-sized tables (chirp, Hann, level-0 twiddles) in tensor memory
 #endif
@@ -42,6 +48,10 @@ template <> struct ldtm_n<32> { static __device__ __forceinline__ void ld(uint32
 template <> struct ldtm_n<64> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[64]) { ldtm64(ta, t); } };
 constexpr int kLongNB = 5;                            // c < 160 covers bandwidth2 / R0 <= 160
 constexpr int kLongKeep = 32 * kLongNB;               // kept outputs per side of each sub-spectrum
+// The kept outputs of sub-sequence d sit in the upper half of region d, shifted by d * (128 / R) bytes (R regions are
+// interleaved over consecutive lanes in the split): the regions are 16 KB apart, so without the shift the R lanes that
+// read the same c from R different regions hit the same banks (R-way conflicts on every split load).
+template <int R> __device__ __forceinline__ constexpr uint32_t keep_off(uint32_t d) { return 8192u + d * (128u / R); }
 
 struct long_params {
     const void* pcm; size_t nframes; uint32_t n;      // n real samples per frame (2048 * R0)
@@ -52,24 +62,110 @@ struct long_params {
 };
 
 template <int R0> struct long_smem {
-    // per warp d: 16 KB region: sub-sequence d as (re pair[1024], im pair[1024]); later tile (8 KB) + kept outputs
-    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + R0 * region, tslot = red + R0 * 64, total = tslot + 16;
+    // pass twiddles | per warp d a 16 KB region: sub-sequence d as (re pair[1024], im pair[1024]); later tile (8 KB) + kept
+    // outputs | PCM stage of one frame (filled by TMA one frame ahead) | reduction slots | mbarrier | TMEM slot
+    static constexpr int tw = 0, sub = 8192, region = 16384, stage = sub + R0 * region, red = stage + ((USC_LONG_STAGE && R0 >= 4) ? R0 * 8192 : 0),
+                         bar = red + 3 * R0 * 16, tslot = bar + 8, total = tslot + 8;
 };
 
+// block-wide exact arg-max of sqrt(p) over this CTA's candidates for both hypotheses, with one square root per hypothesis
+// on the common path: the maximum of p is found first (p >= 0, so bit patterns order like values); if no other candidate
+// lies within 2^-20 of it (two ulps of the root), its root is the maximum and its index the first occurrence; otherwise
+// every root is taken (rare path).  pu/pd: squared magnitudes of this thread's bins k[j], ascending; ok[j]: bin in range.
+template <int R0, int NC>
+__device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float (&pd)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
+                                              float* red, int tid, float& bu, uint32_t& iu, float& bd, uint32_t& id) {
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t* redu = reinterpret_cast<uint32_t*>(red);
+    float qu = 0.0f, qd = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        if (ok[j] && pu[j] > qu) qu = pu[j];
+        if (ok[j] && pd[j] > qd) qd = pd[j];
+    }
+    const uint32_t wu = __reduce_max_sync(0xffffffffu, __float_as_uint(qu)), wd = __reduce_max_sync(0xffffffffu, __float_as_uint(qd));
+    if (lane == 0) { redu[warp * 2] = wu; redu[warp * 2 + 1] = wd; }
+    __syncthreads();
+    uint32_t mu = 0, md = 0;
+#pragma unroll
+    for (int w = 0; w < R0; ++w) { mu = max(mu, redu[w * 2]); md = max(md, redu[w * 2 + 1]); }
+    const float maxu = __uint_as_float(mu), maxd = __uint_as_float(md);
+    const float thru = __fmul_rn(maxu, 0.99999904632568359375f), thrd = __fmul_rn(maxd, 0.99999904632568359375f);   // 1 - 2^-20
+    uint32_t near = 0, ku = 0xffffffffu, kd = 0xffffffffu;             // near: candidates within two ulps of either maximum
+#pragma unroll
+    for (int j = NC - 1; j >= 0; --j) {
+        if (ok[j] && pu[j] >= thru) { ++near; if (pu[j] == maxu) ku = k[j]; }
+        if (ok[j] && pd[j] >= thrd) { near += 0x10000u; if (pd[j] == maxd) kd = k[j]; }
+    }
+    near = __reduce_add_sync(0xffffffffu, near);
+    ku = __reduce_min_sync(0xffffffffu, ku);
+    kd = __reduce_min_sync(0xffffffffu, kd);
+    if (lane == 0) { redu[2 * R0 + warp * 4] = near; redu[2 * R0 + warp * 4 + 1] = ku; redu[2 * R0 + warp * 4 + 2] = kd; }
+    __syncthreads();
+    near = 0; ku = 0xffffffffu; kd = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < R0; ++w) {
+        near += redu[2 * R0 + w * 4];
+        ku = min(ku, redu[2 * R0 + w * 4 + 1]);
+        kd = min(kd, redu[2 * R0 + w * 4 + 2]);
+    }
+    if (near == 0x10001u && maxu == maxu && maxd == maxd) {           // exactly one candidate per hypothesis near its maximum
+        bu = __fsqrt_rn(maxu); iu = ku;
+        bd = __fsqrt_rn(maxd); id = kd;
+        return;
+    }
+    // rare path (block-uniform): every root, first-occurrence arg-max
+    bu = -INFINITY; bd = -INFINITY;
+    iu = 0xffffffffu; id = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const float su = __fsqrt_rn(pu[j]), sd = __fsqrt_rn(pd[j]);
+        if (ok[j] && (iu == 0xffffffffu || bu < su)) { bu = su; iu = k[j]; }
+        if (ok[j] && (id == 0xffffffffu || bd < sd)) { bd = sd; id = k[j]; }
+    }
+    warp_argmax(bu, iu);
+    warp_argmax(bd, id);
+    float* slow = red + 6 * R0;
+    if (lane == 0) {
+        slow[warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(slow)[warp * 4 + 1] = iu;
+        slow[warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(slow)[warp * 4 + 3] = id;
+    }
+    __syncthreads();
+    bu = slow[0]; iu = reinterpret_cast<uint32_t*>(slow)[1]; bd = slow[2]; id = reinterpret_cast<uint32_t*>(slow)[3];
+    for (int w = 1; w < R0; ++w) {
+        argmax_combine(bu, iu, slow[w * 4 + 0], reinterpret_cast<uint32_t*>(slow)[w * 4 + 1]);
+        argmax_combine(bd, id, slow[w * 4 + 2], reinterpret_cast<uint32_t*>(slow)[w * 4 + 3]);
+    }
+}
+
 template <typename PCM, int R0>
-__global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
+__device__ __forceinline__ void demod_long_body(const long_params& p) {
     using L = long_smem<R0>;
     using V2 = typename vec2<PCM>::type;
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
+    constexpr bool kStage = USC_LONG_STAGE && R0 >= 4;      // 4096 points: three staged CTAs per SM lose against four unstaged ones
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + L::bar);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int T = R0 * 32;
+    constexpr uint32_t kFrameBytes = 2048u * R0 * 4u;
     const uint32_t nc = 1024u * R0;                    // complex length
+    const PCM* pcm = static_cast<const PCM*>(p.pcm);
+    auto fetch = [&](size_t f) {                       // one frame of PCM into the stage: 1-D TMA bulk copies, 16 KB each
+        mbar_expect_tx(bar, kFrameBytes);
+#pragma unroll
+        for (uint32_t o = 0; o < kFrameBytes; o += 16384u)
+            bulk_g2s(s_raw + L::stage + o, reinterpret_cast<const char*>(pcm + f * p.n) + o, kFrameBytes < 16384u ? kFrameBytes : 16384u, bar);
+    };
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (kStage && blockIdx.x < p.nframes) fetch(blockIdx.x);
+    }
     for (int i = tid; i < 1024; i += T) s_tw[i] = p.tw_pass[i];
     constexpr bool kTmem = USC_LONG_TMEM && R0 >= 4;
     using TM = long_tmem<R0 >= 4 ? R0 : 4>;
     uint32_t tq = 0;
-    float one = 1.0f;
     if (kTmem) {
         uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw + L::tslot);
         if (warp == 0) tmem_alloc<TM::cols>(s_tslot);
@@ -102,158 +198,172 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
         tmem_fence_before_sync();
     }
     __syncthreads();
-    if (kTmem) { tmem_fence_after_sync(); one = s_tw[lane].x; }   // W^0 = 1.0f from the table: opaque to the compiler
+    if (kTmem) tmem_fence_after_sync();
+    const float one = s_tw[lane].x;                    // W^0 = 1.0f from the table: opaque to the compiler
     const uint32_t bw2 = p.bandwidth2;
     float2 w_split[kLongNB];                           // split twiddles W_n^k of this thread's bins k = tid + T j: frame-invariant
 #pragma unroll
     for (int j = 0; j < kLongNB; ++j) w_split[j] = p.tw_master[min((uint32_t) (tid + T * j), bw2 - 1u)];
 
+    uint32_t parity = 0;
     for (size_t f = blockIdx.x; f < p.nframes; f += gridDim.x) {
-        const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * p.n);
-#ifndef USC_LONG_NO_PREFETCH
-        if (f + gridDim.x < p.nframes) {                 // this CTA's next frame towards L2 while the current one computes
-            const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + gridDim.x) * p.n);
+        const V2* stage = kStage ? reinterpret_cast<const V2*>(s_raw + L::stage) : reinterpret_cast<const V2*>(pcm + f * p.n);
+        if (kStage) {
+            mbar_wait(bar, parity);                      // this frame's PCM has landed in the stage
+            parity ^= 1u;
+        } else if (f + gridDim.x < p.nframes) {          // this CTA's next frame towards L2 while the current one computes
+            const char* nxt = reinterpret_cast<const char*>(pcm + (f + gridDim.x) * p.n);
             constexpr uint32_t per_thread = 2048u * R0 * 4u / T;                             // 256 bytes
 #pragma unroll
             for (uint32_t o = 0; o < per_thread; o += 128u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t) tid * per_thread + o));
         }
-#endif
         // ---- level 0: radix-R0 over b, twiddle, park sub-sequence d ----
-        if (kTmem) {
-            // tables from this thread's TMEM row (one load per round); only the PCM comes from global memory, and the
-            // loads of kLongUnroll rounds are issued together
+        // The PCM loads of kLongUnroll rounds are issued together, ahead of the table loads (a TMEM round trip is an
+        // asm statement the compiler does not move loads across).
+        constexpr int kU = kLongUnroll < 32 / R0 ? kLongUnroll : 32 / R0;
 #pragma unroll 1
-            for (int i0 = 0; i0 < TM::rounds; i0 += kLongUnroll) {
-                V2 raw[kLongUnroll][R0];
+        for (int i0 = 0; i0 < 32 / R0; i0 += kU) {
+            V2 raw[kU][R0];
 #pragma unroll
-                for (int u = 0; u < kLongUnroll; ++u)
+            for (int u = 0; u < kU; ++u)
 #pragma unroll
-                    for (int b = 0; b < R0; ++b) raw[u][b] = src[tid + T * (i0 + u) + 1024u * b];
+                for (int b = 0; b < R0; ++b) raw[u][b] = stage[tid + T * (i0 + u) + 1024u * b];
 #pragma unroll
-                for (int u = 0; u < kLongUnroll; ++u) {
-                    const uint32_t a = tid + T * (i0 + u);
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + u;
+                const uint32_t a = tid + T * i;
+                float2 re[R0], im[R0];
+                float2 twd[R0];
+                if (kTmem) {                             // tables from this thread's TMEM row: one load per round
                     uint32_t t[TM::per_round];
-                    ldtm_n<TM::per_round>::ld(tq + TM::per_round * (i0 + u), t);
-                    float2 re[R0], im[R0];
+                    ldtm_n<TM::per_round>::ld(tq + TM::per_round * i, t);
 #pragma unroll
                     for (int b = 0; b < R0; ++b) {
                         const float x0 = pcm_to_float(raw[u][b].x), x1 = pcm_to_float(raw[u][b].y);
+                        // packed window multiply; the first butterfly stage takes the products as FMAs by 1.0 (usc_arith.cuh)
                         const float2 tr = __fmul2_rn(make_float2(__uint_as_float(t[TM::c_ud + 4 * b]), __uint_as_float(t[TM::c_ud + 4 * b + 1])), bc2(x0));
                         const float2 ti = __fmul2_rn(make_float2(__uint_as_float(t[TM::c_ud + 4 * b + 2]), __uint_as_float(t[TM::c_ud + 4 * b + 3])), bc2(x1));
                         re[b] = __fmul2_rn(tr, bc2(__uint_as_float(t[TM::c_hann + 2 * b])));
                         im[b] = __fmul2_rn(ti, bc2(__uint_as_float(t[TM::c_hann + 2 * b + 1])));
+                        twd[b] = make_float2(__uint_as_float(t[TM::c_tw + 2 * b]), __uint_as_float(t[TM::c_tw + 2 * b + 1]));
                     }
-                    fft_base2_prod<R0>(re, im, one);
+                } else {
 #pragma unroll
-                    for (int d = 0; d < R0; ++d) {
-                        float2 xr = re[d], xi = im[d];
-                        if (d != 0) cmul2(re[d], im[d], __uint_as_float(t[TM::c_tw + 2 * d]), __uint_as_float(t[TM::c_tw + 2 * d + 1]), xr, xi);
-                        float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + d * L::region);
-                        reg[a] = xr;
-                        reg[1024 + a] = xi;
+                    for (int b = 0; b < R0; ++b) {
+                        const uint32_t m = a + 1024u * b;
+                        const float x0 = pcm_to_float(raw[u][b].x), x1 = pcm_to_float(raw[u][b].y);
+                        const float4 c = __ldg(p.chirp_ud + m);
+                        const float2 w = __ldg(p.hann + m);
+                        const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
+                        re[b] = __fmul2_rn(tr, bc2(w.x));
+                        im[b] = __fmul2_rn(ti, bc2(w.y));
+                        twd[b] = __ldg(p.tw_master + (size_t) a * b * 2u);          // W_nc^(a d) = W_n^(2 a d)
                     }
                 }
-            }
-        } else {
-        // (unrolled so the global loads of several rounds are in flight together: the phase is latency-bound)
-#pragma unroll kLongUnroll
-        for (uint32_t a = tid; a < 1024u; a += T) {
-            float2 re[R0], im[R0];
+                fft_base2_prod<R0>(re, im, one);
 #pragma unroll
-            for (int b = 0; b < R0; ++b) {
-                const uint32_t m = a + 1024u * b;
-                const V2 raw = src[m];
-                const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
-                const float4 c = __ldg(p.chirp_ud + m);
-                const float2 w = __ldg(p.hann + m);
-                // packed window multiply; the first butterfly stage takes the products as FMAs by 1.0 (usc_arith.cuh)
-                const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
-                re[b] = __fmul2_rn(tr, bc2(w.x));
-                im[b] = __fmul2_rn(ti, bc2(w.y));
-            }
-            fft_base2_prod<R0>(re, im, s_tw[lane].x);
-#pragma unroll
-            for (int d = 0; d < R0; ++d) {
-                float2 xr = re[d], xi = im[d];
-                if (d != 0) {
-                    const float2 w = __ldg(p.tw_master + (size_t) a * d * 2u);      // W_nc^(a d) = W_n^(2 a d)
-                    cmul2(re[d], im[d], w.x, w.y, xr, xi);
+                for (int d = 0; d < R0; ++d) {
+                    float2 xr = re[d], xi = im[d];
+                    if (d != 0) cmul2(re[d], im[d], twd[d].x, twd[d].y, xr, xi);
+                    float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + d * L::region);
+                    reg[a] = xr;
+                    reg[1024 + a] = xi;
                 }
-                float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + d * L::region);
-                reg[a] = xr;
-                reg[1024 + a] = xi;
             }
         }
-        }
-        __syncthreads();
+        __syncthreads();                                 // sub-sequences parked; every thread is done with the stage
+        if (kStage && tid == 0 && f + gridDim.x < p.nframes) fetch(f + gridDim.x);   // next frame arrives under the core and the split
         // ---- 1024-point packed core on sub-sequence `warp` ----
         float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + warp * L::region);
-        float2 re[32], im[32];
+        {
+            float2 re[32], im[32];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            re[b] = reg[lane + 32 * b];
-            im[b] = reg[1024 + lane + 32 * b];
-        }
-        __syncwarp();
-        fft1024_pair(re, im, reg, s_tw, lane);           // first 8 KB of the region is now the exchange tile
-        // keep Y_d[c] for c < 160 (elements 0..4) and c >= 864 (elements 27..31)
-        float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + 8192);
+            for (int b = 0; b < 32; ++b) {
+                re[b] = reg[lane + 32 * b];
+                im[b] = reg[1024 + lane + 32 * b];
+            }
+            __syncwarp();
+            fft1024_pair(re, im, reg, s_tw, lane);           // first 8 KB of the region is now the exchange tile
+            // keep Y_d[c] for c < 160 (elements 0..4) and c >= 864 (elements 27..31)
+            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + keep_off<R0>(warp));
 #pragma unroll
-        for (int j = 0; j < kLongNB; ++j) {
-            keep[lane + 32 * j] = make_float4(re[j].x, re[j].y, im[j].x, im[j].y);
-            keep[kLongKeep + lane + 32 * j] = make_float4(re[32 - kLongNB + j].x, re[32 - kLongNB + j].y,
-                                                          im[32 - kLongNB + j].x, im[32 - kLongNB + j].y);
+            for (int j = 0; j < kLongNB; ++j) {
+                keep[lane + 32 * j] = make_float4(re[j].x, re[j].y, im[j].x, im[j].y);
+                keep[kLongKeep + lane + 32 * j] = make_float4(re[32 - kLongNB + j].x, re[32 - kLongNB + j].y,
+                                                              im[32 - kLongNB + j].x, im[32 - kLongNB + j].y);
+            }
         }
         __syncthreads();
-        // ---- split, magnitude, arg-max over k < bw2 ----
+        // ---- split, squared magnitude, exact arg-max over k < bw2 ----
         auto Y = [&](uint32_t k) -> float4 {             // Z[k] = Y_{k mod R0}[k / R0], only kept ranges are asked for
             const uint32_t d = k & (R0 - 1u), c = k / R0;
-            const float4* kp = reinterpret_cast<const float4*>(s_raw + L::sub + d * L::region + 8192);
+            const float4* kp = reinterpret_cast<const float4*>(s_raw + L::sub + d * L::region + keep_off<R0>(d));
             return c < (uint32_t) kLongKeep ? kp[c] : kp[kLongKeep + (c - (1024u - kLongKeep))];
         };
-        float bu = -INFINITY, bd = -INFINITY;
-        uint32_t iu = 0xffffffffu, id = 0xffffffffu;
+        float pu[kLongNB], pd[kLongNB];
+        uint32_t kk[kLongNB];
+        bool ok[kLongNB];
 #pragma unroll
         for (int j = 0; j < kLongNB; ++j) {
             const uint32_t k = tid + T * j;                                       // bw2 <= 160 R0 = kLongNB T
-            if (k >= bw2) break;
-            const float4 zk = Y(k);
+            kk[j] = k;
+            ok[j] = k < bw2;
+            const uint32_t kc = ok[j] ? k : 0u;
+            const float4 zk = Y(kc);
+            const float4 zc = Y(kc == 0u ? 0u : nc - kc);
             float2 xr, xi;
-            if (k == 0) {
+            const float2 w = w_split[j];                                          // W_n^k = (cos, -sin)
+            rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
+                        make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
+            if (kc == 0u) {                                                       // packed bin 0 = (X[0], X[N/2])
                 xr = __fadd2_rn(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w));
                 xi = __fadd2_rn(make_float2(zk.x, zk.y), neg2(make_float2(zk.z, zk.w)));
-            } else {
-                const float4 zc = Y(nc - k);
-                const float2 w = w_split[j];                                      // W_n^k = (cos, -sin)
-                rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
-                            make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
             }
             const float2 pw = __ffma2_rn(xr, xr, __fmul2_rn(xi, xi));
-            const float mu = __fsqrt_rn(pw.x), md = __fsqrt_rn(pw.y);
-            if (iu == 0xffffffffu || bu < mu) { bu = mu; iu = k; }
-            if (id == 0xffffffffu || bd < md) { bd = md; id = k; }
+            pu[j] = pw.x;
+            pd[j] = pw.y;
+        }
+        float bu, bd;
+        uint32_t iu, id;
+#if USC_LONG_OLD_TAIL
+        bu = -INFINITY; bd = -INFINITY; iu = 0xffffffffu; id = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < kLongNB; ++j) {
+            if (!ok[j]) break;
+            const float mu = __fsqrt_rn(pu[j]), md = __fsqrt_rn(pd[j]);
+            if (iu == 0xffffffffu || bu < mu) { bu = mu; iu = kk[j]; }
+            if (id == 0xffffffffu || bd < md) { bd = md; id = kk[j]; }
         }
         warp_argmax(bu, iu);
         warp_argmax(bd, id);
-        float* red = reinterpret_cast<float*>(s_raw + L::red);
-        if (lane == 0) {
-            red[warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(red)[warp * 4 + 1] = iu;
-            red[warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(red)[warp * 4 + 3] = id;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w2 = 1; w2 < R0; ++w2) {
-                argmax_combine(bu, iu, red[w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[w2 * 4 + 1]);
-                argmax_combine(bd, id, red[w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[w2 * 4 + 3]);
+        {
+            float* red = reinterpret_cast<float*>(s_raw + L::red);
+            if (lane == 0) {
+                red[warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(red)[warp * 4 + 1] = iu;
+                red[warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(red)[warp * 4 + 3] = id;
             }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w2 = 1; w2 < R0; ++w2) {
+                    argmax_combine(bu, iu, red[w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[w2 * 4 + 1]);
+                    argmax_combine(bd, id, red[w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[w2 * 4 + 3]);
+                }
+            }
+        }
+#else
+        block_argmax2<R0, kLongNB>(pu, pd, kk, ok, reinterpret_cast<float*>(s_raw + L::red), tid, bu, iu, bd, id);
+#endif
+        if (tid == 0) {
             if (p.mag_up) p.mag_up[f] = bu;
             if (p.idx_up) p.idx_up[f] = iu;
             if (p.mag_down) p.mag_down[f] = bd;
             if (p.idx_down) p.idx_down[f] = id;
             if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
         }
+#if USC_LONG_OLD_TAIL
         __syncthreads();
+#endif
     }
     if (kTmem) {
         tmem_fence_before_sync();
@@ -262,25 +372,43 @@ __global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) {
     }
 }
 
+#ifndef USC_LONG_MAXREG4
+#define USC_LONG_MAXREG4 224
+#endif
+template <typename PCM, int R0>
+__global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) { demod_long_body<PCM, R0>(p); }
+// The 4-warp form runs two CTAs per SM, which the register file allows only up to 224 registers per thread (at 238 the
+// occupancy calculator reports one CTA and the run time rises by 40 %): an explicit register cap instead of launch bounds.
+template <typename PCM>
+__global__ void __maxnreg__(USC_LONG_MAXREG4) k_demod_long4(long_params p) { demod_long_body<PCM, 4>(p); }
+template <typename PCM, int R0> struct long_kernel { static constexpr auto fn = k_demod_long<PCM, R0>; };
+template <typename PCM> struct long_kernel<PCM, 4> { static constexpr auto fn = k_demod_long4<PCM>; };
+
 template <typename PCM, int R0>
 static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t st) {
-    static per_device<bool> configured_pd;
-    bool& configured = configured_pd.get();
+    constexpr auto kernel = long_kernel<PCM, R0>::fn;
+    static per_device<int> per_sm_pd;                    // resident CTAs per SM (0: not configured on this device yet)
+    int& per_sm = per_sm_pd.get();
     const int smem = long_smem<R0>::total;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_demod_long<PCM, R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (!per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        // The occupancy calculator reports ONE resident CTA for any kernel that allocates tensor memory (it cannot know how
+        // many columns a CTA takes), although two CTAs with 256 columns each do run side by side (ncu: 8 warps per SM active):
+        // with the tables in TMEM the count comes from the kernel's own budget — two CTAs of the 4-warp form (2 x 107 KB of
+        // shared memory, 2 x 256 TMEM columns, 222 registers), one of the 8-warp form.
+        if (USC_LONG_TMEM && R0 >= 4) {
+            per_sm = R0 == 4 ? 2 : 1;
+        } else {
+            int occ = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, R0 * 32, smem);
+            if (e != cudaSuccess) return e;
+            if (occ < 1) return cudaErrorLaunchOutOfResources;
+            per_sm = occ;
+        }
     }
-#ifndef USC_LONG_PER_SM2
-#define USC_LONG_PER_SM2 4
-#endif
-#ifndef USC_LONG_PER_SM4
-#define USC_LONG_PER_SM4 2
-#endif
-    const int per_sm = R0 == 2 ? USC_LONG_PER_SM2 : (R0 == 4 ? USC_LONG_PER_SM4 : 1);
     size_t ctas = p.nframes < (size_t) num_sms * per_sm ? p.nframes : (size_t) num_sms * per_sm;
-    k_demod_long<PCM, R0><<<(int) ctas, R0 * 32, smem, st>>>(p);
+    kernel<<<(int) ctas, R0 * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -407,7 +535,7 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
             }
             __syncwarp();
             fft1024_pair(re, im, reg, s_tw, lane);
-            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + 8192);
+            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + keep_off<W>(warp));
 #pragma unroll
             for (int j = 0; j < kLongNB; ++j) {
                 keep[lane + 32 * j] = make_float4(re[j].x, re[j].y, im[j].x, im[j].y);
@@ -424,7 +552,7 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
         for (int j = 0; j < kLongNB; ++j) {
             const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl, k = (uint32_t) R0 * c + d;
             if (k >= bw2) continue;
-            const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + 8192)[c];
+            const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + keep_off<W>(dl))[c];
             float2 xr, xi;
             if (k == 0) {
                 xr = __fadd2_rn(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w));
@@ -432,7 +560,7 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
             } else {
                 // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d)
                 const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? 1024u - c : 1023u - c;
-                const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + 8192u + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+                const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
                 const float4 zc = ld_cluster_f4(addr);
                 const float2 w = w_split[j];
                 rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
