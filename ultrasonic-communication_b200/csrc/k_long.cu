@@ -72,7 +72,7 @@ template <int R0> struct long_smem {
 // on the common path: the maximum of p is found first (p >= 0, so bit patterns order like values); if no other candidate
 // lies within 2^-20 of it (two ulps of the root), its root is the maximum and its index the first occurrence; otherwise
 // every root is taken (rare path).  pu/pd: squared magnitudes of this thread's bins k[j], ascending; ok[j]: bin in range.
-template <int R0, int NC>
+template <int NW, int NC>
 __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float (&pd)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
                                               float* red, int tid, float& bu, uint32_t& iu, float& bd, uint32_t& id) {
     const int lane = tid & 31, warp = tid >> 5;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float
     __syncthreads();
     uint32_t mu = 0, md = 0;
 #pragma unroll
-    for (int w = 0; w < R0; ++w) { mu = max(mu, redu[w * 2]); md = max(md, redu[w * 2 + 1]); }
+    for (int w = 0; w < NW; ++w) { mu = max(mu, redu[w * 2]); md = max(md, redu[w * 2 + 1]); }
     const float maxu = __uint_as_float(mu), maxd = __uint_as_float(md);
     const float thru = __fmul_rn(maxu, 0.99999904632568359375f), thrd = __fmul_rn(maxd, 0.99999904632568359375f);   // 1 - 2^-20
     uint32_t near = 0, ku = 0xffffffffu, kd = 0xffffffffu;             // near: candidates within two ulps of either maximum
@@ -100,14 +100,14 @@ __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float
     near = __reduce_add_sync(0xffffffffu, near);
     ku = __reduce_min_sync(0xffffffffu, ku);
     kd = __reduce_min_sync(0xffffffffu, kd);
-    if (lane == 0) { redu[2 * R0 + warp * 4] = near; redu[2 * R0 + warp * 4 + 1] = ku; redu[2 * R0 + warp * 4 + 2] = kd; }
+    if (lane == 0) { redu[2 * NW + warp * 4] = near; redu[2 * NW + warp * 4 + 1] = ku; redu[2 * NW + warp * 4 + 2] = kd; }
     __syncthreads();
     near = 0; ku = 0xffffffffu; kd = 0xffffffffu;
 #pragma unroll
-    for (int w = 0; w < R0; ++w) {
-        near += redu[2 * R0 + w * 4];
-        ku = min(ku, redu[2 * R0 + w * 4 + 1]);
-        kd = min(kd, redu[2 * R0 + w * 4 + 2]);
+    for (int w = 0; w < NW; ++w) {
+        near += redu[2 * NW + w * 4];
+        ku = min(ku, redu[2 * NW + w * 4 + 1]);
+        kd = min(kd, redu[2 * NW + w * 4 + 2]);
     }
     if (near == 0x10001u && maxu == maxu && maxd == maxd) {           // exactly one candidate per hypothesis near its maximum
         bu = __fsqrt_rn(maxu); iu = ku;
@@ -125,14 +125,14 @@ __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float
     }
     warp_argmax(bu, iu);
     warp_argmax(bd, id);
-    float* slow = red + 6 * R0;
+    float* slow = red + 6 * NW;
     if (lane == 0) {
         slow[warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(slow)[warp * 4 + 1] = iu;
         slow[warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(slow)[warp * 4 + 3] = id;
     }
     __syncthreads();
     bu = slow[0]; iu = reinterpret_cast<uint32_t*>(slow)[1]; bd = slow[2]; id = reinterpret_cast<uint32_t*>(slow)[3];
-    for (int w = 1; w < R0; ++w) {
+    for (int w = 1; w < NW; ++w) {
         argmax_combine(bu, iu, slow[w * 4 + 0], reinterpret_cast<uint32_t*>(slow)[w * 4 + 1]);
         argmax_combine(bd, id, slow[w * 4 + 2], reinterpret_cast<uint32_t*>(slow)[w * 4 + 3]);
     }
@@ -428,9 +428,14 @@ static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t
 // slower (65536 points as 8 x 4: 8 %; 16384 points as a 2 x 4 cluster against the plain 8-warp CTA above: 9 %).
 template <int R0, int W> struct cl_smem {                                         // W warps (= sub-sequences) per CTA
     static constexpr int T = 32 * W, CL = R0 / W, NR = 1024 / CL / T, SH = W == 8 ? 3 : 2;   // threads, cluster size, level-0 rounds per thread
-    // pass twiddles | 8 sub-sequences | result slots | this CTA's level-0 twiddles W^(a d), [d][round][thread]
-    static constexpr int tw = 0, sub = 8192, region = 16384, red = sub + W * region, l0 = red + 256,
-                         total = l0 + R0 * NR * T * 8;
+    // pass twiddles | W sub-sequences | this CTA's share of the frame's PCM, [b][a] (filled by TMA one frame ahead) |
+    // result slots of the cluster (CTA 0) + reduction scratch | mbarrier | TMEM slot
+    static constexpr int tw = 0, sub = 8192, region = 16384, stage = sub + W * region, stage_bytes = R0 * (1024 / CL) * 8,
+                         red = stage + stage_bytes, bar = red + 512, tslot = bar + 8, total = tslot + 8;
+    // TMEM columns of a thread (its own lane; warps 4..7 take columns 256..511), per level-0 round 8 R0 columns:
+    // (up, down) chirp of m = a + 1024 b at 4 b | Hann at 4 R0 + 2 b | level-0 twiddle W^(a d) at 6 R0 + 2 d
+    static constexpr int per_round = 8 * R0, c_ud = 0, c_hann = 4 * R0, c_tw = 6 * R0, t_cols = 512;
+    static_assert(NR * per_round == 256, "a thread's table row is 256 TMEM columns");
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -457,21 +462,66 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
 }
 
 template <typename PCM, int R0, int W>
-__global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
+__global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
     using L = cl_smem<R0, W>;
     constexpr int CL = L::CL, NR = L::NR, T = L::T, SH = L::SH;
     constexpr uint32_t n = 2048u * R0;                  // real samples per frame; the complex length is nc = n / 2
+    constexpr uint32_t kShare = 1024u / CL;             // this CTA's a-range
     using V2 = typename vec2<PCM>::type;
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
+    const V2* stage = reinterpret_cast<const V2*>(s_raw + L::stage);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + L::bar);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_rank();
+    const PCM* pcm = static_cast<const PCM*>(p.pcm);
+    // this CTA's share of frame f: for every b the kShare pairs a = rank kShare .. of z[a + 1024 b], one bulk copy per b
+    auto fetch = [&](size_t f) {                        // called by warp 0
+        if (lane == 0) mbar_expect_tx(bar, L::stage_bytes);
+        __syncwarp();
+        for (int b = lane; b < R0; b += 32)
+            bulk_g2s(s_raw + L::stage + b * (kShare * 8u), pcm + f * n + 2u * (1024u * b + rank * kShare), kShare * 8u, bar);
+    };
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < 1024; i += T) s_tw[i] = p.tw_pass[i];
-    float2* s_l0 = reinterpret_cast<float2*>(s_raw + L::l0);
-    for (int d = 1; d < R0; ++d)
-        for (int i = 0; i < NR; ++i)
-            s_l0[(d * NR + i) * T + tid] = tw_l0[d * 1024 + rank * (1024 / CL) + i * T + tid];
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw + L::tslot);
+    if (warp == 0) tmem_alloc<L::t_cols>(s_tslot);
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
+    if (warp == 0 && cluster_id_x() < p.nframes) fetch(cluster_id_x());
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp) + (warp >> 2) * 256u;
+#pragma unroll 1
+    for (int i = 0; i < NR; ++i) {                      // this thread's table row
+        const uint32_t a = rank * kShare + i * T + tid;
+#pragma unroll 1
+        for (int b0 = 0; b0 < R0; b0 += 4) {
+            uint32_t c[16], w[8], z[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t m = a + 1024u * (b0 + j);
+                const float4 cv = __ldg(p.chirp_ud + m);
+                const float2 wv = __ldg(p.hann + m);
+                const float2 zv = __ldg(tw_l0 + (size_t) (b0 + j) * 1024u + a);     // W_nc^(a d), d = b0 + j (d = 0: 1)
+                c[4 * j] = __float_as_uint(cv.x); c[4 * j + 1] = __float_as_uint(cv.y); c[4 * j + 2] = __float_as_uint(cv.z); c[4 * j + 3] = __float_as_uint(cv.w);
+                w[2 * j] = __float_as_uint(wv.x); w[2 * j + 1] = __float_as_uint(wv.y);
+                z[2 * j] = __float_as_uint(zv.x); z[2 * j + 1] = __float_as_uint(zv.y);
+            }
+            const uint32_t c0[8] = {c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]}, c1[8] = {c[8], c[9], c[10], c[11], c[12], c[13], c[14], c[15]};
+            sttm8(tq + L::per_round * i + L::c_ud + 4 * b0, c0);
+            sttm8(tq + L::per_round * i + L::c_ud + 4 * b0 + 8, c1);
+            sttm8(tq + L::per_round * i + L::c_hann + 2 * b0, w);
+            sttm8(tq + L::per_round * i + L::c_tw + 2 * b0, z);
+        }
+    }
+    sttm_wait();
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const float one = s_tw[lane].x;                      // W^0 = 1.0f from the table: opaque to the compiler
     const uint32_t bw2 = p.bandwidth2;
     float2 w_split[kLongNB];                             // split twiddles of this thread's bins, frame-invariant too
 #pragma unroll
@@ -486,44 +536,48 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
     const uint32_t red0 = map_to_rank(s_raw + L::red, 0);
     cluster_sync_all();                                  // every CTA of the cluster is resident before remote traffic
 
+    uint32_t parity = 0;
     for (size_t f = cluster_id_x(); f < p.nframes; f += cluster_count_x()) {
-        const V2* src = reinterpret_cast<const V2*>(static_cast<const PCM*>(p.pcm) + f * n);
-        if (f + cluster_count_x() < p.nframes) {         // next frame of this cluster towards L2 (each CTA its share)
-            const char* nxt = reinterpret_cast<const char*>(static_cast<const PCM*>(p.pcm) + (f + cluster_count_x()) * n);
-            constexpr uint32_t per_thread = n * 4u / (CL * T);                               // 256 bytes
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * T + tid) * per_thread));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t) rank * T + tid) * per_thread + 128));
-        }
-        // ---- level 0 ----
+        mbar_wait(bar, parity);                          // this CTA's share of the frame has landed in the stage
+        parity ^= 1u;
+        // ---- level 0: radix-R0 over b in registers, twiddle, 16-byte remote stores into the owner's sub-sequence ----
 #pragma unroll 1
         for (int i = 0; i < NR; ++i) {
-            const uint32_t a = rank * (1024u / CL) + i * T + tid;
+            const uint32_t al = i * T + tid, a = rank * kShare + al;
             float2 re[R0], im[R0];
 #pragma unroll
-            for (int b = 0; b < R0; ++b) {
-                const uint32_t m = a + 1024u * b;
-                const V2 raw = src[m];
-                const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
-                const float4 c = __ldg(p.chirp_ud + m);
-                const float2 w = __ldg(p.hann + m);
-                const float2 tr = __fmul2_rn(make_float2(c.x, c.y), bc2(x0)), ti = __fmul2_rn(make_float2(c.z, c.w), bc2(x1));
-                re[b] = __fmul2_rn(tr, bc2(w.x));                                      // packed; first stage: FMAs by 1.0
-                im[b] = __fmul2_rn(ti, bc2(w.y));
-            }
-            fft_base2_prod<R0>(re, im, s_tw[lane].x);
+            for (int g = 0; g < R0 / 4; ++g) {           // table values of four b per TMEM round trip
+                uint32_t c[16], w[8];
+                ldtm16_8(tq + L::per_round * i + L::c_ud + 16 * g, c, tq + L::per_round * i + L::c_hann + 8 * g, w);
 #pragma unroll
-            for (int d = 0; d < R0; ++d) {
-                float2 xr = re[d], xi = im[d];
-                if (d != 0) {
-                    const float2 w = s_l0[(d * NR + i) * T + tid];                     // W_nc^(a d)
-                    cmul2(re[d], im[d], w.x, w.y, xr, xi);
+                for (int j = 0; j < 4; ++j) {
+                    const int b = 4 * g + j;
+                    const V2 raw = stage[b * kShare + al];
+                    const float x0 = pcm_to_float(raw.x), x1 = pcm_to_float(raw.y);
+                    const float2 tr = __fmul2_rn(make_float2(__uint_as_float(c[4 * j]), __uint_as_float(c[4 * j + 1])), bc2(x0));
+                    const float2 ti = __fmul2_rn(make_float2(__uint_as_float(c[4 * j + 2]), __uint_as_float(c[4 * j + 3])), bc2(x1));
+                    re[b] = __fmul2_rn(tr, bc2(__uint_as_float(w[2 * j])));              // packed; first stage: FMAs by 1.0
+                    im[b] = __fmul2_rn(ti, bc2(__uint_as_float(w[2 * j + 1])));
                 }
-                const uint32_t base = peer_sub[d >> SH] + (uint32_t) (d & (W - 1)) * L::region;
-                st_cluster_f4(base + a * 16u, make_float4(xr.x, xr.y, xi.x, xi.y));       // one 16-byte remote store per element
+            }
+            fft_base2_prod<R0>(re, im, one);
+#pragma unroll
+            for (int g = 0; g < R0 / 8; ++g) {           // level-0 twiddles, eight per TMEM round trip
+                uint32_t t[16];
+                ldtm16(tq + L::per_round * i + L::c_tw + 16 * g, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int d = 8 * g + j;
+                    float2 xr = re[d], xi = im[d];
+                    if (d != 0) cmul2(re[d], im[d], __uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]), xr, xi);
+                    const uint32_t base = peer_sub[d >> SH] + (uint32_t) (d & (W - 1)) * L::region;
+                    st_cluster_f4(base + a * 16u, make_float4(xr.x, xr.y, xi.x, xi.y));   // one 16-byte remote store per element
+                }
             }
         }
-        cluster_sync_all();
-        // ---- 1024-point packed core on sub-sequence 8 rank + warp ----
+        cluster_sync_all();                              // sub-sequences complete; every thread is done with the stage
+        if (warp == 0 && f + cluster_count_x() < p.nframes) fetch(f + cluster_count_x());   // next share arrives under the core and the split
+        // ---- 1024-point packed core on sub-sequence W rank + warp ----
         {
             float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + warp * L::region);
             float2 re[32], im[32];
@@ -544,48 +598,39 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
             }
         }
         cluster_sync_all();
-        // ---- split, magnitude, arg-max over the bins of this CTA's sub-sequences ----
-        float bu = -INFINITY, bd = -INFINITY;
-        uint32_t iu = 0xffffffffu, id = 0xffffffffu;
-        // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread
+        // ---- split, squared magnitude, arg-max over the bins of this CTA's sub-sequences ----
+        // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread.
+        // Each CTA finds the exact (largest root, first index attaining it) of ITS bins with one square root per
+        // hypothesis; CTA 0 combines the CL results by value, then index — exact for the whole frame.
+        float pu[kLongNB], pd[kLongNB];
+        uint32_t kk[kLongNB];
+        bool ok[kLongNB];
 #pragma unroll
         for (int j = 0; j < kLongNB; ++j) {
             const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl, k = (uint32_t) R0 * c + d;
-            if (k >= bw2) continue;
+            kk[j] = k;
+            ok[j] = k < bw2;
             const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + keep_off<W>(dl))[c];
+            // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d); k = 0 pairs with itself (unused)
+            const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? (c == 0 ? 1023u : 1024u - c) : 1023u - c;
+            const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+            const float4 zc = ld_cluster_f4(addr);
+            const float2 w = w_split[j];
             float2 xr, xi;
+            rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
+                        make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
             if (k == 0) {
                 xr = __fadd2_rn(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w));
                 xi = __fadd2_rn(make_float2(zk.x, zk.y), neg2(make_float2(zk.z, zk.w)));
-            } else {
-                // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d)
-                const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? 1024u - c : 1023u - c;
-                const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
-                const float4 zc = ld_cluster_f4(addr);
-                const float2 w = w_split[j];
-                rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
-                            make_float2(zc.z, zc.w), w.x, -w.y, xr, xi);
             }
             const float2 pw = __ffma2_rn(xr, xr, __fmul2_rn(xi, xi));
-            const float mu = __fsqrt_rn(pw.x), md = __fsqrt_rn(pw.y);
-            if (iu == 0xffffffffu || bu < mu) { bu = mu; iu = k; }
-            if (id == 0xffffffffu || bd < md) { bd = md; id = k; }
+            pu[j] = pw.x;
+            pd[j] = pw.y;
         }
-        warp_argmax(bu, iu);
-        warp_argmax(bd, id);
-        float* red = reinterpret_cast<float*>(s_raw + L::red);
-        if (lane == 0) {
-            red[128 / 4 + warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(red)[128 / 4 + warp * 4 + 1] = iu;
-            red[128 / 4 + warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(red)[128 / 4 + warp * 4 + 3] = id;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w2 = 1; w2 < W; ++w2) {
-                argmax_combine(bu, iu, red[32 + w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 1]);
-                argmax_combine(bd, id, red[32 + w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[32 + w2 * 4 + 3]);
-            }
-            st_cluster_f4(red0 + rank * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
-        }
+        float bu, bd;
+        uint32_t iu, id;
+        block_argmax2<W, kLongNB>(pu, pd, kk, ok, reinterpret_cast<float*>(s_raw + L::red + 64), tid, bu, iu, bd, id);
+        if (tid == 0) st_cluster_f4(red0 + rank * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
         cluster_sync_all();                              // results are in CTA 0; all remote reads of this frame are done
         if (rank == 0 && tid == 0) {
             const float4* r4 = reinterpret_cast<const float4*>(s_raw + L::red);
@@ -603,7 +648,9 @@ __global__ void __launch_bounds__(32 * W, W == 8 ? 1 : 2) k_demod_cluster(long_p
             if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
         }
     }
+    tmem_fence_before_sync();
     cluster_sync_all();                                  // no CTA leaves while a peer may still address its memory
+    if (warp == 0) tmem_dealloc<L::t_cols>(*s_tslot);
 }
 
 template <typename PCM, int R0, int W>
