@@ -19,15 +19,20 @@ namespace usc {
 
 constexpr int kRxWarps = 8;
 constexpr int kRxNB = 5;
-constexpr int kRxSmem = 4 * 8192 + kRxWarps * 8192 + kRxWarps * 128;   // tables | per-warp 8 KB tile | per-warp state
+// shared memory (float2 units): per-warp 8 KB tile | per-warp state (128 B) | TMEM slot | [MULTI] per-warp sum of the window union
+constexpr int kRxTile = 0, kRxState = kRxWarps * 1024, kRxSlot = kRxState + kRxWarps * 16, kRxSum = kRxSlot + 2;
+constexpr int kRxSmem = kRxSum * 8;
 constexpr int kRxSmemMulti = kRxSmem + kRxWarps * 1792 * 8;            // + per-warp sum of the window union (synchronous addition)
 
+// The four tables every dsp() reads — up chirp, down chirp, Hann, inter-pass twiddles — live in tensor memory, one row per
+// lane (usc_tmem.cuh; K1 keeps them the same way): columns 4 b .. 4 b + 3 = (up[2m], down[2m], up[2m+1], down[2m+1]) of
+// m = lane + 32 b | 128 + 2 b = Hann pair | 192 + 2 d = W_1024^(lane d).
+constexpr int kRxTud = 0, kRxThann = 128, kRxTtw = 192, kRxTcols = 256;
 struct rx_tables {
-    const float2* up;       // shared-memory copies
-    const float2* down;
-    const float2* hann;
-    const float2* tw;
+    uint32_t tq;            // this warp's TMEM lane quadrant
+    float one;              // 1.0f read from a table (first butterfly stage as FMAs by 1.0, usc_arith.cuh)
 };
+enum rx_chirps : int { RX_UP_UP = 0, RX_UP_DOWN = 1, RX_DOWN_DOWN = 2 };   // de-chirp tables of the two halves of a packed pass
 
 struct rx_params {
     const void* pcm; uint32_t nstreams; uint32_t nframes; size_t stream_stride;
@@ -50,19 +55,34 @@ __device__ __forceinline__ float2 load_pair(const PCM* __restrict__ stream, int6
     return make_float2(0.0f, 0.0f);                    // before the stream starts the FIFO holds zeros
 }
 
-// second half of dsp(): de-chirp, Hann, FFT, right-window peaks, on samples already in (re, im) = (x[2m], x[2m+1])
-__device__ __forceinline__ void dsp_pair_tail(float2 (&re)[32], float2 (&im)[32], const float2* chirpA, const float2* chirpB,
-                                              const rx_tables& tb, float2* tile, const float2 (&ws)[kRxNB], int lane,
-                                              uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB) {
+// (x * c) * w on both halves, packed; the products meet FMAs by 1.0 in the first butterfly stage (usc_arith.cuh)
+template <int MODE>
+__device__ __forceinline__ void rx_front(float2 (&re)[32], float2 (&im)[32], uint32_t tq) {
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-        const int m = lane + 32 * b;
-        const float2 ca = chirpA[m], cb = chirpB[m], w = tb.hann[m];
-        // (x * c) * w on both halves, packed; the products meet FMAs by 1.0 in the first butterfly stage (usc_arith.cuh)
-        re[b] = __fmul2_rn(__fmul2_rn(re[b], make_float2(ca.x, cb.x)), bc2(w.x));
-        im[b] = __fmul2_rn(__fmul2_rn(im[b], make_float2(ca.y, cb.y)), bc2(w.y));
+    for (int g = 0; g < 8; ++g) {                                     // table values of four rows per TMEM round trip
+        uint32_t c[16], w[8];
+        ldtm16_8(tq + kRxTud + 16 * g, c, tq + kRxThann + 8 * g, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 4 * g + j;
+            const float u0 = __uint_as_float(c[4 * j]), d0 = __uint_as_float(c[4 * j + 1]);
+            const float u1 = __uint_as_float(c[4 * j + 2]), d1 = __uint_as_float(c[4 * j + 3]);
+            const float2 c0 = MODE == RX_UP_UP ? bc2(u0) : (MODE == RX_UP_DOWN ? make_float2(u0, d0) : bc2(d0));
+            const float2 c1 = MODE == RX_UP_UP ? bc2(u1) : (MODE == RX_UP_DOWN ? make_float2(u1, d1) : bc2(d1));
+            re[b] = __fmul2_rn(__fmul2_rn(re[b], c0), bc2(__uint_as_float(w[2 * j])));
+            im[b] = __fmul2_rn(__fmul2_rn(im[b], c1), bc2(__uint_as_float(w[2 * j + 1])));
+        }
     }
-    fft1024_pair<true>(re, im, tile, tb.tw, lane);
+}
+
+// second half of dsp(): de-chirp, Hann, FFT, right-window peaks, on samples already in (re, im) = (x[2m], x[2m+1])
+__device__ __forceinline__ void dsp_pair_tail(float2 (&re)[32], float2 (&im)[32], int chirps, const rx_tables& tb, float2* tile,
+                                              const float2 (&ws)[kRxNB], int lane,
+                                              uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB) {
+    if (chirps == RX_UP_UP) rx_front<RX_UP_UP>(re, im, tb.tq);        // warp-uniform
+    else if (chirps == RX_UP_DOWN) rx_front<RX_UP_DOWN>(re, im, tb.tq);
+    else rx_front<RX_DOWN_DOWN>(re, im, tb.tq);
+    fft1024_pair_tm<true>(re, im, tile, tb.tq + kRxTtw, tb.one, lane);
     peak_window_pair<kRxNB>(re, im, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 
@@ -73,7 +93,7 @@ __device__ __forceinline__ void dsp_pair_tail(float2 (&re)[32], float2 (&im)[32]
 // frame-aligned windows, oldest first, before the de-chirp (synchronous addition).
 template <typename PCM, bool MULTI>
 __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t nsamples, int64_t gA, int64_t gB,
-                                         const float2* chirpA, const float2* chirpB, const rx_tables& tb,
+                                         int chirps, const rx_tables& tb,
                                          uint32_t sync_add, float2* tile, const float2 (&ws)[kRxNB], int lane,
                                          uint32_t bw2, float& magA, uint32_t& idxA, float& magB, uint32_t& idxB,
                                          int64_t gmin = 0) {
@@ -141,30 +161,59 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
             }
         }
     }
-    dsp_pair_tail(re, im, chirpA, chirpB, tb, tile, ws, lane, bw2, magA, idxA, magB, idxB);
+    dsp_pair_tail(re, im, chirps, tb, tile, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 
-__device__ __forceinline__ void load_tables(const rx_params& p, float2* s_up, float2* s_down, float2* s_hann, float2* s_tw) {
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        s_up[i] = p.up[i];
-        s_down[i] = p.down[i];
-        s_hann[i] = p.hann[i];
-        s_tw[i] = p.tw_pass[i];
+// allocate the CTA's TMEM columns and fill every lane quadrant with the table rows (warp q fills quadrant q; warps q and
+// q + 4 read it); ends with a CTA barrier
+__device__ __forceinline__ rx_tables load_tables(const rx_params& p, float2* s_rx, int lane, int warp) {
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_rx + kRxSlot);
+    if (warp == 0) tmem_alloc<kRxTcols>(s_tslot);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp);
+    if (warp < 4) {
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += 4) {
+            float2 u[4], d[4], w[4], z[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                u[j] = p.up[lane + 32 * (b0 + j)];
+                d[j] = p.down[lane + 32 * (b0 + j)];
+                w[j] = p.hann[lane + 32 * (b0 + j)];
+                z[j] = p.tw_pass[(b0 + j) * 32 + lane];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j += 2)
+                sttm_f2x4(tq + kRxTud + 4 * (b0 + j), make_float2(u[j].x, d[j].x), make_float2(u[j].y, d[j].y),
+                          make_float2(u[j + 1].x, d[j + 1].x), make_float2(u[j + 1].y, d[j + 1].y));
+            sttm_f2x4(tq + kRxThann + 2 * b0, w[0], w[1], w[2], w[3]);
+            sttm_f2x4(tq + kRxTtw + 2 * b0, z[0], z[1], z[2], z[3]);
+        }
+        sttm_wait();
     }
+    const float one = p.tw_pass[lane].x;
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    return rx_tables{tq, one};
+}
+__device__ __forceinline__ void free_tables(float2* s_rx, int warp) {
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kRxTcols>(*reinterpret_cast<uint32_t*>(s_rx + kRxSlot));
 }
 
 template <typename PCM>
 __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) {
     extern __shared__ float2 s_rx[];
-    float2 *s_up = s_rx, *s_down = s_rx + 1024, *s_hann = s_rx + 2048, *s_tw = s_rx + 3072;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    load_tables(p, s_up, s_down, s_hann, s_tw);
     float2 ws[kRxNB];
 #pragma unroll
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
-    __syncthreads();
-    const rx_tables tb{s_up, s_down, s_hann, s_tw};
-    float2* tile = s_rx + 4096 + warp * 1024;
+    const rx_tables tb = load_tables(p, s_rx, lane, warp);
+    float2* tile = s_rx + kRxTile + warp * 1024;
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const float thr = p.snr_threshold;
     const uint32_t bw2 = p.bandwidth2;
@@ -188,7 +237,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
         }
         // mag_stat[12] | history mag_max[8] | history mag_mean[4] live in shared memory (the packed core
         // needs the registers); every lane reads them (broadcast), lane 0 writes
-        float* mag_stat = reinterpret_cast<float*>(s_rx + 4096 + kRxWarps * 1024) + warp * 32;
+        float* mag_stat = reinterpret_cast<float*>(s_rx + kRxState) + warp * 32;
         float* hmag = mag_stat + 12;
         float* hmean = mag_stat + 20;
         __syncwarp();
@@ -223,27 +272,26 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
             bool is_down = false, symbol = false;
             for (int pass = 0; pass < 2; ++pass) {
                 int64_t qa, qb;
-                const float2 *ca, *cb;
+                int chirps;
                 bool a_ok = true, b_ok = true;
                 if (searching) {
                     qa = N / 2 + turn * offset + shift * (2 * pass);
                     qb = qa + shift;
-                    ca = cb = tb.up;
+                    chirps = RX_UP_UP;
                 } else if (pass == 0) {
                     qa = qb = pos;
-                    ca = tb.up;
-                    cb = tb.down;
+                    chirps = RX_UP_DOWN;
                 } else {
                     if (!symbol) break;                                   // neither SNR reached the threshold
                     qa = (int64_t) pos - offset;                          // resync (main.c:246-249); probes outside
                     qb = (int64_t) pos + offset;                          // [0, 2N] are hazards H3/H5: snr = -inf
                     a_ok = qa >= 0 && qa <= (int64_t) 2 * N;
                     b_ok = qb >= 0 && qb <= (int64_t) 2 * N;
-                    ca = cb = is_down ? tb.down : tb.up;
+                    chirps = is_down ? RX_DOWN_DOWN : RX_UP_UP;
                 }
                 float ma, mb;
                 uint32_t ka, kb;
-                dsp_pair<PCM, false>(stream, nsamples, fifo0 + (a_ok ? qa : (int64_t) pos), fifo0 + (b_ok ? qb : (int64_t) pos), ca, cb, tb,
+                dsp_pair<PCM, false>(stream, nsamples, fifo0 + (a_ok ? qa : (int64_t) pos), fifo0 + (b_ok ? qb : (int64_t) pos), chirps, tb,
                               1, tile, ws, lane, bw2, ma, ka, mb, kb, gmin);
                 if (searching) {
                     const int sa = (int) (4 * pass + turn), sb = sa + 2;  // history[i*2 + turn]
@@ -346,6 +394,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
             __syncwarp();
         }
     }
+    free_tables(s_rx, warp);
 }
 
 // K4: the search grid of main.c:447-451 for every (stream, frame), after optional synchronous
@@ -354,16 +403,13 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
 template <typename PCM, bool MULTI>
 __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
     extern __shared__ float2 s_rx[];
-    float2 *s_up = s_rx, *s_down = s_rx + 1024, *s_hann = s_rx + 2048, *s_tw = s_rx + 3072;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    load_tables(p, s_up, s_down, s_hann, s_tw);
     float2 ws[kRxNB];
 #pragma unroll
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
-    __syncthreads();
-    const rx_tables tb{s_up, s_down, s_hann, s_tw};
-    float2* tile = s_rx + 4096 + warp * 1024;
-    float2* sum = s_rx + 4096 + kRxWarps * 1024 + kRxWarps * 16 + warp * 1792;     // MULTI only: 14 KB per warp behind the common layout
+    const rx_tables tb = load_tables(p, s_rx, lane, warp);
+    float2* tile = s_rx + kRxTile + warp * 1024;
+    float2* sum = s_rx + kRxSum + warp * 1792;                                     // MULTI only: 14 KB per warp behind the common layout
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const size_t total = (size_t) p.nstreams * p.nframes;
     const size_t nwarps = (size_t) gridDim.x * kRxWarps;
@@ -440,9 +486,9 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
                     re[b] = make_float2(xa.x, xb.x);
                     im[b] = make_float2(xa.y, xb.y);
                 }
-                dsp_pair_tail(re, im, tb.up, tb.up, tb, tile, ws, lane, p.bandwidth2, ma, ka, mb, kb);
+                dsp_pair_tail(re, im, RX_UP_UP, tb, tile, ws, lane, p.bandwidth2, ma, ka, mb, kb);
             } else
-            dsp_pair<PCM, false>(stream, nsamples, fifo0 + pa, fifo0 + pb, tb.up, tb.up, tb, 1, tile, ws, lane, p.bandwidth2,
+            dsp_pair<PCM, false>(stream, nsamples, fifo0 + pa, fifo0 + pb, RX_UP_UP, tb, 1, tile, ws, lane, p.bandwidth2,
                           ma, ka, mb, kb);
             if (lane == 0) {
                 p.ss_mag[w * 4 + i] = ma; p.ss_idx[w * 4 + i] = ka;
@@ -450,6 +496,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
             }
         }
     }
+    free_tables(s_rx, warp);
 }
 
 static rx_params make_params(const rx_launch& a) {
@@ -493,7 +540,7 @@ cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st
 cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st) {
     rx_params p = make_params(a);
     size_t ctas = ((size_t) a.nstreams * a.nframes + kRxWarps - 1) / kRxWarps;
-    const size_t cap = (size_t) num_sms * 2;
+    const size_t cap = (size_t) num_sms;                 // persistent: one CTA of 8 warps per SM (224+ registers per thread)
     if (ctas > cap) ctas = cap;
     cudaError_t e = rx_prepare();
     if (e != cudaSuccess) return e;

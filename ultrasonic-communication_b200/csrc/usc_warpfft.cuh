@@ -3,6 +3,7 @@
 // the exact windowed peak search on the packed real-FFT bins.
 #pragma once
 #include "usc_arith.cuh"
+#include "usc_tmem.cuh"
 
 namespace usc {
 
@@ -122,6 +123,49 @@ __device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32],
     for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
     __syncwarp();
     fft_base2<32>(re, im);
+}
+
+// fft1024_pair with the inter-pass twiddles W_1024^(a d) read from the lane's TMEM row (columns t_tw + 2 d, d < 32; see
+// usc_tmem.cuh) instead of shared memory; `one` = 1.0f from a table (opaque to the compiler) for the PROD form.
+template <bool PROD = false>
+__device__ __forceinline__ void fft1024_pair_tm(float2 (&re)[32], float2 (&im)[32], float2* tile /* 32x32 float2, XOR-swizzled, 8 KB */,
+                                                uint32_t t_tw, float one, int lane) {
+    if (PROD) fft_base2_prod<32>(re, im, one);
+    else fft_base2<32>(re, im);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {                                     // eight twiddles per TMEM round trip
+        uint32_t t[16];
+        ldtm16(t_tw + 16 * g, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d = 8 * g + j;
+            if (d == 0) continue;
+            float2 tr, ti;
+            cmul2(re[d], im[d], __uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]), tr, ti);
+            re[d] = tr;
+            im[d] = ti;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 32; ++a) re[a] = tile[lane * 32 + (a ^ lane)];
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = im[d];
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
+    __syncwarp();
+    fft_base2<32>(re, im);
+}
+
+// table set-up helper: eight consecutive columns of the lane's row from four float2 values
+__device__ __forceinline__ void sttm_f2x4(uint32_t taddr, float2 a, float2 b, float2 c, float2 d) {
+    const uint32_t v[8] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(b.x), __float_as_uint(b.y),
+                           __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(d.x), __float_as_uint(d.y)};
+    sttm8(taddr, v);
 }
 
 // Exact arm_max_f32 over sqrt(p_k) without taking a square root per candidate.  sqrt is monotone,
