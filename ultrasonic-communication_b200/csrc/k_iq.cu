@@ -270,7 +270,12 @@ constexpr int kIqfWarps = 8;
 #define USC_IQF_ROWS 64
 #endif
 constexpr int kIqfRows = USC_IQF_ROWS;                                       // 32-sample rows loaded per lane before any is used
-constexpr int kIqfTables = 8192 + 8192 + 4096 + 16384;                        // twiddles | chirp | Hann | (cos, sin)
+// Tables in tensor memory, one row per lane (usc_tmem.cuh): carrier (cos, sin) of sample 32 r + lane at 2 r, r < 64 |
+// (chirp.re, chirp.im, Hann, -) of m = lane + 32 b at 128 + 4 b | inter-pass twiddle W_1024^(lane d) at 256 + 2 d.
+// Shared memory keeps only the carrier values of the last 32 samples (the history rows of the next frame read them
+// at a lane offset) and the TMEM slot.
+constexpr int kIqfTcs = 0, kIqfTcw = 128, kIqfTtw = 256, kIqfTcols = 512;
+constexpr int kIqfTables = 256 + 16;                                          // carrier tail | TMEM slot
 // NT = 0: the number of taps is a run-time value (<= 32): four outputs per lane and pass, tap pairs predicated.
 // NT > 0: the filter length is a compile-time constant (27 = the reference's, iq_modem.c:16-18): EIGHT outputs per
 // lane and pass — 21 instead of 2 x 19 shared-memory loads per eight outputs, exactly NT FMAs per output, no branches.
@@ -314,20 +319,44 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
     constexpr int kIqfRegion = G::region;
     constexpr uint32_t ROWSTEP = 2u * (16u + (16u >> SK));                   // float2 per 32-sample row of the staged sequence
     extern __shared__ __align__(16) unsigned char s_f[];
-    float2* s_tw = reinterpret_cast<float2*>(s_f);
-    float2* s_c = reinterpret_cast<float2*>(s_f + 8192);
-    float* s_w = reinterpret_cast<float*>(s_f + 16384);
-    float2* s_cs = reinterpret_cast<float2*>(s_f + 20480);
+    float2* s_cs_tail = reinterpret_cast<float2*>(s_f);      // carrier of samples 2016 .. 2047
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_f + 256);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* region = s_f + kIqfTables + warp * kIqfRegion;
     float2* smp = reinterpret_cast<float2*>(region);         // sample j at float2 index 2 * slot(j >> 1) + (j & 1)
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        s_tw[i] = tw_pass[i];
-        s_c[i] = chirp[i];
-        s_w[i] = hann[i];
-    }
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_cs[i] = make_float2(car_cos[i], car_sin[i]);
+    if (threadIdx.x < 32) s_cs_tail[threadIdx.x] = make_float2(car_cos[2016 + threadIdx.x], car_sin[2016 + threadIdx.x]);
+    if (warp == 0) tmem_alloc<kIqfTcols>(s_tslot);
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp);
+    if (warp < 4) {                                           // warp q fills lane quadrant q; warps q and q + 4 read it
+#pragma unroll 1
+        for (int r0 = 0; r0 < 64; r0 += 4) {
+            float2 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = make_float2(car_cos[(r0 + j) * 32 + lane], car_sin[(r0 + j) * 32 + lane]);
+            sttm_f2x4(tq + kIqfTcs + 2 * r0, c[0], c[1], c[2], c[3]);
+        }
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += 4) {
+            float2 c[4], w[4], z[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c[j] = chirp[lane + 32 * (b0 + j)];
+                w[j] = make_float2(hann[lane + 32 * (b0 + j)], 0.0f);
+                z[j] = tw_pass[(b0 + j) * 32 + lane];
+            }
+            sttm_f2x4(tq + kIqfTcw + 4 * b0, c[0], w[0], c[1], w[1]);
+            sttm_f2x4(tq + kIqfTcw + 4 * b0 + 8, c[2], w[2], c[3], w[3]);
+            sttm_f2x4(tq + kIqfTtw + 2 * b0, z[0], z[1], z[2], z[3]);
+        }
+        sttm_wait();
+    }
+    const float one = tw_pass[lane].x;                       // W^0 = 1.0f read from a table: opaque to the compiler
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
     const uint32_t H = ntaps - 1;
     float t[kFirTmax];
 #pragma unroll
@@ -355,20 +384,19 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
                 for (int u = 0; u < kIqfRows; ++u) x[u] = pcm_cast(cur[(r0 + u) * 32 + lane]);
                 // pair pl + 16 r sits in slot pl + (pl >> SK) + (16 + (16 >> SK)) r: a constant number of float2 per row
                 float2* dst = smp + 2 * (pl + (pl >> SK)) + (jl & 1u) + ROWSTEP * r0;
-                const float2* cs = s_cs + r0 * 32 + lane;
 #pragma unroll
-                for (int u0 = 0; u0 < kIqfRows; u0 += 8) {     // carrier values in batches so their loads overlap
-                    float2 c[8];
+                for (int u0 = 0; u0 < kIqfRows; u0 += 8) {     // carrier values of eight rows per TMEM round trip
+                    uint32_t c[16];
+                    ldtm16(tq + kIqfTcs + 2 * (r0 + u0), c);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) c[u] = cs[32 * (u0 + u)];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) st_mul2(dst + ROWSTEP * (u0 + u), x[u0 + u], c[u]);
+                    for (int u = 0; u < 8; ++u)
+                        st_mul2(dst + ROWSTEP * (u0 + u), x[u0 + u], make_float2(__uint_as_float(c[2 * u]), __uint_as_float(c[2 * u + 1])));
                 }
             }
             if ((uint32_t) lane < H) {                         // history: tail of the previous frame (zeros before frame 0)
                 const uint32_t k = n - H + lane, pp = ((uint32_t) lane >> 1) + PS;
                 const float xh = fr > 0 ? pcm_cast(cur[(ptrdiff_t) lane - (ptrdiff_t) H]) : 0.0f;
-                smp[2 * (pp + (pp >> SK)) + (lane & 1)] = __fmul2_rn(bc2(xh), s_cs[k]);
+                smp[2 * (pp + (pp >> SK)) + (lane & 1)] = __fmul2_rn(bc2(xh), s_cs_tail[k - 2016u]);
             }
         }
         __syncwarp();
@@ -420,19 +448,25 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
         // ---- back end: de-chirp both ways, Hann, FFT, windowed peaks ----
         float2 re[32], im[32];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const int m = lane + 32 * b;
-            const float2 r = reinterpret_cast<const float2*>(region)[G::r_index((uint32_t) m)], c = s_c[m];
-            const float w = s_w[m];
-            // cmul(R, conj c) and cmul(R, c) share their two rounded products; the FMAs ride one FFMA2 each
-            const float t0 = __fmul_rn(r.y, c.y), t1 = __fmul_rn(r.y, c.x);
-            const float2 pr2 = __ffma2_rn(bc2(r.x), bc2(c.x), make_float2(t0, -t0));      // (up.re, down.re)
-            const float2 pi2 = __ffma2_rn(bc2(r.x), make_float2(-c.y, c.y), bc2(t1));     // (up.im, down.im)
-            re[b] = __fmul2_rn(pr2, bc2(w));                                              // packed (first stage: FMAs by 1.0)
-            im[b] = __fmul2_rn(pi2, bc2(w));
+        for (int g = 0; g < 8; ++g) {                        // chirp and Hann values of four rows per TMEM round trip
+            uint32_t tv[16];
+            ldtm16(tq + kIqfTcw + 16 * g, tv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 4 * g + j, m = lane + 32 * b;
+                const float2 r = reinterpret_cast<const float2*>(region)[G::r_index((uint32_t) m)];
+                const float2 c = make_float2(__uint_as_float(tv[4 * j]), __uint_as_float(tv[4 * j + 1]));
+                const float w = __uint_as_float(tv[4 * j + 2]);
+                // cmul(R, conj c) and cmul(R, c) share their two rounded products; the FMAs ride one FFMA2 each
+                const float t0 = __fmul_rn(r.y, c.y), t1 = __fmul_rn(r.y, c.x);
+                const float2 pr2 = __ffma2_rn(bc2(r.x), bc2(c.x), make_float2(t0, -t0));      // (up.re, down.re)
+                const float2 pi2 = __ffma2_rn(bc2(r.x), make_float2(-c.y, c.y), bc2(t1));     // (up.im, down.im)
+                re[b] = __fmul2_rn(pr2, bc2(w));                                              // packed (first stage: FMAs by 1.0)
+                im[b] = __fmul2_rn(pi2, bc2(w));
+            }
         }
         __syncwarp();
-        fft1024_pair<true>(re, im, reinterpret_cast<float2*>(region), s_tw, lane);
+        fft1024_pair_tm<true>(re, im, reinterpret_cast<float2*>(region), tq + kIqfTtw, one, lane);
         const float2 pr = __ffma2_rn(re[0], re[0], __fmul2_rn(im[0], im[0]));
         const float2 pl = __ffma2_rn(re[31], re[31], __fmul2_rn(im[31], im[31]));
         const bool in_r = (uint32_t) lane < W, in_l = 992u + lane >= 1024u - W;
@@ -461,6 +495,9 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
         }
         __syncwarp();
     }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kIqfTcols>(*s_tslot);
 }
 
 template <typename PCM, int NT>

@@ -605,16 +605,22 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
         float pu[kLongNB], pd[kLongNB];
         uint32_t kk[kLongNB];
         bool ok[kLongNB];
+        float4 zcs[kLongNB];                                 // the remote partner loads first, all in flight together
+#pragma unroll
+        for (int j = 0; j < kLongNB; ++j) {
+            const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl;
+            // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d); k = 0 pairs with itself (unused)
+            const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? (c == 0 ? 1023u : 1024u - c) : 1023u - c;
+            const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+            zcs[j] = ld_cluster_f4(addr);
+        }
 #pragma unroll
         for (int j = 0; j < kLongNB; ++j) {
             const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl, k = (uint32_t) R0 * c + d;
             kk[j] = k;
             ok[j] = k < bw2;
             const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + keep_off<W>(dl))[c];
-            // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d); k = 0 pairs with itself (unused)
-            const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? (c == 0 ? 1023u : 1024u - c) : 1023u - c;
-            const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
-            const float4 zc = ld_cluster_f4(addr);
+            const float4 zc = zcs[j];
             const float2 w = w_split[j];
             float2 xr, xi;
             rfft_split2(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y),
