@@ -26,7 +26,11 @@
 namespace usc {
 
 constexpr int kOsWarps = 8;
-constexpr int kOsTabs = 8192 + 8192 + 16384;           // pass twiddles | W_2048^a (radix-2 level) | W_4096^k split table
+// Tables in tensor memory, one row per lane (usc_tmem.cuh): radix-2 level twiddle W_2048^a of a = lane + 32 q at 2 q |
+// inter-pass twiddle W_1024^(lane d) at 64 + 2 d | spectral stage of the pair (k, 2048 - k), k = lane + 32 j, at 128 + 8 j:
+// split twiddles (W_4096^k, W_4096^kc) and template spectrum (G[k], G[kc]).  Shared memory keeps the TMEM slot only.
+constexpr int kOsTtw0 = 0, kOsTtw = 64, kOsTspec = 128, kOsTcols = 512;
+constexpr int kOsTabs = 128;                           // TMEM slot (+ padding to keep the per-warp areas 128-byte aligned)
 constexpr int kOsWarpBytes = 3 * 8192;                 // half A | exchange tile | half B
 constexpr int kOsBar = kOsTabs + kOsWarps * kOsWarpBytes;
 constexpr int kOsSmem = kOsBar + kOsWarps * 8;
@@ -42,9 +46,7 @@ struct os_params {
 template <typename PCM>
 __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    float2* s_tw = reinterpret_cast<float2*>(s_raw);
-    float2* s_tw0 = reinterpret_cast<float2*>(s_raw + 8192);
-    float2* s_ws = reinterpret_cast<float2*>(s_raw + 16384);
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = s_raw + kOsTabs + warp * kOsWarpBytes;
     float2* tile = reinterpret_cast<float2*>(wbase + 8192);
@@ -55,14 +57,34 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-        if (i < 1024) {
-            s_tw[i] = p.tw_pass[i];
-            s_tw0[i] = p.tw0[i];
-        }
-        s_ws[i] = p.tw_split[i];
-    }
+    if (warp == 0) tmem_alloc<kOsTcols>(s_tslot);
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp);
+    if (warp < 4) {                                     // warp q fills lane quadrant q; warps q and q + 4 read it
+#pragma unroll 1
+        for (int q0 = 0; q0 < 32; q0 += 4) {
+            float2 a[4], z[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[j] = p.tw0[lane + 32 * (q0 + j)];
+                z[j] = p.tw_pass[(q0 + j) * 32 + lane];
+            }
+            sttm_f2x4(tq + kOsTtw0 + 2 * q0, a[0], a[1], a[2], a[3]);
+            sttm_f2x4(tq + kOsTtw + 2 * q0, z[0], z[1], z[2], z[3]);
+        }
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+            const int k = lane + 32 * j, kc = (2048 - k) & 2047;
+            sttm_f2x4(tq + kOsTspec + 8 * j, p.tw_split[k], p.tw_split[kc], __ldg(p.G + k), __ldg(p.G + kc));
+        }
+        sttm_wait();
+    }
+    const float2 ws1024 = p.tw_split[1024], g1024 = __ldg(p.G + 1024);   // bin 1024 pairs with itself (lane 0)
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
 
     const uint32_t nblocks = p.nframes - 1;
     const size_t nitems = (size_t) p.nstreams * p.nseg;
@@ -88,20 +110,24 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             parity ^= 1u;
             float2 re[32], im[32];                     // (.x, .y) = (even-bin transform, odd-bin transform)
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {             // radix-2 level of the [2,32,32] plan on z[m] = x[2m] + j x[2m+1]
-                const int a = lane + 32 * q;
-                const V2 l = lo_half[a], h = hi_half[a];
-                const float lx = pcm_to_float(l.x), ly = pcm_to_float(l.y), hx = pcm_to_float(h.x), hy = pcm_to_float(h.y);
-                const float er = __fadd_rn(lx, hx), ei = __fadd_rn(ly, hy);
-                const float dr = __fsub_rn(lx, hx), di = __fsub_rn(ly, hy);
-                const float2 w = s_tw0[a];
-                float orr, oii;
-                cmul(dr, di, w.x, w.y, orr, oii);
-                re[q] = make_float2(er, orr);
-                im[q] = make_float2(ei, oii);
+            for (int g = 0; g < 4; ++g) {              // radix-2 level of the [2,32,32] plan on z[m] = x[2m] + j x[2m+1]
+                uint32_t t[16];                        // its twiddles, eight per TMEM round trip
+                ldtm16(tq + kOsTtw0 + 16 * g, t);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int q = 8 * g + u, a = lane + 32 * q;
+                    const V2 l = lo_half[a], h = hi_half[a];
+                    const float lx = pcm_to_float(l.x), ly = pcm_to_float(l.y), hx = pcm_to_float(h.x), hy = pcm_to_float(h.y);
+                    const float er = __fadd_rn(lx, hx), ei = __fadd_rn(ly, hy);
+                    const float dr = __fsub_rn(lx, hx), di = __fsub_rn(ly, hy);
+                    float orr, oii;
+                    cmul(dr, di, __uint_as_float(t[2 * u]), __uint_as_float(t[2 * u + 1]), orr, oii);
+                    re[q] = make_float2(er, orr);
+                    im[q] = make_float2(ei, oii);
+                }
             }
             __syncwarp();                              // the lower half has been consumed by every lane
-            fft1024_pair(re, im, tile, s_tw, lane);
+            fft1024_pair_tm(re, im, tile, tq + kOsTtw, 1.0f, lane);
             // spectrum to shared memory in natural order: lane d0, element d1 holds Z[2c], Z[2c+1], c = d0 + 32 d1
             {
                 float4* z4 = reinterpret_cast<float4*>(zs);
@@ -109,55 +135,64 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
                 for (int d1 = 0; d1 < 32; ++d1) z4[lane + 32 * d1] = make_float4(re[d1].x, im[d1].x, re[d1].y, im[d1].y);
             }
             __syncwarp();
-            // split -> x G -> merge, in place; this lane owns the pairs (k, 2048 - k), k = lane + 32 j
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
+            // split -> x G -> merge, in place; this lane owns the pairs (k, 2048 - k), k = lane + 32 j.  Bin k rides in
+            // the .x half and bin 2048 - k in the .y half of packed operations (each half the scalar operator sequence).
+#pragma unroll 1
+            for (int j0 = 0; j0 < 32; j0 += 4) {
+                uint32_t t4[32];                       // (W_4096^k, W_4096^kc, G[k], G[kc]) of four pairs per TMEM round trip
+                ldtm32(tq + kOsTspec + 8 * j0, t4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                const uint32_t* t = t4 + 8 * u;
                 const int k = lane + 32 * j, kc = (2048 - k) & 2047;
                 const float2 zk = zs[k], zc = zs[kc];
-                const float2 wk = s_ws[k], wc = s_ws[kc];
-                float xr, xi, cr_, ci_;
-                rfft_split(zk.x, zk.y, zc.x, zc.y, wk.x, wk.y, xr, xi);              // X[k]
-                rfft_split(zc.x, zc.y, zk.x, zk.y, wc.x, wc.y, cr_, ci_);            // X[2048 - k]
-                if (k == 0) {                                                         // packed (X[0], X[2048])
-                    xr = __fadd_rn(zk.x, zk.y);
-                    xi = __fsub_rn(zk.x, zk.y);
+                const float2 zr2 = make_float2(zk.x, zc.x), zi2 = make_float2(zk.y, zc.y);
+                const float2 wr2 = make_float2(__uint_as_float(t[0]), __uint_as_float(t[2])), wi2 = make_float2(__uint_as_float(t[1]), __uint_as_float(t[3]));
+                const float2 gr2 = make_float2(__uint_as_float(t[4]), __uint_as_float(t[6])), gi2 = make_float2(__uint_as_float(t[5]), __uint_as_float(t[7]));
+                float2 xr2, xi2;
+                rfft_split2v(zr2, zi2, swap2(zr2), swap2(zi2), wr2, wi2, xr2, xi2);   // (X[k], X[2048 - k])
+                if (k == 0) {                                                         // packed (X[0], X[2048]) in the .x half
+                    xr2.x = __fadd_rn(zk.x, zk.y);
+                    xi2.x = __fsub_rn(zk.x, zk.y);
                 }
-                const float2 gk = __ldg(p.G + k), gc = __ldg(p.G + kc);
-                float yr, yi, ycr, yci;
-                cmul(xr, xi, gk.x, gk.y, yr, yi);                                     // arm_cmplx_mult_cmplx_f32 (quirk at k = 0)
-                cmul(cr_, ci_, gc.x, gc.y, ycr, yci);
-                float zr, zi, zcr, zci;
-                rfft_merge(yr, yi, ycr, yci, wk.x, wk.y, zr, zi);                     // 2 Z'[k]
-                rfft_merge(ycr, yci, yr, yi, wc.x, wc.y, zcr, zci);                   // 2 Z'[2048 - k]
+                float2 yr2, yi2;
+                cmul2v(xr2, xi2, gr2, gi2, yr2, yi2);                                 // arm_cmplx_mult_cmplx_f32 (quirk at k = 0)
+                float2 or2, oi2;
+                rfft_merge2v(yr2, yi2, swap2(yr2), swap2(yi2), wr2, wi2, or2, oi2);   // (2 Z'[k], 2 Z'[2048 - k])
                 if (k == 0) {
-                    zr = __fadd_rn(yr, yi);
-                    zi = __fsub_rn(yr, yi);
+                    or2.x = __fadd_rn(yr2.x, yi2.x);
+                    oi2.x = __fsub_rn(yr2.x, yi2.x);
                 }
-                zs[k] = make_float2(zr, zi);
-                if (k != 0) zs[kc] = make_float2(zcr, zci);
+                zs[k] = make_float2(or2.x, oi2.x);
+                if (k != 0) zs[kc] = make_float2(or2.y, oi2.y);
+                }
             }
             if (lane == 0) {                           // bin 1024 pairs with itself
-                const float2 zk = zs[1024], wk = s_ws[1024];
+                const float2 zk = zs[1024], wk = ws1024;
                 float xr, xi, yr, yi, zr, zi;
                 rfft_split(zk.x, zk.y, zk.x, zk.y, wk.x, wk.y, xr, xi);
-                const float2 gk = __ldg(p.G + 1024);
-                cmul(xr, xi, gk.x, gk.y, yr, yi);
+                cmul(xr, xi, g1024.x, g1024.y, yr, yi);
                 rfft_merge(yr, yi, yr, yi, wk.x, wk.y, zr, zi);
                 zs[1024] = make_float2(zr, zi);
             }
             __syncwarp();
             // inverse = forward transform of the swapped parts (radix-2 level again)
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const int a = lane + 32 * q;
-                const float2 l = zs[a], h = zs[a + 1024];
-                const float er = __fadd_rn(l.y, h.y), ei = __fadd_rn(l.x, h.x);
-                const float dr = __fsub_rn(l.y, h.y), di = __fsub_rn(l.x, h.x);
-                const float2 w = s_tw0[a];
-                float orr, oii;
-                cmul(dr, di, w.x, w.y, orr, oii);
-                re[q] = make_float2(er, orr);
-                im[q] = make_float2(ei, oii);
+            for (int g = 0; g < 4; ++g) {
+                uint32_t t[16];
+                ldtm16(tq + kOsTtw0 + 16 * g, t);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int q = 8 * g + u, a = lane + 32 * q;
+                    const float2 l = zs[a], h = zs[a + 1024];
+                    const float er = __fadd_rn(l.y, h.y), ei = __fadd_rn(l.x, h.x);
+                    const float dr = __fsub_rn(l.y, h.y), di = __fsub_rn(l.x, h.x);
+                    float orr, oii;
+                    cmul(dr, di, __uint_as_float(t[2 * u]), __uint_as_float(t[2 * u + 1]), orr, oii);
+                    re[q] = make_float2(er, orr);
+                    im[q] = make_float2(ei, oii);
+                }
             }
             __syncwarp();                              // the parked spectrum is dead: its half can take the next n samples
             if (lane == 0 && b + 1 < b1) {
@@ -165,7 +200,7 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
                 mbar_expect_tx(bar, 8192u);
                 bulk_g2s(wbase + (odd ? 16384 : 0), stream + (size_t) (b + 2) * 2048, 8192u, bar);
             }
-            fft1024_pair(re, im, tile, s_tw, lane);
+            fft1024_pair_tm(re, im, tile, tq + kOsTtw, 1.0f, lane);
             // y[2m] = z[m].im / 4096, y[2m+1] = z[m].re / 4096; valid lags l = 2m (+1) in [2048, 4096): m = 2c (+1) with
             // c = lane + 32 d1 >= 512, i.e. d1 >= 16 (the other outputs of the last pass are never computed)
             const float sc = 1.0f / 4096.0f;
@@ -194,6 +229,9 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             __syncwarp();
         }
     }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kOsTcols>(*s_tslot);
 }
 
 cudaError_t launch_correlate_os(const void* pcm, uint32_t pcm_format, uint32_t nstreams, uint32_t nframes, size_t stream_stride,

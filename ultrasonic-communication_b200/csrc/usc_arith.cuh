@@ -249,6 +249,28 @@ __device__ __forceinline__ void rfft_merge2(float2 xkr, float2 xki, float2 xcr, 
     zi = __ffma2_rn(qr, bc2(cr), __ffma2_rn(neg2(qi), bc2(si), pi));
 }
 
+// ---- fully packed forms: both halves carry their own second operand (K8's spectral stage: bin k in .x, bin N/2 - k in .y) ----
+__device__ __forceinline__ void cmul2v(float2 ar, float2 ai, float2 br, float2 bi, float2& re, float2& im) {
+    const float2 t0 = __fmul2_rn(ai, bi), t1 = __fmul2_rn(ai, br);
+    re = __ffma2_rn(ar, br, neg2(t0));
+    im = __ffma2_rn(ar, bi, t1);
+}
+__device__ __forceinline__ void rfft_split2v(float2 zkr, float2 zki, float2 zcr, float2 zci, float2 cr, float2 si, float2& xr, float2& xi) {
+    const float2 pr = __fadd2_rn(zkr, zcr), pi = __fadd2_rn(zki, neg2(zci));
+    const float2 qr = __fadd2_rn(zki, zci), qi = __fadd2_rn(zcr, neg2(zkr));
+    const float2 tr = __ffma2_rn(qr, cr, __ffma2_rn(qi, si, pr));
+    const float2 ti = __ffma2_rn(qi, cr, __ffma2_rn(neg2(qr), si, pi));
+    xr = __fmul2_rn(bc2(0.5f), tr);
+    xi = __fmul2_rn(bc2(0.5f), ti);
+}
+__device__ __forceinline__ void rfft_merge2v(float2 xkr, float2 xki, float2 xcr, float2 xci, float2 cr, float2 si, float2& zr, float2& zi) {
+    const float2 pr = __fadd2_rn(xkr, xcr), pi = __fadd2_rn(xki, neg2(xci));
+    const float2 qr = __fadd2_rn(xkr, neg2(xcr)), qi = __fadd2_rn(xki, xci);
+    zr = __ffma2_rn(neg2(qi), cr, __ffma2_rn(neg2(qr), si, pr));
+    zi = __ffma2_rn(qr, cr, __ffma2_rn(neg2(qi), si, pi));
+}
+__device__ __forceinline__ float2 swap2(float2 a) { return make_float2(a.y, a.x); }
+
 // arm_max_f32 combine: keep the larger value; on equal values keep the lower index.
 __device__ __forceinline__ void argmax_combine(float& v, uint32_t& i, float ov, uint32_t oi) {
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
