@@ -301,6 +301,44 @@ __device__ __forceinline__ void peak_tail(const float (&pw)[NB], int lane, uint3
     }
 }
 
+// Exact arm_max_f32 over sqrt(p_k) with ONE square root and no rare path.  With r = sqrt_rn(pmax) and r- its predecessor,
+// a candidate p <= pmax rounds to the same root exactly when sqrt(p) lies above the midpoint m = (r- + r) / 2, i.e. when
+// p > m^2 (sqrt(p) = m is impossible: m has 25 significant bits, so m^2 is not a float).  m^2 = (r- + r)^2 / 4 is exact
+// in double (a 25-bit sum, a 50-bit square), and the smallest float above it is its conversion rounded up: the first
+// index attaining the maximum root is the first k with p_k >= that threshold.  pmax = 0: every root is 0, threshold 0.
+__device__ __forceinline__ float same_root_threshold(float pmax, float& root) {
+    root = __fsqrt_rn(pmax);
+    const uint32_t rb = __float_as_uint(root);
+    const double s = (double) root + (double) __uint_as_float(rb ? rb - 1u : 0u);
+    return rb ? __double2float_ru(0.25 * (s * s)) : 0.0f;
+}
+
+// peak_tail for the two candidate sets of a packed pass, side by side so that the warp-wide reductions of the two
+// searches overlap; results equal peak_tail's, bit for bit.
+template <int NB>
+__device__ __forceinline__ void peak_tail_pair(const float (&pa)[NB], const float (&pb)[NB], int lane, uint32_t bw2,
+                                               float& bestA, uint32_t& idxA, float& bestB, uint32_t& idxB) {
+    float qa = 0.0f, qb = 0.0f;                        // p >= 0: bit patterns order like values
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        const bool in = (uint32_t) lane + 32u * d1 < bw2;
+        qa = in ? fmaxf(qa, pa[d1]) : qa;
+        qb = in ? fmaxf(qb, pb[d1]) : qb;
+    }
+    const float maxA = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(qa)));
+    const float maxB = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(qb)));
+    const float thrA = same_root_threshold(maxA, bestA), thrB = same_root_threshold(maxB, bestB);
+    uint32_t ka = 0xffffffffu, kb = 0xffffffffu;
+#pragma unroll
+    for (int d1 = NB - 1; d1 >= 0; --d1) {             // descending, so the lowest qualifying k of the lane survives
+        const uint32_t k = (uint32_t) lane + 32u * d1;
+        ka = (k < bw2 && pa[d1] >= thrA) ? k : ka;
+        kb = (k < bw2 && pb[d1] >= thrB) ? k : kb;
+    }
+    idxA = __reduce_min_sync(0xffffffffu, ka);
+    idxB = __reduce_min_sync(0xffffffffu, kb);
+}
+
 // squared magnitudes of the real-FFT bins k = lane + 32 d1, d1 < NB, of both halves (no peak search)
 template <int NB>
 __device__ __forceinline__ void mag2_window_pair(const float2 (&zr)[32], const float2 (&zi)[32], const float2 (&ws)[NB],
@@ -351,8 +389,7 @@ __device__ __forceinline__ void peak_window_pair_s(const float2 (&zr)[32], const
         pa[d1] = p.x;
         pb[d1] = p.y;
     }
-    peak_tail<NB>(pa, lane, bw2, bestA, idxA);
-    peak_tail<NB>(pb, lane, bw2, bestB, idxB);
+    peak_tail_pair<NB>(pa, pb, lane, bw2, bestA, idxA, bestB, idxB);
 }
 
 template <int NB>
@@ -378,8 +415,7 @@ __device__ __forceinline__ void peak_window_pair(const float2 (&zr)[32], const f
         pa[d1] = p.x;
         pb[d1] = p.y;
     }
-    peak_tail<NB>(pa, lane, bw2, bestA, idxA);
-    peak_tail<NB>(pb, lane, bw2, bestB, idxB);
+    peak_tail_pair<NB>(pa, pb, lane, bw2, bestA, idxA, bestB, idxB);
 }
 
 }  // namespace usc
