@@ -129,7 +129,7 @@ def kernel_source_hash():
     """sha1 over the sources of the bench kernel: profiles/k1_traffic.json records it at capture time."""
     import hashlib
     hsh = hashlib.sha1()
-    for f in ("k_demod.cu", "usc_warpfft.cuh", "usc_arith.cuh"):
+    for f in ("k_demod.cu", "usc_warpfft.cuh", "usc_arith.cuh", "usc_tmem.cuh"):
         with open(os.path.join(ROOT, "ultrasonic-communication_b200", "csrc", f), "rb") as fh:
             hsh.update(fh.read())
     return hsh.hexdigest()[:16]

@@ -68,10 +68,10 @@ template <int R0> struct long_smem {
                          bar = red + 3 * R0 * 16, tslot = bar + 8, total = tslot + 8;
 };
 
-// block-wide exact arg-max of sqrt(p) over this CTA's candidates for both hypotheses, with one square root per hypothesis
-// on the common path: the maximum of p is found first (p >= 0, so bit patterns order like values); if no other candidate
-// lies within 2^-20 of it (two ulps of the root), its root is the maximum and its index the first occurrence; otherwise
-// every root is taken (rare path).  pu/pd: squared magnitudes of this thread's bins k[j], ascending; ok[j]: bin in range.
+// block-wide exact arg-max of sqrt(p) over this CTA's candidates for both hypotheses, with one square root per hypothesis:
+// the maximum of p is found first (p >= 0, so bit patterns order like values); the first index whose root rounds to the
+// maximum root is the first candidate at or above same_root_threshold (usc_warpfft.cuh).  Two CTA barriers, no rare path.
+// pu/pd: squared magnitudes of this thread's bins k[j]; ok[j]: bin in range.
 template <int NW, int NC>
 __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float (&pd)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
                                               float* red, int tid, float& bu, uint32_t& iu, float& bd, uint32_t& id) {
@@ -80,8 +80,8 @@ __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float
     float qu = 0.0f, qd = 0.0f;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-        if (ok[j] && pu[j] > qu) qu = pu[j];
-        if (ok[j] && pd[j] > qd) qd = pd[j];
+        qu = ok[j] ? fmaxf(qu, pu[j]) : qu;
+        qd = ok[j] ? fmaxf(qd, pd[j]) : qd;
     }
     const uint32_t wu = __reduce_max_sync(0xffffffffu, __float_as_uint(qu)), wd = __reduce_max_sync(0xffffffffu, __float_as_uint(qd));
     if (lane == 0) { redu[warp * 2] = wu; redu[warp * 2 + 1] = wd; }
@@ -89,52 +89,22 @@ __device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float
     uint32_t mu = 0, md = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) { mu = max(mu, redu[w * 2]); md = max(md, redu[w * 2 + 1]); }
-    const float maxu = __uint_as_float(mu), maxd = __uint_as_float(md);
-    const float thru = __fmul_rn(maxu, 0.99999904632568359375f), thrd = __fmul_rn(maxd, 0.99999904632568359375f);   // 1 - 2^-20
-    uint32_t near = 0, ku = 0xffffffffu, kd = 0xffffffffu;             // near: candidates within two ulps of either maximum
-#pragma unroll
-    for (int j = NC - 1; j >= 0; --j) {
-        if (ok[j] && pu[j] >= thru) { ++near; if (pu[j] == maxu) ku = k[j]; }
-        if (ok[j] && pd[j] >= thrd) { near += 0x10000u; if (pd[j] == maxd) kd = k[j]; }
-    }
-    near = __reduce_add_sync(0xffffffffu, near);
-    ku = __reduce_min_sync(0xffffffffu, ku);
-    kd = __reduce_min_sync(0xffffffffu, kd);
-    if (lane == 0) { redu[2 * NW + warp * 4] = near; redu[2 * NW + warp * 4 + 1] = ku; redu[2 * NW + warp * 4 + 2] = kd; }
-    __syncthreads();
-    near = 0; ku = 0xffffffffu; kd = 0xffffffffu;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        near += redu[2 * NW + w * 4];
-        ku = min(ku, redu[2 * NW + w * 4 + 1]);
-        kd = min(kd, redu[2 * NW + w * 4 + 2]);
-    }
-    if (near == 0x10001u && maxu == maxu && maxd == maxd) {           // exactly one candidate per hypothesis near its maximum
-        bu = __fsqrt_rn(maxu); iu = ku;
-        bd = __fsqrt_rn(maxd); id = kd;
-        return;
-    }
-    // rare path (block-uniform): every root, first-occurrence arg-max
-    bu = -INFINITY; bd = -INFINITY;
-    iu = 0xffffffffu; id = 0xffffffffu;
+    const float thru = same_root_threshold(__uint_as_float(mu), bu), thrd = same_root_threshold(__uint_as_float(md), bd);
+    uint32_t ku = 0xffffffffu, kd = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-        const float su = __fsqrt_rn(pu[j]), sd = __fsqrt_rn(pd[j]);
-        if (ok[j] && (iu == 0xffffffffu || bu < su)) { bu = su; iu = k[j]; }
-        if (ok[j] && (id == 0xffffffffu || bd < sd)) { bd = sd; id = k[j]; }
+        ku = (ok[j] && pu[j] >= thru) ? min(ku, k[j]) : ku;
+        kd = (ok[j] && pd[j] >= thrd) ? min(kd, k[j]) : kd;
     }
-    warp_argmax(bu, iu);
-    warp_argmax(bd, id);
-    float* slow = red + 6 * NW;
-    if (lane == 0) {
-        slow[warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(slow)[warp * 4 + 1] = iu;
-        slow[warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(slow)[warp * 4 + 3] = id;
-    }
+    ku = __reduce_min_sync(0xffffffffu, ku);
+    kd = __reduce_min_sync(0xffffffffu, kd);
+    if (lane == 0) { redu[2 * NW + warp * 2] = ku; redu[2 * NW + warp * 2 + 1] = kd; }
     __syncthreads();
-    bu = slow[0]; iu = reinterpret_cast<uint32_t*>(slow)[1]; bd = slow[2]; id = reinterpret_cast<uint32_t*>(slow)[3];
-    for (int w = 1; w < NW; ++w) {
-        argmax_combine(bu, iu, slow[w * 4 + 0], reinterpret_cast<uint32_t*>(slow)[w * 4 + 1]);
-        argmax_combine(bd, id, slow[w * 4 + 2], reinterpret_cast<uint32_t*>(slow)[w * 4 + 3]);
+    iu = 0xffffffffu; id = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        iu = min(iu, redu[2 * NW + w * 2]);
+        id = min(id, redu[2 * NW + w * 2 + 1]);
     }
 }
 

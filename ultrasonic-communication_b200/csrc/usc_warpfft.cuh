@@ -168,64 +168,49 @@ __device__ __forceinline__ void sttm_f2x4(uint32_t taddr, float2 a, float2 b, fl
     sttm8(taddr, v);
 }
 
-// Exact arm_max_f32 over sqrt(p_k) without taking a square root per candidate.  sqrt is monotone,
-// so max_k sqrt(p_k) = sqrt(max_k p_k); the first index attaining it is the first k whose p_k rounds
-// to the same square root.  Any such k other than the first arg-max of p must satisfy
-// p_k >= pmax*(1 - 2^-20) (a gap of two ulps of the root guarantees a smaller rounded root), so the
-// fast path only has to rule that out; otherwise the rare slow path takes every root.
-// Each lane passes NC candidates (squared magnitude p >= 0, index k, validity) in ascending k.
-template <int NC>
-__device__ __forceinline__ void argmax_slow(const float (&p)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
-                                         float& best, uint32_t& best_idx) {
-    best = -INFINITY;
-    best_idx = 0xffffffffu;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        float m = __fsqrt_rn(p[c]);
-        if (ok[c] && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k[c]; }
-    }
-    warp_argmax(best, best_idx);
+// Exact arm_max_f32 over sqrt(p_k) with ONE square root and no rare path.  With r = sqrt_rn(pmax) and r- its predecessor,
+// a candidate p <= pmax rounds to the same root exactly when sqrt(p) lies above the midpoint m = (r- + r) / 2, i.e. when
+// p > m^2 (sqrt(p) = m is impossible: m has 25 significant bits, so m^2 is not a float).  m^2 = (r- + r)^2 / 4 is exact
+// in double (a 25-bit sum, a 50-bit square), and the smallest float above it is its conversion rounded up: the first
+// index attaining the maximum root is the first k with p_k >= that threshold.  pmax = 0: every root is 0, threshold 0.
+__device__ __forceinline__ float same_root_threshold(float pmax, float& root) {
+    root = __fsqrt_rn(pmax);
+    const uint32_t rb = __float_as_uint(root);
+    const double s = (double) root + (double) __uint_as_float(rb ? rb - 1u : 0u);
+    return rb ? __double2float_ru(0.25 * (s * s)) : 0.0f;
 }
 
+// Each lane passes NC candidates (squared magnitude p >= 0, index k, validity); the warp gets the largest root and the
+// first index attaining it (arm_max_f32 over sqrt(p_k)).
 template <int NC>
 __device__ __forceinline__ void argmax_exact(const float (&p)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
                                              float& best, uint32_t& best_idx) {
-    float pb = ok[0] ? p[0] : 0.0f;
-    uint32_t kb = ok[0] ? k[0] : 0xffffffffu;
+    float q = 0.0f;
 #pragma unroll
-    for (int c = 1; c < NC; ++c)
-        if (ok[c] && (p[c] > pb || kb == 0xffffffffu)) { pb = p[c]; kb = k[c]; }
-    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
-    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
-    bool risky = false;
+    for (int c = 0; c < NC; ++c) q = ok[c] ? fmaxf(q, p[c]) : q;
+    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(q)));   // p >= 0: bit patterns order like values
+    const float thr = same_root_threshold(pmax, best);
+    uint32_t kb = 0xffffffffu;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) risky |= ok[c] && (k[c] < kmin) && (p[c] >= thr);
-    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
-        argmax_slow<NC>(p, k, ok, best, best_idx);
-    } else {
-        best = __fsqrt_rn(pmax);
-        best_idx = kmin;
-    }
-}
-
-// rare path of peak_window: every root, then the first-occurrence arg-max
-template <int NB>
-__device__ __noinline__ void peak_slow(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
-    best = -INFINITY;
-    best_idx = 0xffffffffu;
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        float m = __fsqrt_rn(pw[d1]);
-        if (k < bw2 && (best < m || best_idx == 0xffffffffu)) { best = m; best_idx = k; }
-    }
-    warp_argmax(best, best_idx);
+    for (int c = 0; c < NC; ++c) kb = (ok[c] && p[c] >= thr) ? min(kb, k[c]) : kb;
+    best_idx = __reduce_min_sync(0xffffffffu, kb);
 }
 
 // Real-FFT split of this lane's bins k = lane + 32*d1 (d1 < NB), magnitude and arg-max over
 // [0, bw2): the receiver's "right" window (receiver/Src/main.c:208).  zr/zi: lane d0 holds
 // Z[d0 + 32*d1] in element d1; only elements [0, NB) and [32-NB, 32) are read.
+template <int NB>
+__device__ __forceinline__ void peak_tail(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
+    uint32_t k[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        k[d1] = (uint32_t) lane + 32u * d1;
+        ok[d1] = k[d1] < bw2;
+    }
+    argmax_exact<NB>(pw, k, ok, best, best_idx);
+}
+
 template <int NB>
 __device__ __forceinline__ void peak_window(const float (&zr)[32], const float (&zi)[32],
                                             const float2 (&ws)[NB], int lane, uint32_t bw2,
@@ -248,69 +233,7 @@ __device__ __forceinline__ void peak_window(const float (&zr)[32], const float (
         }
         pw[d1] = __fmaf_rn(xr, xr, __fmul_rn(xi, xi));
     }
-    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
-    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
-#pragma unroll
-    for (int d1 = 1; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
-    }
-    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
-    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
-    bool risky = false;
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        risky |= (k < kmin) && (pw[d1] >= thr);        // an earlier bin that might round to the same root
-    }
-    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
-        peak_slow<NB>(pw, lane, bw2, best, best_idx);
-    } else {
-        best = __fsqrt_rn(pmax);
-        best_idx = kmin;
-    }
-}
-
-
-// peak_window on both halves of the packed registers at once: the split and the squared magnitudes
-// are f32x2 operations with the per-lane split twiddle broadcast; the two arg-max searches stay scalar.
-template <int NB>
-__device__ __forceinline__ void peak_tail(const float (&pw)[NB], int lane, uint32_t bw2, float& best, uint32_t& best_idx) {
-    float pb = (uint32_t) lane < bw2 ? pw[0] : 0.0f;
-    uint32_t kb = (uint32_t) lane < bw2 ? (uint32_t) lane : 0xffffffffu;
-#pragma unroll
-    for (int d1 = 1; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        if (k < bw2 && pw[d1] > pb) { pb = pw[d1]; kb = k; }
-    }
-    const float pmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pb)));   // p >= 0
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pb == pmax ? kb : 0xffffffffu);
-    const float thr = __fmul_rn(pmax, 0.99999904632568359375f);                                // 1 - 2^-20
-    bool risky = false;
-#pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        risky |= (k < kmin) && (pw[d1] >= thr);
-    }
-    if (__any_sync(0xffffffffu, risky || !(pmax == pmax))) {
-        peak_slow<NB>(pw, lane, bw2, best, best_idx);
-    } else {
-        best = __fsqrt_rn(pmax);
-        best_idx = kmin;
-    }
-}
-
-// Exact arm_max_f32 over sqrt(p_k) with ONE square root and no rare path.  With r = sqrt_rn(pmax) and r- its predecessor,
-// a candidate p <= pmax rounds to the same root exactly when sqrt(p) lies above the midpoint m = (r- + r) / 2, i.e. when
-// p > m^2 (sqrt(p) = m is impossible: m has 25 significant bits, so m^2 is not a float).  m^2 = (r- + r)^2 / 4 is exact
-// in double (a 25-bit sum, a 50-bit square), and the smallest float above it is its conversion rounded up: the first
-// index attaining the maximum root is the first k with p_k >= that threshold.  pmax = 0: every root is 0, threshold 0.
-__device__ __forceinline__ float same_root_threshold(float pmax, float& root) {
-    root = __fsqrt_rn(pmax);
-    const uint32_t rb = __float_as_uint(root);
-    const double s = (double) root + (double) __uint_as_float(rb ? rb - 1u : 0u);
-    return rb ? __double2float_ru(0.25 * (s * s)) : 0.0f;
+    peak_tail<NB>(pw, lane, bw2, best, best_idx);
 }
 
 // peak_tail for the two candidate sets of a packed pass, side by side so that the warp-wide reductions of the two
