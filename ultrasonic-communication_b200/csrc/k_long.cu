@@ -68,46 +68,6 @@ template <int R0> struct long_smem {
                          bar = red + 3 * R0 * 16, tslot = bar + 8, total = tslot + 8;
 };
 
-// block-wide exact arg-max of sqrt(p) over this CTA's candidates for both hypotheses, with one square root per hypothesis:
-// the maximum of p is found first (p >= 0, so bit patterns order like values); the first index whose root rounds to the
-// maximum root is the first candidate at or above same_root_threshold (usc_warpfft.cuh).  Two CTA barriers, no rare path.
-// pu/pd: squared magnitudes of this thread's bins k[j]; ok[j]: bin in range.
-template <int NW, int NC>
-__device__ __forceinline__ void block_argmax2(const float (&pu)[NC], const float (&pd)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
-                                              float* red, int tid, float& bu, uint32_t& iu, float& bd, uint32_t& id) {
-    const int lane = tid & 31, warp = tid >> 5;
-    uint32_t* redu = reinterpret_cast<uint32_t*>(red);
-    float qu = 0.0f, qd = 0.0f;
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        qu = ok[j] ? fmaxf(qu, pu[j]) : qu;
-        qd = ok[j] ? fmaxf(qd, pd[j]) : qd;
-    }
-    const uint32_t wu = __reduce_max_sync(0xffffffffu, __float_as_uint(qu)), wd = __reduce_max_sync(0xffffffffu, __float_as_uint(qd));
-    if (lane == 0) { redu[warp * 2] = wu; redu[warp * 2 + 1] = wd; }
-    __syncthreads();
-    uint32_t mu = 0, md = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) { mu = max(mu, redu[w * 2]); md = max(md, redu[w * 2 + 1]); }
-    const float thru = same_root_threshold(__uint_as_float(mu), bu), thrd = same_root_threshold(__uint_as_float(md), bd);
-    uint32_t ku = 0xffffffffu, kd = 0xffffffffu;
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        ku = (ok[j] && pu[j] >= thru) ? min(ku, k[j]) : ku;
-        kd = (ok[j] && pd[j] >= thrd) ? min(kd, k[j]) : kd;
-    }
-    ku = __reduce_min_sync(0xffffffffu, ku);
-    kd = __reduce_min_sync(0xffffffffu, kd);
-    if (lane == 0) { redu[2 * NW + warp * 2] = ku; redu[2 * NW + warp * 2 + 1] = kd; }
-    __syncthreads();
-    iu = 0xffffffffu; id = 0xffffffffu;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        iu = min(iu, redu[2 * NW + w * 2]);
-        id = min(id, redu[2 * NW + w * 2 + 1]);
-    }
-}
-
 template <typename PCM, int R0>
 __device__ __forceinline__ void demod_long_body(const long_params& p) {
     using L = long_smem<R0>;
@@ -322,7 +282,21 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
             }
         }
 #else
-        block_argmax2<R0, kLongNB>(pu, pd, kk, ok, reinterpret_cast<float*>(s_raw + L::red), tid, bu, iu, bd, id);
+        // every warp finds the exact (largest root, first index attaining it) of ITS bins with one square root per
+        // hypothesis; combining the R0 results by value, then index, is exact for the frame
+        argmax_exact2<kLongNB>(pu, pd, kk, ok, bu, iu, bd, id);
+        {
+            float4* red = reinterpret_cast<float4*>(s_raw + L::red);
+            if (lane == 0) red[warp] = make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id));
+            __syncthreads();
+            if (tid == 0) {
+                for (int w2 = 1; w2 < R0; ++w2) {
+                    const float4 v = red[w2];
+                    argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
+                    argmax_combine(bd, id, v.z, __float_as_uint(v.w));
+                }
+            }
+        }
 #endif
         if (tid == 0) {
             if (p.mag_up) p.mag_up[f] = bu;
@@ -570,8 +544,8 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
         cluster_sync_all();
         // ---- split, squared magnitude, arg-max over the bins of this CTA's sub-sequences ----
         // thread -> (dl = tid & 7, c = tid >> 3 + 32 j): bins of one c are spread over 8 threads; ascending k per thread.
-        // Each CTA finds the exact (largest root, first index attaining it) of ITS bins with one square root per
-        // hypothesis; CTA 0 combines the CL results by value, then index — exact for the whole frame.
+        // Each WARP finds the exact (largest root, first index attaining it) of ITS bins with one square root per
+        // hypothesis and hands it to CTA 0, which combines the CL W results by value, then index — exact for the frame.
         float pu[kLongNB], pd[kLongNB];
         uint32_t kk[kLongNB];
         bool ok[kLongNB];
@@ -605,14 +579,14 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
         }
         float bu, bd;
         uint32_t iu, id;
-        block_argmax2<W, kLongNB>(pu, pd, kk, ok, reinterpret_cast<float*>(s_raw + L::red + 64), tid, bu, iu, bd, id);
-        if (tid == 0) st_cluster_f4(red0 + rank * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
+        argmax_exact2<kLongNB>(pu, pd, kk, ok, bu, iu, bd, id);
+        if (lane == 0) st_cluster_f4(red0 + (rank * W + warp) * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
         cluster_sync_all();                              // results are in CTA 0; all remote reads of this frame are done
         if (rank == 0 && tid == 0) {
             const float4* r4 = reinterpret_cast<const float4*>(s_raw + L::red);
             float4 v = r4[0];
             bu = v.x; iu = __float_as_uint(v.y); bd = v.z; id = __float_as_uint(v.w);
-            for (int r = 1; r < CL; ++r) {
+            for (int r = 1; r < CL * W; ++r) {
                 v = r4[r];
                 argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
                 argmax_combine(bd, id, v.z, __float_as_uint(v.w));

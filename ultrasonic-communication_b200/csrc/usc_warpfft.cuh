@@ -236,30 +236,42 @@ __device__ __forceinline__ void peak_window(const float (&zr)[32], const float (
     peak_tail<NB>(pw, lane, bw2, best, best_idx);
 }
 
-// peak_tail for the two candidate sets of a packed pass, side by side so that the warp-wide reductions of the two
-// searches overlap; results equal peak_tail's, bit for bit.
-template <int NB>
-__device__ __forceinline__ void peak_tail_pair(const float (&pa)[NB], const float (&pb)[NB], int lane, uint32_t bw2,
-                                               float& bestA, uint32_t& idxA, float& bestB, uint32_t& idxB) {
+// argmax_exact for two candidate sets that share their indices (the two hypotheses / frames of a packed pass), side by
+// side so that the warp-wide reductions of the two searches overlap.
+template <int NC>
+__device__ __forceinline__ void argmax_exact2(const float (&pa)[NC], const float (&pb)[NC], const uint32_t (&k)[NC], const bool (&ok)[NC],
+                                              float& bestA, uint32_t& idxA, float& bestB, uint32_t& idxB) {
     float qa = 0.0f, qb = 0.0f;                        // p >= 0: bit patterns order like values
 #pragma unroll
-    for (int d1 = 0; d1 < NB; ++d1) {
-        const bool in = (uint32_t) lane + 32u * d1 < bw2;
-        qa = in ? fmaxf(qa, pa[d1]) : qa;
-        qb = in ? fmaxf(qb, pb[d1]) : qb;
+    for (int c = 0; c < NC; ++c) {
+        qa = ok[c] ? fmaxf(qa, pa[c]) : qa;
+        qb = ok[c] ? fmaxf(qb, pb[c]) : qb;
     }
     const float maxA = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(qa)));
     const float maxB = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(qb)));
     const float thrA = same_root_threshold(maxA, bestA), thrB = same_root_threshold(maxB, bestB);
     uint32_t ka = 0xffffffffu, kb = 0xffffffffu;
 #pragma unroll
-    for (int d1 = NB - 1; d1 >= 0; --d1) {             // descending, so the lowest qualifying k of the lane survives
-        const uint32_t k = (uint32_t) lane + 32u * d1;
-        ka = (k < bw2 && pa[d1] >= thrA) ? k : ka;
-        kb = (k < bw2 && pb[d1] >= thrB) ? k : kb;
+    for (int c = NC - 1; c >= 0; --c) {                // k ascends with c: descending, the lowest qualifying k of the lane survives
+        ka = (ok[c] && pa[c] >= thrA) ? k[c] : ka;
+        kb = (ok[c] && pb[c] >= thrB) ? k[c] : kb;
     }
     idxA = __reduce_min_sync(0xffffffffu, ka);
     idxB = __reduce_min_sync(0xffffffffu, kb);
+}
+
+// peak_tail for the two candidate sets of a packed pass
+template <int NB>
+__device__ __forceinline__ void peak_tail_pair(const float (&pa)[NB], const float (&pb)[NB], int lane, uint32_t bw2,
+                                               float& bestA, uint32_t& idxA, float& bestB, uint32_t& idxB) {
+    uint32_t k[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) {
+        k[d1] = (uint32_t) lane + 32u * d1;
+        ok[d1] = k[d1] < bw2;
+    }
+    argmax_exact2<NB>(pa, pb, k, ok, bestA, idxA, bestB, idxB);
 }
 
 // squared magnitudes of the real-FFT bins k = lane + 32 d1, d1 < NB, of both halves (no peak search)
