@@ -25,16 +25,13 @@ namespace usc {
 #define USC_LONG_UNROLL 4
 #endif
 constexpr int kLongUnroll = USC_LONG_UNROLL;            // level-0 rounds whose loads are issued together
-#ifndef USC_LONG_OLD_TAIL
-#define USC_LONG_OLD_TAIL 0
-#endif
 #ifndef USC_LONG_STAGE
 #define USC_LONG_STAGE 1                                // PCM of the next frame staged in shared memory by TMA (0: gathered from global memory)
 #endif
 #ifndef USC_LONG_TMEM
 #define USC_LONG_TMEM 1                                 // frame-sized tables (chirp, Hann, level-0 twiddles) in tensor memory
 #endif
-// Tensor-memory layout of the frame-sized tables (R0 >= 4).  Thread tid handles a = tid + T i in level-0 round i and
+// Tensor-memory layout of the frame-sized tables.  Thread tid handles a = tid + T i in level-0 round i and
 // always needs the same table entries: the (up, down) chirp and Hann values of m = a + 1024 b, b < R0, and the level-0
 // twiddles W^(a d), d = 1..R0-1 — 8 R0 - 2 words, padded to 8 R0 columns per round, 32 / R0 rounds: 256 columns of the
 // thread's own TMEM lane (warps 4..7 of the 8-warp form take columns 256..511).  The tables total 30 KB per 8 KB of
@@ -44,6 +41,7 @@ template <int R0> struct long_tmem {
                          cols = R0 == 8 ? 512 : 256;
 };
 template <int N> struct ldtm_n;
+template <> struct ldtm_n<16> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[16]) { ldtm16(ta, t); } };
 template <> struct ldtm_n<32> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[32]) { ldtm32(ta, t); } };
 template <> struct ldtm_n<64> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[64]) { ldtm64(ta, t); } };
 constexpr int kLongNB = 5;                            // c < 160 covers bandwidth2 / R0 <= 160
@@ -61,48 +59,62 @@ struct long_params {
     float* mag_up; uint32_t* idx_up; float* mag_down; uint32_t* idx_down; uint8_t* bit;
 };
 
-template <int R0> struct long_smem {
-    // pass twiddles | per warp d a 16 KB region: sub-sequence d as (re pair[1024], im pair[1024]); later tile (8 KB) + kept
-    // outputs | PCM stage of one frame (filled by TMA one frame ahead) | reduction slots | mbarrier | TMEM slot
-    static constexpr int tw = 0, sub = 8192, region = 16384, stage = sub + R0 * region, red = stage + ((USC_LONG_STAGE && R0 >= 4) ? R0 * 8192 : 0),
-                         bar = red + 3 * R0 * 16, tslot = bar + 8, total = tslot + 8;
+// FR frames per CTA (one group of R0 warps each): the 4096-point form carries two, so that its CTA has four warps — one per
+// TMEM lane quadrant — and two CTAs fill an SM like the 8192-point form.
+template <int R0> struct long_geom {
+    static constexpr int FR = R0 == 2 ? 2 : 1, T = 32 * R0, threads = FR * T;
+    static constexpr bool staged = USC_LONG_STAGE != 0, tmem = USC_LONG_TMEM != 0;
 };
+template <int R0> struct long_smem {
+    using G = long_geom<R0>;
+    // pass twiddles | per group: { per warp d a 16 KB region: sub-sequence d as (re pair[1024], im pair[1024]); later tile
+    // (8 KB) + kept outputs | PCM stage of one frame (filled by TMA one frame ahead) } | reduction slots | mbarriers | TMEM slot
+    static constexpr int tw = 0, group0 = 8192, region = 16384, stage = R0 * region, group_bytes = stage + (G::staged ? R0 * 8192 : 0),
+                         red = group0 + G::FR * group_bytes, bar = red + G::FR * R0 * 16, tslot = bar + G::FR * 8, total = tslot + 8;
+};
+
+__device__ __forceinline__ void group_sync(int group, int nthreads) {     // named barrier 1 + group: the warps of one frame
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(nthreads) : "memory");
+}
 
 template <typename PCM, int R0>
 __device__ __forceinline__ void demod_long_body(const long_params& p) {
     using L = long_smem<R0>;
+    using G = long_geom<R0>;
     using V2 = typename vec2<PCM>::type;
+    constexpr int T = G::T, FR = G::FR;
+    constexpr bool kStage = G::staged, kTmem = G::tmem;
+    using TM = long_tmem<R0>;
     extern __shared__ __align__(128) unsigned char s_raw[];
     float2* s_tw = reinterpret_cast<float2*>(s_raw + L::tw);
-    constexpr bool kStage = USC_LONG_STAGE && R0 >= 4;      // 4096 points: three staged CTAs per SM lose against four unstaged ones
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + L::bar);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int T = R0 * 32;
+    const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5;           // warp of the CTA (TMEM quadrant = cwarp & 3)
+    const int group = FR == 1 ? 0 : cwarp / R0, warp = cwarp - group * R0, tid = threadIdx.x - group * T;   // within the frame's group
+    unsigned char* gbase = s_raw + L::group0 + group * L::group_bytes;     // this group's regions and stage
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + L::bar) + group;
     constexpr uint32_t kFrameBytes = 2048u * R0 * 4u;
     const uint32_t nc = 1024u * R0;                    // complex length
     const PCM* pcm = static_cast<const PCM*>(p.pcm);
+    const size_t f0 = (size_t) blockIdx.x * FR + group, fstep = (size_t) gridDim.x * FR;
     auto fetch = [&](size_t f) {                       // one frame of PCM into the stage: 1-D TMA bulk copies, 16 KB each
         mbar_expect_tx(bar, kFrameBytes);
 #pragma unroll
         for (uint32_t o = 0; o < kFrameBytes; o += 16384u)
-            bulk_g2s(s_raw + L::stage + o, reinterpret_cast<const char*>(pcm + f * p.n) + o, kFrameBytes < 16384u ? kFrameBytes : 16384u, bar);
+            bulk_g2s(gbase + L::stage + o, reinterpret_cast<const char*>(pcm + f * p.n) + o, kFrameBytes < 16384u ? kFrameBytes : 16384u, bar);
     };
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (kStage && blockIdx.x < p.nframes) fetch(blockIdx.x);
+        if (kStage && f0 < p.nframes) fetch(f0);
     }
-    for (int i = tid; i < 1024; i += T) s_tw[i] = p.tw_pass[i];
-    constexpr bool kTmem = USC_LONG_TMEM && R0 >= 4;
-    using TM = long_tmem<R0 >= 4 ? R0 : 4>;
+    for (int i = threadIdx.x; i < 1024; i += G::threads) s_tw[i] = p.tw_pass[i];
     uint32_t tq = 0;
     if (kTmem) {
         uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw + L::tslot);
-        if (warp == 0) tmem_alloc<TM::cols>(s_tslot);
+        if (cwarp == 0) tmem_alloc<TM::cols>(s_tslot);
         tmem_fence_before_sync();
         __syncthreads();
         tmem_fence_after_sync();
-        tq = tmem_quadrant(*s_tslot, warp) + (warp >> 2) * 256u;
+        tq = tmem_quadrant(*s_tslot, cwarp) + (cwarp >> 2) * 256u;
 #pragma unroll 1
         for (int i = 0; i < TM::rounds; ++i) {            // this thread's table row, round by round
             const uint32_t a = tid + T * i;
@@ -136,13 +148,13 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
     for (int j = 0; j < kLongNB; ++j) w_split[j] = p.tw_master[min((uint32_t) (tid + T * j), bw2 - 1u)];
 
     uint32_t parity = 0;
-    for (size_t f = blockIdx.x; f < p.nframes; f += gridDim.x) {
-        const V2* stage = kStage ? reinterpret_cast<const V2*>(s_raw + L::stage) : reinterpret_cast<const V2*>(pcm + f * p.n);
+    for (size_t f = f0; f < p.nframes; f += fstep) {
+        const V2* stage = kStage ? reinterpret_cast<const V2*>(gbase + L::stage) : reinterpret_cast<const V2*>(pcm + f * p.n);
         if (kStage) {
             mbar_wait(bar, parity);                      // this frame's PCM has landed in the stage
             parity ^= 1u;
-        } else if (f + gridDim.x < p.nframes) {          // this CTA's next frame towards L2 while the current one computes
-            const char* nxt = reinterpret_cast<const char*>(pcm + (f + gridDim.x) * p.n);
+        } else if (f + fstep < p.nframes) {              // this group's next frame towards L2 while the current one computes
+            const char* nxt = reinterpret_cast<const char*>(pcm + (f + fstep) * p.n);
             constexpr uint32_t per_thread = 2048u * R0 * 4u / T;                             // 256 bytes
 #pragma unroll
             for (uint32_t o = 0; o < per_thread; o += 128u)
@@ -196,16 +208,16 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
                 for (int d = 0; d < R0; ++d) {
                     float2 xr = re[d], xi = im[d];
                     if (d != 0) cmul2(re[d], im[d], twd[d].x, twd[d].y, xr, xi);
-                    float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + d * L::region);
+                    float2* reg = reinterpret_cast<float2*>(gbase + d * L::region);
                     reg[a] = xr;
                     reg[1024 + a] = xi;
                 }
             }
         }
-        __syncthreads();                                 // sub-sequences parked; every thread is done with the stage
-        if (kStage && tid == 0 && f + gridDim.x < p.nframes) fetch(f + gridDim.x);   // next frame arrives under the core and the split
+        group_sync(group, T);                            // sub-sequences parked; every thread of the group is done with the stage
+        if (kStage && tid == 0 && f + fstep < p.nframes) fetch(f + fstep);   // next frame arrives under the core and the split
         // ---- 1024-point packed core on sub-sequence `warp` ----
-        float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + warp * L::region);
+        float2* reg = reinterpret_cast<float2*>(gbase + warp * L::region);
         {
             float2 re[32], im[32];
 #pragma unroll
@@ -216,7 +228,7 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
             __syncwarp();
             fft1024_pair(re, im, reg, s_tw, lane);           // first 8 KB of the region is now the exchange tile
             // keep Y_d[c] for c < 160 (elements 0..4) and c >= 864 (elements 27..31)
-            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + keep_off<R0>(warp));
+            float4* keep = reinterpret_cast<float4*>(gbase + warp * L::region + keep_off<R0>(warp));
 #pragma unroll
             for (int j = 0; j < kLongNB; ++j) {
                 keep[lane + 32 * j] = make_float4(re[j].x, re[j].y, im[j].x, im[j].y);
@@ -224,11 +236,11 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
                                                               im[32 - kLongNB + j].x, im[32 - kLongNB + j].y);
             }
         }
-        __syncthreads();
+        group_sync(group, T);
         // ---- split, squared magnitude, exact arg-max over k < bw2 ----
         auto Y = [&](uint32_t k) -> float4 {             // Z[k] = Y_{k mod R0}[k / R0], only kept ranges are asked for
             const uint32_t d = k & (R0 - 1u), c = k / R0;
-            const float4* kp = reinterpret_cast<const float4*>(s_raw + L::sub + d * L::region + keep_off<R0>(d));
+            const float4* kp = reinterpret_cast<const float4*>(gbase + d * L::region + keep_off<R0>(d));
             return c < (uint32_t) kLongKeep ? kp[c] : kp[kLongKeep + (c - (1024u - kLongKeep))];
         };
         float pu[kLongNB], pd[kLongNB];
@@ -254,65 +266,31 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
             pu[j] = pw.x;
             pd[j] = pw.y;
         }
-        float bu, bd;
-        uint32_t iu, id;
-#if USC_LONG_OLD_TAIL
-        bu = -INFINITY; bd = -INFINITY; iu = 0xffffffffu; id = 0xffffffffu;
-#pragma unroll
-        for (int j = 0; j < kLongNB; ++j) {
-            if (!ok[j]) break;
-            const float mu = __fsqrt_rn(pu[j]), md = __fsqrt_rn(pd[j]);
-            if (iu == 0xffffffffu || bu < mu) { bu = mu; iu = kk[j]; }
-            if (id == 0xffffffffu || bd < md) { bd = md; id = kk[j]; }
-        }
-        warp_argmax(bu, iu);
-        warp_argmax(bd, id);
-        {
-            float* red = reinterpret_cast<float*>(s_raw + L::red);
-            if (lane == 0) {
-                red[warp * 4 + 0] = bu; reinterpret_cast<uint32_t*>(red)[warp * 4 + 1] = iu;
-                red[warp * 4 + 2] = bd; reinterpret_cast<uint32_t*>(red)[warp * 4 + 3] = id;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                for (int w2 = 1; w2 < R0; ++w2) {
-                    argmax_combine(bu, iu, red[w2 * 4 + 0], reinterpret_cast<uint32_t*>(red)[w2 * 4 + 1]);
-                    argmax_combine(bd, id, red[w2 * 4 + 2], reinterpret_cast<uint32_t*>(red)[w2 * 4 + 3]);
-                }
-            }
-        }
-#else
         // every warp finds the exact (largest root, first index attaining it) of ITS bins with one square root per
         // hypothesis; combining the R0 results by value, then index, is exact for the frame
+        float bu, bd;
+        uint32_t iu, id;
         argmax_exact2<kLongNB>(pu, pd, kk, ok, bu, iu, bd, id);
-        {
-            float4* red = reinterpret_cast<float4*>(s_raw + L::red);
-            if (lane == 0) red[warp] = make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id));
-            __syncthreads();
-            if (tid == 0) {
-                for (int w2 = 1; w2 < R0; ++w2) {
-                    const float4 v = red[w2];
-                    argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
-                    argmax_combine(bd, id, v.z, __float_as_uint(v.w));
-                }
-            }
-        }
-#endif
+        float4* red = reinterpret_cast<float4*>(s_raw + L::red) + group * R0;
+        if (lane == 0) red[warp] = make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id));
+        group_sync(group, T);
         if (tid == 0) {
+            for (int w2 = 1; w2 < R0; ++w2) {
+                const float4 v = red[w2];
+                argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
+                argmax_combine(bd, id, v.z, __float_as_uint(v.w));
+            }
             if (p.mag_up) p.mag_up[f] = bu;
             if (p.idx_up) p.idx_up[f] = iu;
             if (p.mag_down) p.mag_down[f] = bd;
             if (p.idx_down) p.idx_down[f] = id;
             if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
         }
-#if USC_LONG_OLD_TAIL
-        __syncthreads();
-#endif
     }
     if (kTmem) {
         tmem_fence_before_sync();
         __syncthreads();
-        if (warp == 0) tmem_dealloc<TM::cols>(*reinterpret_cast<uint32_t*>(s_raw + L::tslot));
+        if (cwarp == 0) tmem_dealloc<TM::cols>(*reinterpret_cast<uint32_t*>(s_raw + L::tslot));
     }
 }
 
@@ -320,39 +298,35 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
 #define USC_LONG_MAXREG4 224
 #endif
 template <typename PCM, int R0>
-__global__ void __launch_bounds__(R0 * 32, 1) k_demod_long(long_params p) { demod_long_body<PCM, R0>(p); }
-// The 4-warp form runs two CTAs per SM, which the register file allows only up to 224 registers per thread (at 238 the
-// occupancy calculator reports one CTA and the run time rises by 40 %): an explicit register cap instead of launch bounds.
-template <typename PCM>
-__global__ void __maxnreg__(USC_LONG_MAXREG4) k_demod_long4(long_params p) { demod_long_body<PCM, 4>(p); }
+__global__ void __launch_bounds__(long_geom<R0>::threads, 1) k_demod_long(long_params p) { demod_long_body<PCM, R0>(p); }
+// The 128-thread forms (8192 points; 4096 points with two frames per CTA) run two CTAs per SM: 2 x 107 KB of shared memory,
+// 2 x 256 TMEM columns, and at most 224 registers per thread — an explicit cap, because launch bounds of 128 threads let
+// ptxas take up to 255 (it took 238-244).
+template <typename PCM, int R0>
+__global__ void __maxnreg__(USC_LONG_MAXREG4) k_demod_long4(long_params p) { demod_long_body<PCM, R0>(p); }
 template <typename PCM, int R0> struct long_kernel { static constexpr auto fn = k_demod_long<PCM, R0>; };
-template <typename PCM> struct long_kernel<PCM, 4> { static constexpr auto fn = k_demod_long4<PCM>; };
+template <typename PCM> struct long_kernel<PCM, 4> { static constexpr auto fn = k_demod_long4<PCM, 4>; };
+template <typename PCM> struct long_kernel<PCM, 2> { static constexpr auto fn = k_demod_long4<PCM, 2>; };
 
 template <typename PCM, int R0>
 static cudaError_t launch_long_t(const long_params& p, int num_sms, cudaStream_t st) {
     constexpr auto kernel = long_kernel<PCM, R0>::fn;
-    static per_device<int> per_sm_pd;                    // resident CTAs per SM (0: not configured on this device yet)
-    int& per_sm = per_sm_pd.get();
+    using G = long_geom<R0>;
+    static per_device<bool> configured_pd;
+    bool& configured = configured_pd.get();
     const int smem = long_smem<R0>::total;
-    if (!per_sm) {
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        // The occupancy calculator reports ONE resident CTA for any kernel that allocates tensor memory (it cannot know how
-        // many columns a CTA takes), although two CTAs with 256 columns each do run side by side (ncu: 8 warps per SM active):
-        // with the tables in TMEM the count comes from the kernel's own budget — two CTAs of the 4-warp form (2 x 107 KB of
-        // shared memory, 2 x 256 TMEM columns, 222 registers), one of the 8-warp form.
-        if (USC_LONG_TMEM && R0 >= 4) {
-            per_sm = R0 == 4 ? 2 : 1;
-        } else {
-            int occ = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, R0 * 32, smem);
-            if (e != cudaSuccess) return e;
-            if (occ < 1) return cudaErrorLaunchOutOfResources;
-            per_sm = occ;
-        }
+        configured = true;
     }
-    size_t ctas = p.nframes < (size_t) num_sms * per_sm ? p.nframes : (size_t) num_sms * per_sm;
-    kernel<<<(int) ctas, R0 * 32, smem, st>>>(p);
+    // Resident CTAs per SM from the kernel's own budget: the occupancy calculator reports ONE for any kernel that allocates
+    // tensor memory (it cannot know how many columns a CTA takes), although two CTAs with 256 columns each do run side by
+    // side (ncu: 8 warps per SM active).  128-thread forms: two CTAs; the 8-warp form (16384 points, 512 columns): one.
+    const int per_sm = G::threads == 128 ? 2 : 1;
+    const size_t want = (p.nframes + G::FR - 1) / G::FR;
+    size_t ctas = want < (size_t) num_sms * per_sm ? want : (size_t) num_sms * per_sm;
+    kernel<<<(int) ctas, G::threads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
