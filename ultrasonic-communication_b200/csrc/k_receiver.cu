@@ -20,9 +20,11 @@ namespace usc {
 constexpr int kRxWarps = 8;
 constexpr int kRxNB = 5;
 // shared memory (float2 units): per-warp 8 KB tile | per-warp state (128 B) | TMEM slot | [MULTI] per-warp sum of the window union
-constexpr int kRxTile = 0, kRxState = kRxWarps * 1024, kRxSlot = kRxState + kRxWarps * 16, kRxSum = kRxSlot + 2;
+constexpr int kRxTile = 0, kRxState = kRxWarps * 1024, kRxSlot = kRxState + kRxWarps * 16, kRxBar = kRxSlot + 2, kRxSum = kRxBar + kRxWarps;
 constexpr int kRxSmem = kRxSum * 8;
-constexpr int kRxSmemMulti = kRxSmem + kRxWarps * 1792 * 8;            // + per-warp sum of the window union (synchronous addition)
+// + per warp 14 KB for the union of a frame's four search windows (1.75 N samples): the staged PCM of K4 (filled by one TMA
+// bulk copy per work item, one item ahead), or its K-frame sum (synchronous addition)
+constexpr int kRxSmemMulti = kRxSmem + kRxWarps * 1792 * 8;
 
 // The four tables every dsp() reads — up chirp, down chirp, Hann, inter-pass twiddles — live in tensor memory, one row per
 // lane (usc_tmem.cuh; K1 keeps them the same way): columns 4 b .. 4 b + 3 = (up[2m], down[2m], up[2m+1], down[2m+1]) of
@@ -43,6 +45,7 @@ struct rx_params {
     uint32_t sync_add; float* ss_mag; uint32_t* ss_idx;
     // chunked operation of K7: `carry` frames of history precede the nframes new ones; state is loaded / stored
     uint32_t carry; rx_state_rec* rx_state;
+    uint32_t staged;        // K4: stream bases are 16-byte aligned, so window unions can arrive by TMA bulk copies
 };
 
 template <typename PCM>
@@ -409,15 +412,83 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
     const rx_tables tb = load_tables(p, s_rx, lane, warp);
     float2* tile = s_rx + kRxTile + warp * 1024;
-    float2* sum = s_rx + kRxSum + warp * 1792;                                     // MULTI only: 14 KB per warp behind the common layout
+    float2* sum = s_rx + kRxSum + warp * 1792;                                     // 14 KB per warp: staged union (PCM) or its K-frame sum
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_rx + kRxBar) + warp;
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const size_t total = (size_t) p.nstreams * p.nframes;
     const size_t nwarps = (size_t) gridDim.x * kRxWarps;
+    const int64_t nsamples = (int64_t) p.nframes * N;
+    using V2 = typename vec2<PCM>::type;
+    const bool staged = !MULTI && p.staged != 0;
+    // the union of work item wi's four windows: [base, base + 3584) of its stream; `inside`: wholly within the stream
+    auto item_union = [&](size_t wi, const PCM*& strm, int64_t& base) -> bool {
+        const uint32_t si = (uint32_t) (wi / p.nframes), ti = (uint32_t) (wi - (size_t) si * p.nframes);
+        strm = static_cast<const PCM*>(p.pcm) + (size_t) si * p.stream_stride;
+        base = ((int64_t) ti - 2) * N + N / 2 + (ti & 1u) * offset;
+        return base >= 0 && base + 3584 <= nsamples;
+    };
+    auto fetch_union = [&](size_t wi) {                                            // lane 0: one 14 KB bulk copy, if the union is inside
+        const PCM* strm;
+        int64_t base;
+        if (wi < total && item_union(wi, strm, base)) {
+            mbar_expect_tx(bar, 14336u);
+            bulk_g2s(sum, strm + base, 14336u, bar);
+        }
+    };
+    uint32_t parity = 0;
+    if (staged) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fetch_union((size_t) blockIdx.x * kRxWarps + warp);
+        }
+        __syncwarp();
+    }
     for (size_t w = (size_t) blockIdx.x * kRxWarps + warp; w < total; w += nwarps) {
         const uint32_t s = (uint32_t) (w / p.nframes), t = (uint32_t) (w - (size_t) s * p.nframes);
         const PCM* stream = static_cast<const PCM*>(p.pcm) + (size_t) s * p.stream_stride;
-        const int64_t nsamples = (int64_t) p.nframes * N;
         const int64_t fifo0 = ((int64_t) t - 2) * N;
+        if (staged) {
+            // ---- staged form: the union arrived by TMA while the previous item computed ----
+            const PCM* strm;
+            int64_t base;
+            const bool inside = item_union(w, strm, base);
+            if (inside) {
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            } else if (lane == 0) {
+                fetch_union(w + nwarps);                                           // this item gathers from global memory: the stage is free
+            }
+            for (uint32_t i = 0; i < 4; i += 2) {
+                const uint32_t pa = N / 2 + (t & 1u) * offset + shift * i, pb = pa + shift;
+                float ma, mb;
+                uint32_t ka, kb;
+                if (inside) {
+                    float2 re[32], im[32];
+                    const V2* sa = reinterpret_cast<const V2*>(sum) + (shift / 2) * i + lane;
+                    const V2* sb = sa + shift / 2;
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) {
+                        const V2 ra = sa[32 * b], rb = sb[32 * b];
+                        re[b] = make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x));
+                        im[b] = make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y));
+                    }
+                    if (i == 2) {                                                  // the stage has been consumed: next item's union
+                        __syncwarp();
+                        if (lane == 0) fetch_union(w + nwarps);
+                    }
+                    dsp_pair_tail(re, im, RX_UP_UP, tb, tile, ws, lane, p.bandwidth2, ma, ka, mb, kb);
+                } else {
+                    dsp_pair<PCM, false>(stream, nsamples, fifo0 + pa, fifo0 + pb, RX_UP_UP, tb, 1, tile, ws, lane, p.bandwidth2,
+                                         ma, ka, mb, kb);
+                }
+                if (lane == 0) {
+                    p.ss_mag[w * 4 + i] = ma; p.ss_idx[w * 4 + i] = ka;
+                    p.ss_mag[w * 4 + i + 1] = mb; p.ss_idx[w * 4 + i + 1] = kb;
+                }
+            }
+            continue;
+        }
         {   // pull the next work item's window union (1.75 N samples = 14 KB) towards L2 while this one computes
             const size_t wn = w + nwarps;
             if (wn < total) {
@@ -434,7 +505,6 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
         if (MULTI) {
             // Synchronous addition: the four search windows overlap (hop N/4), so the K-frame sum is formed ONCE over
             // their union (1.75 N samples, oldest FIFO first as the per-window form does) and parked in shared memory.
-            using V2 = typename vec2<PCM>::type;
             const int64_t base = fifo0 + N / 2 + (t & 1u) * offset;
             const int64_t oldest = base - (int64_t) (p.sync_add - 1) * N;
             const bool inside = oldest >= 0 && base + 3584 <= nsamples;
@@ -517,8 +587,8 @@ static cudaError_t rx_prepare() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_receiver_run<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
     if ((e = cudaFuncSetAttribute(k_receiver_run<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
     if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
     if ((e = cudaFuncSetAttribute(k_sync_search<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
     done = true;
@@ -545,12 +615,13 @@ cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st)
     cudaError_t e = rx_prepare();
     if (e != cudaSuccess) return e;
     const bool multi = p.sync_add > 1;
+    p.staged = (reinterpret_cast<uintptr_t>(a.pcm) % 16u == 0 && a.stream_stride % 4u == 0) ? 1u : 0u;
     if (a.pcm_format == 1u) {
         if (multi) k_sync_search<int32_t, true><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
-        else k_sync_search<int32_t, false><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+        else k_sync_search<int32_t, false><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
     } else {
         if (multi) k_sync_search<float, true><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
-        else k_sync_search<float, false><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+        else k_sync_search<float, false><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
     }
     return cudaGetLastError();
 }
