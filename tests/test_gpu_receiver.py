@@ -95,6 +95,27 @@ def test_sync_search_matches_oracle(h, rx, sync_add):
         assert np.array_equal(mag[s].view(np.uint32), wm.view(np.uint32))
 
 
+def test_sync_search_unaligned_streams_take_the_gathered_form(h, rx):
+    """K4 stages a frame's window union by TMA bulk copies when the streams are 16-byte aligned; a PCM pointer or a stream
+    stride that is not must give the same bits through the gathered form."""
+    pcm = _streams()[:3, :40]
+    S, F = pcm.shape[:2]
+    stride = F * N + 2                                        # the API asks for 8-byte alignment only: stride = 2 (mod 4) samples
+    flat = np.zeros(2 + S * stride, dtype=np.int32)
+    for s in range(S):
+        flat[2 + s * stride: 2 + s * stride + F * N] = pcm[s].reshape(-1)
+    d = h.buffer(flat)
+    d_m, d_i = h.empty(4 * S * F * 4), h.empty(4 * S * F * 4)
+    h.sync_search(d.ptr + 8, usc.PCM_I32, S, F, stride, 1, d_m, d_i)      # base pointer 8 bytes past a 16-byte boundary
+    h.sync()
+    mag = d_m.to_numpy(np.float32).reshape(S, F, 4)
+    idx = d_i.to_numpy(np.uint32).reshape(S, F, 4)
+    for s in range(S):
+        wm, wi = R.sync_search(rx, pcm[s], 1)
+        assert np.array_equal(idx[s], wi)
+        assert np.array_equal(mag[s].view(np.uint32), wm.view(np.uint32))
+
+
 def test_synchronous_addition_raises_the_peak(h):
     """SynchronousAddition.ipynb cells 5-6: adding K frame-aligned preamble frames grows the
     de-chirped peak ~K-fold while noise grows ~sqrt(K).  Needs a transmitter whose symbol period is

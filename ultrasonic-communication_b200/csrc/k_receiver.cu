@@ -17,9 +17,6 @@
 
 namespace usc {
 
-#ifndef USC_RX_L1_PREFETCH
-#define USC_RX_L1_PREFETCH 1
-#endif
 constexpr int kRxWarps = 8;
 constexpr int kRxNB = 5;
 // shared memory (float2 units): per-warp 8 KB tile | per-warp state (128 B) | TMEM slot | [MULTI] per-warp sum of the window union
@@ -297,29 +294,6 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
                 }
                 float ma, mb;
                 uint32_t ka, kb;
-#if USC_RX_L1_PREFETCH
-                {   // the windows the NEXT pass will most likely read (same mode, turn flips, sync_position stays) towards L1:
-                    // its gather then finds them a hit away instead of an L2 round trip per pass
-                    int64_t na, nb;
-                    if (searching) {
-                        na = pass == 0 ? fifo0 + qa + 2 * shift : fifo0 + N + N / 2 + (turn ^ 1u) * offset;
-                        nb = na + shift;
-                    } else if (pass == 0) {
-                        na = fifo0 + (int64_t) pos - offset;
-                        nb = fifo0 + (int64_t) pos + offset;
-                    } else {
-                        na = nb = fifo0 + N + (int64_t) pos;
-                    }
-                    if (na >= gmin && nb + 2048 <= nsamples) {
-                        const char* ca = reinterpret_cast<const char*>(stream + na) + lane * 128;
-                        const char* cb = reinterpret_cast<const char*>(stream + nb) + lane * 128;
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(ca));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(ca + 4096));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(cb));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(cb + 4096));
-                    }
-                }
-#endif
                 dsp_pair<PCM, false>(stream, nsamples, fifo0 + (a_ok ? qa : (int64_t) pos), fifo0 + (b_ok ? qb : (int64_t) pos), chirps, tb,
                               1, tile, ws, lane, bw2, ma, ka, mb, kb, gmin);
                 if (searching) {
