@@ -30,6 +30,12 @@ constexpr int kWarpsPerCta = 4;
 #ifndef USC_K1_TMEM
 #define USC_K1_TMEM 1                                   // tables in tensor memory (0: in shared memory, the round-1 form)
 #endif
+#ifndef USC_K1_WS_REGS
+#define USC_K1_WS_REGS 1                                // split twiddles of the bins below bandwidth2 in registers (0: in shared memory)
+#endif
+#ifndef USC_K1_TW32
+#define USC_K1_TW32 1                                   // sixteen (0: eight) inter-pass twiddles per TMEM round trip
+#endif
 #ifndef USC_K1_TG
 #define USC_K1_TG 4                                     // front-end rows per TMEM load group (4 or 8)
 #endif
@@ -135,6 +141,11 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
     __syncthreads();
     tmem_fence_after_sync();
 
+#if USC_K1_WS_REGS
+    float2 ws_r[NB];
+#pragma unroll
+    for (int d1 = 0; d1 < NB; ++d1) ws_r[d1] = p.tw_split[lane + 32 * d1];
+#endif
     uint32_t parity = 0;
     for (; f < p.nframes; f += nwarps) {
         mbar_wait(bar, parity);
@@ -184,6 +195,22 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
         }
 #if USC_K1_TMEM
         fft_base2_prod<32>(re, im, one);
+#if USC_K1_TW32
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {                                 // inter-pass twiddle, both hypotheses: 16 per TMEM round trip
+            uint32_t t[32];
+            ldtm32(tq + L::t_tw + 32 * g, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int d = 16 * g + j;
+                if (d == 0) continue;
+                float2 tr, ti;
+                cmul2(re[d], im[d], __uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]), tr, ti);
+                re[d] = tr;
+                im[d] = ti;
+            }
+        }
+#else
 #pragma unroll
         for (int g = 0; g < 4; ++g) {                                 // inter-pass twiddle, both hypotheses: 8 per TMEM round trip
             uint32_t t[16];
@@ -198,6 +225,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
                 im[d] = ti;
             }
         }
+#endif
 #else
         fft_base2_prod<32>(re, im, s_tw[lane].x);                     // W^0 = 1.0f, read from the table: opaque to the compiler
 #pragma unroll
@@ -226,7 +254,11 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
         fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
+#if USC_K1_WS_REGS
+        peak_window_pair<NB>(re, im, ws_r, lane, p.bandwidth2, mu, iu, md, id);
+#else
         peak_window_pair_s<NB>(re, im, s_ws, lane, p.bandwidth2, mu, iu, md, id);
+#endif
         if (lane == 0) {
             if (p.mag_up) p.mag_up[f] = mu;
             if (p.idx_up) p.idx_up[f] = iu;
