@@ -43,13 +43,14 @@ constexpr int kWarpsPerCta = 4;
 // (.x = up-chirp, .y = down-chirp).  The PCM, the Hann table and the inter-pass twiddles are loaded
 // once for both; the two 32-point register FFTs issue as FADD2/FFMA2.
 //
-// Persistent: ONE CTA of 8 warps per SM, every warp loops over frames.  Shared memory (224 KB):
-//   twiddles 8 KB | (up,down) chirp table 16 KB | Hann 8 KB | per warp: exchange tile 16 KB + PCM stage 8 KB
+// Persistent: ONE CTA of 8 warps per SM, every warp loops over frames.  Shared memory (164 KB):
+//   per warp: exchange tile 8 KB + PCM stage 8 KB | mbarriers
 // The PCM of a warp's NEXT frame is fetched by a 1-D TMA bulk copy (cp.async.bulk, mbarrier
 // completion) issued right after the current frame has been pulled into registers, so DRAM latency
-// is hidden behind a whole frame of arithmetic; tables sit in shared memory so every operand of
-// the front end is one LDS away.  The L1/shared data path (128 B per clock per SM) carries, per
-// frame, PCM 8 KB + table 16 KB + Hann 8 KB + exchange 2 x 16 KB + twiddles 8 KB = 72 KB.
+// is hidden behind a whole frame of arithmetic.  The (up, down) chirp table, the Hann table and the inter-pass
+// twiddles are read from TENSOR MEMORY (usc_tmem.cuh: one lane-private row of 256 columns per lane, filled once per
+// CTA), which takes 254 of the 633 wavefronts a frame used to cost off the L1/shared data path (128 B per clock per
+// SM): that path now carries PCM 8 KB + exchange 2 x 16 KB per frame, and the kernel is bound by the fp32 pipe.
 constexpr int kDualWarps = 8;                         // warps per CTA of the pair kernel below
 
 // Shared memory of the dual kernel with W warps: twiddles 8 KB | (up,down) table 16 KB | Hann 8 KB |

@@ -4,16 +4,18 @@
 //
 // The N/2-point complex FFT has the canonical plan [R0, 32, 32]: one radix-R0 level over a
 // (m = a + 1024 b), then R0 independent 1024-point transforms whose outputs interleave
-// (k = R0 c + d).  One CTA of R0 warps owns a frame:
-//   level 0   all threads: gather z[a + 1024 b] straight from global PCM (coalesced across a), apply
+// (k = R0 c + d).  A group of R0 warps owns a frame (one group per CTA; two at 4096 points):
+//   stage     the frame's PCM arrives in shared memory by TMA bulk copies issued one frame ahead
+//   level 0   all threads: z[a + 1024 b] from the stage; chirp, Hann and level-0 twiddle values of the thread's a from
+//             its own row of TENSOR MEMORY (one tcgen05.ld per round: the frame-sized tables, 60-240 KB, live there);
 //             de-chirp x Hann for both hypotheses (f32x2 halves), radix-R0 butterfly, x W^(a d), park
 //             sub-sequence d in shared memory
 //   core      warp d runs the packed 32x32 register core of K1 on sub-sequence d; its parked region
 //             doubles as the exchange tile once the data is in registers; only c < ceil(bw2/R0) and the
 //             partner range near 1024 are produced (pruned last pass)
 //   split     the needed sub-spectra meet in shared memory; threads take bins k < bw2, fetch
-//             Z[k] = Y_{k mod R0}[k / R0] and Z[n-k], apply the real split, magnitudes, block arg-max
-//             (first occurrence, exact: every root is taken — 2*bw2 roots are noise next to the FFT).
+//             Z[k] = Y_{k mod R0}[k / R0] and Z[n-k], apply the real split, squared magnitudes; every warp finds the
+//             exact (largest root, first index) of its bins with one square root (usc_warpfft.cuh), one thread combines
 #include "usc_kernels.cuh"
 #include "usc_launch.h"
 #include "usc_warpfft.cuh"
