@@ -31,10 +31,13 @@ constexpr int kWarpsPerCta = 4;
 #define USC_K1_TMEM 1                                   // tables in tensor memory (0: in shared memory, the round-1 form)
 #endif
 #ifndef USC_K1_WS_REGS
-#define USC_K1_WS_REGS 1                                // split twiddles of the bins below bandwidth2 in registers (0: in shared memory)
+#define USC_K1_WS_REGS 0                                // split twiddles of the bins below bandwidth2 in shared memory (1: in registers)
 #endif
 #ifndef USC_K1_TW32
-#define USC_K1_TW32 1                                   // sixteen (0: eight) inter-pass twiddles per TMEM round trip
+#define USC_K1_TW32 0                                   // eight inter-pass twiddles per TMEM round trip (1: sixteen, 2: four)
+#endif
+#ifndef USC_K1_PAD
+#define USC_K1_PAD 1                                    // exchange tile with padded rows (0: XOR-swizzled 32 x 32)
 #endif
 #ifndef USC_K1_TG
 #define USC_K1_TG 4                                     // front-end rows per TMEM load group (4 or 8)
@@ -57,7 +60,7 @@ constexpr int kDualWarps = 8;                         // warps per CTA of the pa
 // per warp: XOR-swizzled 32x32 float2 tile 8 KB + PCM stage 8 KB | mbarriers.
 template <int W> struct dual_smem {
 #if USC_K1_TMEM
-    static constexpr int tw = 0, ud = 0, hann = 0, warp = 0, warp_bytes = 8192 + 8192,     // the three tables live in TMEM
+    static constexpr int tw = 0, ud = 0, hann = 0, warp = 0, warp_bytes = (USC_K1_PAD ? 8704 : 8192) + 8192,     // the three tables live in TMEM
 #else
     static constexpr int tw = 0, ud = 8192, hann = ud + 16384, warp = hann + 8192, warp_bytes = 8192 + 8192,
 #endif
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* tile = reinterpret_cast<float2*>(s_raw + L::warp + warp * L::warp_bytes);
     using V2 = typename vec2<PCM>::type;
-    V2* xstage = reinterpret_cast<V2*>(s_raw + L::warp + warp * L::warp_bytes + 8192);
+    V2* xstage = reinterpret_cast<V2*>(s_raw + L::warp + warp * L::warp_bytes + (USC_K1_PAD ? 8704 : 8192));
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + L::bar) + warp;
 
     const size_t nwarps = (size_t) gridDim.x * W;
@@ -161,6 +164,9 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
 #if USC_K1_TG == 8
             uint32_t c[32], w[16];
             ldtm32_16(tq + L::t_ud + 32 * g, c, tq + L::t_hann + 16 * g, w);
+#elif USC_K1_TG == 2
+            uint32_t c[8], w[4];
+            ldtm8_4(tq + L::t_ud + 8 * g, c, tq + L::t_hann + 4 * g, w);
 #else
             uint32_t c[16], w[8];
             ldtm16_8(tq + L::t_ud + 16 * g, c, tq + L::t_hann + 8 * g, w);
@@ -196,7 +202,22 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
         }
 #if USC_K1_TMEM
         fft_base2_prod<32>(re, im, one);
-#if USC_K1_TW32
+#if USC_K1_TW32 == 2
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {                                 // inter-pass twiddle, both hypotheses: 4 per TMEM round trip
+            uint32_t t[8];
+            ldtm8(tq + L::t_tw + 8 * g, t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = 4 * g + j;
+                if (d == 0) continue;
+                float2 tr, ti;
+                cmul2(re[d], im[d], __uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]), tr, ti);
+                re[d] = tr;
+                im[d] = ti;
+            }
+        }
+#elif USC_K1_TW32
 #pragma unroll
         for (int g = 0; g < 2; ++g) {                                 // inter-pass twiddle, both hypotheses: 16 per TMEM round trip
             uint32_t t[32];
@@ -240,6 +261,21 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
 #endif
         // exchange in two rounds (real parts, then imaginary parts): each 64-bit word is an (up, down)
         // register pair, so values land in place; XOR swizzle keeps both directions conflict-free
+#if USC_K1_PAD
+        // padded rows (33 float2): every store and load of a round is one base register plus an immediate offset
+#pragma unroll
+        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = re[d];
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) re[a] = tile[lane * kTileStride + a];
+        __syncwarp();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) tile[d * kTileStride + lane] = im[d];
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < 32; ++a) im[a] = tile[lane * kTileStride + a];
+        __syncwarp();
+#else
 #pragma unroll
         for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
         __syncwarp();
@@ -252,6 +288,7 @@ __global__ void __launch_bounds__(W * 32, 1) k_demod2048(demod_params p) {
 #pragma unroll
         for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
         __syncwarp();
+#endif
         fft_base2<32>(re, im);
         float mu, md;
         uint32_t iu, id;
@@ -533,7 +570,7 @@ static int grid_for(size_t nwork, int num_sms) {
 }
 
 #ifndef USC_DUAL_WARPS
-#define USC_DUAL_WARPS 8
+#define USC_DUAL_WARPS 12                                  // three warps per scheduler at <= 168 registers (8: two at <= 255)
 #endif
 template <int NB>
 static cudaError_t launch_demod_nb(const demod_params& p, uint32_t pcm_format, int num_sms, cudaStream_t st) {

@@ -71,6 +71,13 @@ __device__ __forceinline__ void ldtm16_8(uint32_t ta, uint32_t (&a)[16], uint32_
                  "tcgen05.wait::ld.sync.aligned;"
                  : USC_R8(a, 0), USC_R8(a, 8), USC_R8(b, 0) : "r"(ta), "r"(tb) : "memory");
 }
+// 8 + 4 columns (two front-end rows)
+__device__ __forceinline__ void ldtm8_4(uint32_t ta, uint32_t (&a)[8], uint32_t tb, uint32_t (&b)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%12];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8,%9,%10,%11}, [%13];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : USC_R8(a, 0), "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(ta), "r"(tb) : "memory");
+}
 // 32 + 16 columns (eight front-end rows)
 __device__ __forceinline__ void ldtm32_16(uint32_t ta, uint32_t (&a)[32], uint32_t tb, uint32_t (&b)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
