@@ -17,14 +17,22 @@
 
 namespace usc {
 
-constexpr int kRxWarps = 8;
 constexpr int kRxNB = 5;
+#ifndef USC_RX_WARPS
+#define USC_RX_WARPS 8                                  // K7 (12 = three warps per scheduler at 168 registers: 139 spilled words, 23.3 against 19.9 ms)
+#endif
+#ifndef USC_SS_WARPS
+#define USC_SS_WARPS 8                                  // K4 without synchronous addition (12: gathered instead of TMA-staged windows)
+#endif
 // shared memory (float2 units): per-warp 8 KB tile | per-warp state (128 B) | TMEM slot | [MULTI] per-warp sum of the window union
-constexpr int kRxTile = 0, kRxState = kRxWarps * 1024, kRxSlot = kRxState + kRxWarps * 16, kRxBar = kRxSlot + 2, kRxSum = kRxBar + kRxWarps;
-constexpr int kRxSmem = kRxSum * 8;
-// + per warp 14 KB for the union of a frame's four search windows (1.75 N samples): the staged PCM of K4 (filled by one TMA
-// bulk copy per work item, one item ahead), or its K-frame sum (synchronous addition)
-constexpr int kRxSmemMulti = kRxSmem + kRxWarps * 1792 * 8;
+template <int W> struct rx_smem {                       // W warps per CTA
+    static constexpr int tile_f2 = kTileFloat2;         // padded 32 x 33 float2 tile per warp (8448 bytes)
+    static constexpr int tile = 0, state = W * tile_f2, slot = state + W * 16, bar = slot + 2, sum = bar + W + (W & 1);
+    static constexpr int bytes = sum * 8;
+    // + per warp 14 KB for the union of a frame's four search windows (1.75 N samples): the staged PCM of K4 (filled by one
+    // TMA bulk copy per work item, one item ahead), or its K-frame sum (synchronous addition)
+    static constexpr int bytes_union = bytes + W * 1792 * 8;
+};
 
 // The four tables every dsp() reads — up chirp, down chirp, Hann, inter-pass twiddles — live in tensor memory, one row per
 // lane (usc_tmem.cuh; K1 keeps them the same way): columns 4 b .. 4 b + 3 = (up[2m], down[2m], up[2m+1], down[2m+1]) of
@@ -85,7 +93,7 @@ __device__ __forceinline__ void dsp_pair_tail(float2 (&re)[32], float2 (&im)[32]
     if (chirps == RX_UP_UP) rx_front<RX_UP_UP>(re, im, tb.tq);        // warp-uniform
     else if (chirps == RX_UP_DOWN) rx_front<RX_UP_DOWN>(re, im, tb.tq);
     else rx_front<RX_DOWN_DOWN>(re, im, tb.tq);
-    fft1024_pair_tm<true>(re, im, tile, tb.tq + kRxTtw, tb.one, lane);
+    fft1024_pair_tm<true, true>(re, im, tile, tb.tq + kRxTtw, tb.one, lane);
     peak_window_pair<kRxNB>(re, im, ws, lane, bw2, magA, idxA, magB, idxB);
 }
 
@@ -169,8 +177,7 @@ __device__ __forceinline__ void dsp_pair(const PCM* __restrict__ stream, int64_t
 
 // allocate the CTA's TMEM columns and fill every lane quadrant with the table rows (warp q fills quadrant q; warps q and
 // q + 4 read it); ends with a CTA barrier
-__device__ __forceinline__ rx_tables load_tables(const rx_params& p, float2* s_rx, int lane, int warp) {
-    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_rx + kRxSlot);
+__device__ __forceinline__ rx_tables load_tables(const rx_params& p, uint32_t* s_tslot, int lane, int warp) {
     if (warp == 0) tmem_alloc<kRxTcols>(s_tslot);
     tmem_fence_before_sync();
     __syncthreads();
@@ -202,21 +209,23 @@ __device__ __forceinline__ rx_tables load_tables(const rx_params& p, float2* s_r
     tmem_fence_after_sync();
     return rx_tables{tq, one};
 }
-__device__ __forceinline__ void free_tables(float2* s_rx, int warp) {
+__device__ __forceinline__ void free_tables(uint32_t* s_tslot, int warp) {
     tmem_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<kRxTcols>(*reinterpret_cast<uint32_t*>(s_rx + kRxSlot));
+    if (warp == 0) tmem_dealloc<kRxTcols>(*s_tslot);
 }
 
-template <typename PCM>
-__global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) {
+template <typename PCM, int W>
+__global__ void __launch_bounds__(W * 32, 1) k_receiver_run(rx_params p) {
+    using L = rx_smem<W>;
+    constexpr int kRxWarps = W;
     extern __shared__ float2 s_rx[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2 ws[kRxNB];
 #pragma unroll
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
-    const rx_tables tb = load_tables(p, s_rx, lane, warp);
-    float2* tile = s_rx + kRxTile + warp * 1024;
+    const rx_tables tb = load_tables(p, reinterpret_cast<uint32_t*>(s_rx + L::slot), lane, warp);
+    float2* tile = s_rx + L::tile + warp * L::tile_f2;
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const float thr = p.snr_threshold;
     const uint32_t bw2 = p.bandwidth2;
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
         }
         // mag_stat[12] | history mag_max[8] | history mag_mean[4] live in shared memory (the packed core
         // needs the registers); every lane reads them (broadcast), lane 0 writes
-        float* mag_stat = reinterpret_cast<float*>(s_rx + kRxState) + warp * 32;
+        float* mag_stat = reinterpret_cast<float*>(s_rx + L::state) + warp * 32;
         float* hmag = mag_stat + 12;
         float* hmean = mag_stat + 20;
         __syncwarp();
@@ -397,29 +406,32 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_receiver_run(rx_params p) 
             __syncwarp();
         }
     }
-    free_tables(s_rx, warp);
+    free_tables(reinterpret_cast<uint32_t*>(s_rx + L::slot), warp);
 }
 
 // K4: the search grid of main.c:447-451 for every (stream, frame), after optional synchronous
 // addition of sync_add frame-aligned FIFOs (oldest first).  One warp per (stream, frame), two packed
 // passes of two offsets each.
-template <typename PCM, bool MULTI>
-__global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
+template <typename PCM, bool MULTI, int W>
+__global__ void __launch_bounds__(W * 32, 1) k_sync_search(rx_params p) {
+    using L = rx_smem<W>;
+    constexpr int kRxWarps = W;
+    constexpr bool kUnion = W == 8;                                                // the 14 KB per-warp union area exists (8-warp forms)
     extern __shared__ float2 s_rx[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2 ws[kRxNB];
 #pragma unroll
     for (int d1 = 0; d1 < kRxNB; ++d1) ws[d1] = p.tw_split[lane + 32 * d1];
-    const rx_tables tb = load_tables(p, s_rx, lane, warp);
-    float2* tile = s_rx + kRxTile + warp * 1024;
-    float2* sum = s_rx + kRxSum + warp * 1792;                                     // 14 KB per warp: staged union (PCM) or its K-frame sum
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_rx + kRxBar) + warp;
+    const rx_tables tb = load_tables(p, reinterpret_cast<uint32_t*>(s_rx + L::slot), lane, warp);
+    float2* tile = s_rx + L::tile + warp * L::tile_f2;
+    float2* sum = s_rx + L::sum + warp * 1792;                                     // 14 KB per warp: staged union (PCM) or its K-frame sum
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_rx + L::bar) + warp;
     const uint32_t N = 2048, offset = N / 8, shift = N / 4;
     const size_t total = (size_t) p.nstreams * p.nframes;
     const size_t nwarps = (size_t) gridDim.x * kRxWarps;
     const int64_t nsamples = (int64_t) p.nframes * N;
     using V2 = typename vec2<PCM>::type;
-    const bool staged = !MULTI && p.staged != 0;
+    const bool staged = kUnion && !MULTI && p.staged != 0;
     // the union of work item wi's four windows: [base, base + 3584) of its stream; `inside`: wholly within the stream
     auto item_union = [&](size_t wi, const PCM*& strm, int64_t& base) -> bool {
         const uint32_t si = (uint32_t) (wi / p.nframes), ti = (uint32_t) (wi - (size_t) si * p.nframes);
@@ -566,7 +578,7 @@ __global__ void __launch_bounds__(kRxWarps * 32, 1) k_sync_search(rx_params p) {
             }
         }
     }
-    free_tables(s_rx, warp);
+    free_tables(reinterpret_cast<uint32_t*>(s_rx + L::slot), warp);
 }
 
 static rx_params make_params(const rx_launch& a) {
@@ -580,48 +592,52 @@ static rx_params make_params(const rx_launch& a) {
     return p;
 }
 
+constexpr int kRxW = USC_RX_WARPS, kSsW = USC_SS_WARPS;
 static cudaError_t rx_prepare() {
     static per_device<bool> done_pd;
     bool& done = done_pd.get();
     if (done) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_receiver_run<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_receiver_run<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmem))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
-    if ((e = cudaFuncSetAttribute(k_sync_search<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRxSmemMulti))) return e;
+    if ((e = cudaFuncSetAttribute(k_receiver_run<int32_t, kRxW>, cudaFuncAttributeMaxDynamicSharedMemorySize, rx_smem<kRxW>::bytes))) return e;
+    if ((e = cudaFuncSetAttribute(k_receiver_run<float, kRxW>, cudaFuncAttributeMaxDynamicSharedMemorySize, rx_smem<kRxW>::bytes))) return e;
+    constexpr int ss_bytes = kSsW == 8 ? rx_smem<8>::bytes_union : rx_smem<kSsW>::bytes;
+    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, false, kSsW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss_bytes))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<float, false, kSsW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss_bytes))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<int32_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rx_smem<8>::bytes_union))) return e;
+    if ((e = cudaFuncSetAttribute(k_sync_search<float, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rx_smem<8>::bytes_union))) return e;
     done = true;
     return cudaSuccess;
 }
 
 cudaError_t launch_receiver_run(const rx_launch& a, int num_sms, cudaStream_t st) {
     rx_params p = make_params(a);
-    size_t ctas = ((size_t) a.nstreams + kRxWarps - 1) / kRxWarps;
-    const size_t cap = (size_t) num_sms;                 // persistent: one CTA of 8 warps per SM
+    size_t ctas = ((size_t) a.nstreams + kRxW - 1) / kRxW;
+    const size_t cap = (size_t) num_sms;                 // persistent: one CTA per SM
     if (ctas > cap) ctas = cap;
     cudaError_t e = rx_prepare();
     if (e != cudaSuccess) return e;
-    if (a.pcm_format == 1u) k_receiver_run<int32_t><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
-    else k_receiver_run<float><<<(int) ctas, kRxWarps * 32, kRxSmem, st>>>(p);
+    if (a.pcm_format == 1u) k_receiver_run<int32_t, kRxW><<<(int) ctas, kRxW * 32, rx_smem<kRxW>::bytes, st>>>(p);
+    else k_receiver_run<float, kRxW><<<(int) ctas, kRxW * 32, rx_smem<kRxW>::bytes, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sync_search(const rx_launch& a, int num_sms, cudaStream_t st) {
     rx_params p = make_params(a);
-    size_t ctas = ((size_t) a.nstreams * a.nframes + kRxWarps - 1) / kRxWarps;
-    const size_t cap = (size_t) num_sms;                 // persistent: one CTA of 8 warps per SM (224+ registers per thread)
+    const bool multi = p.sync_add > 1;
+    const int w = multi ? 8 : kSsW;
+    size_t ctas = ((size_t) a.nstreams * a.nframes + w - 1) / w;
+    const size_t cap = (size_t) num_sms;                 // persistent: one CTA per SM
     if (ctas > cap) ctas = cap;
     cudaError_t e = rx_prepare();
     if (e != cudaSuccess) return e;
-    const bool multi = p.sync_add > 1;
     p.staged = (reinterpret_cast<uintptr_t>(a.pcm) % 16u == 0 && a.stream_stride % 4u == 0) ? 1u : 0u;
+    constexpr int ss_bytes = kSsW == 8 ? rx_smem<8>::bytes_union : rx_smem<kSsW>::bytes;
     if (a.pcm_format == 1u) {
-        if (multi) k_sync_search<int32_t, true><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
-        else k_sync_search<int32_t, false><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
+        if (multi) k_sync_search<int32_t, true, 8><<<(int) ctas, 8 * 32, rx_smem<8>::bytes_union, st>>>(p);
+        else k_sync_search<int32_t, false, kSsW><<<(int) ctas, kSsW * 32, ss_bytes, st>>>(p);
     } else {
-        if (multi) k_sync_search<float, true><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
-        else k_sync_search<float, false><<<(int) ctas, kRxWarps * 32, kRxSmemMulti, st>>>(p);
+        if (multi) k_sync_search<float, true, 8><<<(int) ctas, 8 * 32, rx_smem<8>::bytes_union, st>>>(p);
+        else k_sync_search<float, false, kSsW><<<(int) ctas, kSsW * 32, ss_bytes, st>>>(p);
     }
     return cudaGetLastError();
 }

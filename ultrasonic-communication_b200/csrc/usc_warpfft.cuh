@@ -127,7 +127,9 @@ __device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32],
 
 // fft1024_pair with the inter-pass twiddles W_1024^(a d) read from the lane's TMEM row (columns t_tw + 2 d, d < 32; see
 // usc_tmem.cuh) instead of shared memory; `one` = 1.0f from a table (opaque to the compiler) for the PROD form.
-template <bool PROD = false>
+// PAD: the tile has padded rows (32 x 33 float2, 8448 bytes) instead of the XOR swizzle: every store and load of a round is
+// one base register plus an immediate offset, which is what lets a kernel hold three warps per scheduler at 168 registers.
+template <bool PROD = false, bool PAD = false>
 __device__ __forceinline__ void fft1024_pair_tm(float2 (&re)[32], float2 (&im)[32], float2* tile /* 32x32 float2, XOR-swizzled, 8 KB */,
                                                 uint32_t t_tw, float one, int lane) {
     if (PROD) fft_base2_prod<32>(re, im, one);
@@ -147,16 +149,16 @@ __device__ __forceinline__ void fft1024_pair_tm(float2 (&re)[32], float2 (&im)[3
         }
     }
 #pragma unroll
-    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
+    for (int d = 0; d < 32; ++d) tile[PAD ? d * kTileStride + lane : d * 32 + (lane ^ d)] = re[d];
     __syncwarp();
 #pragma unroll
-    for (int a = 0; a < 32; ++a) re[a] = tile[lane * 32 + (a ^ lane)];
+    for (int a = 0; a < 32; ++a) re[a] = tile[PAD ? lane * kTileStride + a : lane * 32 + (a ^ lane)];
     __syncwarp();
 #pragma unroll
-    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = im[d];
+    for (int d = 0; d < 32; ++d) tile[PAD ? d * kTileStride + lane : d * 32 + (lane ^ d)] = im[d];
     __syncwarp();
 #pragma unroll
-    for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
+    for (int a = 0; a < 32; ++a) im[a] = tile[PAD ? lane * kTileStride + a : lane * 32 + (a ^ lane)];
     __syncwarp();
     fft_base2<32>(re, im);
 }
