@@ -51,7 +51,10 @@ constexpr int kLongKeep = 32 * kLongNB;               // kept outputs per side o
 // The kept outputs of sub-sequence d sit in the upper half of region d, shifted by d * (128 / R) bytes (R regions are
 // interleaved over consecutive lanes in the split): the regions are 16 KB apart, so without the shift the R lanes that
 // read the same c from R different regions hit the same banks (R-way conflicts on every split load).
-template <int R> __device__ __forceinline__ constexpr uint32_t keep_off(uint32_t d) { return 8192u + d * (128u / R); }
+#ifndef USC_LONG_PAD
+#define USC_LONG_PAD 1                                  // exchange tile of the core with padded rows (8448 bytes) instead of the XOR swizzle
+#endif
+template <int R, bool PAD = (USC_LONG_PAD != 0)> __device__ __forceinline__ constexpr uint32_t keep_off(uint32_t d) { return (PAD ? 8448u : 8192u) + d * (128u / R); }
 
 struct long_params {
     const void* pcm; size_t nframes; uint32_t n;      // n real samples per frame (2048 * R0)
@@ -228,7 +231,7 @@ __device__ __forceinline__ void demod_long_body(const long_params& p) {
                 im[b] = reg[1024 + lane + 32 * b];
             }
             __syncwarp();
-            fft1024_pair(re, im, reg, s_tw, lane);           // first 8 KB of the region is now the exchange tile
+            fft1024_pair<false, USC_LONG_PAD != 0>(re, im, reg, s_tw, lane);           // first 8 KB of the region is now the exchange tile
             // keep Y_d[c] for c < 160 (elements 0..4) and c >= 864 (elements 27..31)
             float4* keep = reinterpret_cast<float4*>(gbase + warp * L::region + keep_off<R0>(warp));
 #pragma unroll
@@ -508,8 +511,8 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
                 im[b] = make_float2(v.z, v.w);
             }
             __syncwarp();
-            fft1024_pair(re, im, reg, s_tw, lane);
-            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + keep_off<W>(warp));
+            fft1024_pair(re, im, reg, s_tw, lane);                           // XOR-swizzled tile: the padded one measured 3 % slower here
+            float4* keep = reinterpret_cast<float4*>(s_raw + L::sub + warp * L::region + keep_off<W, false>(warp));
 #pragma unroll
             for (int j = 0; j < kLongNB; ++j) {
                 keep[lane + 32 * j] = make_float4(re[j].x, re[j].y, im[j].x, im[j].y);
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
             const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl;
             // nc - k = R0 (1024 - c) for d = 0 (c >= 1), else R0 (1023 - c) + (R0 - d); k = 0 pairs with itself (unused)
             const uint32_t d2 = ((uint32_t) R0 - d) & (uint32_t) (R0 - 1), c2 = d == 0 ? (c == 0 ? 1023u : 1024u - c) : 1023u - c;
-            const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
+            const uint32_t addr = peer_sub[d2 >> SH] + (d2 & (W - 1u)) * L::region + keep_off<W, false>(d2 & (W - 1u)) + (kLongKeep + (c2 - (1024u - kLongKeep))) * 16u;
             zcs[j] = ld_cluster_f4(addr);
         }
 #pragma unroll
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
             const uint32_t c = (tid >> SH) + 32u * j, dl = tid & (W - 1u), d = rank * W + dl, k = (uint32_t) R0 * c + d;
             kk[j] = k;
             ok[j] = k < bw2;
-            const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + keep_off<W>(dl))[c];
+            const float4 zk = reinterpret_cast<const float4*>(s_raw + L::sub + dl * L::region + keep_off<W, false>(dl))[c];
             const float4 zc = zcs[j];
             const float2 w = w_split[j];
             float2 xr, xi;

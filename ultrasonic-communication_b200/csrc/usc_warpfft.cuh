@@ -97,8 +97,8 @@ __device__ __forceinline__ void fft1024_warp2(float2 (&re)[32], float2 (&im)[32]
 // pass 1, inter-pass twiddle, two-round exchange (real parts, imaginary parts), pass 2 — on pairs.
 // PROD: the inputs are packed products (window multiplies): the first butterfly stage runs as FMAs by 1.0 (s_tw row 0
 // holds W^0 = 1.0f), see bfly2_one_fma in usc_arith.cuh; same bits.
-template <bool PROD = false>
-__device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32], float2* tile /* 32x32 float2, XOR-swizzled, 8 KB */,
+template <bool PROD = false, bool PAD = false>
+__device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32], float2* tile /* 32x32 float2 XOR-swizzled (8 KB), or 32x33 padded */,
                                              const float2* __restrict__ s_tw, int lane) {
     if (PROD) fft_base2_prod<32>(re, im, s_tw[lane].x);
     else fft_base2<32>(re, im);
@@ -111,16 +111,16 @@ __device__ __forceinline__ void fft1024_pair(float2 (&re)[32], float2 (&im)[32],
         im[d] = ti;
     }
 #pragma unroll
-    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = re[d];
+    for (int d = 0; d < 32; ++d) tile[PAD ? d * kTileStride + lane : d * 32 + (lane ^ d)] = re[d];
     __syncwarp();
 #pragma unroll
-    for (int a = 0; a < 32; ++a) re[a] = tile[lane * 32 + (a ^ lane)];
+    for (int a = 0; a < 32; ++a) re[a] = tile[PAD ? lane * kTileStride + a : lane * 32 + (a ^ lane)];
     __syncwarp();
 #pragma unroll
-    for (int d = 0; d < 32; ++d) tile[d * 32 + (lane ^ d)] = im[d];
+    for (int d = 0; d < 32; ++d) tile[PAD ? d * kTileStride + lane : d * 32 + (lane ^ d)] = im[d];
     __syncwarp();
 #pragma unroll
-    for (int a = 0; a < 32; ++a) im[a] = tile[lane * 32 + (a ^ lane)];
+    for (int a = 0; a < 32; ++a) im[a] = tile[PAD ? lane * kTileStride + a : lane * 32 + (a ^ lane)];
     __syncwarp();
     fft_base2<32>(re, im);
 }
