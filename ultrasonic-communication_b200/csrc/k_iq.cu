@@ -265,6 +265,9 @@ cudaError_t launch_iq_backend(const float* R, size_t nframes, const float* chirp
 // arm_fir_f32.  The baseband frame R goes through the warp's region once (blocked -> strided), then the
 // back end above runs unchanged.  R never touches HBM.
 
+#ifndef USC_IQF_PAD
+#define USC_IQF_PAD 1                                   // exchange tile with padded rows (0: XOR-swizzled)
+#endif
 constexpr int kIqfWarps = 8;
 #ifndef USC_IQF_ROWS
 #define USC_IQF_ROWS 64
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(kIqfWarps * 32, 1) k_iq_fused(const PCM* __res
             }
         }
         __syncwarp();
-        fft1024_pair_tm<true>(re, im, reinterpret_cast<float2*>(region), tq + kIqfTtw, one, lane);
+        fft1024_pair_tm<true, USC_IQF_PAD != 0>(re, im, reinterpret_cast<float2*>(region), tq + kIqfTtw, one, lane);
         const float2 pr = __ffma2_rn(re[0], re[0], __fmul2_rn(im[0], im[0]));
         const float2 pl = __ffma2_rn(re[31], re[31], __fmul2_rn(im[31], im[31]));
         const bool in_r = (uint32_t) lane < W, in_l = 992u + lane >= 1024u - W;
