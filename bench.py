@@ -656,8 +656,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "kernel": "k_demod2048<int,5,8>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL * NFRAMES,
-                         "note": "tables served from tensor memory (tcgen05.ld); bound by the fp32 pipe (74 % busy, 1034 packed FP instructions per frame), L1/shared path 55 %, DESIGN.md 4.1; frac is vs HBM"},
+                         "kernel": "k_demod2048<int,5,12>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL * NFRAMES,
+                         "note": "tables served from tensor memory (tcgen05.ld), 12 warps per SM; bound by the fp32 pipe (77 % busy, 1034 packed FP instructions per frame), L1/shared path 55 %, DESIGN.md 4.1; frac is vs HBM"},
             # secondary roofline: algorithmic fp32 work of two real-FFT chains per symbol, 2.5 N log2 N + 8 N flops
             # each, against the fp32 FMA peak of the measured SM clock (148 SMs x 128 lanes x 2 flops)
             "roofline_fp32": {"bound": "fp32", "achieved": 2 * (2.5 * N * 11 + 8 * N) * NFRAMES / (ms_per_step * 1e-3) / 1e12,
