@@ -22,8 +22,12 @@
 namespace usc {
 
 constexpr int kCWarps = 8;
-constexpr int kCSmemTabs = 4 * 8192;                  // pass twiddles | window | H | split twiddles
-constexpr int kCWarpBytes = 8192 + 16384;             // XOR-swizzled float2 tile + 2-frame PCM stage
+// Tables in tensor memory, one row per lane (usc_tmem.cuh): window pair of m = lane + 32 b at 2 b | inter-pass twiddle
+// W_1024^(lane d) at 64 + 2 d | spectral stage, step j: (ws[ka], H[ka], ws[kb], H[kb]) with ka = lane + 32 j,
+// kb = lane + 32 (31 - j), at 128 + 8 j | lane 0's column: (ws[32 lane], H[32 lane]) at 256.
+constexpr int kCTwin = 0, kCTtw = 64, kCTspec = 128, kCTcol0 = 256, kCTcols = 512;
+constexpr int kCSmemTabs = 128;                       // TMEM slot (+ padding: the per-warp areas stay 128-byte aligned)
+constexpr int kCWarpBytes = 8448 + 16384;             // 2-frame PCM stage + float2 tile with padded rows (32 x 33)
 constexpr int kCSmemBar = kCSmemTabs + kCWarps * kCWarpBytes;
 constexpr int kCSmemTotal = kCSmemBar + kCWarps * 8;
 
@@ -59,9 +63,7 @@ __device__ __forceinline__ void merge_swap(float2 pkr, float2 pki, float2 pcr, f
 // every pair inside one step and lets the results overwrite their inputs.  Lane 0's own column
 // (k = 32 d1, partner 32 (32 - d1), same lane) does not fit that order; it is spread over the 32 lanes
 // through the (idle) exchange tile, processed one bin per lane, and gathered back.
-__device__ __forceinline__ void spectral_in_place(float2 (&re)[32], float2 (&im)[32], float4* tile4,
-                                                  const float2* __restrict__ s_H, const float2* __restrict__ s_ws,
-                                                  int lane) {
+__device__ __forceinline__ void spectral_in_place(float2 (&re)[32], float2 (&im)[32], float4* tile4, uint32_t tq, int lane) {
     // ---- column of lane 0 ----
     if (lane == 0) {
 #pragma unroll
@@ -71,8 +73,9 @@ __device__ __forceinline__ void spectral_in_place(float2 (&re)[32], float2 (&im)
     {
         const int pl = (32 - lane) & 31;
         const float4 zk = tile4[lane], zc = tile4[pl];
-        const int k = 32 * lane;
-        const float2 w = s_ws[k], h = s_H[k];
+        uint32_t t0[8];
+        ldtm8(tq + kCTcol0, t0);
+        const float2 w = make_float2(__uint_as_float(t0[0]), __uint_as_float(t0[1])), h = make_float2(__uint_as_float(t0[2]), __uint_as_float(t0[3]));
         float2 pr, pi, o_re, o_im;
         split_mul(make_float2(zk.x, zk.y), make_float2(zk.z, zk.w), make_float2(zc.x, zc.y), make_float2(zc.z, zc.w), w, h,
                   lane == 0, pr, pi);
@@ -87,10 +90,12 @@ __device__ __forceinline__ void spectral_in_place(float2 (&re)[32], float2 (&im)
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int ja = j, jb = 31 - j;
+        uint32_t t[8];                                                          // table values of this step
+        ldtm8(tq + kCTspec + 8 * j, t);
         const float2 zcar = shfl2(re[jb], src), zcai = shfl2(im[jb], src);     // partner of my element ja
         const float2 zcbr = shfl2(re[ja], src), zcbi = shfl2(im[ja], src);     // partner of my element jb
-        const int ka = lane + 32 * ja, kb = lane + 32 * jb;
-        const float2 wa = s_ws[ka], wb = s_ws[kb], ha = s_H[ka], hb = s_H[kb];
+        const float2 wa = make_float2(__uint_as_float(t[0]), __uint_as_float(t[1])), ha = make_float2(__uint_as_float(t[2]), __uint_as_float(t[3]));
+        const float2 wb = make_float2(__uint_as_float(t[4]), __uint_as_float(t[5])), hb = make_float2(__uint_as_float(t[6]), __uint_as_float(t[7]));
         float2 par, pai, pbr, pbi;
         split_mul(re[ja], im[ja], zcar, zcai, wa, ha, false, par, pai);
         split_mul(re[jb], im[jb], zcbr, zcbi, wb, hb, false, pbr, pbi);
@@ -122,10 +127,7 @@ struct compress_params {
 template <typename PCM>
 __global__ void __launch_bounds__(kCWarps * 32, 1) k_compress2048(compress_params p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    float2* s_tw = reinterpret_cast<float2*>(s_raw);
-    float2* s_win = reinterpret_cast<float2*>(s_raw + 8192);
-    float2* s_H = reinterpret_cast<float2*>(s_raw + 16384);
-    float2* s_ws = reinterpret_cast<float2*>(s_raw + 24576);
+    uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = s_raw + kCSmemTabs + warp * kCWarpBytes;
     using V2 = typename vec2<PCM>::type;
@@ -146,13 +148,35 @@ __global__ void __launch_bounds__(kCWarps * 32, 1) k_compress2048(compress_param
             bulk_g2s(xstage, pcm + q * 4096, pair_bytes(q), bar);
         }
     }
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        s_tw[i] = p.tw_pass[i];
-        s_win[i] = p.window[i];
-        s_H[i] = p.H[i];
-        s_ws[i] = p.tw_split[i];
-    }
+    if (warp == 0) tmem_alloc<kCTcols>(s_tslot);
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tq = tmem_quadrant(*s_tslot, warp);
+    if (warp < 4) {                                     // warp q fills lane quadrant q; warps q and q + 4 read it
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += 4) {
+            float2 w[4], z[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                w[j] = p.window[lane + 32 * (b0 + j)];
+                z[j] = p.tw_pass[(b0 + j) * 32 + lane];
+            }
+            sttm_f2x4(tq + kCTwin + 2 * b0, w[0], w[1], w[2], w[3]);
+            sttm_f2x4(tq + kCTtw + 2 * b0, z[0], z[1], z[2], z[3]);
+        }
+#pragma unroll 1
+        for (int j = 0; j < 16; ++j) {
+            const int ka = lane + 32 * j, kb = lane + 32 * (31 - j);
+            sttm_f2x4(tq + kCTspec + 8 * j, p.tw_split[ka], p.H[ka], p.tw_split[kb], p.H[kb]);
+        }
+        sttm_f2x4(tq + kCTcol0, p.tw_split[32 * lane], p.H[32 * lane], make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f));
+        sttm_wait();
+    }
+    const float one = p.tw_pass[lane].x;                // W^0 = 1.0f read from a table: opaque to the compiler
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
 
     uint32_t parity = 0;
     for (; q < npairs; q += nwarps) {
@@ -161,23 +185,27 @@ __global__ void __launch_bounds__(kCWarps * 32, 1) k_compress2048(compress_param
         parity ^= 1u;
         float2 re[32], im[32];                         // (.x, .y) = (frame 2q, frame 2q+1)
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const int m = lane + 32 * b;
-            const V2 ra = xstage[m];
-            const V2 rb = two ? xstage[1024 + m] : ra;
-            const float2 w = s_win[m];
-            // packed window multiply; the first butterfly stage takes the products as FMAs by 1.0 (usc_arith.cuh)
-            re[b] = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(w.x));
-            im[b] = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(w.y));
+        for (int g = 0; g < 4; ++g) {                   // window values of eight rows per TMEM round trip
+            uint32_t t[16];
+            ldtm16(tq + kCTwin + 16 * g, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = 8 * g + j, m = lane + 32 * b;
+                const V2 ra = xstage[m];
+                const V2 rb = two ? xstage[1024 + m] : ra;
+                // packed window multiply; the first butterfly stage takes the products as FMAs by 1.0 (usc_arith.cuh)
+                re[b] = __fmul2_rn(make_float2(pcm_to_float(ra.x), pcm_to_float(rb.x)), bc2(__uint_as_float(t[2 * j])));
+                im[b] = __fmul2_rn(make_float2(pcm_to_float(ra.y), pcm_to_float(rb.y)), bc2(__uint_as_float(t[2 * j + 1])));
+            }
         }
         __syncwarp();
         if (lane == 0 && q + nwarps < npairs) {
             mbar_expect_tx(bar, pair_bytes(q + nwarps));
             bulk_g2s(xstage, pcm + (q + nwarps) * 4096, pair_bytes(q + nwarps), bar);
         }
-        fft1024_pair<true>(re, im, tile, s_tw, lane);
-        spectral_in_place(re, im, reinterpret_cast<float4*>(tile), s_H, s_ws, lane);
-        fft1024_pair(re, im, tile, s_tw, lane);
+        fft1024_pair_tm<true, true>(re, im, tile, tq + kCTtw, one, lane);
+        spectral_in_place(re, im, reinterpret_cast<float4*>(tile), tq, lane);
+        fft1024_pair_tm<false, true>(re, im, tile, tq + kCTtw, one, lane);
         // swap back and scale by 1/N: a[2m] = z.im/N, a[2m+1] = z.re/N
         const float sc = 1.0f / 2048.0f;
         float ba = -INFINITY, bb = -INFINITY;
@@ -202,6 +230,9 @@ __global__ void __launch_bounds__(kCWarps * 32, 1) k_compress2048(compress_param
             if (p.max_idx) { p.max_idx[2 * q] = ia; if (two) p.max_idx[2 * q + 1] = ib; }
         }
     }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kCTcols>(*s_tslot);
 }
 
 cudaError_t launch_compress2048(const void* pcm, uint32_t pcm_format, size_t nframes, const float2* window,
