@@ -31,7 +31,9 @@ constexpr int kOsWarps = 8;
 // split twiddles (W_4096^k, W_4096^kc) and template spectrum (G[k], G[kc]).  Shared memory keeps the TMEM slot only.
 constexpr int kOsTtw0 = 0, kOsTtw = 64, kOsTspec = 128, kOsTcols = 512;
 constexpr int kOsTabs = 128;                           // TMEM slot (+ padding to keep the per-warp areas 128-byte aligned)
-constexpr int kOsWarpBytes = 3 * 8192;                 // half A | exchange tile | half B
+constexpr int kOsTile = 8448;                          // exchange tile with padded rows (32 x 33 float2)
+constexpr int kOsHalfB = 8192 + kOsTile;               // byte offset of half B
+constexpr int kOsWarpBytes = kOsHalfB + 8192;          // half A | exchange tile | half B
 constexpr int kOsBar = kOsTabs + kOsWarps * kOsWarpBytes;
 constexpr int kOsSmem = kOsBar + kOsWarps * 8;
 
@@ -99,12 +101,12 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
         if (lane == 0) {                               // first block of the item: both halves
             mbar_expect_tx(bar, 16384u);
             bulk_g2s(wbase, stream + (size_t) b0 * 2048, 8192u, bar);
-            bulk_g2s(wbase + 16384, stream + (size_t) (b0 + 1) * 2048, 8192u, bar);
+            bulk_g2s(wbase + kOsHalfB, stream + (size_t) (b0 + 1) * 2048, 8192u, bar);
         }
         for (uint32_t b = b0; b < b1; ++b) {
             const uint32_t odd = (b - b0) & 1u;        // which physical half holds the older n samples
-            const V2* lo_half = reinterpret_cast<const V2*>(wbase + (odd ? 16384 : 0));
-            const V2* hi_half = reinterpret_cast<const V2*>(wbase + (odd ? 0 : 16384));
+            const V2* lo_half = reinterpret_cast<const V2*>(wbase + (odd ? kOsHalfB : 0));
+            const V2* hi_half = reinterpret_cast<const V2*>(wbase + (odd ? 0 : kOsHalfB));
             float2* zs = reinterpret_cast<float2*>(wbase + (odd ? 8192 : 0));       // 2048 float2: dead lower half + tile
             mbar_wait(bar, parity);
             parity ^= 1u;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
                 }
             }
             __syncwarp();                              // the lower half has been consumed by every lane
-            fft1024_pair_tm(re, im, tile, tq + kOsTtw, 1.0f, lane);
+            fft1024_pair_tm<false, true>(re, im, tile, tq + kOsTtw, 1.0f, lane);
             // spectrum to shared memory in natural order: lane d0, element d1 holds Z[2c], Z[2c+1], c = d0 + 32 d1
             {
                 float4* z4 = reinterpret_cast<float4*>(zs);
@@ -198,9 +200,9 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             if (lane == 0 && b + 1 < b1) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of the parked spectrum before the bulk copy
                 mbar_expect_tx(bar, 8192u);
-                bulk_g2s(wbase + (odd ? 16384 : 0), stream + (size_t) (b + 2) * 2048, 8192u, bar);
+                bulk_g2s(wbase + (odd ? kOsHalfB : 0), stream + (size_t) (b + 2) * 2048, 8192u, bar);
             }
-            fft1024_pair_tm(re, im, tile, tq + kOsTtw, 1.0f, lane);
+            fft1024_pair_tm<false, true>(re, im, tile, tq + kOsTtw, 1.0f, lane);
             // y[2m] = z[m].im / 4096, y[2m+1] = z[m].re / 4096; valid lags l = 2m (+1) in [2048, 4096): m = 2c (+1) with
             // c = lane + 32 d1 >= 512, i.e. d1 >= 16 (the other outputs of the last pass are never computed)
             const float sc = 1.0f / 4096.0f;
