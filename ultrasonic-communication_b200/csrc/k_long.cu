@@ -367,6 +367,8 @@ __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_to_rank(const void* local, uint32_t rank) {       // shared::cluster address of a peer's copy
     uint32_t l = (uint32_t) __cvta_generic_to_shared(local), r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
@@ -384,6 +386,9 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+#ifndef USC_CL_SPLITBAR
+#define USC_CL_SPLITBAR 1
+#endif
 template <typename PCM, int R0, int W>
 __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, const float2* __restrict__ tw_l0) {
     using L = cl_smem<R0, W>;
@@ -459,7 +464,29 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
     const uint32_t red0 = map_to_rank(s_raw + L::red, 0);
     cluster_sync_all();                                  // every CTA of the cluster is resident before remote traffic
 
+    // CTA 0 combines the R0 per-warp results of a frame: one slot per lane, then the warp-wide exact arg-max
+    auto emit = [&](size_t f) {
+        const float4 v = reinterpret_cast<const float4*>(s_raw + L::red)[lane & (R0 - 1)];
+        float bu = v.x, bd = v.z;
+        uint32_t iu = __float_as_uint(v.y), id = __float_as_uint(v.w);
+        warp_argmax(bu, iu);
+        warp_argmax(bd, id);
+        if (lane == 0) {
+            if (p.mag_up) p.mag_up[f] = bu;
+            if (p.idx_up) p.idx_up[f] = iu;
+            if (p.mag_down) p.mag_down[f] = bd;
+            if (p.idx_down) p.idx_down[f] = id;
+            if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
+        }
+    };
+    // The barrier that closes a frame is split (USC_CL_SPLITBAR): a thread ARRIVES as soon as its reads of the frame's
+    // sub-spectra are done and WAITS only before its first remote store of the next frame, so the arg-max tail, the wait
+    // for the next PCM share and the next level-0 front end and butterflies run while slower CTAs finish their split.
+    // The per-warp results (stored after the arrive) become visible to CTA 0 with the next frame's first barrier —
+    // they are combined between that barrier and the second one, before any warp can store the following results.
     uint32_t parity = 0;
+    bool pending = false;                                // a frame's results wait in CTA 0 / its closing barrier is open
+    size_t fprev = 0;
     for (size_t f = cluster_id_x(); f < p.nframes; f += cluster_count_x()) {
         mbar_wait(bar, parity);                          // this CTA's share of the frame has landed in the stage
         parity ^= 1u;
@@ -484,6 +511,9 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
                 }
             }
             fft_base2_prod<R0>(re, im, one);
+#if USC_CL_SPLITBAR
+            if (i == 0 && pending) cluster_wait();       // every peer has read the previous frame's sub-spectra
+#endif
 #pragma unroll
             for (int g = 0; g < R0 / 8; ++g) {           // level-0 twiddles, eight per TMEM round trip
                 uint32_t t[16];
@@ -500,6 +530,9 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
         }
         cluster_sync_all();                              // sub-sequences complete; every thread is done with the stage
         if (warp == 0 && f + cluster_count_x() < p.nframes) fetch(f + cluster_count_x());   // next share arrives under the core and the split
+#if USC_CL_SPLITBAR
+        if (pending && rank == 0 && warp == W - 1) emit(fprev);
+#endif
         // ---- 1024-point packed core on sub-sequence W rank + warp ----
         {
             float2* reg = reinterpret_cast<float2*>(s_raw + L::sub + warp * L::region);
@@ -556,29 +589,29 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
             pu[j] = pw.x;
             pd[j] = pw.y;
         }
+#if USC_CL_SPLITBAR
+        cluster_arrive();                                // this thread's reads of the frame's sub-spectra are done
+#endif
         float bu, bd;
         uint32_t iu, id;
         argmax_exact2<kLongNB>(pu, pd, kk, ok, bu, iu, bd, id);
         if (lane == 0) st_cluster_f4(red0 + (rank * W + warp) * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
+#if USC_CL_SPLITBAR
+        pending = true;
+        fprev = f;
+#else
         cluster_sync_all();                              // results are in CTA 0; all remote reads of this frame are done
-        if (rank == 0 && tid == 0) {
-            const float4* r4 = reinterpret_cast<const float4*>(s_raw + L::red);
-            float4 v = r4[0];
-            bu = v.x; iu = __float_as_uint(v.y); bd = v.z; id = __float_as_uint(v.w);
-            for (int r = 1; r < CL * W; ++r) {
-                v = r4[r];
-                argmax_combine(bu, iu, v.x, __float_as_uint(v.y));
-                argmax_combine(bd, id, v.z, __float_as_uint(v.w));
-            }
-            if (p.mag_up) p.mag_up[f] = bu;
-            if (p.idx_up) p.idx_up[f] = iu;
-            if (p.mag_down) p.mag_down[f] = bd;
-            if (p.idx_down) p.idx_down[f] = id;
-            if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
-        }
+        if (rank == 0 && warp == 0) emit(f);
+#endif
     }
+#if USC_CL_SPLITBAR
+    if (pending) cluster_wait();
+#endif
     tmem_fence_before_sync();
     cluster_sync_all();                                  // no CTA leaves while a peer may still address its memory
+#if USC_CL_SPLITBAR
+    if (pending && rank == 0 && warp == 0) emit(fprev);  // the last frame's results arrived with the barrier above
+#endif
     if (warp == 0) tmem_dealloc<L::t_cols>(*s_tslot);
 }
 
