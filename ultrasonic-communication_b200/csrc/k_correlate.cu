@@ -28,7 +28,8 @@ namespace usc {
 constexpr int kOsWarps = 8;
 // Tables in tensor memory, one row per lane (usc_tmem.cuh): radix-2 level twiddle W_2048^a of a = lane + 32 q at 2 q |
 // inter-pass twiddle W_1024^(lane d) at 64 + 2 d | spectral stage of the pair (k, 2048 - k), k = lane + 32 j, at 128 + 8 j:
-// split twiddles (W_4096^k, W_4096^kc) and template spectrum (G[k], G[kc]).  Shared memory keeps the TMEM slot only.
+// split twiddles and template spectrum as the packed operands of the stage — (re k, re kc), (im k, im kc) of W_4096 and of G,
+// so every f32x2 operand is an aligned register pair of the load.  Shared memory keeps the TMEM slot only.
 constexpr int kOsTtw0 = 0, kOsTtw = 64, kOsTspec = 128, kOsTcols = 512;
 constexpr int kOsTabs = 128;                           // TMEM slot (+ padding to keep the per-warp areas 128-byte aligned)
 constexpr int kOsTile = 8448;                          // exchange tile with padded rows (32 x 33 float2)
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
 #pragma unroll 1
         for (int j = 0; j < 32; ++j) {
             const int k = lane + 32 * j, kc = (2048 - k) & 2047;
-            sttm_f2x4(tq + kOsTspec + 8 * j, p.tw_split[k], p.tw_split[kc], __ldg(p.G + k), __ldg(p.G + kc));
+            const float2 wk = p.tw_split[k], wc = p.tw_split[kc], gk = __ldg(p.G + k), gc = __ldg(p.G + kc);
+            sttm_f2x4(tq + kOsTspec + 8 * j, make_float2(wk.x, wc.x), make_float2(wk.y, wc.y), make_float2(gk.x, gc.x), make_float2(gk.y, gc.y));
         }
         sttm_wait();
     }
@@ -107,7 +109,10 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             const uint32_t odd = (b - b0) & 1u;        // which physical half holds the older n samples
             const V2* lo_half = reinterpret_cast<const V2*>(wbase + (odd ? kOsHalfB : 0));
             const V2* hi_half = reinterpret_cast<const V2*>(wbase + (odd ? 0 : kOsHalfB));
-            float2* zs = reinterpret_cast<float2*>(wbase + (odd ? 8192 : 0));       // 2048 float2: dead lower half + tile
+            // parked spectrum, 2048 bins as two planes (real parts | imaginary parts): dead lower half + tile.  Planar, so
+            // that the (k, 2048 - k) operands of the packed spectral stage are formed by the loads themselves (no moves)
+            float* zre = reinterpret_cast<float*>(wbase + (odd ? 8192 : 0));
+            float* zim = zre + 2048;
             mbar_wait(bar, parity);
             parity ^= 1u;
             float2 re[32], im[32];                     // (.x, .y) = (even-bin transform, odd-bin transform)
@@ -131,10 +136,10 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             __syncwarp();                              // the lower half has been consumed by every lane
             fft1024_pair_tm<false, true>(re, im, tile, tq + kOsTtw, 1.0f, lane);
             // spectrum to shared memory in natural order: lane d0, element d1 holds Z[2c], Z[2c+1], c = d0 + 32 d1
-            {
-                float4* z4 = reinterpret_cast<float4*>(zs);
 #pragma unroll
-                for (int d1 = 0; d1 < 32; ++d1) z4[lane + 32 * d1] = make_float4(re[d1].x, im[d1].x, re[d1].y, im[d1].y);
+            for (int d1 = 0; d1 < 32; ++d1) {
+                reinterpret_cast<float2*>(zre)[lane + 32 * d1] = re[d1];
+                reinterpret_cast<float2*>(zim)[lane + 32 * d1] = im[d1];
             }
             __syncwarp();
             // split -> x G -> merge, in place; this lane owns the pairs (k, 2048 - k), k = lane + 32 j.  Bin k rides in
@@ -148,15 +153,14 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
                 const int j = j0 + u;
                 const uint32_t* t = t4 + 8 * u;
                 const int k = lane + 32 * j, kc = (2048 - k) & 2047;
-                const float2 zk = zs[k], zc = zs[kc];
-                const float2 zr2 = make_float2(zk.x, zc.x), zi2 = make_float2(zk.y, zc.y);
-                const float2 wr2 = make_float2(__uint_as_float(t[0]), __uint_as_float(t[2])), wi2 = make_float2(__uint_as_float(t[1]), __uint_as_float(t[3]));
-                const float2 gr2 = make_float2(__uint_as_float(t[4]), __uint_as_float(t[6])), gi2 = make_float2(__uint_as_float(t[5]), __uint_as_float(t[7]));
+                const float2 zr2 = make_float2(zre[k], zre[kc]), zi2 = make_float2(zim[k], zim[kc]);
+                const float2 wr2 = make_float2(__uint_as_float(t[0]), __uint_as_float(t[1])), wi2 = make_float2(__uint_as_float(t[2]), __uint_as_float(t[3]));
+                const float2 gr2 = make_float2(__uint_as_float(t[4]), __uint_as_float(t[5])), gi2 = make_float2(__uint_as_float(t[6]), __uint_as_float(t[7]));
                 float2 xr2, xi2;
                 rfft_split2v(zr2, zi2, swap2(zr2), swap2(zi2), wr2, wi2, xr2, xi2);   // (X[k], X[2048 - k])
                 if (k == 0) {                                                         // packed (X[0], X[2048]) in the .x half
-                    xr2.x = __fadd_rn(zk.x, zk.y);
-                    xi2.x = __fsub_rn(zk.x, zk.y);
+                    xr2.x = __fadd_rn(zr2.x, zi2.x);
+                    xi2.x = __fsub_rn(zr2.x, zi2.x);
                 }
                 float2 yr2, yi2;
                 cmul2v(xr2, xi2, gr2, gi2, yr2, yi2);                                 // arm_cmplx_mult_cmplx_f32 (quirk at k = 0)
@@ -166,17 +170,22 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
                     or2.x = __fadd_rn(yr2.x, yi2.x);
                     oi2.x = __fsub_rn(yr2.x, yi2.x);
                 }
-                zs[k] = make_float2(or2.x, oi2.x);
-                if (k != 0) zs[kc] = make_float2(or2.y, oi2.y);
+                zre[k] = or2.x;
+                zim[k] = oi2.x;
+                if (k != 0) {
+                    zre[kc] = or2.y;
+                    zim[kc] = oi2.y;
+                }
                 }
             }
             if (lane == 0) {                           // bin 1024 pairs with itself
-                const float2 zk = zs[1024], wk = ws1024;
+                const float2 zk = make_float2(zre[1024], zim[1024]), wk = ws1024;
                 float xr, xi, yr, yi, zr, zi;
                 rfft_split(zk.x, zk.y, zk.x, zk.y, wk.x, wk.y, xr, xi);
                 cmul(xr, xi, g1024.x, g1024.y, yr, yi);
                 rfft_merge(yr, yi, yr, yi, wk.x, wk.y, zr, zi);
-                zs[1024] = make_float2(zr, zi);
+                zre[1024] = zr;
+                zim[1024] = zi;
             }
             __syncwarp();
             // inverse = forward transform of the swapped parts (radix-2 level again)
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int q = 8 * g + u, a = lane + 32 * q;
-                    const float2 l = zs[a], h = zs[a + 1024];
+                    const float2 l = make_float2(zre[a], zim[a]), h = make_float2(zre[a + 1024], zim[a + 1024]);
                     const float er = __fadd_rn(l.y, h.y), ei = __fadd_rn(l.x, h.x);
                     const float dr = __fsub_rn(l.y, h.y), di = __fsub_rn(l.x, h.x);
                     float orr, oii;
