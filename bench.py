@@ -433,7 +433,7 @@ def configs_report(t, ok, infos, world, peak):
         c4["sync_search"]["K%d" % K] = {"kernel": "k_sync_search", "frames_added": K, "value": fr4 * world / (ms * 1e-3), "unit": "frames/s",
                                         "ms": ms, "roofline": roof(fr4 * (N * 4 + 32), ms)}
     ms = t["c4_os_ms"]
-    c4["overlap_save"] = {"kernel": "k_correlate_os<int>", "call": "usc_correlate_os", "what": "linear matched filter at every lag (2n windows, hop n, 4096-point real transforms), peak per block",
+    c4["overlap_save"] = {"kernel": "k_correlate_os<int, false>", "call": "usc_correlate_os", "what": "linear matched filter at every lag (2n windows, hop n, 4096-point real transforms), peak per block",
                           "value": i4["streams"] * (i4["frames_per_stream"] - 1) * world / (ms * 1e-3), "unit": "blocks/s", "ms": ms,
                           "roofline": roof(fr4 * N * 4 + i4["streams"] * (i4["frames_per_stream"] - 1) * 8, ms)}
     out["4"] = c4

@@ -46,7 +46,9 @@ struct os_params {
     float* out; float* max_val; uint32_t* max_idx;
 };
 
-template <typename PCM>
+// OUT: the n filtered samples of every block are stored as well (otherwise only the peaks: the float4 transposition of the
+// outputs and sixteen stores per lane leave the loop)
+template <typename PCM, bool OUT>
 __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     uint32_t* s_tslot = reinterpret_cast<uint32_t*>(s_raw);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             const float sc = 1.0f / 4096.0f;
             float best = -INFINITY;
             uint32_t best_idx = 0xffffffffu;
-            float4* o4 = p.out ? reinterpret_cast<float4*>(p.out + ((size_t) s * nblocks + b) * 2048) : nullptr;
+            float4* o4 = OUT ? reinterpret_cast<float4*>(p.out + ((size_t) s * nblocks + b) * 2048) : nullptr;
 #pragma unroll
             for (int d1 = 16; d1 < 32; ++d1) {
                 const int c = lane + 32 * d1;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
                 if (v.y > best) { best = v.y; best_idx = l0 + 1; }
                 if (v.z > best) { best = v.z; best_idx = l0 + 2; }
                 if (v.w > best) { best = v.w; best_idx = l0 + 3; }
-                if (o4) o4[c - 512] = v;
+                if (OUT) o4[c - 512] = v;
             }
             if (best_idx == 0xffffffffu) best_idx = 4u * (uint32_t) (lane + 512) - 2048u;   // all NaN / -inf: first own lag
             warp_argmax(best, best_idx);
@@ -251,8 +253,10 @@ cudaError_t launch_correlate_os(const void* pcm, uint32_t pcm_format, uint32_t n
     static per_device<bool> configured_pd;
     bool& configured = configured_pd.get();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_correlate_os<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_correlate_os<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_correlate_os<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_correlate_os<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_correlate_os<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_correlate_os<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -274,8 +278,13 @@ cudaError_t launch_correlate_os(const void* pcm, uint32_t pcm_format, uint32_t n
     p.nseg = (nblocks + seg - 1) / seg;
     size_t ctas = ((size_t) nstreams * p.nseg + kOsWarps - 1) / kOsWarps;
     if (ctas > (size_t) num_sms) ctas = (size_t) num_sms;
-    if (pcm_format == 1u) k_correlate_os<int32_t><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
-    else k_correlate_os<float><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+    if (pcm_format == 1u) {
+        if (out) k_correlate_os<int32_t, true><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+        else k_correlate_os<int32_t, false><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+    } else {
+        if (out) k_correlate_os<float, true><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+        else k_correlate_os<float, false><<<(int) ctas, kOsWarps * 32, kOsSmem, st>>>(p);
+    }
     return cudaGetLastError();
 }
 
