@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n,frames,snr", [(256, 33, 0.0), (1024, 17, -5.0), (4096, 9, -10.0), (8192, 9, -15.0),
-                                          (16384, 5, -15.0), (32768, 3, -15.0), (32768, 71, -20.0), (65536, 3, -20.0), (65536, 77, -15.0)])
+                                          (16384, 5, -15.0), (32768, 3, -15.0), (32768, 71, -20.0), (65536, 3, -20.0), (65536, 77, -15.0),
+                                          # eight frames and more per cluster: the split-phase closing barrier of the cluster kernel
+                                          # (a cluster's next level 0 overlapping its peers' split) is exercised on every frame but the first
+                                          (32768, 530, -20.0), (65536, 270, -15.0)])
 def test_long_frame_demod_bit_exact(n, frames, snr):
     h = usc.Handle(usc.default_config(n=n))
     rx = R.RefReceiver(n=n)

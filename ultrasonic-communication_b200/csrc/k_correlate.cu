@@ -38,6 +38,14 @@ constexpr int kOsWarpBytes = kOsHalfB + 8192;          // half A | exchange tile
 constexpr int kOsBar = kOsTabs + kOsWarps * kOsWarpBytes;
 constexpr int kOsSmem = kOsBar + kOsWarps * 8;
 
+#ifndef USC_OS_SPECU
+#define USC_OS_SPECU 4
+#endif
+constexpr int kOsSpecU = USC_OS_SPECU;                 // spectral pairs per lane and loop iteration (independent chains in flight)
+template <int N> struct ldtm_os;
+template <> struct ldtm_os<32> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[32]) { ldtm32(ta, t); } };
+template <> struct ldtm_os<64> { static __device__ __forceinline__ void ld(uint32_t ta, uint32_t (&t)[64]) { ldtm64(ta, t); } };
+
 struct os_params {
     const void* pcm; uint32_t nstreams, nframes; size_t stream_stride;
     const float2* G;                                   // packed spectrum of the zero-padded template, 2048 float2
@@ -147,11 +155,11 @@ __global__ void __launch_bounds__(kOsWarps * 32, 1) k_correlate_os(os_params p) 
             // split -> x G -> merge, in place; this lane owns the pairs (k, 2048 - k), k = lane + 32 j.  Bin k rides in
             // the .x half and bin 2048 - k in the .y half of packed operations (each half the scalar operator sequence).
 #pragma unroll 1
-            for (int j0 = 0; j0 < 32; j0 += 4) {
-                uint32_t t4[32];                       // (W_4096^k, W_4096^kc, G[k], G[kc]) of four pairs per TMEM round trip
-                ldtm32(tq + kOsTspec + 8 * j0, t4);
+            for (int j0 = 0; j0 < 32; j0 += kOsSpecU) {
+                uint32_t t4[8 * kOsSpecU];             // packed (W re, W im, G re, G im) of kOsSpecU pairs per TMEM round trip
+                ldtm_os<8 * kOsSpecU>::ld(tq + kOsTspec + 8 * j0, t4);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kOsSpecU; ++u) {
                 const int j = j0 + u;
                 const uint32_t* t = t4 + 8 * u;
                 const int k = lane + 32 * j, kc = (2048 - k) & 2047;

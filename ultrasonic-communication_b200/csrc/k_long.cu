@@ -479,11 +479,11 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
             if (p.bit) p.bit[f] = bd > bu ? 0 : 1;
         }
     };
-    // The barrier that closes a frame is split (USC_CL_SPLITBAR): a thread ARRIVES as soon as its reads of the frame's
-    // sub-spectra are done and WAITS only before its first remote store of the next frame, so the arg-max tail, the wait
-    // for the next PCM share and the next level-0 front end and butterflies run while slower CTAs finish their split.
-    // The per-warp results (stored after the arrive) become visible to CTA 0 with the next frame's first barrier —
-    // they are combined between that barrier and the second one, before any warp can store the following results.
+    // The barrier that closes a frame is split (USC_CL_SPLITBAR): a thread ARRIVES when its work on the frame is done (reads
+    // of the sub-spectra, its warp's result stored in CTA 0) and WAITS only before its first remote store of the next frame,
+    // so the wait for the next PCM share and the next level-0 front end and butterflies run while slower CTAs finish
+    // their split.  CTA 0 combines the per-warp results between the next frame's first and second barrier — after every
+    // arrive of the closing barrier, before any warp can store the following results (those come after the second).
     uint32_t parity = 0;
     bool pending = false;                                // a frame's results wait in CTA 0 / its closing barrier is open
     size_t fprev = 0;
@@ -589,14 +589,12 @@ __global__ void __launch_bounds__(32 * W, 1) k_demod_cluster(long_params p, cons
             pu[j] = pw.x;
             pd[j] = pw.y;
         }
-#if USC_CL_SPLITBAR
-        cluster_arrive();                                // this thread's reads of the frame's sub-spectra are done
-#endif
         float bu, bd;
         uint32_t iu, id;
         argmax_exact2<kLongNB>(pu, pd, kk, ok, bu, iu, bd, id);
         if (lane == 0) st_cluster_f4(red0 + (rank * W + warp) * 16u, make_float4(bu, __uint_as_float(iu), bd, __uint_as_float(id)));
 #if USC_CL_SPLITBAR
+        cluster_arrive();                                // everything this thread does for frame f is done: reads of the sub-spectra, its result
         pending = true;
         fprev = f;
 #else
