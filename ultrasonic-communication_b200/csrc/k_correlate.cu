@@ -13,8 +13,10 @@
 // samples arrive per block, by a 1-D TMA bulk copy issued as soon as the old lower half is dead.
 // Per block: 4096-point real FFT = 2048-point complex FFT in the canonical plan [2, 32, 32] (even- and odd-bin
 // 1024-point transforms ride in the f32x2 halves of the packed register core) -> spectrum parked in natural order in
-// shared memory (the dead lower half + the idle exchange tile, 16 KB) -> split, x G, merge in place, one lane per
-// (k, 2048 - k) pair -> 2048-point inverse by forward-on-swapped-parts -> only the upper half of the outputs is live,
+// shared memory as two planes, real parts | imaginary parts (the dead lower half + the idle exchange tile, 16 KB) ->
+// split, x G, merge in place, one lane per (k, 2048 - k) pair, bin k in the .x and bin 2048 - k in the .y half of packed
+// operations whose operands the scalar loads form directly (no register moves) -> 2048-point inverse by
+// forward-on-swapped-parts -> only the upper half of the outputs is live,
 // so half of the last pass is pruned -> signed first-occurrence arg-max over the n valid lags (arm_max_f32) and an
 // optional coalesced store of the n filtered samples.
 // Arithmetic: the canonical order of DESIGN.md §3 — bit-identical to the oracle's operator chain
